@@ -1,0 +1,233 @@
+/*
+ * gpd_b200.h — C-ABI of libgpd_b200.so: the B200-native grasp-candidate hot path.
+ *
+ * This is the drop-in boundary for the ONE path of atenpas/gpd that this repo
+ * accelerates (GraspDetector::detectGrasps steps 1-4, reference
+ * src/gpd/grasp_detector.cpp:192-273):
+ *
+ *   sample index -> FrameEstimator local frame -> HandSearch/HandSet/FingerHand
+ *   rotation sweep -> workspace/aperture filter -> ImageGenerator 60x60xC grasp
+ *   image -> LeNet score.
+ *
+ * Conventions follow the reference's only C-ABI precedent,
+ * src/detect_grasps_python.cpp:49-65,431-447,598-601: plain C structs and
+ * pointers, return value = count (>= 0) or negative error code, no exceptions
+ * cross the boundary, errors are also printed to stderr, the callee allocates
+ * result arrays and the caller releases them with a library free function,
+ * inputs are borrowed for the duration of the call only.
+ *
+ * Every entry point cites the reference interface it replaces. INTEGRATION.md
+ * shows the reference-side bindings (a `CudaClassifier : net::Classifier`,
+ * `HandSearch::searchHands`, `ImageGenerator::createImages`,
+ * `GraspDetector::detectGrasps` shims) a maintainer would add.
+ *
+ * There is NO CPU fallback behind these symbols: every compute entry point
+ * returns GPDB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GPD_B200_H_
+#define GPD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPDB_VERSION 1
+
+/* error codes (all negative; >= 0 is success / a count) */
+#define GPDB_OK 0
+#define GPDB_ERR_INVALID (-1)   /* bad argument / parameter                      */
+#define GPDB_ERR_CUDA (-2)      /* CUDA runtime error or no usable device        */
+#define GPDB_ERR_STATE (-3)     /* call order: cloud or weights not set          */
+#define GPDB_ERR_IO (-4)        /* weight file missing or of the wrong size      */
+#define GPDB_ERR_CAPACITY (-5)  /* a neighbourhood exceeded the on-chip tile     */
+#define GPDB_ERR_NCCL (-6)      /* communicator error (multi-GPU entry points)   */
+
+#define GPDB_MAX_CAMERAS 8
+#define GPDB_MAX_HAND_AXES 3
+
+/* pose_flags bits (one byte per (sample, axis, angle) pose) */
+#define GPDB_POSE_VALID 1u     /* HandSet::is_valid_ after evalHands (hand_set.cpp:111)        */
+#define GPDB_POSE_FILTERED 2u  /* survives filterGraspsWorkspace [+ filterGraspsDirection]     */
+#define GPDB_POSE_HALF 4u      /* Hand::isHalfAntipodal (hand_set.cpp:255-261)                 */
+#define GPDB_POSE_FULL 8u      /* Hand::isFullAntipodal                                        */
+
+/* shadow_mode for the 15-channel occlusion channels */
+#define GPDB_SHADOW_DETERMINISTIC 0 /* counter-based draws; defined in include/gpd_b200_shadow.h */
+
+/*
+ * All parameters of the path. Field names are the reference's cfg keys; the
+ * defaults are the reference's defaults (grasp_detector.cpp:48-86,130-185,
+ * hand_geometry.cpp:25-30, image_geometry.cpp:24-28). gpdb_params_default()
+ * fills them.
+ */
+typedef struct gpdb_params {
+  /* candidate::HandGeometry (cfg/hand_geometry.cfg:8-12) */
+  double finger_width;
+  double hand_outer_diameter;
+  double hand_depth;
+  double hand_height;
+  double init_bite;
+  /* descriptor::ImageGeometry (cfg/image_geometry_15channels.cfg:8-12) */
+  double volume_width;  /* ImageGeometry::outer_diameter_ */
+  double volume_depth;
+  double volume_height;
+  int32_t image_size;
+  int32_t image_num_channels; /* 1, 3, 12 or 15 */
+  /* candidate::HandSearch::Parameters (grasp_detector.cpp:67-86) */
+  double nn_radius; /* nn_radius_frames_ */
+  int32_t num_orientations;
+  int32_t num_finger_placements;
+  int32_t num_hand_axes;
+  int32_t hand_axes[GPDB_MAX_HAND_AXES];
+  int32_t deepen_hand;
+  double friction_coeff;
+  int32_t min_viable;
+  /* GraspDetector filters (grasp_detector.cpp:158-174) */
+  double min_aperture;
+  double max_aperture;
+  double workspace_grasps[6];
+  int32_t filter_approach_direction;
+  double direction[3];
+  double thresh_rad;
+  /* net::Classifier (grasp_detector.cpp:130-138) */
+  int32_t batch_size;       /* images per LeNet launch; 0 = library default          */
+  int32_t relu_after_conv;  /* 0: Caffe/Eigen LeNet (no ReLU after conv, A14);        */
+                            /* 1: the PyTorch/OpenVINO 12-channel net (pytorch/network.py:32-47) */
+  /* library */
+  int32_t shadow_mode;      /* GPDB_SHADOW_DETERMINISTIC                              */
+  int32_t device;           /* CUDA device ordinal                                    */
+  int32_t chunk_samples;    /* samples per device pass; 0 = library default           */
+  int32_t keep_images;      /* gpdb_detect also returns the grasp images              */
+  int32_t lenet_impl;       /* 0 = default (tcgen05 when built), 1 = force SIMT fp32  */
+} gpdb_params;
+
+/* One grasp candidate = candidate::Hand (include/gpd/candidate/hand.h:267-276). */
+typedef struct gpdb_pose {
+  double sample[3];   /* Hand::sample_                                             */
+  double frame[9];    /* Hand::orientation_, column-major: approach|binormal|axis  */
+  double position[3]; /* Hand::position_ (hand.cpp:41-45)                          */
+  double top;         /* BoundingBox::top_                                         */
+  double bottom;
+  double center;
+  double width;       /* Hand::grasp_width_                                        */
+  float score;        /* Label::score_ = logits[1] - logits[0] (eigen_classifier.cpp:74) */
+  int32_t sample_index; /* index of the sample in the cloud                        */
+  int32_t sample_slot;  /* position in the sample_idx array passed to the call     */
+  int16_t pose_slot;    /* axis_i * num_orientations + angle_i                     */
+  int16_t finger_idx;   /* Hand::finger_placement_index_                           */
+  uint8_t half_antipodal;
+  uint8_t full_antipodal;
+  uint8_t pad_[2];
+} gpdb_pose;
+
+/* Result of gpdb_detect / gpdb_hand_search: callee-allocated, release with gpdb_free_result. */
+typedef struct gpdb_result {
+  int32_t n_samples;
+  int32_t poses_per_sample; /* num_hand_axes * num_orientations                     */
+  uint8_t *frame_valid;     /* [n_samples] 0 where calculateFrame found no neighbour */
+  double *frames;           /* [n_samples*9] LocalFrame: normal|binormal|curvature_axis */
+  uint8_t *pose_flags;      /* [n_samples*P] GPDB_POSE_* bits                        */
+  float *pose_scores;       /* [n_samples*P] score, NaN where no image was classified */
+  int32_t n_candidates;     /* poses with VALID and FILTERED set                     */
+  gpdb_pose *candidates;    /* [n_candidates] in (sample slot, pose slot) order =    */
+                            /* hands_out order of image_generator.cpp:91-98          */
+  uint8_t *images;          /* [n_candidates*S*S*C] HWC uint8 (cv::Mat CV_8UC(C)) or NULL */
+  double ms_candidates;     /* device time of "1. Candidate generation"  (grasp_detector.cpp:313) */
+  double ms_images;         /*                "2. Descriptor extraction"                     */
+  double ms_classify;       /*                "3. Classification"                            */
+  int64_t kernel_launches;  /* CUDA kernels launched by this call                     */
+} gpdb_result;
+
+typedef struct gpdb_ctx gpdb_ctx;
+
+/* Fill *p with the reference defaults (15-channel images, hand_axes = {2}). */
+void gpdb_params_default(gpdb_params *p);
+
+/* Replaces: GraspDetector::GraspDetector(cfg) (grasp_detector.cpp:5-190). One context = one
+ * CUDA device + stream; calls on one context are serialised by the caller. */
+int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out);
+void gpdb_destroy(gpdb_ctx *ctx);
+
+/* Message of the last error on this context (or of the last failed gpdb_create when ctx==NULL). */
+const char *gpdb_last_error(const gpdb_ctx *ctx);
+
+/* Replaces: EigenClassifier::EigenClassifier weight loading (eigen_classifier.cpp:24-47).
+ * `dir` is the `weights_file` cfg value: a directory (with trailing '/') holding
+ * {conv1,conv2,ip1,ip2}_{weights,biases}.bin in the reference's raw float32 layout. */
+int gpdb_load_weights_dir(gpdb_ctx *ctx, const char *dir);
+
+/* Same, from memory, in the layout of the .bin files (A14): conv = OIHW row-major,
+ * ip = column-major (out, in). Sizes: conv1 20*C*25, conv2 50*20*25, ip1 500*7200, ip2 2*500. */
+int gpdb_set_weights(gpdb_ctx *ctx, const float *conv1_w, const float *conv1_b,
+                     const float *conv2_w, const float *conv2_b, const float *ip1_w,
+                     const float *ip1_b, const float *ip2_w, const float *ip2_b);
+
+/* Replaces: the util::Cloud accessors the path reads (include/gpd/util/cloud.h:300-366):
+ *   xyz          getCloudProcessed() points, packed float32 x,y,z (3*N)
+ *   normals      getNormals(), 3 x N float64 column-major
+ *   cam_source   getCameraSource(), k x N int32 column-major (may be NULL: all ones)
+ *   view_points  getViewPoints(), 3 x k float64 column-major
+ * Builds the device neighbour grid (replaces the two KdTreeFLANN builds,
+ * hand_search.cpp:29-31, image_generator.cpp:37-38). */
+int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals,
+                   const int32_t *cam_source, int32_t n_points, const double *view_points,
+                   int32_t n_cams);
+
+/* Replaces: GraspDetector::detectGrasps steps 1-4 (grasp_detector.cpp:222-273) for the
+ * samples cloud.getSampleIndices() (cloud.h:345). Returns n_candidates or a negative error. */
+int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, gpdb_result *out);
+
+/* Stage-level entry points (used by the parity tests and by partial drop-ins). */
+
+/* Replaces: FrameEstimator::calculateLocalFrames (frame_estimator.cpp:6-35).
+ * frames_out [n*9] normal|binormal|curvature_axis, valid_out [n]. */
+int gpdb_frames(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, double *frames_out,
+                uint8_t *valid_out);
+
+/* Replaces: HandSearch::searchHands (hand_search.cpp:24-64) + filterGraspsWorkspace /
+ * filterGraspsDirection (grasp_detector.cpp:334-398,422-456). No images, no scores. */
+int gpdb_hand_search(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples,
+                     gpdb_result *out);
+
+/* Replaces: ImageGenerator::createImages (image_generator.cpp:17-70) for given hands.
+ * images_out [n_poses * S*S*C] HWC uint8. */
+int gpdb_images(gpdb_ctx *ctx, const gpdb_pose *poses, int32_t n_poses, uint8_t *images_out);
+
+/* Replaces: Classifier::classifyImages (classifier.h:72-73; eigen_classifier.cpp:59-79).
+ * images_hwc [n * S*S*C] continuous cv::Mat data; scores_out [n]; logits_out [n*2] or NULL. */
+int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n_images, float *scores_out,
+                  float *logits_out);
+
+/* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). */
+void gpdb_free_result(gpdb_result *r);
+
+/* --- multi-GPU: one process per GPU, samples sharded by slice ------------- */
+
+/* 128-byte NCCL unique id, created on rank 0 and distributed by the host (torch.distributed,
+ * MPI, a file ...). */
+int gpdb_comm_unique_id(uint8_t id_out[128]);
+/* Join the communicator: afterwards gpdb_set_cloud on rank 0 may be followed by
+ * gpdb_bcast_cloud so that the other ranks receive the cloud over NVLink. */
+int gpdb_comm_init(gpdb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t n_ranks);
+/* ncclBroadcast of the device-resident cloud from `root` (N, k must be passed on all ranks). */
+int gpdb_bcast_cloud(gpdb_ctx *ctx, int32_t root, int32_t n_points, int32_t n_cams);
+/* Each rank runs the path on its contiguous slice [rank*n/R, (rank+1)*n/R) of sample_idx and
+ * ONE ncclAllGather of fixed-stride score slots makes scores_out [n_samples*P] (NaN = no
+ * candidate) and flags_out [n_samples*P] identical on all ranks. Returns this rank's
+ * n_candidates. `local` (may be NULL) receives this rank's gpdb_result for its slice. */
+int gpdb_detect_sharded(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples,
+                        float *scores_out, uint8_t *flags_out, gpdb_result *local);
+
+/* --- introspection ------------------------------------------------------------------------- */
+/* Device-side stage timings of the last gpdb_detect call, CUDA events on the context stream:
+ * ms[0] grid/frames, ms[1] hand search, ms[2] images, ms[3] lenet, ms[4] total. */
+int gpdb_last_timings(const gpdb_ctx *ctx, double ms_out[8]);
+/* Version / build info string (arch, lenet implementation). */
+const char *gpdb_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPD_B200_H_ */
