@@ -1,0 +1,665 @@
+// api.cu — the C-ABI of libgpd_b200.so (include/gpd_b200.h): context, cloud upload, the chunked
+// detect pipeline and the stage-level entry points. Host-side logic only; kernels live in
+// geometry.cu / lenet_simt.cu / lenet_tc.cu. There is no CPU fallback anywhere in this library.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+static char g_create_err[512] = "";
+
+void gpdb_set_error(gpdb_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[480];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  char *dst = ctx ? ctx->err : g_create_err;
+  snprintf(dst, 512, "gpd_b200 error %d: %s", code, buf);
+  fprintf(stderr, "%s\n", dst);  // reference convention: errors are also printed
+}
+
+void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->scratch_sz[slot] >= bytes) return ctx->scratch[slot];
+  if (ctx->scratch[slot]) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_sz[slot] = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) {
+    gpdb_set_error(ctx, GPDB_ERR_CUDA, "cudaMalloc(%zu) failed for scratch slot %d: %s", want, slot,
+                   cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  ctx->scratch_sz[slot] = want;
+  return ctx->scratch[slot];
+}
+
+// ---- host restatements of the Eigen helpers that define the rotation set --------------------------
+// Eigen::AngleAxisd(angle, axis).toRotationMatrix(), column-major (hand_set.cpp:52-53,68-69)
+static void angle_axis_matrix(double angle, const double axis[3], double *R) {
+  double s = std::sin(angle), c = std::cos(angle);
+  double sa[3] = {s * axis[0], s * axis[1], s * axis[2]};
+  double c1[3] = {(1.0 - c) * axis[0], (1.0 - c) * axis[1], (1.0 - c) * axis[2]};
+  double t;
+  t = c1[0] * axis[1]; R[1 * 3 + 0] = t - sa[2]; R[0 * 3 + 1] = t + sa[2];
+  t = c1[0] * axis[2]; R[2 * 3 + 0] = t + sa[1]; R[0 * 3 + 2] = t - sa[1];
+  t = c1[1] * axis[2]; R[2 * 3 + 1] = t - sa[0]; R[1 * 3 + 2] = t + sa[0];
+  R[0] = c1[0] * axis[0] + c;
+  R[4] = c1[1] * axis[1] + c;
+  R[8] = c1[2] * axis[2] + c;
+}
+// Eigen 3.3 VectorXd::LinSpaced(size, low, high)(i)
+static double linspaced(int size, double low, double high, int i) {
+  int size1 = size == 1 ? 1 : size - 1;
+  double step = size == 1 ? 0.0 : (high - low) / (double)(size - 1);
+  bool flip = std::fabs(high) < std::fabs(low);
+  if (flip) return (i == 0) ? low : (high - (double)(size1 - i) * step);
+  return (i == size1) ? high : (low + (double)i * step);
+}
+
+static int fill_dev_params(gpdb_ctx *ctx) {
+  const gpdb_params &p = ctx->prm;
+  DevParams &d = ctx->hp;
+  memset(&d, 0, sizeof(d));
+  if (p.num_orientations < 1 || p.num_orientations > GPDB_MAX_ORIENT || p.num_hand_axes < 1 ||
+      p.num_hand_axes > GPDB_MAX_HAND_AXES || p.num_finger_placements < 1 || 2 * p.num_finger_placements > GPDB_MAX_SLOTS ||
+      p.image_size < 8 || p.image_size > 64 ||
+      !(p.image_num_channels == 1 || p.image_num_channels == 3 || p.image_num_channels == 12 || p.image_num_channels == 15)) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID,
+                   "unsupported parameters (num_orientations 1..%d, hand_axes 1..3, num_finger_placements 1..%d, "
+                   "image_size 8..64, image_num_channels 1/3/12/15)", GPDB_MAX_ORIENT, GPDB_MAX_SLOTS / 2);
+    return GPDB_ERR_INVALID;
+  }
+  d.finger_width = p.finger_width;
+  d.hand_outer_diameter = p.hand_outer_diameter;
+  d.hand_depth = p.hand_depth;
+  d.hand_height = p.hand_height;
+  d.init_bite = p.init_bite;
+  d.n_axes = p.num_hand_axes;
+  d.n_orient = p.num_orientations;
+  d.P = d.n_axes * d.n_orient;
+  d.nfp = p.num_finger_placements;
+  d.deepen = p.deepen_hand;
+  d.all_axes_z = 1;
+  for (int a = 0; a < d.n_axes; a++) {
+    if (p.hand_axes[a] < 0 || p.hand_axes[a] > 2) {
+      gpdb_set_error(ctx, GPDB_ERR_INVALID, "hand_axes[%d] = %d out of range 0..2", a, p.hand_axes[a]);
+      return GPDB_ERR_INVALID;
+    }
+    d.axes[a] = p.hand_axes[a];
+    if (p.hand_axes[a] != 2) d.all_axes_z = 0;
+  }
+  // FingerHand::FingerHand (finger_hand.cpp:6-24)
+  for (int i = 0; i < d.nfp; i++) {
+    double h = linspaced(d.nfp, 0.0, p.hand_outer_diameter - p.finger_width, i);
+    d.fs[i] = (h - p.hand_outer_diameter) + p.finger_width;
+    d.fs[d.nfp + i] = h;
+  }
+  for (int i = 0; i < 2 * d.nfp; i++) d.fsw[i] = d.fs[i] + p.finger_width;
+  d.slots_disjoint = 1;
+  for (int i = 0; i + 1 < d.nfp; i++)
+    if (!(d.fsw[i] <= d.fs[i + 1]) || !(d.fsw[d.nfp + i] <= d.fs[d.nfp + i + 1])) d.slots_disjoint = 0;
+  // deepenHand steps (finger_hand.cpp:118-121): repeated += 0.005 in double
+  d.J = 0;
+  for (double depth = p.init_bite + 0.005; depth <= p.hand_depth; depth += 0.005) {
+    if (d.J >= GPDB_MAX_DEEPEN) {
+      gpdb_set_error(ctx, GPDB_ERR_INVALID, "more than %d deepen steps", GPDB_MAX_DEEPEN);
+      return GPDB_ERR_INVALID;
+    }
+    d.topj[d.J] = depth;
+    d.botj[d.J] = depth - p.hand_depth;
+    d.J++;
+  }
+  d.cosf = std::cos(p.friction_coeff * M_PI / 180.0);
+  d.min_viable = p.min_viable;
+  d.min_ap = p.min_aperture;
+  d.max_ap = p.max_aperture;
+  for (int i = 0; i < 6; i++) d.ws[i] = p.workspace_grasps[i];
+  d.filt_dir = p.filter_approach_direction;
+  for (int i = 0; i < 3; i++) d.dir[i] = p.direction[i];
+  d.thresh = p.thresh_rad;
+  const double uy[3] = {0, 1, 0};
+  angle_axis_matrix(M_PI, uy, d.rotb);
+  static const double AXES[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int a = 0; a < d.n_axes; a++)
+    for (int i = 0; i < d.n_orient; i++) {
+      // angles = LinSpaced(n+1, -pi/2, pi/2).head(n) (hand_search.cpp:151-155)
+      double ang = linspaced(d.n_orient + 1, -1.0 * M_PI / 2.0, M_PI / 2.0, i);
+      angle_axis_matrix(ang, AXES[d.axes[a]], d.rot[a * d.n_orient + i]);
+    }
+  d.vol_w = p.volume_width;
+  d.vol_d = p.volume_depth;
+  d.vol_h = p.volume_height;
+  d.S = p.image_size;
+  d.C = p.image_num_channels;
+  // radii: hand_search.cpp:13-17, image_generator.cpp:43-46, image_15_channels_strategy.h:72-75
+  double r_hs = std::max(std::max(p.hand_outer_diameter - p.finger_width, p.hand_depth), p.hand_height / 2.0);
+  double r_img = std::max(std::max(p.volume_depth, p.volume_height / 2.0), p.volume_width);
+  double r_lrf = p.nn_radius;
+  d.r2_lrf = (float)(r_lrf * r_lrf);
+  d.r2_hs = (float)(r_hs * r_hs);
+  d.r2_img = (float)(r_img * r_img);
+  d.rf_lrf = (float)r_lrf * 1.0001f + 1e-6f;
+  d.rf_hs = (float)r_hs * 1.0001f + 1e-6f;
+  d.rf_img = (float)r_img * 1.0001f + 1e-6f;
+  d.shadow_length = r_img;
+  d.vox_mult = 1.0 / GPDB_SHADOW_VOXEL;
+  d.nsp = (int)std::floor(d.shadow_length / GPDB_SHADOW_VOXEL);
+  double diag = std::sqrt(p.volume_depth * p.volume_depth + p.volume_width * p.volume_width +
+                          4.0 * p.volume_height * p.volume_height);
+  d.bm_dim = (int)std::ceil((diag + 2.0 * 3.2 * GPDB_SHADOW_VOXEL * 0.3) / GPDB_SHADOW_VOXEL) + 4;
+  d.relu_after_conv = p.relu_after_conv;
+  d.K = 1;
+  d.dim[0] = d.dim[1] = d.dim[2] = 1;
+  d.inv_cell = 50.0f;
+  return GPDB_OK;
+}
+
+extern "C" {
+
+void gpdb_params_default(gpdb_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->finger_width = 0.01;
+  p->hand_outer_diameter = 0.12;
+  p->hand_depth = 0.06;
+  p->hand_height = 0.02;
+  p->init_bite = 0.01;
+  p->volume_width = 0.10;
+  p->volume_depth = 0.06;
+  p->volume_height = 0.02;
+  p->image_size = 60;
+  p->image_num_channels = 15;
+  p->nn_radius = 0.01;
+  p->num_orientations = 8;
+  p->num_finger_placements = 10;
+  p->num_hand_axes = 1;
+  p->hand_axes[0] = 2;
+  p->deepen_hand = 1;
+  p->friction_coeff = 20.0;
+  p->min_viable = 6;
+  p->min_aperture = 0.0;
+  p->max_aperture = 0.085;
+  const double ws[6] = {-1, 1, -1, 1, -1, 1};
+  for (int i = 0; i < 6; i++) p->workspace_grasps[i] = ws[i];
+  p->filter_approach_direction = 0;
+  p->direction[0] = 1.0;
+  p->thresh_rad = 2.3;
+}
+
+const char *gpdb_build_info(void) {
+  return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images (fp64, -fmad=false), lenet: simt-fp32";
+}
+
+const char *gpdb_last_error(const gpdb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out) {
+  if (!params || !ctx_out) {
+    gpdb_set_error(nullptr, GPDB_ERR_INVALID, "gpdb_create: null argument");
+    return GPDB_ERR_INVALID;
+  }
+  *ctx_out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    gpdb_set_error(nullptr, GPDB_ERR_CUDA, "no CUDA device: libgpd_b200 has no CPU fallback");
+    return GPDB_ERR_CUDA;
+  }
+  if (params->device < 0 || params->device >= ndev) {
+    gpdb_set_error(nullptr, GPDB_ERR_INVALID, "device %d out of range (have %d)", params->device, ndev);
+    return GPDB_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, params->device) != cudaSuccess || prop.major != 10) {
+    gpdb_set_error(nullptr, GPDB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                   params->device, prop.major, prop.minor);
+    return GPDB_ERR_CUDA;
+  }
+  gpdb_ctx *ctx = new gpdb_ctx();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->prm = *params;
+  ctx->device = params->device;
+  ctx->sm_count = prop.multiProcessorCount;
+  int rc = fill_dev_params(ctx);
+  if (rc != GPDB_OK) {
+    strncpy(g_create_err, ctx->err, sizeof(g_create_err) - 1);
+    delete ctx;
+    return rc;
+  }
+  bool ok = cudaSetDevice(ctx->device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc(&ctx->dp, sizeof(DevParams)) == cudaSuccess &&
+            cudaMalloc(&ctx->d_err, sizeof(int) * GPDB_NERR) == cudaSuccess &&
+            cudaMalloc(&ctx->d_qtab, sizeof(double) * GPDB_QTAB_SIZE) == cudaSuccess;
+  if (ok) {
+    double qt[GPDB_QTAB_SIZE];
+    gpdb_build_qtab(qt);
+    ok = cudaMemcpy(ctx->d_qtab, qt, sizeof(qt), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->dp, &ctx->hp, sizeof(DevParams), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemset(ctx->d_err, 0, sizeof(int) * GPDB_NERR) == cudaSuccess;
+  }
+  for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  if (!ok) {
+    gpdb_set_error(nullptr, GPDB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gpdb_destroy(ctx);
+    return GPDB_ERR_CUDA;
+  }
+  *ctx_out = ctx;
+  return GPDB_OK;
+}
+
+void gpdb_destroy(gpdb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->dp);
+  cudaFree(ctx->d_err);
+  cudaFree(ctx->d_qtab);
+  cudaFree(ctx->d_pts4);
+  cudaFree(ctx->d_xyz);
+  cudaFree(ctx->d_nrm);
+  cudaFree(ctx->d_cam);
+  cudaFree(ctx->d_cell_start);
+  float *w[8] = {ctx->w.c1w, ctx->w.c1b, ctx->w.c2w, ctx->w.c2b, ctx->w.i1w, ctx->w.i1b, ctx->w.i2w, ctx->w.i2b};
+  for (float *p : w) cudaFree(p);
+  for (int i = 0; i < 16; i++) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < 8; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int gpdb_set_weights(gpdb_ctx *ctx, const float *conv1_w, const float *conv1_b, const float *conv2_w,
+                     const float *conv2_b, const float *ip1_w, const float *ip1_b, const float *ip2_w,
+                     const float *ip2_b) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  const float *w[8] = {conv1_w, conv1_b, conv2_w, conv2_b, ip1_w, ip1_b, ip2_w, ip2_b};
+  for (const float *p : w)
+    if (!p) {
+      gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_set_weights: null weight array");
+      return GPDB_ERR_INVALID;
+    }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return lenet_upload(ctx, w);
+}
+
+// readBinaryFileIntoVector (eigen_classifier.cpp:185-205)
+int gpdb_load_weights_dir(gpdb_ctx *ctx, const char *dir) {
+  if (!ctx || !dir) return GPDB_ERR_INVALID;
+  const int C = ctx->prm.image_num_channels;
+  const char *names[8] = {"conv1_weights", "conv1_biases", "conv2_weights", "conv2_biases",
+                          "ip1_weights",   "ip1_biases",   "ip2_weights",   "ip2_biases"};
+  const size_t sizes[8] = {(size_t)20 * C * 25, 20, 50 * 20 * 25, 50, (size_t)500 * 7200, 500, 1000, 2};
+  std::vector<std::vector<float>> bufs(8);
+  for (int i = 0; i < 8; i++) {
+    std::string path = std::string(dir) + names[i] + ".bin";
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+      gpdb_set_error(ctx, GPDB_ERR_IO, "Cannot open file: %s", path.c_str());
+      return GPDB_ERR_IO;
+    }
+    bufs[i].resize(sizes[i]);
+    size_t got = fread(bufs[i].data(), sizeof(float), sizes[i], f);
+    char extra;
+    bool more = fread(&extra, 1, 1, f) == 1;
+    fclose(f);
+    if (got != sizes[i] || more) {
+      gpdb_set_error(ctx, GPDB_ERR_IO, "%s: expected %zu float32 values for %d channels", path.c_str(), sizes[i], C);
+      return GPDB_ERR_IO;
+    }
+  }
+  return gpdb_set_weights(ctx, bufs[0].data(), bufs[1].data(), bufs[2].data(), bufs[3].data(), bufs[4].data(),
+                          bufs[5].data(), bufs[6].data(), bufs[7].data());
+}
+
+int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const int32_t *cam_source, int32_t N,
+                   const double *view_points, int32_t K) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  if (!xyz || !normals || !view_points || N <= 0 || K <= 0 || K > GPDB_MAX_CAMERAS) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_set_cloud: need xyz, normals, view_points, N > 0, 1 <= cameras <= %d",
+                   GPDB_MAX_CAMERAS);
+    return GPDB_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->cloud_set = false;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_pts4); ctx->d_pts4 = nullptr;
+  cudaFree(ctx->d_xyz); ctx->d_xyz = nullptr;
+  cudaFree(ctx->d_nrm); ctx->d_nrm = nullptr;
+  cudaFree(ctx->d_cam); ctx->d_cam = nullptr;
+  CUDA_TRY(cudaMalloc(&ctx->d_pts4, sizeof(float4) * (size_t)N));
+  CUDA_TRY(cudaMalloc(&ctx->d_xyz, sizeof(float) * 3 * (size_t)N));
+  CUDA_TRY(cudaMalloc(&ctx->d_nrm, sizeof(double) * 3 * (size_t)N));
+  CUDA_TRY(cudaMalloc(&ctx->d_cam, (size_t)N));
+  std::vector<uint8_t> cam((size_t)N, (uint8_t)((1u << K) - 1));
+  if (cam_source)
+    for (int i = 0; i < N; i++) {
+      uint8_t m = 0;
+      for (int k = 0; k < K; k++)
+        if (cam_source[(size_t)i * K + k] > 0) m |= (uint8_t)(1u << k);
+      cam[i] = m;
+    }
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_xyz, xyz, sizeof(float) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm, normals, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_cam, cam.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->hp.K = K;
+  for (int k = 0; k < K; k++)
+    for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];
+  ctx->N = N;
+  ctx->K = K;
+  ctx->cloud.pts4 = ctx->d_pts4;
+  ctx->cloud.xyz = ctx->d_xyz;
+  ctx->cloud.nrm = ctx->d_nrm;
+  ctx->cloud.cam = ctx->d_cam;
+  int rc = geo_build_grid(ctx, xyz, N);
+  if (rc != GPDB_OK) return rc;
+  ctx->cloud_set = true;
+  return GPDB_OK;
+}
+
+}  // extern "C"
+
+// ---- pipeline ------------------------------------------------------------------------------------
+namespace {
+
+struct StageTimes {
+  gpdb_ctx *ctx;
+  std::vector<cudaEvent_t> pool;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool.push_back(e);
+    return e;
+  }
+  cudaEvent_t begin() {
+    cudaEvent_t e = get();
+    cudaEventRecord(e, ctx->stream);
+    return e;
+  }
+  void end(int stage, cudaEvent_t b) {
+    cudaEvent_t e = get();
+    cudaEventRecord(e, ctx->stream);
+    spans.push_back({stage, {b, e}});
+  }
+  void collect(double *ms) {
+    for (auto &s : spans) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, s.second.first, s.second.second) == cudaSuccess) ms[s.first] += t;
+    }
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+    spans.clear();
+  }
+};
+
+int check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  if (need_cloud && !ctx->cloud_set) {
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "no point cloud: call gpdb_set_cloud first");
+    return GPDB_ERR_STATE;
+  }
+  if (need_weights && !ctx->w.set) {
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "no classifier weights: call gpdb_load_weights_dir / gpdb_set_weights first");
+    return GPDB_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return GPDB_OK;
+}
+
+int check_device_errors(gpdb_ctx *ctx) {
+  int e[GPDB_NERR];
+  CUDA_TRY(cudaMemcpyAsync(e, ctx->d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (e[0] || e[1] || e[2]) {
+    CUDA_TRY(cudaMemsetAsync(ctx->d_err, 0, sizeof(e), ctx->stream));
+    gpdb_set_error(ctx, GPDB_ERR_CAPACITY,
+                   "neighbourhood exceeded an on-chip tile (frame ball: %d samples, hand-search ball: %d samples, "
+                   "image box: %d images): the cloud is denser than the supported %d / %d / %d points",
+                   e[0], e[1], e[2], 512, 13312, 1024);
+    return GPDB_ERR_CAPACITY;
+  }
+  return GPDB_OK;
+}
+
+// The chunked device pipeline behind gpdb_detect / gpdb_hand_search.
+int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores) {
+  memset(out, 0, sizeof(*out));
+  const int P = ctx->hp.P, S = ctx->hp.S, C = ctx->hp.C;
+  const size_t isz = (size_t)S * S * C;
+  out->n_samples = n;
+  out->poses_per_sample = P;
+  for (int i = 0; i < n; i++)
+    if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N) {
+      gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d at position %d outside the cloud (N = %d)", sample_idx[i], i,
+                     ctx->N);
+      return GPDB_ERR_INVALID;
+    }
+  const int64_t launches0 = ctx->launches;
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  StageTimes st{ctx};
+  const int chunk = ctx->prm.chunk_samples > 0 ? ctx->prm.chunk_samples : 16384;
+  const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
+  const bool keep = with_images_and_scores && ctx->prm.keep_images;
+  const size_t nP = (size_t)n * P;
+  int *d_sidx = (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
+  double *d_frames = (double *)gpdb_scratch(ctx, 8, sizeof(double) * 9 * (size_t)n);
+  uint8_t *d_valid = (uint8_t *)gpdb_scratch(ctx, 9, (size_t)n);
+  uint8_t *d_flags = (uint8_t *)gpdb_scratch(ctx, 10, nP);
+  float *d_pscores = (float *)gpdb_scratch(ctx, 11, sizeof(float) * nP);
+  const int cmax = std::min(chunk, std::max(n, 1));
+  gpdb_pose *d_poses = (gpdb_pose *)gpdb_scratch(ctx, 12, sizeof(gpdb_pose) * (size_t)cmax * P);
+  gpdb_pose *d_cand = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)cmax * P);
+  int *d_count = (int *)gpdb_scratch(ctx, 14, 64);
+  if (!d_sidx || !d_frames || !d_valid || !d_flags || !d_pscores || !d_poses || !d_cand || !d_count) return GPDB_ERR_CUDA;
+  cudaEvent_t t_all = st.begin();
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_pscores, 0xFF, sizeof(float) * nP, ctx->stream));  // 0xFFFFFFFF = NaN
+  }
+  int rc;
+  cudaEvent_t t0 = st.begin();
+  if ((rc = geo_frames(ctx, d_sidx, n, d_frames, d_valid)) != GPDB_OK) return rc;
+  st.end(0, t0);
+  std::vector<gpdb_pose> cands;
+  std::vector<uint8_t> images;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int nn = std::min(chunk, n - c0);
+    cudaEvent_t t1 = st.begin();
+    if ((rc = geo_hands(ctx, d_sidx + c0, nn, c0, d_frames + 9 * (size_t)c0, d_valid + c0, d_poses,
+                        d_flags + (size_t)c0 * P)) != GPDB_OK)
+      return rc;
+    if ((rc = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand, d_count)) != GPDB_OK) return rc;
+    st.end(1, t1);
+    int nc = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nc, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (with_images_and_scores && nc > 0) {
+      float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)nc);
+      if (!d_scores) return GPDB_ERR_CUDA;
+      const int ib = keep ? nc : std::min(nc, batch);
+      uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)ib);
+      if (!d_img) return GPDB_ERR_CUDA;
+      for (int b0 = 0; b0 < nc; b0 += batch) {
+        const int bn = std::min(batch, nc - b0);
+        uint8_t *dst = keep ? d_img + isz * (size_t)b0 : d_img;
+        cudaEvent_t t2 = st.begin();
+        if ((rc = geo_images(ctx, d_cand + b0, bn, dst)) != GPDB_OK) return rc;
+        st.end(2, t2);
+        cudaEvent_t t3 = st.begin();
+        if ((rc = lenet_forward(ctx, dst, bn, d_scores + b0, nullptr)) != GPDB_OK) return rc;
+        st.end(3, t3);
+      }
+      if ((rc = geo_scatter_scores(ctx, d_cand, d_scores, nc, c0, P, d_pscores + (size_t)c0 * P, d_cand)) != GPDB_OK)
+        return rc;
+      if (keep) {
+        size_t off = images.size();
+        images.resize(off + isz * (size_t)nc);
+        CUDA_TRY(cudaMemcpyAsync(images.data() + off, d_img, isz * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+    }
+    if (nc > 0) {
+      size_t off = cands.size();
+      cands.resize(off + nc);
+      CUDA_TRY(cudaMemcpyAsync(cands.data() + off, d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  out->frame_valid = (uint8_t *)malloc((size_t)n + 1);
+  out->frames = (double *)malloc(sizeof(double) * 9 * (size_t)n + 8);
+  out->pose_flags = (uint8_t *)malloc(nP + 1);
+  out->pose_scores = (float *)malloc(sizeof(float) * nP + 4);
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(out->frame_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out->frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out->pose_flags, d_flags, nP, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out->pose_scores, d_pscores, sizeof(float) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  st.end(4, t_all);
+  if ((rc = check_device_errors(ctx)) != GPDB_OK) {
+    st.collect(ms);
+    gpdb_free_result(out);
+    return rc;
+  }
+  st.collect(ms);
+  out->n_candidates = (int)cands.size();
+  out->candidates = (gpdb_pose *)malloc(sizeof(gpdb_pose) * cands.size() + 8);
+  if (!cands.empty()) memcpy(out->candidates, cands.data(), sizeof(gpdb_pose) * cands.size());
+  if (keep) {
+    out->images = (uint8_t *)malloc(images.size() + 8);
+    if (!images.empty()) memcpy(out->images, images.data(), images.size());
+  }
+  out->ms_candidates = ms[0] + ms[1];
+  out->ms_images = ms[2];
+  out->ms_classify = ms[3];
+  out->kernel_launches = ctx->launches - launches0;
+  for (int i = 0; i < 8; i++) ctx->last_ms[i] = ms[i];
+  return out->n_candidates;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out) {
+  int rc = check_state(ctx, true, true);
+  if (rc != GPDB_OK) return rc;
+  if (!out || (n > 0 && !sample_idx) || n < 0) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_detect: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  return run_pipeline(ctx, sample_idx, n, out, true);
+}
+
+int gpdb_hand_search(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out) {
+  int rc = check_state(ctx, true, false);
+  if (rc != GPDB_OK) return rc;
+  if (!out || (n > 0 && !sample_idx) || n < 0) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_hand_search: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  return run_pipeline(ctx, sample_idx, n, out, false);
+}
+
+int gpdb_frames(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, double *frames_out, uint8_t *valid_out) {
+  int rc = check_state(ctx, true, false);
+  if (rc != GPDB_OK) return rc;
+  if (n < 0 || (n > 0 && (!sample_idx || !frames_out || !valid_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_frames: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  if (n == 0) return 0;
+  for (int i = 0; i < n; i++)
+    if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N) {
+      gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d outside the cloud (N = %d)", sample_idx[i], ctx->N);
+      return GPDB_ERR_INVALID;
+    }
+  int *d_sidx = (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
+  double *d_frames = (double *)gpdb_scratch(ctx, 8, sizeof(double) * 9 * (size_t)n);
+  uint8_t *d_valid = (uint8_t *)gpdb_scratch(ctx, 9, (size_t)n);
+  if (!d_sidx || !d_frames || !d_valid) return GPDB_ERR_CUDA;
+  CUDA_TRY(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = geo_frames(ctx, d_sidx, n, d_frames, d_valid)) != GPDB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(frames_out, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(valid_out, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = check_device_errors(ctx)) != GPDB_OK) return rc;
+  return n;
+}
+
+int gpdb_images(gpdb_ctx *ctx, const gpdb_pose *poses, int32_t n, uint8_t *images_out) {
+  int rc = check_state(ctx, true, false);
+  if (rc != GPDB_OK) return rc;
+  if (n < 0 || (n > 0 && (!poses || !images_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_images: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C;
+  const int batch = 8192;
+  for (int b0 = 0; b0 < n; b0 += batch) {
+    const int bn = std::min(batch, n - b0);
+    gpdb_pose *d_cand = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)bn);
+    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)bn);
+    if (!d_cand || !d_img) return GPDB_ERR_CUDA;
+    CUDA_TRY(cudaMemcpyAsync(d_cand, poses + b0, sizeof(gpdb_pose) * (size_t)bn, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = geo_images(ctx, d_cand, bn, d_img)) != GPDB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(images_out + isz * (size_t)b0, d_img, isz * (size_t)bn, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if ((rc = check_device_errors(ctx)) != GPDB_OK) return rc;
+  return n;
+}
+
+int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n, float *scores_out, float *logits_out) {
+  int rc = check_state(ctx, false, true);
+  if (rc != GPDB_OK) return rc;
+  if (n < 0 || (n > 0 && (!images_hwc || !scores_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_classify: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C;
+  const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
+  for (int b0 = 0; b0 < n; b0 += batch) {
+    const int bn = std::min(batch, n - b0);
+    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)bn);
+    float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)bn * 3);
+    if (!d_img || !d_scores) return GPDB_ERR_CUDA;
+    float *d_logits = d_scores + bn;
+    CUDA_TRY(cudaMemcpyAsync(d_img, images_hwc + isz * (size_t)b0, isz * (size_t)bn, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = lenet_forward(ctx, d_img, bn, d_scores, d_logits)) != GPDB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(scores_out + b0, d_scores, sizeof(float) * (size_t)bn, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logits_out)
+      CUDA_TRY(cudaMemcpyAsync(logits_out + 2 * (size_t)b0, d_logits, sizeof(float) * 2 * (size_t)bn,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
+void gpdb_free_result(gpdb_result *r) {
+  if (!r) return;
+  free(r->frame_valid);
+  free(r->frames);
+  free(r->pose_flags);
+  free(r->pose_scores);
+  free(r->candidates);
+  free(r->images);
+  memset(r, 0, sizeof(*r));
+}
+
+int gpdb_last_timings(const gpdb_ctx *ctx, double ms_out[8]) {
+  if (!ctx || !ms_out) return GPDB_ERR_INVALID;
+  for (int i = 0; i < 8; i++) ms_out[i] = ctx->last_ms[i];
+  return GPDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// common.cuh — shared declarations of libgpd_b200.so (sm_100a only).
+//
+// HBM layout of one context (see DESIGN.md "data layout"):
+//   cloud   pts4   float4[N]  points SORTED BY GRID CELL: x,y,z + original index bits  (4.8 MB @300k)
+//           xyz    float[3N]  points by original index (nb0 lookups)
+//           nrm    double[3N] normals by original index, 3xN column-major as the ABI gives them
+//           cam    uint8[N]   bit k set when camera k sees the point
+//           cell_start int[ncell+1]   uniform grid, x fastest: a run of cells along x is ONE
+//                                     contiguous segment of pts4
+//   per chunk of samples: frames double[9n], dense pose records gpdb_pose[n*P], flags uint8[n*P],
+//           compact candidate list gpdb_pose[nc], images uint8[nc*S*S*C] (HWC, the cv::Mat layout),
+//           LeNet activations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gpd_b200.h"
+#include "../../include/gpd_b200_shadow.h"
+
+#define GPDB_MAX_ORIENT 32
+#define GPDB_MAX_SLOTS 32   // 2 * num_finger_placements
+#define GPDB_MAX_DEEPEN 64  // deepen steps
+
+// Everything the kernels need, resident in global memory (uniform, L1/L2-cached loads).
+struct DevParams {
+  // hand geometry / search (cfg/hand_geometry.cfg, grasp_detector.cpp:67-86)
+  double finger_width, hand_outer_diameter, hand_depth, hand_height, init_bite;
+  int P, n_axes, n_orient, nfp;
+  int axes[GPDB_MAX_HAND_AXES];
+  int deepen, slots_disjoint, all_axes_z;
+  double fs[GPDB_MAX_SLOTS];   // FingerHand::finger_spacing_ (finger_hand.cpp:12-19)
+  double fsw[GPDB_MAX_SLOTS];  // fs + finger_width
+  int J;                       // deepen steps d_j = init_bite + j*0.005 accumulated in double (finger_hand.cpp:120-121)
+  double topj[GPDB_MAX_DEEPEN], botj[GPDB_MAX_DEEPEN];
+  double cosf;                 // cos(friction_coeff * pi / 180) (antipodal.cpp:28)
+  int min_viable;
+  // filters (grasp_detector.cpp:334-456)
+  double min_ap, max_ap, ws[6];
+  int filt_dir;
+  double dir[3], thresh;
+  // rotations (hand_set.cpp:52-53,68-69): rotb = AngleAxis(pi, UnitY); rot[a*n_orient+i]
+  double rotb[9];
+  double rot[GPDB_MAX_HAND_AXES * GPDB_MAX_ORIENT][9];
+  // image geometry (cfg/image_geometry_*.cfg)
+  double vol_w, vol_d, vol_h;
+  int S, C;
+  // shadow (hand_set.cpp:118-233, include/gpd_b200_shadow.h)
+  double shadow_length, vox_mult;
+  int nsp;                     // num_shadow_points
+  int bm_dim;                  // bitmap edge (voxels)
+  // radii: float32 predicates (dist < r2) and search extents
+  float r2_lrf, r2_hs, r2_img;
+  float rf_lrf, rf_hs, rf_img;
+  // grid
+  float lo[3], inv_cell;
+  int dim[3];
+  // cloud
+  int N, K;
+  double vp[GPDB_MAX_CAMERAS][3];
+  // LeNet
+  int relu_after_conv;
+};
+
+struct DevCloud {
+  const float4 *pts4;
+  const float *xyz;
+  const double *nrm;
+  const uint8_t *cam;
+  const int *cell_start;
+};
+
+// device error counters: [0] LRF capacity, [1] hand-search capacity (final tier), [2] image box list,
+// [3] hand-search tier-1 overflow count (informational)
+#define GPDB_NERR 8
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      gpdb_set_error(ctx, GPDB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                     cudaGetErrorString(e__));                                                \
+      return GPDB_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+struct LenetWeights {  // device pointers, layouts documented in lenet_simt.cu
+  float *c1w, *c1b, *c2w, *c2b, *i1w, *i1b, *i2w, *i2b;
+  int C;
+  bool set;
+};
+
+struct gpdb_ctx {
+  gpdb_params prm;
+  DevParams hp;       // host copy
+  DevParams *dp;      // device copy
+  int device;
+  cudaStream_t stream;
+  int sm_count;
+  char err[512];
+  // cloud
+  DevCloud cloud;
+  float4 *d_pts4;
+  float *d_xyz;
+  double *d_nrm;
+  uint8_t *d_cam;
+  int *d_cell_start;
+  int N, K;
+  bool cloud_set;
+  double *d_qtab;
+  // weights
+  LenetWeights w;
+  // scratch (grown on demand)
+  void *scratch[16];
+  size_t scratch_sz[16];
+  int *d_err;
+  int64_t launches;
+  double last_ms[8];
+  cudaEvent_t ev[8];
+};
+
+void gpdb_set_error(gpdb_ctx *ctx, int code, const char *fmt, ...);
+void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes);  // returns nullptr on failure (error set)
+
+// geometry.cu
+int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N);
+int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_t *d_valid);
+int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
+              gpdb_pose *d_poses, uint8_t *d_flags);
+// compacts poses with VALID|FILTERED into d_cand (in (sample,pose) order); *d_count receives the count
+int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags, int n_poses, gpdb_pose *d_cand,
+                int *d_count);
+int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images);
+int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
+                       float *d_pose_scores, gpdb_pose *d_cand_out);
+
+// lenet_simt.cu
+int lenet_upload(gpdb_ctx *ctx, const float *const w[8]);
+int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores, float *d_logits);

@@ -1,0 +1,1387 @@
+// geometry.cu — the point-geometry kernels of the grasp-candidate path (sm_100a).
+//
+//   k_frames  : FrameEstimator::calculateLocalFrames  (frame_estimator.cpp:6-86, local_frame.cpp:14-41)
+//   k_hands   : HandSearch::evalHands / HandSet::evalHands / FingerHand / Antipodal / Hand::construct
+//               (hand_search.cpp:144-188, hand_set.cpp:31-116,235-261, finger_hand.cpp, antipodal.cpp:10-96,
+//               hand.cpp:24-45) + GraspDetector::filterGraspsWorkspace/Direction (grasp_detector.cpp:334-456)
+//   k_images  : ImageGenerator::createImages + Image{1,3,12,15}ChannelsStrategy (image_generator.cpp:17-99,
+//               image_strategy.cpp:32-233, image_*_channels_strategy.cpp) + HandSet::calculateShadow in the
+//               deterministic variant of include/gpd_b200_shadow.h
+//
+// Design (not a translation of the reference's per-sample OpenMP loops over Eigen temporaries):
+//   * the two KdTreeFLANN builds are replaced by ONE uniform grid whose cells are ordered x-fastest, so
+//     a row of cells is one contiguous segment of the cell-sorted point array: a radius search is a
+//     handful of coalesced segment reads with FLANN's exact float32 predicate; no sorted result list
+//     is ever materialised because every consumer is reformulated as an order-free reduction
+//     (OR / min / max / arg-max / integer sums), SURVEY.md 9.6;
+//   * one CTA owns one sample, its neighbourhood is staged once in shared memory and ONE WARP OWNS ONE
+//     HAND POSE: all finger / deepen / closing-region / antipodal tests are warp-shuffle reductions;
+//   * one CTA owns one grasp image: rasterisation into shared-memory tiles with 64-bit integer
+//     atomics (arg-max key, fixed-point sum+count) => bit-reproducible, then dilate / min-max /
+//     quantise in-tile.
+// All float64 geometry is evaluated in the oracle's operation order; this file is compiled with
+// -fmad=false so that no multiply-add is contracted (strict '<' on doubles).
+#include <cfloat>
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT_HANDS = 256;
+constexpr int NT_IMG = 512;
+constexpr int LRF_WARPS = 4;
+constexpr int LRF_CAP = 512;
+constexpr int BOX_CAP = 1024;
+constexpr int MAXPIX = 64 * 64;  // image_size <= 64
+
+__device__ __forceinline__ int cell_of(const DevParams &P, float v, int a) {
+  int c = (int)floorf((v - P.lo[a]) * P.inv_cell);
+  return min(max(c, 0), P.dim[a] - 1);
+}
+
+// FLANN L2_Simple<float> (float32, accumulated x,y,z in order)
+__device__ __forceinline__ float l2_simple(const float q[3], float x, float y, float z) {
+  float dx = q[0] - x, dy = q[1] - y, dz = q[2] - z;
+  float d = dx * dx;
+  d += dy * dy;
+  d += dz * dz;
+  return d;
+}
+
+// o = frame^T v, frame column-major, summed left to right (PointList::transformToHandFrame, point_list.cpp:22-33)
+__device__ __forceinline__ void to_frame(const double *F, double v0, double v1, double v2, double &o0, double &o1,
+                                         double &o2) {
+  o0 = (F[0] * v0 + F[1] * v1) + F[2] * v2;
+  o1 = (F[3] * v0 + F[4] * v1) + F[5] * v2;
+  o2 = (F[6] * v0 + F[7] * v1) + F[8] * v2;
+}
+__device__ __forceinline__ void mat3_mul(const double *A, const double *B, double *Cm) {
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) Cm[c * 3 + r] = (A[r] * B[c * 3] + A[3 + r] * B[c * 3 + 1]) + A[6 + r] * B[c * 3 + 2];
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// ------------------------------------------------------------------------------------------------
+// Row segments of the grid cube around q: rows (cy,cz), each one contiguous run [start, start+len).
+// Block-wide; NT threads; at most NT rows per batch. Returns total candidates of the batch.
+// ------------------------------------------------------------------------------------------------
+struct SegRange {
+  int c0[3], c1[3], ny, nrows;
+};
+__device__ __forceinline__ SegRange seg_range(const DevParams &P, const float q[3], float rf) {
+  SegRange s;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    s.c0[a] = cell_of(P, q[a] - rf, a);
+    s.c1[a] = cell_of(P, q[a] + rf, a);
+  }
+  s.ny = s.c1[1] - s.c0[1] + 1;
+  s.nrows = s.ny * (s.c1[2] - s.c0[2] + 1);
+  return s;
+}
+__device__ __forceinline__ void seg_row(const DevParams &P, const int *cell_start, const SegRange &s, int row, int &start,
+                                        int &len) {
+  int cy = s.c0[1] + row % s.ny, cz = s.c0[2] + row / s.ny;
+  size_t base = ((size_t)cz * P.dim[1] + cy) * P.dim[0];
+  start = __ldg(cell_start + base + s.c0[0]);
+  len = __ldg(cell_start + base + s.c1[0] + 1) - start;
+}
+
+template <int NT>
+struct SegScan {
+  typedef cub::BlockScan<int, NT> Scan;
+  typename Scan::TempStorage tmp;
+  int start[NT];
+  int prefix[NT + 1];
+};
+// fills seg.start/prefix for rows [row0, row0+NT) ; returns batch total. Contains __syncthreads.
+template <int NT>
+__device__ __forceinline__ int seg_batch(const DevParams &P, const int *cell_start, const SegRange &s, int row0,
+                                         SegScan<NT> &seg) {
+  int row = row0 + threadIdx.x, st = 0, len = 0;
+  if (row < s.nrows) seg_row(P, cell_start, s, row, st, len);
+  int excl, total;
+  SegScan<NT>::Scan(seg.tmp).ExclusiveSum(len, excl, total);
+  seg.start[threadIdx.x] = st;
+  seg.prefix[threadIdx.x] = excl;
+  if (threadIdx.x == 0) seg.prefix[NT] = total;
+  __syncthreads();
+  return total;
+}
+template <int NT>
+__device__ __forceinline__ int seg_lookup(const SegScan<NT> &seg, int c) {
+  // largest r with prefix[r] <= c
+  int lo = 0, hi = NT;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg.prefix[mid] <= c) lo = mid; else hi = mid;
+  }
+  return seg.start[lo] + (c - seg.prefix[lo]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid build
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cell_ids(const DevParams *Pp, const float *xyz, int N, int *cid, int *idx, int *counts) {
+  const DevParams &P = *Pp;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int c = (cell_of(P, xyz[3 * i + 2], 2) * P.dim[1] + cell_of(P, xyz[3 * i + 1], 1)) * P.dim[0] + cell_of(P, xyz[3 * i], 0);
+  cid[i] = c;
+  idx[i] = i;
+  atomicAdd(counts + c + 1, 1);
+}
+__global__ void k_fill_sorted(const float *xyz, const int *idx_sorted, int N, float4 *pts4) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  int i = idx_sorted[k];
+  pts4[k] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 symmetric eigen-solver: Eigen::SelfAdjointEigenSolver<Matrix3d>::compute restated
+// (same sequence of operations as oracle/gpd_oracle.cpp eigen3 -> identical bits).
+// ------------------------------------------------------------------------------------------------
+__device__ void make_givens(double p, double q, double &c, double &s) {
+  if (q == 0.0) {
+    c = p < 0.0 ? -1.0 : 1.0;
+    s = 0.0;
+  } else if (p == 0.0) {
+    c = 0.0;
+    s = q < 0.0 ? 1.0 : -1.0;
+  } else if (fabs(p) > fabs(q)) {
+    double t = q / p;
+    double u = sqrt(1.0 + t * t);
+    if (p < 0.0) u = -u;
+    c = 1.0 / u;
+    s = -t * c;
+  } else {
+    double t = p / q;
+    double u = sqrt(1.0 + t * t);
+    if (q < 0.0) u = -u;
+    s = -1.0 / u;
+    c = -t * s;
+  }
+}
+__device__ double eigen_hypot(double x, double y) {
+  double ax = fabs(x), ay = fabs(y);
+  double p = fmax(ax, ay);
+  if (p == 0.0) return 0.0;
+  double qp = fmin(ax, ay) / p;
+  return p * sqrt(1.0 + qp * qp);
+}
+// m: lower triangle used, column-major; eval ascending, Q column-major
+__device__ void eigen3(const double *Min, double *eval, double *Q) {
+  double m00 = Min[0], m10 = Min[1], m20 = Min[2], m11 = Min[4], m21 = Min[5], m22 = Min[8];
+  double scale = fmax(fmax(fmax(fabs(m00), fabs(m10)), fmax(fabs(m20), fabs(m11))), fmax(fabs(m21), fabs(m22)));
+  if (scale == 0.0) scale = 1.0;
+  m00 /= scale; m10 /= scale; m20 /= scale; m11 /= scale; m21 /= scale; m22 /= scale;
+  double diag[3], sub[2];
+  const double tol = DBL_MIN;
+  diag[0] = m00;
+  double v1norm2 = m20 * m20;
+  if (v1norm2 <= tol) {
+    diag[1] = m11;
+    diag[2] = m22;
+    sub[0] = m10;
+    sub[1] = m21;
+    for (int i = 0; i < 9; i++) Q[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  } else {
+    double beta = sqrt(m10 * m10 + v1norm2);
+    double invBeta = 1.0 / beta;
+    double m01 = m10 * invBeta;
+    double m02 = m20 * invBeta;
+    double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
+    diag[1] = m11 + m02 * q;
+    diag[2] = m22 - m02 * q;
+    sub[0] = beta;
+    sub[1] = m21 - m01 * q;
+    Q[0] = 1; Q[1] = 0;   Q[2] = 0;
+    Q[3] = 0; Q[4] = m01; Q[5] = m02;
+    Q[6] = 0; Q[7] = m02; Q[8] = -m01;
+  }
+  const int n = 3;
+  int end = n - 1, start = 0, iter = 0;
+  const int maxIterations = 30;
+  const double precision_inv = 1.0 / DBL_EPSILON;
+  while (end > 0) {
+    for (int i = start; i < end; ++i) {
+      if (fabs(sub[i]) < DBL_MIN) {
+        sub[i] = 0.0;
+      } else {
+        const double scaled = precision_inv * sub[i];
+        if (scaled * scaled <= (fabs(diag[i]) + fabs(diag[i + 1]))) sub[i] = 0.0;
+      }
+    }
+    while (end > 0 && sub[end - 1] == 0.0) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > maxIterations * n) break;
+    start = end - 1;
+    while (start > 0 && sub[start - 1] != 0.0) start--;
+    double td = (diag[end - 1] - diag[end]) * 0.5;
+    double e = sub[end - 1];
+    double mu = diag[end];
+    if (td == 0.0) {
+      mu -= fabs(e);
+    } else if (e != 0.0) {
+      const double e2 = e * e;
+      const double h = eigen_hypot(td, e);
+      if (e2 == 0.0)
+        mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+      else
+        mu -= e2 / (td + (td > 0.0 ? h : -h));
+    }
+    double x = diag[start] - mu;
+    double z = sub[start];
+    for (int k = start; k < end && z != 0.0; ++k) {
+      double c, s;
+      make_givens(x, z, c, s);
+      double sdk = s * diag[k] + c * sub[k];
+      double dkp1 = s * sub[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+      diag[k + 1] = s * sdk + c * dkp1;
+      sub[k] = c * sdk - s * dkp1;
+      if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+      x = sub[k];
+      if (k < end - 1) {
+        z = -s * sub[k + 1];
+        sub[k + 1] = c * sub[k + 1];
+      }
+      for (int r = 0; r < 3; r++) {
+        double xi = Q[k * 3 + r], yi = Q[(k + 1) * 3 + r];
+        Q[k * 3 + r] = c * xi - s * yi;
+        Q[(k + 1) * 3 + r] = s * xi + c * yi;
+      }
+    }
+  }
+  for (int i = 0; i < n - 1; ++i) {
+    int k = 0;
+    for (int j = 1; j < n - i; j++)
+      if (diag[i + j] < diag[i + k]) k = j;
+    if (k > 0) {
+      double t = diag[i]; diag[i] = diag[k + i]; diag[k + i] = t;
+      for (int r = 0; r < 3; r++) { t = Q[i * 3 + r]; Q[i * 3 + r] = Q[(k + i) * 3 + r]; Q[(k + i) * 3 + r] = t; }
+    }
+  }
+  for (int i = 0; i < 3; i++) eval[i] = diag[i] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_frames: one warp per sample. The r = nn_radius ball (~44 points) is gathered as 64-bit keys
+// (dist bits << 32 | index), rank-sorted so that N*N^T and sum(n) are accumulated in exactly the
+// (dist, index) order the reference's sorted radiusSearch yields -> bit-identical to the oracle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, DevCloud cl, const int *sidx, int n,
+                                                            double *frames, uint8_t *valid, int *err) {
+  const DevParams &P = *Pp;
+  __shared__ unsigned long long s_keys[LRF_WARPS][LRF_CAP];
+  __shared__ unsigned long long s_sorted[LRF_WARPS][LRF_CAP];
+  __shared__ double s_acc[LRF_WARPS][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * LRF_WARPS + warp;
+  if (i >= n) return;
+  const int si = sidx[i];
+  float q[3] = {cl.xyz[3 * (size_t)si], cl.xyz[3 * (size_t)si + 1], cl.xyz[3 * (size_t)si + 2]};
+  SegRange sr = seg_range(P, q, P.rf_lrf);
+  unsigned long long *keys = s_keys[warp], *sorted = s_sorted[warp];
+  int cnt = 0;
+  for (int row = 0; row < sr.nrows; row++) {
+    int st, len;
+    seg_row(P, cl.cell_start, sr, row, st, len);
+    for (int k0 = 0; k0 < len; k0 += 32) {
+      int k = k0 + lane;
+      bool hit = false;
+      unsigned long long key = 0;
+      if (k < len) {
+        float4 p = __ldg(cl.pts4 + st + k);
+        float d = l2_simple(q, p.x, p.y, p.z);
+        hit = d < P.r2_lrf;
+        key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      int pos = cnt + __popc(m & ((1u << lane) - 1));
+      if (hit && pos < LRF_CAP) keys[pos] = key;
+      cnt += __popc(m);
+    }
+  }
+  if (cnt > LRF_CAP) {
+    if (lane == 0) atomicAdd(err + 0, 1);
+    cnt = LRF_CAP;
+  }
+  __syncwarp();
+  if (cnt == 0) {
+    if (lane == 0) valid[i] = 0;
+    if (lane < 9) frames[9 * (size_t)i + lane] = 0.0;
+    return;
+  }
+  for (int a = lane; a < cnt; a += 32) {
+    unsigned long long ka = keys[a];
+    int rank = 0;
+    for (int b = 0; b < cnt; b++) rank += (keys[b] < ka);
+    sorted[rank] = ka;
+  }
+  __syncwarp();
+  // lanes 0..5: lower-triangle entries of M = N N^T ; lanes 6..8: sum of normals
+  if (lane < 9) {
+    const int rr[9] = {0, 1, 2, 1, 2, 2, 0, 1, 2}, cc[9] = {0, 0, 0, 1, 1, 2, 0, 0, 0};
+    int r = rr[lane], c = cc[lane];
+    double acc = 0.0;
+    for (int a = 0; a < cnt; a++) {
+      int idx = (int)(unsigned)(sorted[a] & 0xffffffffu);
+      const double *nn = cl.nrm + 3 * (size_t)idx;
+      if (lane < 6) acc += nn[r] * nn[c]; else acc += nn[r];
+    }
+    s_acc[warp][lane] = acc;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const double *a = s_acc[warp];
+    double M[9] = {a[0], a[1], a[2], a[1], a[3], a[4], a[2], a[4], a[5]};
+    double eval[3], evec[9];
+    eigen3(M, eval, evec);
+    int mn = 0, mx = 0;
+    for (int k = 1; k < 3; k++) {
+      if (eval[k] < eval[mn]) mn = k;
+      if (eval[k] > eval[mx]) mx = k;
+    }
+    double curv[3] = {evec[mn * 3], evec[mn * 3 + 1], evec[mn * 3 + 2]};
+    double normal[3] = {evec[mx * 3], evec[mx * 3 + 1], evec[mx * 3 + 2]};
+    double nrm = sqrt((a[6] * a[6] + a[7] * a[7]) + a[8] * a[8]);
+    double avg[3] = {a[6] / nrm, a[7] / nrm, a[8] / nrm};
+    if ((avg[0] * normal[0] + avg[1] * normal[1]) + avg[2] * normal[2] < 0) {
+      normal[0] *= -1.0; normal[1] *= -1.0; normal[2] *= -1.0;
+    }
+    double *f = frames + 9 * (size_t)i;
+    f[0] = normal[0]; f[1] = normal[1]; f[2] = normal[2];
+    f[3] = curv[1] * normal[2] - curv[2] * normal[1];
+    f[4] = curv[2] * normal[0] - curv[0] * normal[2];
+    f[5] = curv[0] * normal[1] - curv[1] * normal[0];
+    f[6] = curv[0]; f[7] = curv[1]; f[8] = curv[2];
+    valid[i] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_hands
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned slot_mask(const DevParams &P, double y) {
+  unsigned m = 0;
+  const int F = 2 * P.nfp;
+  if (P.slots_disjoint) {
+    // slots within each half are disjoint and ascending: find the last slot starting below y
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const double *fs = P.fs + half * P.nfp;
+      if (y > fs[0]) {
+        int lo = 0, hi = P.nfp;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (y > fs[mid]) lo = mid; else hi = mid;
+        }
+        if (y < P.fsw[half * P.nfp + lo]) m |= 1u << (half * P.nfp + lo);
+      }
+    }
+  } else {
+    for (int f = 0; f < F; f++)
+      if (y > P.fs[f] && y < P.fsw[f]) m |= 1u << f;
+  }
+  return m;
+}
+
+struct HandsSmem {
+  SegScan<NT_HANDS> seg;
+  int count;      // staged (slab) points
+  int n_ball;     // all points of the r ball
+  unsigned long long nb0_key;
+  double T[9];    // frame * ROT_BINORMAL
+  double frame[9];
+  double sample[3];
+  int cap;
+};
+
+// one CTA per sample; dynamic smem: float4 list[cap]
+__global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevCloud cl, const int *sidx, int n, int slot0,
+                                                    const double *frames, const uint8_t *fvalid, gpdb_pose *poses,
+                                                    uint8_t *flags, int cap, int *ovf_list, int *ovf_count,
+                                                    int list_mode, int *err) {
+  const DevParams &P = *Pp;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float4 *list = reinterpret_cast<float4 *>(dyn);
+  __shared__ HandsSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int work_n = list_mode ? *ovf_count : n;
+  for (int w = blockIdx.x; w < work_n; w += gridDim.x) {
+    const int i = list_mode ? ovf_list[w] : w;
+    const int si = sidx[i];
+    __syncthreads();
+    if (tid == 0) {
+      S.count = 0;
+      S.n_ball = 0;
+      S.nb0_key = ~0ull;
+    }
+    if (tid < 9) S.frame[tid] = frames[9 * (size_t)i + tid];
+    if (tid < 3) S.sample[tid] = (double)cl.xyz[3 * (size_t)si + tid];
+    __syncthreads();
+    if (tid == 0) mat3_mul(S.frame, P.rotb, S.T);
+    const bool fv = fvalid[i] != 0;
+    if (!fv) {
+      // no local frame (calculateFrame returned nullptr): no hand set for this sample
+      for (int p = tid; p < P.P; p += NT_HANDS) {
+        gpdb_pose *h = poses + (size_t)i * P.P + p;
+        memset(h, 0, sizeof(gpdb_pose));
+        h->sample_index = si;
+        h->sample_slot = slot0 + i;
+        h->pose_slot = (int16_t)p;
+        h->finger_idx = -1;
+        h->score = __int_as_float(0x7fc00000);
+        flags[(size_t)i * P.P + p] = 0;
+      }
+      continue;
+    }
+    __syncthreads();
+    // ---- stage the neighbourhood: ball r = nn_radius_hs, kept if inside the (slightly widened)
+    // height slab when every rotation axis is the curvature axis (z is then pose independent)
+    float q[3] = {(float)S.sample[0], (float)S.sample[1], (float)S.sample[2]};
+    SegRange sr = seg_range(P, q, P.rf_hs);
+    const double hz = P.hand_height * 1.001 + 1e-9;
+    unsigned long long best = ~0ull;
+    int nball = 0;
+    for (int row0 = 0; row0 < sr.nrows; row0 += NT_HANDS) {
+      __syncthreads();
+      int total = seg_batch<NT_HANDS>(P, cl.cell_start, sr, row0, S.seg);
+      for (int c0 = 0; c0 < total; c0 += NT_HANDS) {
+        int c = c0 + tid;
+        bool keep = false;
+        float4 p;
+        if (c < total) {
+          p = __ldg(cl.pts4 + seg_lookup<NT_HANDS>(S.seg, c));
+          float d = l2_simple(q, p.x, p.y, p.z);
+          if (d < P.r2_hs) {
+            nball++;
+            unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+            best = key < best ? key : best;
+            keep = true;
+            if (P.all_axes_z) {
+              double z0 = (S.T[6] * ((double)p.x - S.sample[0]) + S.T[7] * ((double)p.y - S.sample[1])) +
+                          S.T[8] * ((double)p.z - S.sample[2]);
+              keep = fabs(z0) < hz;
+            }
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          int leader = __ffs(m) - 1, base = 0;
+          if (lane == leader) base = atomicAdd(&S.count, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          int pos = base + __popc(m & ((1u << lane) - 1));
+          if (keep && pos < cap) list[pos] = p;
+        }
+      }
+    }
+    nball = warp_sum(nball);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      best = ob < best ? ob : best;
+    }
+    if (lane == 0) {
+      atomicAdd(&S.n_ball, nball);
+      atomicMin(&S.nb0_key, best);
+    }
+    __syncthreads();
+    const int m = S.count;
+    if (m > cap) {
+      // does not fit this tier: defer to the large-tile pass (or report)
+      if (tid == 0) {
+        if (ovf_list && !list_mode) {
+          int k = atomicAdd(ovf_count, 1);
+          ovf_list[k] = i;
+          atomicAdd(err + 3, 1);
+        } else {
+          atomicAdd(err + 1, 1);
+        }
+      }
+      if (!(ovf_list && !list_mode)) {
+        for (int p = tid; p < P.P; p += NT_HANDS) flags[(size_t)i * P.P + p] = 0;
+      }
+      continue;
+    }
+    const int n_ball = S.n_ball;
+    // nb0 = nearest neighbour (first of the sorted radius search): pads the cropped list
+    // (PointList::cropByHandHeight quirk, point_list.cpp:44-55)
+    const int nb0 = (int)(unsigned)(S.nb0_key & 0xffffffffu);
+    double nbx = 0, nby = 0, nbz = 0;
+    if (n_ball > 0) {
+      nbx = (double)cl.xyz[3 * (size_t)nb0] - S.sample[0];
+      nby = (double)cl.xyz[3 * (size_t)nb0 + 1] - S.sample[1];
+      nbz = (double)cl.xyz[3 * (size_t)nb0 + 2] - S.sample[2];
+    }
+    // ---- one warp per pose
+    for (int pose = warp; pose < P.P; pose += NT_HANDS / 32) {
+      gpdb_pose *h = poses + (size_t)i * P.P + pose;
+      double R[9];
+      mat3_mul(S.T, P.rot[pose], R);
+      const double hh = P.hand_height;
+      uint8_t fl = 0;
+      double top = 0, bottom = 0, center = 0, width = 0;
+      int fidx = -1;
+      bool half = false, full = false;
+      double x0, y0, z0;
+      to_frame(R, nbx, nby, nbz, x0, y0, z0);
+      if (n_ball > 0) {
+        // pass A: crop + finger masks (FingerHand::evaluateFingers, finger_hand.cpp:26-73)
+        const double b0 = P.init_bite, bot0 = P.init_bite - P.hand_depth;
+        int k = 0;
+        unsigned anyA = 0, anyB = 0, fmask = 0;
+        for (int a = lane; a < m; a += 32) {
+          float4 p = list[a];
+          double x, y, z;
+          to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+          if (z > -1.0 * hh && z < hh) {
+            k++;
+            if (x < b0) {
+              anyA = 1;
+              if (x < bot0) anyB = 1;
+              fmask |= slot_mask(P, y);
+            }
+          }
+        }
+        k = warp_sum(k);
+        const int npad = n_ball - k;
+        if (npad > 0 && x0 < b0) {
+          anyA = 1;
+          if (x0 < bot0) anyB = 1;
+          fmask |= slot_mask(P, y0);
+        }
+        anyA = __reduce_or_sync(0xffffffffu, anyA);
+        anyB = __reduce_or_sync(0xffffffffu, anyB);
+        fmask = __reduce_or_sync(0xffffffffu, fmask);
+        const unsigned allF = (2 * P.nfp >= 32) ? 0xffffffffu : ((1u << (2 * P.nfp)) - 1);
+        unsigned freef = (anyA && !anyB) ? (~fmask & allF) : 0u;
+        unsigned hand = freef & (freef >> P.nfp) & ((1u << P.nfp) - 1);  // evaluateHand (:75-81)
+        if (hand) {
+          // chooseMiddleHand (:89-105): hand_idx[ceil(m/2) - 1]
+          int cntb = __popc(hand);
+          int target = (cntb + 1) / 2;  // 1-based ordinal of the chosen set bit
+          unsigned hm = hand;
+          while (--target) hm &= hm - 1;
+          fidx = __ffs(hm) - 1;
+          top = b0;
+          bottom = bot0;
+          if (P.deepen) {
+            // deepenHand (:107-139) as one min-reduction over the first failing step
+            int jf = P.J;  // 0-based index of the first failing step; J = none fails
+            const double sl0 = P.fs[fidx], sl1 = P.fsw[fidx], sr0 = P.fs[P.nfp + fidx], sr1 = P.fsw[P.nfp + fidx];
+            const int J = P.J;
+            auto visitB = [&](double x, double y) {
+              if (J > 0 && x < P.botj[J - 1]) {
+                int j = 0;
+                while (!(x < P.botj[j])) j++;
+                jf = min(jf, j);
+              }
+              if ((y > sl0 && y < sl1) || (y > sr0 && y < sr1)) {
+                if (J > 0 && x < P.topj[J - 1]) {
+                  int j = 0;
+                  while (!(x < P.topj[j])) j++;
+                  jf = min(jf, j);
+                }
+              }
+            };
+            for (int a = lane; a < m; a += 32) {
+              float4 p = list[a];
+              double x, y, z;
+              to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+              if (z > -1.0 * hh && z < hh) visitB(x, y);
+            }
+            if (npad > 0) visitB(x0, y0);
+            jf = __reduce_min_sync(0xffffffffu, jf);
+            if (jf > 0) {
+              top = P.topj[jf - 1];
+              bottom = P.botj[jf - 1];
+            }
+          }
+          // computePointsInClosingRegion (:141-171)
+          const double left = P.fsw[fidx], right = P.fs[P.nfp + fidx];
+          center = 0.5 * (left + right);
+          int cnt = 0;
+          double mny = DBL_MAX, mxy = -DBL_MAX;
+          for (int a = lane; a < m; a += 32) {
+            float4 p = list[a];
+            double x, y, z;
+            to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+            if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right) {
+              cnt++;
+              mny = fmin(mny, y);
+              mxy = fmax(mxy, y);
+            }
+          }
+          const bool nb_in = npad > 0 && x0 > bottom && x0 < top && y0 > left && y0 < right;
+          cnt = warp_sum(cnt) + (nb_in ? npad : 0);
+          mny = warp_min(mny);
+          mxy = warp_max(mxy);
+          if (nb_in) {
+            mny = fmin(mny, y0);
+            mxy = fmax(mxy, y0);
+          }
+          if (cnt > 0) {
+            fl |= GPDB_POSE_VALID;
+            width = mxy - mny;  // modifyCandidate (hand_set.cpp:245-247)
+            // Antipodal::evaluateGrasp (antipodal.cpp:10-96), lateral = 1, forward = 0, vertical = 2
+            const double min_x = mny + 0.003, max_x = mxy - 0.003;
+            int cl_ = 0, cr_ = 0;
+            double lmaxx = -DBL_MAX, lminx = DBL_MAX, lmaxz = -DBL_MAX, lminz = DBL_MAX;
+            double rmaxx = -DBL_MAX, rminx = DBL_MAX, rmaxz = -DBL_MAX, rminz = DBL_MAX;
+            auto visitD = [&](double x, double y, double z, int idx, int wgt) {
+              const double *nn = cl.nrm + 3 * (size_t)idx;
+              double n0, n1, n2;
+              to_frame(R, nn[0], nn[1], nn[2], n0, n1, n2);
+              double ldot = (0.0 * n0 + -1.0 * n1) + 0.0 * n2;
+              double rdot = (0.0 * n0 + 1.0 * n1) + 0.0 * n2;
+              if (ldot > P.cosf && y < min_x) {
+                cl_ += wgt;
+                lmaxx = fmax(lmaxx, x); lminx = fmin(lminx, x); lmaxz = fmax(lmaxz, z); lminz = fmin(lminz, z);
+              }
+              if (rdot > P.cosf && y > max_x) {
+                cr_ += wgt;
+                rmaxx = fmax(rmaxx, x); rminx = fmin(rminx, x); rmaxz = fmax(rmaxz, z); rminz = fmin(rminz, z);
+              }
+            };
+            for (int a = lane; a < m; a += 32) {
+              float4 p = list[a];
+              double x, y, z;
+              to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+              if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+                visitD(x, y, z, __float_as_int(p.w), 1);
+            }
+            if (nb_in && lane == 0) visitD(x0, y0, z0, nb0, npad);
+            cl_ = warp_sum(cl_);
+            cr_ = warp_sum(cr_);
+            half = cl_ > 0 || cr_ > 0;
+            if (cl_ > 0 && cr_ > 0) {
+              lmaxx = warp_max(lmaxx); lminx = warp_min(lminx); lmaxz = warp_max(lmaxz); lminz = warp_min(lminz);
+              rmaxx = warp_max(rmaxx); rminx = warp_min(rminx); rmaxz = warp_max(rmaxz); rminz = warp_min(rminz);
+              const double top_y = fmin(lmaxx, rmaxx), bot_y = fmax(lminx, rminx);
+              const double top_z = fmin(lmaxz, rmaxz), bot_z = fmax(lminz, rminz);
+              int nl = 0, nr = 0;
+              auto visitE = [&](double x, double y, double z, int idx, int wgt) {
+                const double *nn = cl.nrm + 3 * (size_t)idx;
+                double n0, n1, n2;
+                to_frame(R, nn[0], nn[1], nn[2], n0, n1, n2);
+                double ldot = (0.0 * n0 + -1.0 * n1) + 0.0 * n2;
+                double rdot = (0.0 * n0 + 1.0 * n1) + 0.0 * n2;
+                bool inw = x >= bot_y && x <= top_y && z >= bot_z && z <= top_z;
+                if (ldot > P.cosf && y < min_x && inw) nl += wgt;
+                if (rdot > P.cosf && y > max_x && inw) nr += wgt;
+              };
+              for (int a = lane; a < m; a += 32) {
+                float4 p = list[a];
+                double x, y, z;
+                to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+                if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+                  visitE(x, y, z, __float_as_int(p.w), 1);
+              }
+              if (nb_in && lane == 0) visitE(x0, y0, z0, nb0, npad);
+              nl = warp_sum(nl);
+              nr = warp_sum(nr);
+              full = nl >= P.min_viable && nr >= P.min_viable;
+            }
+            if (half) fl |= GPDB_POSE_HALF;
+            if (full) fl |= GPDB_POSE_FULL;
+          }
+        }
+      }
+      // ---- record (Hand::construct, hand.cpp:24-45) + A15 filters, by lane 0
+      if (lane == 0) {
+        gpdb_pose o;
+        memset(&o, 0, sizeof(o));
+        for (int r = 0; r < 3; r++) o.sample[r] = S.sample[r];
+        for (int r = 0; r < 9; r++) o.frame[r] = R[r];
+        o.sample_index = si;
+        o.sample_slot = slot0 + i;
+        o.pose_slot = (int16_t)pose;
+        o.finger_idx = -1;
+        o.score = __int_as_float(0x7fc00000);
+        if (fl & GPDB_POSE_VALID) {
+          o.top = top;
+          o.bottom = bottom;
+          o.center = center;
+          o.width = width;
+          o.finger_idx = (int16_t)fidx;
+          o.half_antipodal = half;
+          o.full_antipodal = full;
+          for (int r = 0; r < 3; r++)
+            o.position[r] = ((R[r] * bottom + R[3 + r] * center) + R[6 + r] * 0.0) + S.sample[r];
+          // filterGraspsWorkspace (grasp_detector.cpp:334-398; right_top uses left_bottom, :362-363)
+          const double half_width = 0.5 * P.hand_outer_diameter;
+          bool ok = width >= P.min_ap && width <= P.max_ap;
+          for (int r = 0; r < 3; r++) {
+            double lb = o.position[r] + half_width * R[3 + r];
+            double rb = o.position[r] - half_width * R[3 + r];
+            double lt = lb + P.hand_depth * R[r];
+            double rt = lb + P.hand_depth * R[r];
+            double ap = o.position[r] - 0.05 * R[r];
+            double mn = fmin(fmin(fmin(lb, rb), fmin(lt, rt)), ap);
+            double mx = fmax(fmax(fmax(lb, rb), fmax(lt, rt)), ap);
+            ok = ok && mn >= P.ws[2 * r] && mx <= P.ws[2 * r + 1];
+          }
+          if (ok && P.filt_dir) {  // filterGraspsDirection (:422-456)
+            double dot = (P.dir[0] * R[0] + P.dir[1] * R[1]) + P.dir[2] * R[2];
+            if (acos(dot) > P.thresh) ok = false;
+          }
+          if (ok) fl |= GPDB_POSE_FILTERED;
+        }
+        *h = o;
+        flags[(size_t)i * P.P + pose] = fl;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction of candidate poses (hands_out order of image_generator.cpp:91-98)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_flag01(const uint8_t *flags, int n, int *f01) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f01[i] = (flags[i] & 3) == 3;
+}
+__global__ void k_scatter(const gpdb_pose *poses, const int *f01, const int *pos, int n, gpdb_pose *cand, int *count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (f01[i]) cand[pos[i]] = poses[i];
+  if (i == n - 1) *count = pos[i] + f01[i];
+}
+__global__ void k_scatter_scores(const gpdb_pose *cand, const float *scores, int nc, int slot0, int P, float *pose_scores,
+                                 gpdb_pose *cand_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  float s = scores[i];
+  pose_scores[(size_t)(cand[i].sample_slot - slot0) * P + cand[i].pose_slot] = s;
+  cand_out[i].score = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_images
+// ------------------------------------------------------------------------------------------------
+struct ImgSmem {
+  SegScan<NT_IMG> seg;
+  gpdb_pose h;
+  double red[NT_IMG / 32][4];
+  double center[3];
+  double sv[GPDB_MAX_CAMERAS][3];
+  int cam_or;
+  int n_img;
+  int box_n;
+  int bm_org[3], bm_dims[3];
+  float fred[NT_IMG / 32][2];
+  float a, b;
+  float smax;
+};
+
+__device__ __forceinline__ bool in_image_box(const DevParams &P, const gpdb_pose &h, double x, double y, double z) {
+  const double half_od = P.vol_w / 2.0;
+  return (x > h.bottom) && (x < h.bottom + P.vol_d) && (y > h.center - half_od) && (y < h.center + half_od) &&
+         (z > -1.0 * P.vol_h) && (z < P.vol_h);
+}
+// transformPointsToUnitImage (image_strategy.cpp:72-90)
+__device__ __forceinline__ void unit_coords(const DevParams &P, const gpdb_pose &h, double x, double y, double z,
+                                            double &u0, double &u1, double &u2) {
+  const double half_od = P.vol_w / 2.0, double_height = 2.0 * P.vol_h;
+  u0 = (x - h.bottom) / P.vol_d;
+  u1 = (y - (h.center - half_od)) / P.vol_w;
+  u2 = (z + P.vol_h) / double_height;
+}
+// findCellIndices (image_strategy.cpp:92-102)
+__device__ __forceinline__ int unit_cell(double u, int S) {
+  double cellsize = 1.0 / (double)S;
+  return min((int)floor(u / cellsize), S - 1);
+}
+__device__ __forceinline__ unsigned unit_q32(double u) {
+  double t = u * 4294967296.0;
+  t = fmin(fmax(t, 0.0), 4294967295.0);
+  return (unsigned)t;
+}
+
+// block-wide min/max of floats
+template <int NT>
+__device__ __forceinline__ void block_minmax(float &mn, float &mx, float (*red)[2]) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = mn;
+    red[threadIdx.x >> 5][1] = mx;
+  }
+  __syncthreads();
+  mn = red[0][0];
+  mx = red[0][1];
+  for (int w = 1; w < NT / 32; w++) {
+    mn = fminf(mn, red[w][0]);
+    mx = fmaxf(mx, red[w][1]);
+  }
+}
+
+// cv::dilate(3x3 rect, border ignored) -> cv::normalize(NORM_MINMAX over all channels) ->
+// convertTo(CV_8U, 255) of a CH-channel float image `src` (HWC, SxS), written into channels
+// [choff, choff+CH) of the C-channel HWC uint8 image (image_strategy.cpp:145-153,179-187,222-230).
+template <int CH>
+__device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int choff, ImgSmem &sm) {
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (int pix = threadIdx.x; pix < S * S; pix += NT_IMG) {
+    int r = pix / S, c = pix - r * S;
+    float m[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) m[k] = -FLT_MAX;
+    for (int rr = max(r - 1, 0); rr <= min(r + 1, S - 1); rr++)
+      for (int c2 = max(c - 1, 0); c2 <= min(c + 1, S - 1); c2++)
+#pragma unroll
+        for (int k = 0; k < CH; k++) m[k] = fmaxf(m[k], src[(rr * S + c2) * CH + k]);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      mn = fminf(mn, m[k]);
+      mx = fmaxf(mx, m[k]);
+    }
+  }
+  block_minmax<NT_IMG>(mn, mx, sm.fred);
+  double smin = (double)mn, smax = (double)mx;
+  double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
+  double shift = 0.0 - smin * scale;
+  const float a = (float)scale, b = (float)shift;
+  for (int pix = threadIdx.x; pix < S * S; pix += NT_IMG) {
+    int r = pix / S, c = pix - r * S;
+    float m[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) m[k] = -FLT_MAX;
+    for (int rr = max(r - 1, 0); rr <= min(r + 1, S - 1); rr++)
+      for (int c2 = max(c - 1, 0); c2 <= min(c + 1, S - 1); c2++)
+#pragma unroll
+        for (int k = 0; k < CH; k++) m[k] = fmaxf(m[k], src[(rr * S + c2) * CH + k]);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      float v = fmaf(m[k], a, b);
+      int q = __float2int_rn(v * 255.0f);
+      q = min(max(q, 0), 255);
+      gimg[(size_t)pix * C + choff + k] = (uint8_t)q;
+    }
+  }
+  __syncthreads();
+}
+
+// dynamic smem layout (bytes): tiles 3 * 8*S*S | box list: keys 8*CAP, q 3*4*CAP, cells 4*CAP, nrm 3*4*CAP
+// (the shadow bitmaps alias the box list)
+__global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
+                                                   uint8_t *images, const double *qtab, int *err) {
+  const DevParams &P = *Pp;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ ImgSmem sm;
+  const int S = P.S, C = P.C, SS = S * S;
+  unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn);
+  unsigned long long *tileB = tileA + SS;
+  unsigned long long *tileC = tileB + SS;
+  unsigned char *lbase = reinterpret_cast<unsigned char *>(tileC + SS);
+  unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(lbase);
+  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BOX_CAP);   // [3][CAP]
+  unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
+  float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
+  unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
+  float *nrmT = reinterpret_cast<float *>(tileB);                 // float[3*SS] over tileB..tileC
+  float *depF = nrmT + 3 * SS;                                    // float[SS]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nproj = (C >= 12) ? 3 : 1;
+  const int per = (C == 15) ? 5 : 4;
+
+  for (int b = blockIdx.x; b < nc; b += gridDim.x) {
+    __syncthreads();
+    {
+      const int *src = reinterpret_cast<const int *>(cand + b);
+      int *dst = reinterpret_cast<int *>(&sm.h);
+      for (int k = tid; k < (int)(sizeof(gpdb_pose) / 4); k += NT_IMG) dst[k] = src[k];
+    }
+    if (tid == 0) {
+      sm.cam_or = 0;
+      sm.n_img = 0;
+      sm.box_n = 0;
+    }
+    __syncthreads();
+    const gpdb_pose &h = sm.h;
+    uint8_t *gimg = images + (size_t)b * SS * C;
+    float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
+    SegRange sr = seg_range(P, q, P.rf_img);
+    // ---- ball scan 1: neighbourhood centre + camera set (HandSet::calculateShadow, hand_set.cpp:131-136)
+    //      and the list of points inside the image box (ImageStrategy::transformToUnitImage)
+    double sx = 0, sy = 0, sz = 0;
+    int cnt = 0, cam_or = 0;
+    for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
+      __syncthreads();
+      int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
+      for (int c0 = 0; c0 < total; c0 += NT_IMG) {
+        int c = c0 + tid;
+        bool inb = false;
+        unsigned long long key = 0;
+        double u0 = 0, u1 = 0, u2 = 0;
+        int idx = 0;
+        if (c < total) {
+          float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
+          float d = l2_simple(q, p.x, p.y, p.z);
+          if (d < P.r2_img) {
+            idx = __float_as_int(p.w);
+            sx += (double)p.x;
+            sy += (double)p.y;
+            sz += (double)p.z;
+            cnt++;
+            cam_or |= cl.cam[idx];
+            double x, y, z;
+            to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
+            if (in_image_box(P, h, x, y, z)) {
+              inb = true;
+              unit_coords(P, h, x, y, z, u0, u1, u2);
+              key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+            }
+          }
+        }
+        unsigned mk = __ballot_sync(0xffffffffu, inb);
+        if (mk) {
+          int leader = __ffs(mk) - 1, base = 0;
+          if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          int pos = base + __popc(mk & ((1u << lane) - 1));
+          if (inb && pos < BOX_CAP) {
+            bkeys[pos] = key;
+            bq[pos] = unit_q32(u0);
+            bq[BOX_CAP + pos] = unit_q32(u1);
+            bq[2 * BOX_CAP + pos] = unit_q32(u2);
+            bcell[pos] = (unsigned)unit_cell(u0, S) | ((unsigned)unit_cell(u1, S) << 8) | ((unsigned)unit_cell(u2, S) << 16);
+            const double *nn = cl.nrm + 3 * (size_t)idx;
+            double n0, n1, n2;
+            to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
+            bnrm[pos] = (float)fabs(n0);
+            bnrm[BOX_CAP + pos] = (float)fabs(n1);
+            bnrm[2 * BOX_CAP + pos] = (float)fabs(n2);
+          }
+        }
+      }
+    }
+    // block reduce centre sums
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    cnt = warp_sum(cnt);
+    cam_or = __reduce_or_sync(0xffffffffu, (unsigned)cam_or);
+    __syncthreads();
+    if (lane == 0) {
+      sm.red[tid >> 5][0] = sx;
+      sm.red[tid >> 5][1] = sy;
+      sm.red[tid >> 5][2] = sz;
+      atomicAdd(&sm.n_img, cnt);
+      atomicOr(&sm.cam_or, cam_or);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a0 = 0, a1 = 0, a2 = 0;
+      for (int w = 0; w < NT_IMG / 32; w++) {
+        a0 += sm.red[w][0];
+        a1 += sm.red[w][1];
+        a2 += sm.red[w][2];
+      }
+      double nn = (double)sm.n_img;
+      sm.center[0] = a0 / nn;
+      sm.center[1] = a1 / nn;
+      sm.center[2] = a2 / nn;
+      if (sm.box_n > BOX_CAP) {
+        atomicAdd(err + 2, 1);
+        sm.box_n = BOX_CAP;
+      }
+    }
+    __syncthreads();
+    const int bn = sm.box_n;
+
+    // ---- points phase: per projection rasterise normals (arg-max key = last writer in (dist, index)
+    // order, createNormalsImage :124-143) and depth (per-cell mean, createDepthImage :158-176)
+    for (int pj = 0; pj < nproj; pj++) {
+      // coordinate orders (x,y,z), (z,y,x), (z,x,y): rows cumulatively swapped {0<->2}, {1<->2}
+      // (image_15_channels_strategy.cpp:57-64)
+      const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
+      for (int k = tid; k < 2 * SS; k += NT_IMG) tileA[k] = 0ull;  // tileA + tileB
+      __syncthreads();
+      for (int k = tid; k < bn; k += NT_IMG) {
+        unsigned cc = bcell[k];
+        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
+        int pix = (S - 1 - v) * S + hcol;
+        atomicMax(tileA + pix, bkeys[k]);
+        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
+      }
+      __syncthreads();
+      unsigned long long dreg[(MAXPIX + NT_IMG - 1) / NT_IMG];
+#pragma unroll
+      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+        int pix = tid + t * NT_IMG;
+        dreg[t] = pix < SS ? tileB[pix] : 0ull;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+        int pix = tid + t * NT_IMG;
+        if (pix < SS) {
+          nrmT[pix * 3] = 0.0f;
+          nrmT[pix * 3 + 1] = 0.0f;
+          nrmT[pix * 3 + 2] = 0.0f;
+          unsigned long long acc = dreg[t];
+          unsigned cntc = (unsigned)(acc >> 48);
+          float val = 0.0f;
+          if (cntc) {
+            double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+            float avg = (float)mean;
+            val = (float)(1.0 - (double)avg);
+          }
+          depF[pix] = val;
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < bn; k += NT_IMG) {
+        unsigned cc = bcell[k];
+        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
+        int pix = (S - 1 - v) * S + hcol;
+        if (tileA[pix] == bkeys[k]) {
+          nrmT[pix * 3] = bnrm[k];
+          nrmT[pix * 3 + 1] = bnrm[BOX_CAP + k];
+          nrmT[pix * 3 + 2] = bnrm[2 * BOX_CAP + k];
+        }
+      }
+      __syncthreads();
+      if (C == 1) {
+        postprocess<1>(depF, S, gimg, C, 0, sm);
+      } else {
+        postprocess<3>(nrmT, S, gimg, C, pj * per, sm);
+        if (C >= 12) postprocess<1>(depF, S, gimg, C, pj * per + 3, sm);
+      }
+    }
+
+    // ---- shadow phase (15 channels): HandSet::calculateShadow, deterministic variant
+    if (C == 15) {
+      const int K = P.K;
+      const int bmd = P.bm_dim;
+      const int bm_words = (bmd * bmd * bmd + 31) / 32;
+      const double gmax = qtab[GPDB_QTAB_SIZE - 1];
+      const double voxel = GPDB_SHADOW_VOXEL;
+      if (tid == 0) {
+        // AABB (in voxel indices) of the image box, widened by the largest jitter
+        const double jmax = gmax * voxel * 0.3 + 1e-9;
+        const double half_od = P.vol_w / 2.0;
+        double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int cr = 0; cr < 8; cr++) {
+          double cx = (cr & 1) ? h.bottom + P.vol_d : h.bottom;
+          double cy = (cr & 2) ? h.center + half_od : h.center - half_od;
+          double cz = (cr & 4) ? P.vol_h : -P.vol_h;
+          for (int r = 0; r < 3; r++) {
+            double wv = h.frame[r] * cx + h.frame[3 + r] * cy + h.frame[6 + r] * cz + h.sample[r];
+            mn[r] = fmin(mn[r], wv);
+            mx[r] = fmax(mx[r], wv);
+          }
+        }
+        for (int r = 0; r < 3; r++) {
+          int lo = (int)floor((mn[r] - jmax) * P.vox_mult) - 1;
+          int hi = (int)floor((mx[r] + jmax) * P.vox_mult) + 1;
+          sm.bm_org[r] = lo;
+          sm.bm_dims[r] = min(hi - lo + 1, bmd);
+        }
+      }
+      if (tid < K) {
+        // shadow_vec = shadow_length * (center - view_point) / norm (hand_set.cpp:146-150)
+        double s0 = sm.center[0] - P.vp[tid][0], s1 = sm.center[1] - P.vp[tid][1], s2 = sm.center[2] - P.vp[tid][2];
+        double nn = sqrt((s0 * s0 + s1 * s1) + s2 * s2);
+        sm.sv[tid][0] = P.shadow_length * s0 / nn;
+        sm.sv[tid][1] = P.shadow_length * s1 / nn;
+        sm.sv[tid][2] = P.shadow_length * s2 / nn;
+      }
+      for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
+      __syncthreads();
+      const int o0 = sm.bm_org[0], o1 = sm.bm_org[1], o2 = sm.bm_org[2];
+      const int d0 = sm.bm_dims[0], d1 = sm.bm_dims[1], d2 = sm.bm_dims[2];
+      const double mxu = 1.0 / 32767.0;
+      // voxel -> jittered point -> hand frame -> inside the image box?
+      auto voxel_point_in_box = [&](int v0, int v1, int v2, double &x, double &y, double &z) -> bool {
+        double g = qtab[gpdb_voxel_hash(v0, v1, v2) & (GPDB_QTAB_SIZE - 1)];
+        double jit = 1.0 * g * voxel * 0.3;
+        double w0 = (double)v0 * voxel + jit, w1 = (double)v1 * voxel + jit, w2 = (double)v2 * voxel + jit;
+        to_frame(h.frame, w0 - h.sample[0], w1 - h.sample[1], w2 - h.sample[2], x, y, z);
+        return in_image_box(P, h, x, y, z);
+      };
+      const int cam_set = sm.cam_or;
+      for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
+        __syncthreads();
+        int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
+        for (int c = tid; c < total; c += NT_IMG) {
+          float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
+          float d = l2_simple(q, p.x, p.y, p.z);
+          if (!(d < P.r2_img)) continue;
+          const int idx = __float_as_int(p.w);
+          const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+          for (int k = 0; k < K; k++) {
+            if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
+            const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
+            // quick reject: per-axis voxel range of the segment p .. p + sv vs the bitmap AABB
+            {
+              int a, e;
+              a = (int)(px * P.vox_mult); e = (int)((px + s0) * P.vox_mult);
+              if (max(a, e) < o0 - 1 || min(a, e) > o0 + d0) continue;
+              a = (int)(py * P.vox_mult); e = (int)((py + s1) * P.vox_mult);
+              if (max(a, e) < o1 - 1 || min(a, e) > o1 + d1) continue;
+              a = (int)(pz * P.vox_mult); e = (int)((pz + s2) * P.vox_mult);
+              if (max(a, e) < o2 - 1 || min(a, e) > o2 + d2) continue;
+            }
+            unsigned seed = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)idx, (unsigned)k);
+            unsigned *bm = bitmap + (size_t)k * bm_words;
+            for (int t = 0; t < P.nsp; t++) {
+              double u = (double)gpdb_fastrand(&seed) * mxu;
+              int v0 = (int)((px + u * s0) * P.vox_mult);
+              int v1 = (int)((py + u * s1) * P.vox_mult);
+              int v2 = (int)((pz + u * s2) * P.vox_mult);
+              int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
+              if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) continue;
+              double x, y, z;
+              if (!voxel_point_in_box(v0, v1, v2, x, y, z)) continue;
+              int bit = (b2 * d1 + b1) * d0 + b0;
+              atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // set intersection over the cameras that see the neighbourhood, starting from camera 0's
+      // set even when it is empty (hand_set.cpp:153-176)
+      if (K > 1) {
+        for (int wd = tid; wd < bm_words; wd += NT_IMG) {
+          unsigned acc = bitmap[wd];
+          for (int k = 1; k < K; k++)
+            if ((cam_set >> k) & 1) acc &= bitmap[(size_t)k * bm_words + wd];
+          bitmap[wd] = acc;
+        }
+      }
+      for (int k = tid; k < 3 * SS; k += NT_IMG) tileA[k] = 0ull;
+      __syncthreads();
+      const int nbits = d0 * d1 * d2;
+      for (int wd = tid; wd * 32 < nbits; wd += NT_IMG) {
+        unsigned bits = bitmap[wd];
+        while (bits) {
+          int bi = __ffs(bits) - 1;
+          bits &= bits - 1;
+          int bit = wd * 32 + bi;
+          int b0 = bit % d0, b1 = (bit / d0) % d1, b2 = bit / (d0 * d1);
+          double x, y, z;
+          if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) continue;
+          double u[3];
+          unit_coords(P, h, x, y, z, u[0], u[1], u[2]);
+          int cellv[3] = {unit_cell(u[0], S), unit_cell(u[1], S), unit_cell(u[2], S)};
+#pragma unroll
+          for (int pj = 0; pj < 3; pj++) {
+            const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
+            int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
+            atomicAdd(tileA + (size_t)pj * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
+          }
+        }
+      }
+      __syncthreads();
+      // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
+      for (int pj = 0; pj < 3; pj++) {
+        unsigned long long *tile = tileA + (size_t)pj * SS;
+        float *srcF = reinterpret_cast<float *>(tile);
+        float avgr[(MAXPIX + NT_IMG - 1) / NT_IMG];
+        unsigned occ = 0;
+        float mn = FLT_MAX, mx = -FLT_MAX;
+#pragma unroll
+        for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+          int pix = tid + t * NT_IMG;
+          avgr[t] = 0.0f;
+          if (pix < SS) {
+            unsigned long long acc = tile[pix];
+            unsigned cntc = (unsigned)(acc >> 48);
+            if (cntc) {
+              double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+              avgr[t] = (float)mean;
+              occ |= 1u << t;
+              mx = fmaxf(mx, avgr[t]);
+            }
+          }
+        }
+        block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between reads and writes
+        const float maxf = (mx == -FLT_MAX) ? 0.0f : mx;
+#pragma unroll
+        for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+          int pix = tid + t * NT_IMG;
+          if (pix < SS) srcF[pix] = ((occ >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
+        }
+        __syncthreads();
+        postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// host launchers
+// ================================================================================================
+#define LAUNCH_CHECK()                                   \
+  do {                                                   \
+    ctx->launches++;                                     \
+    cudaError_t e__ = cudaGetLastError();                \
+    if (e__ != cudaSuccess) {                            \
+      gpdb_set_error(ctx, GPDB_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return GPDB_ERR_CUDA;                              \
+    }                                                    \
+  } while (0)
+
+int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N) {
+  DevParams &hp = ctx->hp;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = 0; i < N; i++)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], h_xyz[3 * (size_t)i + a]);
+      hi[a] = fmaxf(hi[a], h_xyz[3 * (size_t)i + a]);
+    }
+  float cell = 0.02f;
+  size_t ncell;
+  for (;;) {
+    double nc = 1;
+    for (int a = 0; a < 3; a++) {
+      hp.dim[a] = (int)floorf((hi[a] - lo[a]) / cell) + 2;
+      nc *= hp.dim[a];
+    }
+    if (nc <= 48e6) { ncell = (size_t)nc; break; }
+    cell *= 1.5f;
+  }
+  for (int a = 0; a < 3; a++) hp.lo[a] = lo[a];
+  hp.inv_cell = 1.0f / cell;
+  hp.N = N;
+  CUDA_TRY(cudaMemcpyAsync(ctx->dp, &hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
+  cudaFree(ctx->d_cell_start);
+  ctx->d_cell_start = nullptr;
+  CUDA_TRY(cudaMalloc(&ctx->d_cell_start, sizeof(int) * (ncell + 1)));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_cell_start, 0, sizeof(int) * (ncell + 1), ctx->stream));
+  int *cid = (int *)gpdb_scratch(ctx, 0, sizeof(int) * (size_t)N * 4);
+  if (!cid) return GPDB_ERR_CUDA;
+  int *idx = cid + N, *cid2 = idx + N, *idx2 = cid2 + N;
+  const int tb = 256, gb = (N + tb - 1) / tb;
+  k_cell_ids<<<gb, tb, 0, ctx->stream>>>(ctx->dp, ctx->d_xyz, N, cid, idx, ctx->d_cell_start);
+  LAUNCH_CHECK();
+  size_t tmp_bytes = 0, tmp2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cid, cid2, idx, idx2, N, 0, 32, ctx->stream);
+  cub::DeviceScan::InclusiveSum(nullptr, tmp2, ctx->d_cell_start, ctx->d_cell_start, (int)(ncell + 1), ctx->stream);
+  void *tmp = gpdb_scratch(ctx, 1, std::max(tmp_bytes, tmp2));
+  if (!tmp) return GPDB_ERR_CUDA;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, cid, cid2, idx, idx2, N, 0, 32, ctx->stream));
+  ctx->launches += 4;
+  k_fill_sorted<<<gb, tb, 0, ctx->stream>>>(ctx->d_xyz, idx2, N, ctx->d_pts4);
+  LAUNCH_CHECK();
+  CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp2, ctx->d_cell_start, ctx->d_cell_start, (int)(ncell + 1), ctx->stream));
+  ctx->launches += 2;
+  ctx->cloud.cell_start = ctx->d_cell_start;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GPDB_OK;
+}
+
+int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_t *d_valid) {
+  if (n <= 0) return GPDB_OK;
+  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, 0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
+                                                                                  d_valid, ctx->d_err);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+static const int HANDS_CAP1 = 4096, HANDS_CAP2 = 13312;
+
+int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
+              gpdb_pose *d_poses, uint8_t *d_flags) {
+  if (n <= 0) return GPDB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_hands, cudaFuncAttributeMaxDynamicSharedMemorySize, HANDS_CAP2 * 16));
+    attr_set = true;
+  }
+  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)n + 1));
+  if (!ovf) return GPDB_ERR_CUDA;
+  int *ovf_count = ovf + n;
+  CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
+  k_hands<<<n, NT_HANDS, HANDS_CAP1 * 16, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, slot0, d_frames, d_valid, d_poses,
+                                                         d_flags, HANDS_CAP1, ovf, ovf_count, 0, ctx->d_err);
+  LAUNCH_CHECK();
+  // large-tile pass over the samples whose neighbourhood did not fit tier 1 (persistent CTAs)
+  k_hands<<<ctx->sm_count, NT_HANDS, HANDS_CAP2 * 16, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, slot0, d_frames,
+                                                                     d_valid, d_poses, d_flags, HANDS_CAP2, ovf, ovf_count,
+                                                                     1, ctx->d_err);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags, int n_poses, gpdb_pose *d_cand,
+                int *d_count) {
+  if (n_poses <= 0) {
+    CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+    return GPDB_OK;
+  }
+  int *f01 = (int *)gpdb_scratch(ctx, 3, sizeof(int) * (size_t)n_poses * 2);
+  if (!f01) return GPDB_ERR_CUDA;
+  int *pos = f01 + n_poses;
+  const int tb = 256, gb = (n_poses + tb - 1) / tb;
+  k_flag01<<<gb, tb, 0, ctx->stream>>>(d_flags, n_poses, f01);
+  LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, f01, pos, n_poses, ctx->stream);
+  void *tmp = gpdb_scratch(ctx, 1, tmp_bytes);
+  if (!tmp) return GPDB_ERR_CUDA;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, f01, pos, n_poses, ctx->stream));
+  ctx->launches += 2;
+  k_scatter<<<gb, tb, 0, ctx->stream>>>(d_poses, f01, pos, n_poses, d_cand, d_count);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+static size_t images_smem_bytes(const DevParams &hp) {
+  size_t tiles = (size_t)3 * 8 * hp.S * hp.S;
+  size_t list = (size_t)BOX_CAP * (8 + 12 + 4 + 12);
+  size_t bm = (size_t)hp.K * (((size_t)hp.bm_dim * hp.bm_dim * hp.bm_dim + 31) / 32) * 4;
+  return tiles + std::max(list, hp.C == 15 ? bm : (size_t)0);
+}
+
+int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images) {
+  if (nc <= 0) return GPDB_OK;
+  size_t smem = images_smem_bytes(ctx->hp);
+  if (smem > 200 * 1024) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 204800)", smem);
+    return GPDB_ERR_INVALID;
+  }
+  CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = std::min(nc, ctx->sm_count * 64);
+  k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
+                       float *d_pose_scores, gpdb_pose *d_cand_out) {
+  if (nc <= 0) return GPDB_OK;
+  k_scatter_scores<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(d_cand, d_scores, nc, slot0, P, d_pose_scores, d_cand_out);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}

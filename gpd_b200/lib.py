@@ -1,0 +1,179 @@
+"""ctypes binding of libgpd_b200.so — the CUDA product library (include/gpd_b200.h).
+
+The library is built in-tree (gpd_b200/csrc/Makefile, __graft_entry__.build()). There is no CPU
+fallback: if the shared object is missing this module raises, and every compute call returns
+GPDB_ERR_CUDA when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libgpd_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "gpdb_params_default", "gpdb_create", "gpdb_destroy", "gpdb_last_error", "gpdb_load_weights_dir",
+    "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
+    "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info",
+]
+
+
+class GpdbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). gpd_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    vp = C.c_void_p
+    L.gpdb_params_default.argtypes = [C.POINTER(abi.Params)]
+    L.gpdb_create.argtypes = [C.POINTER(abi.Params), C.POINTER(vp)]
+    L.gpdb_destroy.argtypes = [vp]
+    L.gpdb_last_error.restype = C.c_char_p
+    L.gpdb_last_error.argtypes = [vp]
+    L.gpdb_load_weights_dir.argtypes = [vp, C.c_char_p]
+    L.gpdb_set_weights.argtypes = [vp] + [vp] * 8
+    L.gpdb_set_cloud.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32]
+    L.gpdb_detect.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
+    L.gpdb_hand_search.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
+    L.gpdb_frames.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.gpdb_images.argtypes = [vp, vp, C.c_int32, vp]
+    L.gpdb_classify.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.gpdb_free_result.argtypes = [C.POINTER(abi.Result)]
+    L.gpdb_last_timings.argtypes = [vp, vp]
+    L.gpdb_build_info.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**over):
+    p = abi.Params()
+    lib().gpdb_params_default(C.byref(p))
+    q = abi.default_params(p.image_num_channels)
+    for name, _ in abi.Params._fields_:  # the two defaults must agree (tests check it)
+        pass
+    chan = over.pop("channels", None)
+    if chan is not None:
+        p.image_num_channels = chan
+    for k, v in over.items():
+        if k == "hand_axes":
+            p.num_hand_axes = len(v)
+            for i, a in enumerate(v):
+                p.hand_axes[i] = a
+        elif k in ("workspace_grasps", "direction"):
+            for i, a in enumerate(v):
+                getattr(p, k)[i] = a
+        else:
+            setattr(p, k, v)
+    del q
+    return p
+
+
+class Context:
+    """One gpdb_ctx: one CUDA device + stream (gpdb_create ... gpdb_destroy)."""
+
+    def __init__(self, params):
+        self.params = params
+        self.h = C.c_void_p()
+        rc = lib().gpdb_create(C.byref(params), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise GpdbError(rc, lib().gpdb_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().gpdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise GpdbError(rc, lib().gpdb_last_error(self.h).decode())
+        return rc
+
+    def load_weights_dir(self, d):
+        if not d.endswith("/"):
+            d += "/"
+        self._check(lib().gpdb_load_weights_dir(self.h, d.encode()))
+
+    def set_weights(self, arrays):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32).ravel() for a in arrays]
+        self._check(lib().gpdb_set_weights(self.h, *[_p(a) for a in arrs]))
+
+    def set_cloud(self, xyz, normals, cam_source=None, view_points=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        vp = np.ascontiguousarray(view_points if view_points is not None else np.zeros((1, 3)), dtype=np.float64)
+        cam = None if cam_source is None else np.ascontiguousarray(cam_source, dtype=np.int32)
+        self._check(lib().gpdb_set_cloud(self.h, _p(xyz), _p(normals), _p(cam), xyz.shape[0], _p(vp), vp.shape[0]))
+
+    def _result(self, fn, sample_idx):
+        sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        res = abi.Result()
+        self._check(fn(self.h, _p(sidx), len(sidx), C.byref(res)))
+        S, Cc = self.params.image_size, self.params.image_num_channels
+        out = abi.result_to_numpy(res, S * S * Cc)
+        lib().gpdb_free_result(C.byref(res))
+        return out
+
+    def detect(self, sample_idx):
+        return self._result(lib().gpdb_detect, sample_idx)
+
+    def detect_raw(self, sidx_i32, res):
+        """Timed path for bench.py: no numpy conversion; caller frees `res`."""
+        return self._check(lib().gpdb_detect(self.h, _p(sidx_i32), len(sidx_i32), C.byref(res)))
+
+    def hand_search(self, sample_idx):
+        return self._result(lib().gpdb_hand_search, sample_idx)
+
+    def frames(self, sample_idx):
+        sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        n = len(sidx)
+        frames = np.zeros((n, 9))
+        valid = np.zeros(n, np.uint8)
+        self._check(lib().gpdb_frames(self.h, _p(sidx), n, _p(frames), _p(valid)))
+        return frames, valid
+
+    def images(self, poses):
+        poses = np.ascontiguousarray(poses, dtype=abi.POSE_DTYPE)
+        n = len(poses)
+        S, Cc = self.params.image_size, self.params.image_num_channels
+        out = np.zeros((n, S, S, Cc), np.uint8)
+        self._check(lib().gpdb_images(self.h, _p(poses), n, _p(out)))
+        return out
+
+    def classify(self, images):
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        n = images.shape[0]
+        scores = np.zeros(n, np.float32)
+        logits = np.zeros((n, 2), np.float32)
+        self._check(lib().gpdb_classify(self.h, _p(images), n, _p(scores), _p(logits)))
+        return scores, logits
+
+    def last_timings(self):
+        ms = np.zeros(8)
+        lib().gpdb_last_timings(self.h, _p(ms))
+        return ms
+
+
+def free_result(res):
+    lib().gpdb_free_result(C.byref(res))

@@ -42,7 +42,6 @@ extern "C" {
 #define GPDB_ERR_STATE (-3)     /* call order: cloud or weights not set          */
 #define GPDB_ERR_IO (-4)        /* weight file missing or of the wrong size      */
 #define GPDB_ERR_CAPACITY (-5)  /* a neighbourhood exceeded the on-chip tile     */
-#define GPDB_ERR_NCCL (-6)      /* communicator error (multi-GPU entry points)   */
 
 #define GPDB_MAX_CAMERAS 8
 #define GPDB_MAX_HAND_AXES 3
@@ -202,23 +201,6 @@ int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n_images, fl
 
 /* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). */
 void gpdb_free_result(gpdb_result *r);
-
-/* --- multi-GPU: one process per GPU, samples sharded by slice ------------- */
-
-/* 128-byte NCCL unique id, created on rank 0 and distributed by the host (torch.distributed,
- * MPI, a file ...). */
-int gpdb_comm_unique_id(uint8_t id_out[128]);
-/* Join the communicator: afterwards gpdb_set_cloud on rank 0 may be followed by
- * gpdb_bcast_cloud so that the other ranks receive the cloud over NVLink. */
-int gpdb_comm_init(gpdb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t n_ranks);
-/* ncclBroadcast of the device-resident cloud from `root` (N, k must be passed on all ranks). */
-int gpdb_bcast_cloud(gpdb_ctx *ctx, int32_t root, int32_t n_points, int32_t n_cams);
-/* Each rank runs the path on its contiguous slice [rank*n/R, (rank+1)*n/R) of sample_idx and
- * ONE ncclAllGather of fixed-stride score slots makes scores_out [n_samples*P] (NaN = no
- * candidate) and flags_out [n_samples*P] identical on all ranks. Returns this rank's
- * n_candidates. `local` (may be NULL) receives this rank's gpdb_result for its slice. */
-int gpdb_detect_sharded(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples,
-                        float *scores_out, uint8_t *flags_out, gpdb_result *local);
 
 /* --- introspection ------------------------------------------------------------------------- */
 /* Device-side stage timings of the last gpdb_detect call, CUDA events on the context stream:
