@@ -13,6 +13,42 @@
 
 static char g_create_err[512] = "";
 
+struct StageTimes {
+  struct Span { int stage; cudaEvent_t b, e; };
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<Span> spans;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  ~StageTimes() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+cudaEvent_t gpdb_st_begin(gpdb_ctx *ctx) {
+  cudaEvent_t e = ctx->st->get();
+  cudaEventRecord(e, ctx->stream);
+  return e;
+}
+void gpdb_st_end(gpdb_ctx *ctx, int stage, cudaEvent_t begin) {
+  cudaEvent_t e = ctx->st->get();
+  cudaEventRecord(e, ctx->stream);
+  ctx->st->spans.push_back({stage, begin, e});
+}
+static void st_collect(gpdb_ctx *ctx, double *ms) {
+  for (auto &sp : ctx->st->spans) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sp.b, sp.e) == cudaSuccess) ms[sp.stage] += t;
+  }
+  ctx->st->spans.clear();
+  ctx->st->used = 0;
+}
+
+
+
 void gpdb_set_error(gpdb_ctx *ctx, int code, const char *fmt, ...) {
   char buf[480];
   va_list ap;
@@ -225,6 +261,8 @@ int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out) {
   }
   gpdb_ctx *ctx = new gpdb_ctx();
   memset(ctx, 0, sizeof(*ctx));
+  ctx->st = new StageTimes();
+  ctx->own_stream = true;
   ctx->prm = *params;
   ctx->device = params->device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -273,7 +311,8 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   for (int i = 0; i < 16; i++) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx->st;
   delete ctx;
 }
 
@@ -369,38 +408,8 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const
 }  // extern "C"
 
 // ---- pipeline ------------------------------------------------------------------------------------
-namespace {
 
-struct StageTimes {
-  gpdb_ctx *ctx;
-  std::vector<cudaEvent_t> pool;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
-  cudaEvent_t get() {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    pool.push_back(e);
-    return e;
-  }
-  cudaEvent_t begin() {
-    cudaEvent_t e = get();
-    cudaEventRecord(e, ctx->stream);
-    return e;
-  }
-  void end(int stage, cudaEvent_t b) {
-    cudaEvent_t e = get();
-    cudaEventRecord(e, ctx->stream);
-    spans.push_back({stage, {b, e}});
-  }
-  void collect(double *ms) {
-    for (auto &s : spans) {
-      float t = 0;
-      if (cudaEventElapsedTime(&t, s.second.first, s.second.second) == cudaSuccess) ms[s.first] += t;
-    }
-    for (cudaEvent_t e : pool) cudaEventDestroy(e);
-    pool.clear();
-    spans.clear();
-  }
-};
+namespace {
 
 int check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) {
   if (!ctx) return GPDB_ERR_INVALID;
@@ -431,58 +440,67 @@ int check_device_errors(gpdb_ctx *ctx) {
   return GPDB_OK;
 }
 
-// The chunked device pipeline behind gpdb_detect / gpdb_hand_search.
-int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores) {
+// The chunked device pipeline behind gpdb_detect / gpdb_hand_search / gpdb_detect_resident.
+//   resident == false: sample_idx is a HOST array, every result is copied back to the host (out)
+//   resident == true : sample_idx, flags_ext, scores_ext are DEVICE arrays; nothing but the per-chunk
+//                      candidate count crosses PCIe (out receives counts and timings only)
+int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
+                 bool resident, uint8_t *flags_ext, float *scores_ext) {
   memset(out, 0, sizeof(*out));
   const int P = ctx->hp.P, S = ctx->hp.S, C = ctx->hp.C;
   const size_t isz = (size_t)S * S * C;
   out->n_samples = n;
   out->poses_per_sample = P;
-  for (int i = 0; i < n; i++)
-    if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N) {
-      gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d at position %d outside the cloud (N = %d)", sample_idx[i], i,
-                     ctx->N);
-      return GPDB_ERR_INVALID;
-    }
+  if (!resident)
+    for (int i = 0; i < n; i++)
+      if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N) {
+        gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d at position %d outside the cloud (N = %d)", sample_idx[i],
+                       i, ctx->N);
+        return GPDB_ERR_INVALID;
+      }
   const int64_t launches0 = ctx->launches;
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  StageTimes st{ctx};
   const int chunk = ctx->prm.chunk_samples > 0 ? ctx->prm.chunk_samples : 16384;
   const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
-  const bool keep = with_images_and_scores && ctx->prm.keep_images;
+  const bool keep = with_images_and_scores && ctx->prm.keep_images && !resident;
   const size_t nP = (size_t)n * P;
-  int *d_sidx = (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
+  int *d_sidx = resident ? const_cast<int *>(sample_idx) : (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
   double *d_frames = (double *)gpdb_scratch(ctx, 8, sizeof(double) * 9 * (size_t)n);
   uint8_t *d_valid = (uint8_t *)gpdb_scratch(ctx, 9, (size_t)n);
-  uint8_t *d_flags = (uint8_t *)gpdb_scratch(ctx, 10, nP);
-  float *d_pscores = (float *)gpdb_scratch(ctx, 11, sizeof(float) * nP);
+  uint8_t *d_flags = resident ? flags_ext : (uint8_t *)gpdb_scratch(ctx, 10, nP);
+  float *d_pscores = resident ? scores_ext : (float *)gpdb_scratch(ctx, 11, sizeof(float) * nP);
   const int cmax = std::min(chunk, std::max(n, 1));
   gpdb_pose *d_poses = (gpdb_pose *)gpdb_scratch(ctx, 12, sizeof(gpdb_pose) * (size_t)cmax * P);
   gpdb_pose *d_cand = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)cmax * P);
   int *d_count = (int *)gpdb_scratch(ctx, 14, 64);
   if (!d_sidx || !d_frames || !d_valid || !d_flags || !d_pscores || !d_poses || !d_cand || !d_count) return GPDB_ERR_CUDA;
-  cudaEvent_t t_all = st.begin();
+  ctx->st->spans.clear();
+  ctx->st->used = 0;
+  cudaEvent_t t_all = gpdb_st_begin(ctx);
   if (n > 0) {
-    CUDA_TRY(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!resident)
+      CUDA_TRY(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d_pscores, 0xFF, sizeof(float) * nP, ctx->stream));  // 0xFFFFFFFF = NaN
   }
   int rc;
-  cudaEvent_t t0 = st.begin();
+  cudaEvent_t t0 = gpdb_st_begin(ctx);
   if ((rc = geo_frames(ctx, d_sidx, n, d_frames, d_valid)) != GPDB_OK) return rc;
-  st.end(0, t0);
+  gpdb_st_end(ctx, 0, t0);
   std::vector<gpdb_pose> cands;
   std::vector<uint8_t> images;
+  int total_nc = 0;
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int nn = std::min(chunk, n - c0);
-    cudaEvent_t t1 = st.begin();
+    cudaEvent_t t1 = gpdb_st_begin(ctx);
     if ((rc = geo_hands(ctx, d_sidx + c0, nn, c0, d_frames + 9 * (size_t)c0, d_valid + c0, d_poses,
                         d_flags + (size_t)c0 * P)) != GPDB_OK)
       return rc;
     if ((rc = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand, d_count)) != GPDB_OK) return rc;
-    st.end(1, t1);
+    gpdb_st_end(ctx, 1, t1);
     int nc = 0;
     CUDA_TRY(cudaMemcpyAsync(&nc, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    total_nc += nc;
     if (with_images_and_scores && nc > 0) {
       float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)nc);
       if (!d_scores) return GPDB_ERR_CUDA;
@@ -492,12 +510,12 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
       for (int b0 = 0; b0 < nc; b0 += batch) {
         const int bn = std::min(batch, nc - b0);
         uint8_t *dst = keep ? d_img + isz * (size_t)b0 : d_img;
-        cudaEvent_t t2 = st.begin();
+        cudaEvent_t t2 = gpdb_st_begin(ctx);
         if ((rc = geo_images(ctx, d_cand + b0, bn, dst)) != GPDB_OK) return rc;
-        st.end(2, t2);
-        cudaEvent_t t3 = st.begin();
+        gpdb_st_end(ctx, 2, t2);
+        cudaEvent_t t3 = gpdb_st_begin(ctx);
         if ((rc = lenet_forward(ctx, dst, bn, d_scores + b0, nullptr)) != GPDB_OK) return rc;
-        st.end(3, t3);
+        gpdb_st_end(ctx, 3, t3);
       }
       if ((rc = geo_scatter_scores(ctx, d_cand, d_scores, nc, c0, P, d_pscores + (size_t)c0 * P, d_cand)) != GPDB_OK)
         return rc;
@@ -507,7 +525,7 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
         CUDA_TRY(cudaMemcpyAsync(images.data() + off, d_img, isz * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
       }
     }
-    if (nc > 0) {
+    if (nc > 0 && !resident) {
       size_t off = cands.size();
       cands.resize(off + nc);
       CUDA_TRY(cudaMemcpyAsync(cands.data() + off, d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToHost,
@@ -515,29 +533,33 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
       CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
   }
-  out->frame_valid = (uint8_t *)malloc((size_t)n + 1);
-  out->frames = (double *)malloc(sizeof(double) * 9 * (size_t)n + 8);
-  out->pose_flags = (uint8_t *)malloc(nP + 1);
-  out->pose_scores = (float *)malloc(sizeof(float) * nP + 4);
-  if (n > 0) {
-    CUDA_TRY(cudaMemcpyAsync(out->frame_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(out->frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(out->pose_flags, d_flags, nP, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(out->pose_scores, d_pscores, sizeof(float) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!resident) {
+    out->frame_valid = (uint8_t *)malloc((size_t)n + 1);
+    out->frames = (double *)malloc(sizeof(double) * 9 * (size_t)n + 8);
+    out->pose_flags = (uint8_t *)malloc(nP + 1);
+    out->pose_scores = (float *)malloc(sizeof(float) * nP + 4);
+    if (n > 0) {
+      CUDA_TRY(cudaMemcpyAsync(out->frame_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(out->frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(out->pose_flags, d_flags, nP, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(out->pose_scores, d_pscores, sizeof(float) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+    }
   }
-  st.end(4, t_all);
-  if ((rc = check_device_errors(ctx)) != GPDB_OK) {
-    st.collect(ms);
+  gpdb_st_end(ctx, 4, t_all);
+  rc = check_device_errors(ctx);
+  st_collect(ctx, ms);
+  if (rc != GPDB_OK) {
     gpdb_free_result(out);
     return rc;
   }
-  st.collect(ms);
-  out->n_candidates = (int)cands.size();
-  out->candidates = (gpdb_pose *)malloc(sizeof(gpdb_pose) * cands.size() + 8);
-  if (!cands.empty()) memcpy(out->candidates, cands.data(), sizeof(gpdb_pose) * cands.size());
-  if (keep) {
-    out->images = (uint8_t *)malloc(images.size() + 8);
-    if (!images.empty()) memcpy(out->images, images.data(), images.size());
+  out->n_candidates = total_nc;
+  if (!resident) {
+    out->candidates = (gpdb_pose *)malloc(sizeof(gpdb_pose) * cands.size() + 8);
+    if (!cands.empty()) memcpy(out->candidates, cands.data(), sizeof(gpdb_pose) * cands.size());
+    if (keep) {
+      out->images = (uint8_t *)malloc(images.size() + 8);
+      if (!images.empty()) memcpy(out->images, images.data(), images.size());
+    }
   }
   out->ms_candidates = ms[0] + ms[1];
   out->ms_images = ms[2];
@@ -558,7 +580,28 @@ int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_detect: bad arguments");
     return GPDB_ERR_INVALID;
   }
-  return run_pipeline(ctx, sample_idx, n, out, true);
+  return run_pipeline(ctx, sample_idx, n, out, true, false, nullptr, nullptr);
+}
+
+int gpdb_detect_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx, int32_t n, uint8_t *d_flags_out,
+                         float *d_scores_out, gpdb_result *stats) {
+  int rc = check_state(ctx, true, true);
+  if (rc != GPDB_OK) return rc;
+  if (!stats || n < 0 || (n > 0 && (!d_sample_idx || !d_flags_out || !d_scores_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_detect_resident: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  return run_pipeline(ctx, d_sample_idx, n, stats, true, true, d_flags_out, d_scores_out);
+}
+
+int gpdb_set_stream(gpdb_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return GPDB_OK;
 }
 
 int gpdb_hand_search(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out) {
@@ -568,7 +611,7 @@ int gpdb_hand_search(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_r
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_hand_search: bad arguments");
     return GPDB_ERR_INVALID;
   }
-  return run_pipeline(ctx, sample_idx, n, out, false);
+  return run_pipeline(ctx, sample_idx, n, out, false, false, nullptr, nullptr);
 }
 
 int gpdb_frames(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, double *frames_out, uint8_t *valid_out) {

@@ -89,12 +89,16 @@ struct LenetWeights {  // device pointers, layouts documented in lenet_simt.cu
   bool set;
 };
 
+struct StageTimes;  // api.cu
+
 struct gpdb_ctx {
   gpdb_params prm;
   DevParams hp;       // host copy
   DevParams *dp;      // device copy
   int device;
   cudaStream_t stream;
+  bool own_stream;
+  StageTimes *st;
   int sm_count;
   char err[512];
   // cloud
@@ -119,6 +123,10 @@ struct gpdb_ctx {
 };
 
 void gpdb_set_error(gpdb_ctx *ctx, int code, const char *fmt, ...);
+// device-side stage timers (CUDA events on the context stream). stages: 0 frames, 1 hand search +
+// compaction, 2 images, 3 LeNet, 4 whole call, 5 conv1, 6 conv2, 7 ip1+ip2
+cudaEvent_t gpdb_st_begin(gpdb_ctx *ctx);
+void gpdb_st_end(gpdb_ctx *ctx, int stage, cudaEvent_t begin);
 void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes);  // returns nullptr on failure (error set)
 
 // geometry.cu

@@ -293,14 +293,20 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
   size_t sm2 = sizeof(float) * (NF1 * 25 * NF2 + NF1 * P1 * P1);
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  cudaEvent_t e1 = gpdb_st_begin(ctx);
   k_conv1_pool<<<std::min(n, ctx->sm_count * 2), 224, sm1, ctx->stream>>>(d_images, n, S, C, w.c1w, w.c1b, relu, p1);
   LAUNCH_CHECK();
+  gpdb_st_end(ctx, 5, e1);
+  cudaEvent_t e2 = gpdb_st_begin(ctx);
   k_conv2_pool<<<std::min(n, ctx->sm_count), 240, sm2, ctx->stream>>>(p1, n, P1, w.c2w, w.c2b, relu, p2);
   LAUNCH_CHECK();
+  gpdb_st_end(ctx, 6, e2);
+  cudaEvent_t e3 = gpdb_st_begin(ctx);
   dim3 g3((n + 63) / 64, (NH + 63) / 64);
   k_ip1<<<g3, 256, 0, ctx->stream>>>(p2, n, K, w.i1w, w.i1b, h3);
   LAUNCH_CHECK();
   k_ip2<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(h3, n, w.i2w, w.i2b, d_scores, d_logits);
   LAUNCH_CHECK();
+  gpdb_st_end(ctx, 7, e3);
   return GPDB_OK;
 }

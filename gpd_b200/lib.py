@@ -18,7 +18,8 @@ _LIB = None
 EXPORTS = [
     "gpdb_params_default", "gpdb_create", "gpdb_destroy", "gpdb_last_error", "gpdb_load_weights_dir",
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
-    "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info",
+    "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
+    "gpdb_set_stream",
 ]
 
 
@@ -54,6 +55,8 @@ def lib():
     L.gpdb_free_result.argtypes = [C.POINTER(abi.Result)]
     L.gpdb_last_timings.argtypes = [vp, vp]
     L.gpdb_build_info.restype = C.c_char_p
+    L.gpdb_detect_resident.argtypes = [vp, vp, C.c_int32, vp, vp, C.POINTER(abi.Result)]
+    L.gpdb_set_stream.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -141,6 +144,14 @@ class Context:
     def detect_raw(self, sidx_i32, res):
         """Timed path for bench.py: no numpy conversion; caller frees `res`."""
         return self._check(lib().gpdb_detect(self.h, _p(sidx_i32), len(sidx_i32), C.byref(res)))
+
+    def detect_resident(self, d_sidx_ptr, n, d_flags_ptr, d_scores_ptr, stats):
+        """Device-resident path (raw device pointers as ints); returns n_candidates."""
+        return self._check(lib().gpdb_detect_resident(self.h, C.c_void_p(d_sidx_ptr), n, C.c_void_p(d_flags_ptr),
+                                                      C.c_void_p(d_scores_ptr), C.byref(stats)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(lib().gpdb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
     def hand_search(self, sample_idx):
         return self._result(lib().gpdb_hand_search, sample_idx)

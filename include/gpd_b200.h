@@ -178,6 +178,18 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals,
  * samples cloud.getSampleIndices() (cloud.h:345). Returns n_candidates or a negative error. */
 int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, gpdb_result *out);
 
+/* Device-resident variant of gpdb_detect: d_sample_idx [n], d_flags_out [n*P] and d_scores_out [n*P]
+ * are DEVICE pointers on the context's device; no input or result crosses PCIe (only the per-chunk
+ * candidate count is read back to size the image / classifier launches). `stats` receives
+ * n_candidates, stage timings and the launch count; its array members stay NULL. The caller
+ * guarantees 0 <= sample index < N. Used to measure the path with inputs resident in HBM. */
+int gpdb_detect_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx, int32_t n_samples, uint8_t *d_flags_out,
+                         float *d_scores_out, gpdb_result *stats);
+
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g. the
+ * host framework's current stream, instead of the context's own stream. */
+int gpdb_set_stream(gpdb_ctx *ctx, void *cuda_stream);
+
 /* Stage-level entry points (used by the parity tests and by partial drop-ins). */
 
 /* Replaces: FrameEstimator::calculateLocalFrames (frame_estimator.cpp:6-35).
@@ -204,7 +216,8 @@ void gpdb_free_result(gpdb_result *r);
 
 /* --- introspection ------------------------------------------------------------------------- */
 /* Device-side stage timings of the last gpdb_detect call, CUDA events on the context stream:
- * ms[0] grid/frames, ms[1] hand search, ms[2] images, ms[3] lenet, ms[4] total. */
+ * ms[0] frames, ms[1] hand search + compaction, ms[2] images, ms[3] LeNet, ms[4] whole call,
+ * ms[5] conv1+pool, ms[6] conv2+pool, ms[7] ip1+ip2. */
 int gpdb_last_timings(const gpdb_ctx *ctx, double ms_out[8]);
 /* Version / build info string (arch, lenet implementation). */
 const char *gpdb_build_info(void);

@@ -1333,6 +1333,15 @@ void gpdo_dilate_normalize_u8(const float *img /* S*S*ch HWC */, int32_t S, int3
   dilate3x3(img, d.data(), S, ch);
   normalize_to_u8(d.data(), S * S, out, ch, 0, ch);
 }
+// ConvLayer(width,height,depth,num_filters,spatial_extent,1,0)::forward (conv_layer.cpp:26-56) for the
+// known-answer test of src/tests/test_conv_layer.cpp:9-40
+void gpdo_conv_forward(const float *x, int32_t C, int32_t H, int32_t Wd, const float *w, const float *b, int32_t M,
+                       int32_t k, float *out) {
+  int oh = H - k + 1, ow = Wd - k + 1;
+  std::vector<float> col((size_t)C * k * k * oh * ow);
+  im2col(x, C, H, Wd, k, col.data());
+  gemm_bias(w, b, col.data(), out, M, C * k * k, oh * ow);
+}
 void gpdo_angle_axis(double angle, const double *axis, double *R) { angle_axis_matrix(angle, axis, R); }
 void gpdo_qtab(double *tab) { std::memcpy(tab, qtab(), sizeof(double) * GPDB_QTAB_SIZE); }
 int gpdo_num_threads(void) {

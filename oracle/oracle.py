@@ -49,6 +49,7 @@ def lib():
     L.gpdo_detect.argtypes = [vp, C.POINTER(abi.Params), vp, vp, C.c_int32, C.POINTER(abi.Result), C.c_int32, vp]
     L.gpdo_free_result.argtypes = [C.POINTER(abi.Result)]
     L.gpdo_dilate_normalize_u8.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.gpdo_conv_forward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp]
     L.gpdo_angle_axis.argtypes = [C.c_double, vp, vp]
     L.gpdo_qtab.argtypes = [vp]
     L.gpdo_num_threads.restype = C.c_int
@@ -174,3 +175,15 @@ def qtab():
     t = np.zeros(1024)
     lib().gpdo_qtab(_p(t))
     return t
+
+
+def conv_forward(x, w, b, k):
+    """ConvLayer::forward: x [C,H,W], w [M,C,k,k], b [M] -> [M, oh*ow]."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    Cc, H, Wd = x.shape
+    M = w.shape[0]
+    out = np.zeros((M, (H - k + 1) * (Wd - k + 1)), np.float32)
+    lib().gpdo_conv_forward(_p(x), Cc, H, Wd, _p(w), _p(b), M, k, _p(out))
+    return out

@@ -1,0 +1,207 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on identical
+seeded inputs, plus size-independent properties at BASELINE's full sizes.
+
+Tolerances: integer / boolean outputs exact; float64 geometry within 1e-9 absolute (the kernels
+follow the oracle's operation order with FMA contraction off, so in practice bit-equal); images uint8-equal except
+<= 1 LSB on <= 0.1 % of pixels (the per-cell means are exact fixed-point sums on the GPU, a float32 running mean in
+the reference); scores within 1e-4 relative to the largest |score| (float32 accumulation order).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_weights
+from gpd_b200 import lib, scenes
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make(cloud, ch, **over):
+    w, relu = load_weights(ch)
+    p = lib.default_params(channels=ch, relu_after_conv=relu, **over)
+    ctx = lib.Context(p)
+    ctx.set_weights(w)
+    ctx.set_cloud(cloud["xyz"], cloud["normals"], cloud["cam_source"], cloud["view_points"])
+    oc = oracle.OracleCloud(cloud["xyz"], cloud["normals"], cloud["cam_source"], cloud["view_points"])
+    return p, ctx, oc, oracle.WeightPack(w)
+
+
+def assert_parity(ro, rg, ch):
+    assert np.array_equal(ro["frame_valid"], rg["frame_valid"])
+    assert np.allclose(ro["frames"], rg["frames"], atol=1e-9, rtol=0)
+    assert np.array_equal(ro["pose_flags"], rg["pose_flags"])
+    assert ro["n_candidates"] == rg["n_candidates"]
+    co, cg = ro["candidates"], rg["candidates"]
+    for f in ("sample_index", "sample_slot", "pose_slot", "finger_idx", "half_antipodal", "full_antipodal"):
+        assert np.array_equal(co[f], cg[f]), f
+    for f in ("sample", "frame", "position", "top", "bottom", "center", "width"):
+        assert np.allclose(co[f], cg[f], atol=1e-9, rtol=0), f
+    if ro["images"] is not None and len(co):
+        d = np.abs(ro["images"].astype(np.int32) - rg["images"].astype(np.int32))
+        assert d.max() <= 1
+        assert np.count_nonzero(d) <= 1e-3 * d.size
+    if len(co):
+        so, sg = co["score"], cg["score"]
+        assert np.abs(so - sg).max() <= 1e-4 * np.abs(so).max()
+        assert np.array_equal(np.isnan(ro["pose_scores"]), np.isnan(rg["pose_scores"]))
+
+
+@pytest.mark.parametrize("ch,n", [(15, 160), (3, 96), (1, 40)])
+def test_krylon_matches_oracle(ch, n):
+    k = scenes.krylon_cloud()
+    if ch == 1:
+        pytest.skip("no 1-channel LeNet weights ship with the reference; images covered in test_images_entry_point")
+    p, ctx, oc, w = make(k, ch, keep_images=1)
+    sidx = scenes.sample_indices(2, len(k["xyz"]), n)
+    assert_parity(oc.detect(p, w, sidx), ctx.detect(sidx), ch)
+    ctx.close()
+
+
+def test_synthetic_table_15ch_matches_oracle():
+    s = scenes.synthetic_table_scene(7, n_points=60000)
+    p, ctx, oc, w = make(s, 15, keep_images=1)
+    sidx = scenes.sample_indices(3, 60000, 400)
+    assert_parity(oc.detect(p, w, sidx), ctx.detect(sidx), 15)
+    ctx.close()
+
+
+def test_two_view_12ch_relu_net_matches_oracle():
+    s = scenes.synthetic_table_scene(5, n_points=60000, two_cameras=True)
+    p, ctx, oc, w = make(s, 12, keep_images=1)
+    sidx = scenes.sample_indices(5, 60000, 300)
+    assert_parity(oc.detect(p, w, sidx), ctx.detect(sidx), 12)
+    ctx.close()
+
+
+def test_two_view_15ch_all_axes_and_filters():
+    s = scenes.synthetic_table_scene(5, n_points=60000, two_cameras=True)
+    p, ctx, oc, w = make(s, 15, keep_images=1, hand_axes=[0, 1, 2], num_orientations=4, num_finger_placements=7,
+                         deepen_hand=0, filter_approach_direction=1, direction=[0.0, 0.0, 1.0], thresh_rad=1.2,
+                         max_aperture=0.07, workspace_grasps=[-0.5, 0.5, -0.4, 0.4, 0.0, 1.0])
+    sidx = scenes.sample_indices(5, 60000, 120)
+    ro, rg = oc.detect(p, w, sidx), ctx.detect(sidx)
+    assert (ro["pose_flags"] & 1).sum() > (ro["pose_flags"] & 2).sum() // 2 > 0  # the filters actually filter
+    assert_parity(ro, rg, 15)
+    ctx.close()
+
+
+def test_stage_entry_points():
+    k = scenes.krylon_cloud()
+    p, ctx, oc, w = make(k, 15)
+    sidx = scenes.sample_indices(2, len(k["xyz"]), 64)
+    fo, vo = oc.frames(p, sidx)
+    fg, vg = ctx.frames(sidx)
+    assert np.array_equal(vo, vg) and np.array_equal(fo, fg)
+    hs = ctx.hand_search(sidx)
+    po, flo = oc.hand_search(p, sidx, fo, vo)
+    assert np.array_equal(hs["pose_flags"], flo)
+    cand = hs["candidates"]
+    assert len(cand) == ((flo & 3) == 3).sum() and np.isnan(cand["score"]).all()
+    io, ig = oc.images(p, cand[:40]), ctx.images(cand[:40])
+    d = np.abs(io.astype(int) - ig.astype(int))
+    assert d.max() <= 1 and np.count_nonzero(d) <= 1e-3 * d.size
+    sg, lg = ctx.classify(io)
+    so, lo = oracle.classify(p, w, io)
+    assert np.abs(lg - lo).max() <= 1e-4 * np.abs(lo).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("ch", [1, 3, 12])
+def test_images_entry_point_other_channel_counts(ch):
+    k = scenes.krylon_cloud()
+    p3, ctx3, oc, _ = make(k, 3)
+    cand = ctx3.hand_search(scenes.sample_indices(2, len(k["xyz"]), 24))["candidates"][:48]
+    ctx3.close()
+    p = lib.default_params(channels=ch)
+    ctx = lib.Context(p)
+    ctx.set_cloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    io, ig = oc.images(p, cand), ctx.images(cand)
+    d = np.abs(io.astype(int) - ig.astype(int))
+    assert io.max() > 0 and d.max() <= 1 and np.count_nonzero(d) <= 1e-3 * d.size
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,ch", [("lenet_caffe_15ch", 15), ("lenet_caffe_3ch", 3), ("lenet_ir_12ch", 12)])
+def test_classifier_against_reference_model_goldens(golden_dir, name, ch):
+    import os
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    w, relu = load_weights(ch)
+    p = lib.default_params(channels=ch, relu_after_conv=relu)
+    ctx = lib.Context(p)
+    ctx.set_weights(w)
+    s, lg = ctx.classify(g["images"])
+    assert np.abs(lg - g["logits"]).max() <= 1e-4 * np.abs(g["logits"]).max()
+    ctx.close()
+
+
+def test_edge_cases_and_errors():
+    k = scenes.krylon_cloud()
+    p, ctx, oc, w = make(k, 15)
+    r = ctx.detect(np.zeros(0, np.int32))
+    assert r["n_candidates"] == 0 and r["pose_flags"].shape == (0, 8)
+    r = ctx.detect(np.array([100, 100, 7], np.int32))
+    assert np.array_equal(r["pose_flags"][0], r["pose_flags"][1])
+    with pytest.raises(lib.GpdbError) as e:
+        ctx.detect(np.array([len(k["xyz"])], np.int32))
+    assert e.value.code == -1
+    ctx2 = lib.Context(p)
+    with pytest.raises(lib.GpdbError) as e:
+        ctx2.detect(np.array([0], np.int32))
+    assert e.value.code == -3
+    with pytest.raises(lib.GpdbError) as e:
+        ctx2.load_weights_dir("/nonexistent/")
+    assert e.value.code == -4
+    ctx2.close()
+    # isolated point: the hand closes on the single point, outside the workspace
+    xyz = np.vstack([k["xyz"], [[5.0, 5.0, 5.0]]]).astype(np.float32)
+    nrm = np.vstack([k["normals"], [[0.0, 0.0, 1.0]]])
+    ctx.set_cloud(xyz, nrm, None, np.zeros((1, 3)))
+    oc2 = oracle.OracleCloud(xyz, nrm, None, np.zeros((1, 3)))
+    sidx = np.array([len(xyz) - 1, 3], np.int32)
+    assert_parity(oc2.detect(p, w, sidx), ctx.detect(sidx), 15)
+    ctx.close()
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 at full size (300k points, 100k samples): properties that need no oracle at that size —
+    determinism, chunk-size independence, permutation equivariance, device-resident == host path — plus exact
+    parity on a random subset small enough for the oracle."""
+    import torch
+    s = scenes.synthetic_table_scene(3)
+    sidx = scenes.sample_indices(3, len(s["xyz"]))
+    p, ctx, oc, w = make(s, 15)
+    a = ctx.detect(sidx)
+    b = ctx.detect(sidx)
+    assert np.array_equal(a["pose_flags"], b["pose_flags"]) and np.array_equal(a["pose_scores"], b["pose_scores"], equal_nan=True)
+    assert a["n_candidates"] > 50000
+    # chunking does not change results
+    p2, ctx2, _, _ = make(s, 15, chunk_samples=4096, batch_size=1000)
+    sub = sidx[:20000]
+    c = ctx2.detect(sub)
+    assert np.array_equal(c["pose_flags"], a["pose_flags"][:20000])
+    assert np.array_equal(c["pose_scores"], a["pose_scores"][:20000], equal_nan=True)
+    ctx2.close()
+    # permutation equivariance
+    perm = np.random.default_rng(0).permutation(20000)
+    d = ctx.detect(sub[perm])
+    assert np.array_equal(d["pose_flags"], a["pose_flags"][:20000][perm])
+    assert np.array_equal(d["pose_scores"], a["pose_scores"][:20000][perm], equal_nan=True)
+    # device-resident entry point gives the same flags / scores
+    from gpd_b200 import abi
+    dev = torch.device("cuda", 0)
+    d_sidx = torch.from_numpy(sidx).to(dev)
+    d_flags = torch.zeros(len(sidx) * 8, dtype=torch.uint8, device=dev)
+    d_scores = torch.zeros(len(sidx) * 8, dtype=torch.float32, device=dev)
+    st = abi.Result()
+    nc = ctx.detect_resident(d_sidx.data_ptr(), len(sidx), d_flags.data_ptr(), d_scores.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert nc == a["n_candidates"]
+    assert np.array_equal(d_flags.cpu().numpy().reshape(-1, 8), a["pose_flags"])
+    assert np.array_equal(d_scores.cpu().numpy().reshape(-1, 8), a["pose_scores"], equal_nan=True)
+    # exact parity on a subset
+    pick = np.random.default_rng(1).choice(len(sidx), 300, replace=False)
+    ro = oc.detect(p, w, sidx[pick])
+    assert np.array_equal(ro["pose_flags"], a["pose_flags"][pick])
+    m = ~np.isnan(ro["pose_scores"])
+    assert np.abs(ro["pose_scores"][m] - a["pose_scores"][pick][m]).max() <= 1e-4 * np.abs(ro["pose_scores"][m]).max()
+    ctx.close()

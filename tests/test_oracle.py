@@ -1,0 +1,164 @@
+"""CPU tests: the oracle (oracle/gpd_oracle.cpp) against every pin available for this path.
+
+The reference ships no asserting tests or golden vectors; the pins are
+ * the known-answer conv example of src/tests/test_conv_layer.cpp:11-16,
+ * real OpenCV (cv2.dilate / normalize / convertTo) outputs, committed in tests/golden/cv_pins.npz,
+ * cv2.dnn forward passes of the reference's own .prototxt/.caffemodel (3 and 15 channels) and a
+   float64 torch restatement of the OpenVINO IR 12-channel net (tests/golden/lenet_*.npz),
+ * numpy.linalg for the eigen-solver, brute force for the radius search,
+ * a regression fixture of the oracle itself on the tutorial cloud.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import load_weights
+from gpd_b200 import abi, scenes
+from oracle import oracle
+
+
+def test_conv_layer_known_answer():
+    # src/tests/test_conv_layer.cpp:11-16 — 5x5 input, 3x3 kernel, zero bias
+    X = np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 1, 1, 0, 0, 1, 1, 0, 0], np.float32).reshape(1, 5, 5)
+    W = np.array([1, 0, 1, 0, 1, 0, 1, 0, 1], np.float32).reshape(1, 1, 3, 3)
+    Y = oracle.conv_forward(X, W, np.zeros(1, np.float32), 3).reshape(3, 3)
+    assert np.array_equal(Y, np.array([[4, 3, 4], [2, 4, 3], [2, 3, 4]], np.float32))
+
+
+def test_opencv_pins(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv_pins.npz"))
+    bad = total = 0
+    for img, ref, ch in zip(g["inputs"], g["outputs"], g["channels"]):
+        out = oracle.dilate_normalize_u8(img[:, :, :ch])
+        d = np.abs(out.astype(int) - ref[:, :, :ch].astype(int))
+        assert d.max() <= 1
+        bad += np.count_nonzero(d)
+        total += d.size
+    assert bad <= 2, f"{bad} of {total} pixels differ from cv2"
+
+
+@pytest.mark.parametrize("ch,name", [(15, "lenet_caffe_15ch"), (3, "lenet_caffe_3ch"), (12, "lenet_ir_12ch")])
+def test_lenet_against_reference_models(golden_dir, ch, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    w, relu = load_weights(ch)
+    p = abi.default_params(ch, relu_after_conv=relu)
+    scores, logits = oracle.classify(p, oracle.WeightPack(w), g["images"])
+    ref = g["logits"]
+    assert np.abs(logits - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.allclose(scores, ref[:, 1] - ref[:, 0], rtol=0, atol=2e-5 * np.abs(ref).max())
+
+
+def test_eigen3_is_a_symmetric_eigensolver():
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        N = rng.standard_normal((3, rng.integers(3, 60)))
+        M = N @ N.T
+        ev, evec = oracle.eigen3(M)
+        w, v = np.linalg.eigh(M)
+        assert np.all(np.diff(ev) >= 0)
+        assert np.abs(ev - w).max() <= 1e-12 * max(w.max(), 1e-300)
+        assert np.abs(evec.T @ evec - np.eye(3)).max() < 1e-12
+        assert np.abs(M @ evec - evec * ev).max() <= 1e-11 * w.max()
+    # degenerate inputs must not produce NaN
+    for M in (np.zeros((3, 3)), np.eye(3), np.diag([1.0, 1.0, 0.0])):
+        ev, evec = oracle.eigen3(M)
+        assert np.isfinite(ev).all() and np.isfinite(evec).all()
+
+
+def test_radius_search_flann_semantics():
+    k = scenes.krylon_cloud()
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    xyz = k["xyz"]
+    for qi, r in [(10, 0.11), (500, 0.01), (2000, 0.10), (7, 0.0)]:
+        q = xyz[qi]
+        idx, d = oc.radius_search(q, r)
+        dx = (q - xyz).astype(np.float32)
+        dd = (dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1]) + dx[:, 2] * dx[:, 2]
+        bf = np.where(dd < np.float32(r * r))[0]
+        assert set(idx.tolist()) == set(bf.tolist())
+        order = np.lexsort((bf, dd[bf]))  # (dist, index)
+        assert np.array_equal(idx, bf[order])
+        assert np.array_equal(d, dd[bf][order])
+
+
+def test_krylon_regression_fixture(golden_dir, weights15):
+    g = np.load(os.path.join(golden_dir, "krylon_oracle_15ch.npz"))
+    k = scenes.krylon_cloud()
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    p = abi.default_params(15, keep_images=1)
+    r = oc.detect(p, oracle.WeightPack(weights15), g["sample_idx"])
+    assert np.array_equal(r["pose_flags"], g["pose_flags"])
+    assert np.array_equal(r["frame_valid"], g["frame_valid"])
+    assert np.allclose(r["frames"], g["frames"], atol=1e-12, rtol=0)
+    for f in ("position", "frame", "top", "bottom", "center", "width"):
+        assert np.allclose(r["candidates"][f], g["candidates"][f], atol=1e-12, rtol=0), f
+    assert np.array_equal(r["candidates"]["finger_idx"], g["candidates"]["finger_idx"])
+    crc = np.array([zlib.crc32(im.tobytes()) for im in r["images"]], np.uint32)
+    assert np.array_equal(crc, g["image_crc32"])
+    assert np.allclose(r["candidates"]["score"], g["candidates"]["score"], rtol=1e-5, atol=1e-2)
+
+
+def test_structural_invariants_of_the_path():
+    """Properties the reference semantics imply, checked on the oracle (and on the GPU in test_gpu_parity)."""
+    s = scenes.synthetic_table_scene(11, n_points=30000)
+    oc = oracle.OracleCloud(s["xyz"], s["normals"], s["cam_source"], s["view_points"])
+    p = abi.default_params(3)
+    sidx = scenes.sample_indices(3, 30000, 120)
+    fr, valid = oc.frames(p, sidx)
+    assert valid.all()
+    F = fr.reshape(-1, 3, 3)  # rows: normal, binormal, curvature
+    assert np.allclose(np.einsum("nij,nkj->nik", F, F), np.eye(3), atol=1e-9)
+    poses, flags = oc.hand_search(p, sidx, fr, valid)
+    v = (flags & 1) == 1
+    assert v.any()
+    pv = poses[v]
+    R = pv["frame"].reshape(-1, 3, 3)
+    assert np.allclose(np.einsum("nij,nkj->nik", R, R), np.eye(3), atol=1e-9)
+    assert (pv["top"] - pv["bottom"] - 0.06 < 1e-12).all() and (pv["top"] >= 0.01 - 1e-15).all() and (pv["top"] <= 0.06 + 1e-12).all()
+    assert (pv["width"] >= 0).all() and (pv["width"] <= 0.10 + 1e-9).all()
+    assert ((flags & 8) <= ((flags & 4) << 1)).all()  # full antipodal implies half
+    assert ((flags & 2) <= ((flags & 1) << 1)).all()  # filtered implies valid
+    # sample order does not matter (each sample is independent)
+    perm = np.random.default_rng(0).permutation(len(sidx))
+    poses2, flags2 = oc.hand_search(p, sidx[perm], fr[perm], valid[perm])
+    assert np.array_equal(flags2, flags[perm])
+    assert np.array_equal(poses2["position"], poses["position"][perm])
+
+
+def test_edge_cases():
+    k = scenes.krylon_cloud()
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    p = abi.default_params(3)
+    r = oc.detect(p, None, np.zeros(0, np.int32))
+    assert r["n_candidates"] == 0 and r["pose_flags"].shape == (0, 8)
+    # a single isolated far-away point: the frame exists (the point itself) and the hand closes on that one
+    # point (width 0), but the grasp lies outside workspace_grasps = [-1, 1]^3 -> valid, not filtered
+    xyz = np.vstack([k["xyz"], [[5.0, 5.0, 5.0]]]).astype(np.float32)
+    nrm = np.vstack([k["normals"], [[0.0, 0.0, 1.0]]])
+    oc2 = oracle.OracleCloud(xyz, nrm, None, np.zeros((1, 3)))
+    r = oc2.detect(p, None, np.array([len(xyz) - 1, 3], np.int32))
+    assert r["frame_valid"].tolist() == [1, 1]
+    assert ((r["pose_flags"][0] & 1) == 1).all() and ((r["pose_flags"][0] & 2) == 0).all()
+    # duplicated sample indices give duplicated results
+    r = oc.detect(p, None, np.array([100, 100, 7], np.int32))
+    assert np.array_equal(r["pose_flags"][0], r["pose_flags"][1])
+
+
+def test_shadow_variant_is_deterministic_and_documented():
+    t = oracle.qtab()
+    assert len(t) == 1024 and np.all(np.diff(t) > 0) and abs(t[511] + t[512]) < 1e-12 and 3.0 < t[-1] < 3.3
+    k = scenes.krylon_cloud()
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    p = abi.default_params(15, keep_images=1)
+    sidx = np.array([1987, 42], np.int32)
+    a = oc.detect(p, None, sidx, nthreads=1)
+    b = oc.detect(p, None, sidx[::-1].copy(), nthreads=4)
+    ia = {(c["sample_index"], c["pose_slot"]): im for c, im in zip(a["candidates"], a["images"])}
+    ib = {(c["sample_index"], c["pose_slot"]): im for c, im in zip(b["candidates"], b["images"])}
+    assert ia.keys() == ib.keys() and len(ia) > 0
+    for key in ia:
+        assert np.array_equal(ia[key], ib[key])
+    # shadow channels are populated
+    assert any(im.reshape(-1, 15)[:, 4].max() > 0 for im in a["images"])

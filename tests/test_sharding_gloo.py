@@ -1,0 +1,71 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: contiguous slices of the sample indices over a
+broadcast cloud, one all-gather of fixed-stride score slots (gpd_b200/sharding.py). The per-rank compute is
+stood in by the oracle here (no GPU in this container); on the B200 box the same code runs with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from gpd_b200 import sharding
+
+
+def test_slices_partition_the_samples():
+    for n in (0, 1, 7, 100, 100001):
+        for world in (1, 2, 3, 8):
+            b = [sharding.slice_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+            assert sharding.slot_stride(n, world) == max(hi - lo for lo, hi in b)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from gpd_b200 import abi, scenes
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cloud = scenes.krylon_cloud() if rank == 0 else None
+    cloud = sharding.broadcast_cloud(cloud, rank, dist)
+    n = 21  # uneven split on purpose
+    sidx = scenes.sample_indices(2, len(cloud["xyz"]), n)
+    lo, hi = sharding.slice_bounds(n, rank, world)
+    p = abi.default_params(3)
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpd_b200", "weights",
+                             "lenet_3ch.npz"))
+    w = oracle.WeightPack([z[k] for k in oracle.WeightPack.NAMES])
+    oc = oracle.OracleCloud(cloud["xyz"], cloud["normals"], cloud["cam_source"], cloud["view_points"])
+    local = oc.detect(p, w, sidx[lo:hi], nthreads=2)
+    full = sharding.gather_scores(local["pose_scores"].reshape(-1), n, 8, rank, world, dist)
+    if rank == 0:
+        ref = oc.detect(p, w, sidx, nthreads=2)
+        q.put((full.numpy(), ref["pose_scores"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allgather_matches_single_rank():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    full, ref = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert full.shape == ref.shape == (21, 8)
+    assert np.array_equal(np.isnan(full), np.isnan(ref))
+    m = ~np.isnan(ref)
+    assert m.any() and np.array_equal(full[m], ref[m])
