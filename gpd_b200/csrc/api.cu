@@ -232,7 +232,8 @@ void gpdb_params_default(gpdb_params *p) {
 }
 
 const char *gpdb_build_info(void) {
-  return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images (fp64, -fmad=false), lenet: simt-fp32";
+  return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images (fp64, -fmad=false), lenet: conv1/conv2 tcgen05 "
+         "implicit GEMM (bf16x3 / fp16x2 split, fp32 accumulate in TMEM) + ip1/ip2 simt-fp32; lenet_impl=1 forces simt";
 }
 
 const char *gpdb_last_error(const gpdb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -308,6 +309,8 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   cudaFree(ctx->d_cell_start);
   float *w[8] = {ctx->w.c1w, ctx->w.c1b, ctx->w.c2w, ctx->w.c2b, ctx->w.i1w, ctx->w.i1b, ctx->w.i2w, ctx->w.i2b};
   for (float *p : w) cudaFree(p);
+  cudaFree(ctx->tc.b1);
+  cudaFree(ctx->tc.b2);
   for (int i = 0; i < 16; i++) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -89,6 +89,13 @@ struct LenetWeights {  // device pointers, layouts documented in lenet_simt.cu
   bool set;
 };
 
+struct LenetTc {  // tensor-core (tcgen05) weight blobs, lenet_tc.cu
+  void *b1, *b2;
+  int npl, nch1;
+  float w2_scale, a2_scale;
+  bool ready;
+};
+
 struct StageTimes;  // api.cu
 
 struct gpdb_ctx {
@@ -113,6 +120,7 @@ struct gpdb_ctx {
   double *d_qtab;
   // weights
   LenetWeights w;
+  LenetTc tc;
   // scratch (grown on demand)
   void *scratch[16];
   size_t scratch_sz[16];
@@ -144,3 +152,7 @@ int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_sc
 // lenet_simt.cu
 int lenet_upload(gpdb_ctx *ctx, const float *const w[8]);
 int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores, float *d_logits);
+
+// lenet_tc.cu (tcgen05 conv1 / conv2)
+int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]);
+int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, float *p2);

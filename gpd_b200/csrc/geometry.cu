@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
       const double hh = P.hand_height;
       uint8_t fl = 0;
       double top = 0, bottom = 0, center = 0, width = 0;
-      int fidx = -1;
+      int fidx = -1, fpi = -1;
       bool half = false, full = false;
       double x0, y0, z0;
       to_frame(R, nbx, nby, nbz, x0, y0, z0);
@@ -581,6 +581,9 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
           unsigned hm = hand;
           while (--target) hm &= hm - 1;
           fidx = __ffs(hm) - 1;
+          // Hand::construct (hand.cpp:33-38): finger_placement_index_ = FIRST set bit of hand_; deepenHand
+          // resets hand_ to the eroded index only (finger_hand.cpp:134-136), chooseMiddleHand does not
+          fpi = P.deepen ? fidx : (__ffs(hand) - 1);
           top = b0;
           bottom = bot0;
           if (P.deepen) {
@@ -721,7 +724,7 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
           o.bottom = bottom;
           o.center = center;
           o.width = width;
-          o.finger_idx = (int16_t)fidx;
+          o.finger_idx = (int16_t)fpi;
           o.half_antipodal = half;
           o.full_antipodal = full;
           for (int r = 0; r < 3; r++)

@@ -272,6 +272,7 @@ int lenet_upload(gpdb_ctx *ctx, const float *const w[8]) {
   free(t2);
   d.C = C;
   d.set = (rc == GPDB_OK);
+  if (rc == GPDB_OK) rc = lenet_tc_upload(ctx, w);
   return rc;
 }
 
@@ -293,6 +294,11 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
   size_t sm2 = sizeof(float) * (NF1 * 25 * NF2 + NF1 * P1 * P1);
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  const bool use_tc = ctx->tc.ready && ctx->prm.lenet_impl != 1;
+  if (use_tc) {
+    int rc = lenet_tc_convs(ctx, d_images, n, p1, p2);
+    if (rc != GPDB_OK) return rc;
+  } else {
   cudaEvent_t e1 = gpdb_st_begin(ctx);
   k_conv1_pool<<<std::min(n, ctx->sm_count * 2), 224, sm1, ctx->stream>>>(d_images, n, S, C, w.c1w, w.c1b, relu, p1);
   LAUNCH_CHECK();
@@ -301,6 +307,7 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
   k_conv2_pool<<<std::min(n, ctx->sm_count), 240, sm2, ctx->stream>>>(p1, n, P1, w.c2w, w.c2b, relu, p2);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 6, e2);
+  }
   cudaEvent_t e3 = gpdb_st_begin(ctx);
   dim3 g3((n + 63) / 64, (NH + 63) / 64);
   k_ip1<<<g3, 256, 0, ctx->stream>>>(p2, n, K, w.i1w, w.i1b, h3);

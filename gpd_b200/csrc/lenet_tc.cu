@@ -1,0 +1,396 @@
+// lenet_tc.cu — LeNet conv1 / conv2 (A14) on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Both convolutions are IM2COL-FREE implicit GEMMs. The activations of one image live in shared memory as
+// "channel planes": plane p holds channels 8p..8p+7 of every pixel as one 16-byte group, pixels in row-major
+// order. For output pixel m = y*W + x (W = input width) and filter tap (kh, kw) the 8 channels it needs are the
+// 16-byte group  plane_p[m + kh*W + kw]  — so the A operand of the GEMM (rows = output pixels, K = taps x
+// channels) is a Hankel matrix over that plane: row stride 16 B, K-chunk stride 16 B. This is exactly a K-major
+// no-swizzle UMMA shared-memory descriptor with SBO = 128 B (8 rows x 16 B) and LBO = the byte distance between
+// the two 8-element K-chunks of one K=16 instruction (tools/umma_probe.cu T2/T4 verify this addressing on B200).
+// No patch matrix is ever materialised; every tcgen05.mma reads the plane directly.
+//
+// Precision: the reference computes in float32 on raw 0..255 inputs (logits ~1e3), tolerance 1e-4 relative.
+//   conv1: activations are uint8 -> exact in bf16; weights are split w = w1 + w2 + w3 (bf16 each, 24 bits);
+//          the three terms are stacked along N (N = 3 x 32) so ONE instruction stream with N = 96 reads A once;
+//          the epilogue adds the three 32-column groups in float32.
+//   conv2: activations a and weights w are scaled by powers of two (exact) and split in two fp16 terms each;
+//          D[:, 0:64] += a_hi w_hi + a_lo w_hi, D[:, 64:128] += a_hi w_lo  (error ~2^-22), summed in the epilogue.
+// Output pixels with x beyond the valid width are computed and discarded (7 % / 14 % of the rows).
+//
+// One CTA per SM, persistent over images; weights stay resident in shared memory (76.8 KB / 155.6 KB).
+// The 2x2 max-pool + bias (+ReLU for the 12-channel net) is fused into the epilogue: TMEM -> registers ->
+// x-pair max by shuffle -> small smem stage -> y-pair max -> global.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int NF1 = 20, NF2 = 50, NH = 500;
+
+struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row 0
+  uint32_t a_off, a_lbo;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// conv1: image 60x60xC uint8 (HWC) -> P1 [784 px][20] float32 (pixel-major), 2x2 max-pooled
+// tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
+constexpr int C1_N = 96, C1_BCHUNK = C1_N * 16;
+
+__global__ void __launch_bounds__(128, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C, int npl,
+                                                     const uint8_t *__restrict__ wblob, int nch, const float *__restrict__ bias,
+                                                     int relu, float *__restrict__ p1) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  __shared__ MmaTab tab[32];
+  __shared__ float sbias[NF1];
+  const int nmma = (nch + 1) / 2;
+  uint8_t *sB = smem;                                  // nch(+1) chunks x 96 rows x 16 B
+  uint8_t *sPl = sB + (size_t)(2 * nmma) * C1_BCHUNK;  // npl planes
+  float *stage = reinterpret_cast<float *>(sPl + (size_t)npl * C1_PLANE);  // 2 x [60][20]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < (2 * nmma) * C1_BCHUNK / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
+  for (int i = tid; i < npl * C1_PLANE / 16; i += 128) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < NF1) sbias[tid] = bias[tid];
+  if (tid < nmma) {
+    // chunk order c = (p*5 + kh)*5 + kw ; address of row 0: p*PLANE + (kh*60 + kw)*16 (monotonic in c)
+    auto off = [&](int c) {
+      if (c >= nch) c = nch - 1;  // dummy chunk (zero weights): any valid address
+      int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
+      return (uint32_t)(p * C1_PLANE + (kh * C1_W + kw) * 16);
+    };
+    uint32_t a0 = off(2 * tid), a1 = off(2 * tid + 1);
+    tab[tid].a_off = a0;
+    tab[tid].a_lbo = (2 * tid + 1 >= nch) ? 16u : (a1 - a0);
+  }
+  if (tid == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base;
+  const uint32_t idesc = umma::instr_desc(128, C1_N, umma::BF16);
+  const uint32_t sB_u = umma::smem_u32(sB), sPl_u = umma::smem_u32(sPl);
+  uint32_t phase = 0;
+  int stage_sel = 0;
+
+  for (int im = blockIdx.x; im < n; im += gridDim.x) {
+    // ---- uint8 HWC -> bf16 channel planes (exact). 16-byte coalesced global reads, 2-byte smem scatter.
+    const uint8_t *g = images + (size_t)im * (C1_W * C1_W) * C;
+    const int nbytes = C1_W * C1_W * C;
+    for (int v = tid; v < nbytes / 16; v += 128) {
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(g) + v);
+      const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
+      int j = v * 16;
+      int pix = j / C, ch = j - pix * C;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        __nv_bfloat16 val = __float2bfloat16((float)qb[e]);
+        *reinterpret_cast<__nv_bfloat16 *>(sPl + (size_t)(ch >> 3) * C1_PLANE + (size_t)pix * 16 + (ch & 7) * 2) = val;
+        if (++ch == C) { ch = 0; pix++; }
+      }
+    }
+    for (int j = (nbytes / 16) * 16 + tid; j < nbytes; j += 128) {
+      int pix = j / C, ch = j - pix * C;
+      *reinterpret_cast<__nv_bfloat16 *>(sPl + (size_t)(ch >> 3) * C1_PLANE + (size_t)pix * 16 + (ch & 7) * 2) =
+          __float2bfloat16((float)g[j]);
+    }
+    umma::fence_async_smem();
+    __syncthreads();
+    float *out = p1 + (size_t)im * 784 * NF1;
+    for (int t = 0; t < C1_TILES; t++) {
+      if (tid == 0) {
+        umma::fence_after_sync();
+        const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
+        for (int i = 0; i < nmma; i++) {
+          uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
+          uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128);
+          umma::mma_f16(tb, da, db, idesc, i > 0);
+        }
+        umma::commit(&mbar);
+      }
+      umma::mbar_wait(&mbar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+      // ---- epilogue: row r = tid of the tile; sum the three weight terms; x-pair max; stage
+      float *stg = stage + stage_sel * (60 * NF1);
+      const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
+      const int r = tid;
+      float v[32];
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        float a[16], b[16], c[16];
+        umma::tmem_ld16(trow + hb * 16, a);
+        umma::tmem_ld16(trow + 32 + hb * 16, b);
+        umma::tmem_ld16(trow + 64 + hb * 16, c);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[hb * 16 + j] = (a[j] + b[j]) + c[j];
+      }
+#pragma unroll
+      for (int j = 0; j < NF1; j++) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+      if ((r & 1) == 0 && r < C1_TILE_ROWS) {
+        int rr = r >> 1;  // 0..59: [dy][x/2]
+        if ((rr % 30) < 28) {
+#pragma unroll
+          for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
+        }
+      }
+      umma::fence_before_sync();
+      __syncthreads();
+      for (int i = tid; i < 28 * NF1; i += 128) {
+        int px = i / NF1, ch = i - px * NF1;
+        float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
+        if (relu) m = fmaxf(m, 0.0f);
+        out[(size_t)(t * 28 + px) * NF1 + ch] = m;
+      }
+      stage_sel ^= 1;
+    }
+    __syncthreads();  // planes are rewritten by the next image
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv2: P1 [784 px][20] f32 -> P2 [j = 12x12][50] f32 (k = c + 50 j, the ip1 input order), max-pooled.
+// The image is processed in two halves (input rows 12h .. 12h+15) of 3 tiles each; tile t = output rows
+// 12h + 4t .. +3 = GEMM rows m0 = 112 t .. +111 (of 128) in half-local pixel indices.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int C2_W = 28, C2_NPIX = 472, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
+constexpr int C2_BCHUNK = 128 * 16;
+
+__global__ void __launch_bounds__(128, 1) k_conv2_tc(const float *__restrict__ p1, int n, const uint8_t *__restrict__ wblob,
+                                                     const float *__restrict__ bias, float a_scale, float out_scale, int relu,
+                                                     float *__restrict__ p2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  __shared__ MmaTab tab[C2_NMMA];
+  __shared__ float sbias[64];
+  uint8_t *sB = smem;                                      // 76 chunks x 128 rows x 16 B
+  uint8_t *sPl = sB + (size_t)(2 * C2_NMMA) * C2_BCHUNK;   // 6 planes: hi p0..2, lo p0..2
+  float *stage = reinterpret_cast<float *>(sPl + 6 * C2_PLANE);  // 2 x [56][50]
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int i = tid; i < (2 * C2_NMMA) * C2_BCHUNK / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
+  for (int i = tid; i < 6 * C2_PLANE / 16; i += 128) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 64) sbias[tid] = tid < NF2 ? bias[tid] : 0.0f;
+  if (tid < C2_NMMA) {
+    auto off = [&](int c) {
+      if (c >= C2_NCH) c = C2_NCH - 1;
+      int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
+      return (uint32_t)(p * C2_PLANE + (kh * C2_W + kw) * 16);
+    };
+    uint32_t a0 = off(2 * tid), a1 = off(2 * tid + 1);
+    tab[tid].a_off = a0;
+    tab[tid].a_lbo = (2 * tid + 1 >= C2_NCH) ? 16u : (a1 - a0);
+  }
+  if (tid == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base;
+  const uint32_t idesc_hi = umma::instr_desc(128, 128, umma::F16), idesc_lo = umma::instr_desc(128, 64, umma::F16);
+  const uint32_t sB_u = umma::smem_u32(sB), sPl_u = umma::smem_u32(sPl);
+  uint32_t phase = 0;
+  int stage_sel = 0;
+
+  for (int im = blockIdx.x; im < n; im += gridDim.x) {
+    const float *g = p1 + (size_t)im * 784 * NF1;
+    float *out = p2 + (size_t)im * 7200;
+    for (int h = 0; h < 2; h++) {
+      // ---- float32 -> scaled fp16 hi/lo channel planes for input rows 12h .. 12h+15 (448 px)
+      for (int i = tid; i < 448 * 3; i += 128) {
+        int lp = i / 3, p = i - lp * 3;
+        const float *src = g + (size_t)(12 * h * C2_W + lp) * NF1 + p * 8;
+        float x[8];
+        float4 q0 = *reinterpret_cast<const float4 *>(src);
+        x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w;
+        if (p < 2) {
+          float4 q1 = *reinterpret_cast<const float4 *>(src + 4);
+          x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+        } else {
+          x[4] = x[5] = x[6] = x[7] = 0.0f;
+        }
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          float a = x[e] * a_scale;
+          hi[e] = __float2half_rn(a);
+          lo[e] = __float2half_rn(a - __half2float(hi[e]));
+        }
+        *reinterpret_cast<uint4 *>(sPl + (size_t)p * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(sPl + (size_t)(3 + p) * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(lo);
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      for (int t = 0; t < 3; t++) {
+        if (tid == 0) {
+          umma::fence_after_sync();
+          const uint32_t arow = sPl_u + (uint32_t)(t * 112) * 16;
+          for (int i = 0; i < C2_NMMA; i++) {  // a_hi x [w_hi | w_lo]
+            uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
+            uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128);
+            umma::mma_f16(tb, da, db, idesc_hi, i > 0);
+          }
+          for (int i = 0; i < C2_NMMA; i++) {  // a_lo x w_hi
+            uint64_t da = umma::smem_desc(arow + 3 * C2_PLANE + tab[i].a_off, tab[i].a_lbo, 128);
+            uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128);
+            umma::mma_f16(tb, da, db, idesc_lo, true);
+          }
+          umma::commit(&mbar);
+        }
+        umma::mbar_wait(&mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+        float *stg = stage + stage_sel * (56 * NF2);
+        const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
+        const int r = tid;
+        const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
+        const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) {
+          float a[16], b[16];
+          umma::tmem_ld16(trow + cb * 16, a);
+          umma::tmem_ld16(trow + 64 + cb * 16, b);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            float v = (a[j] + b[j]) * out_scale;
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
+          }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        for (int i = tid; i < 2 * 12 * NF2; i += 128) {
+          int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
+          float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
+          if (relu) m = fmaxf(m, 0.0f);
+          int j = (6 * h + 2 * t + q) * 12 + px;
+          out[(size_t)j * NF2 + ch] = m;
+        }
+        stage_sel ^= 1;
+      }
+      __syncthreads();  // planes are rewritten by the next half
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 128);
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK()                                   \
+  do {                                                   \
+    ctx->launches++;                                     \
+    cudaError_t e__ = cudaGetLastError();                \
+    if (e__ != cudaSuccess) {                            \
+      gpdb_set_error(ctx, GPDB_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return GPDB_ERR_CUDA;                              \
+    }                                                    \
+  } while (0)
+
+static float pow2_scale(float maxabs, float target) {
+  if (!(maxabs > 0.0f)) return 1.0f;
+  return std::exp2(std::floor(std::log2(target / maxabs)));
+}
+
+// Build the tensor-core weight blobs from the reference's .bin layout (conv OIHW row-major).
+int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
+  const int C = ctx->prm.image_num_channels;
+  LenetTc &t = ctx->tc;
+  t.npl = (C + 7) / 8;
+  t.nch1 = t.npl * 25;
+  const int nmma1 = (t.nch1 + 1) / 2;
+  // conv1 blob: [chunk c][row n = term*32 + o][8 x bf16], c = (p*5+kh)*5+kw, channel = 8p + e
+  std::vector<__nv_bfloat16> b1((size_t)(2 * nmma1) * C1_N * 8, __float2bfloat16(0.0f));
+  for (int c = 0; c < t.nch1; c++) {
+    int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
+    for (int o = 0; o < NF1; o++)
+      for (int e = 0; e < 8; e++) {
+        int ch = p * 8 + e;
+        if (ch >= C) continue;
+        float wv = w[0][(((size_t)o * C + ch) * 5 + kh) * 5 + kw];
+        __nv_bfloat16 w1 = __float2bfloat16(wv);
+        float r1 = wv - __bfloat162float(w1);
+        __nv_bfloat16 w2 = __float2bfloat16(r1);
+        float r2 = r1 - __bfloat162float(w2);
+        __nv_bfloat16 w3 = __float2bfloat16(r2);
+        __nv_bfloat16 terms[3] = {w1, w2, w3};
+        for (int tm = 0; tm < 3; tm++) b1[((size_t)c * C1_N + tm * 32 + o) * 8 + e] = terms[tm];
+      }
+  }
+  // conv2 blob: [chunk c][row n: 0..63 = w_hi (50 used), 64..127 = w_lo][8 x fp16], weights scaled by 2^k
+  float mx = 0.0f;
+  for (size_t i = 0; i < (size_t)NF2 * NF1 * 25; i++) mx = std::fmax(mx, std::fabs(w[2][i]));
+  t.w2_scale = pow2_scale(mx, 16.0f);
+  t.a2_scale = 1.0f / 16.0f;
+  std::vector<__half> b2((size_t)(2 * C2_NMMA) * 128 * 8, __float2half(0.0f));
+  for (int c = 0; c < C2_NCH; c++) {
+    int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
+    for (int o = 0; o < NF2; o++)
+      for (int e = 0; e < 8; e++) {
+        int ch = p * 8 + e;
+        if (ch >= NF1) continue;
+        float wv = w[2][(((size_t)o * NF1 + ch) * 5 + kh) * 5 + kw] * t.w2_scale;
+        __half hi = __float2half_rn(wv);
+        __half lo = __float2half_rn(wv - __half2float(hi));
+        b2[((size_t)c * 128 + o) * 8 + e] = hi;
+        b2[((size_t)c * 128 + 64 + o) * 8 + e] = lo;
+      }
+  }
+  cudaFree(t.b1);
+  cudaFree(t.b2);
+  t.b1 = t.b2 = nullptr;
+  t.ready = false;
+  if (cudaMalloc(&t.b1, b1.size() * 2) != cudaSuccess || cudaMalloc(&t.b2, b2.size() * 2) != cudaSuccess ||
+      cudaMemcpy(t.b1, b1.data(), b1.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.b2, b2.data(), b2.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    gpdb_set_error(ctx, GPDB_ERR_CUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return GPDB_ERR_CUDA;
+  }
+  t.ready = ctx->prm.image_size == 60;
+  return GPDB_OK;
+}
+
+// conv1 + pool and conv2 + pool on tcgen05; p1 [n][784][20], p2 [n][7200]
+int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, float *p2) {
+  const LenetTc &t = ctx->tc;
+  const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
+  const int nmma1 = (t.nch1 + 1) / 2;
+  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + 1024;
+  size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float) + 1024;
+  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  cudaEvent_t e1 = gpdb_st_begin(ctx);
+  k_conv1_tc<<<std::min(n, ctx->sm_count), 128, sm1, ctx->stream>>>(d_images, n, C, t.npl, (const uint8_t *)t.b1, t.nch1,
+                                                                     ctx->w.c1b, relu, p1);
+  LAUNCH_CHECK();
+  gpdb_st_end(ctx, 5, e1);
+  cudaEvent_t e2 = gpdb_st_begin(ctx);
+  k_conv2_tc<<<std::min(n, ctx->sm_count), 128, sm2, ctx->stream>>>(p1, n, (const uint8_t *)t.b2, ctx->w.c2b, t.a2_scale,
+                                                                     1.0f / (t.a2_scale * t.w2_scale), relu, p2);
+  LAUNCH_CHECK();
+  gpdb_st_end(ctx, 6, e2);
+  return GPDB_OK;
+}

@@ -121,12 +121,13 @@ def test_images_entry_point_other_channel_counts(ch):
     ctx.close()
 
 
+@pytest.mark.parametrize("impl", [0, 1])  # 0 = tcgen05 convolutions, 1 = SIMT float32
 @pytest.mark.parametrize("name,ch", [("lenet_caffe_15ch", 15), ("lenet_caffe_3ch", 3), ("lenet_ir_12ch", 12)])
-def test_classifier_against_reference_model_goldens(golden_dir, name, ch):
+def test_classifier_against_reference_model_goldens(golden_dir, name, ch, impl):
     import os
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     w, relu = load_weights(ch)
-    p = lib.default_params(channels=ch, relu_after_conv=relu)
+    p = lib.default_params(channels=ch, relu_after_conv=relu, lenet_impl=impl)
     ctx = lib.Context(p)
     ctx.set_weights(w)
     s, lg = ctx.classify(g["images"])
@@ -205,3 +206,28 @@ def test_full_size_properties_config3():
     m = ~np.isnan(ro["pose_scores"])
     assert np.abs(ro["pose_scores"][m] - a["pose_scores"][pick][m]).max() <= 1e-4 * np.abs(ro["pose_scores"][m]).max()
     ctx.close()
+
+
+@pytest.mark.parametrize("ch", [15, 3, 12])
+def test_tensor_core_lenet_matches_simt_and_oracle_on_many_images(ch):
+    """tcgen05 implicit-GEMM convolutions (bf16x3 / fp16x2 split operands) vs the float32 SIMT kernels vs the oracle
+    on a few thousand images, random-init weights of the reference's architecture and scale."""
+    rng = np.random.default_rng(ch)
+    n = 1500
+    imgs = rng.integers(0, 256, (n, 60, 60, ch), dtype=np.uint8)
+    imgs[: n // 2] = ((rng.random((n // 2, 60, 60, ch)) < 0.2) * imgs[: n // 2]).astype(np.uint8)
+    imgs[0] = 0
+    imgs[1] = 255
+    w = scenes.random_lenet_weights(ch, seed=ch)
+    out = {}
+    for impl in (0, 1):
+        p = lib.default_params(channels=ch, lenet_impl=impl, relu_after_conv=int(ch == 12))
+        ctx = lib.Context(p)
+        ctx.set_weights(w)
+        out[impl] = ctx.classify(imgs)[1]
+        ctx.close()
+    so, lo = oracle.classify(p, oracle.WeightPack(w), imgs[:200])
+    scale = np.abs(lo).max()
+    assert np.abs(out[1][:200] - lo).max() <= 1e-4 * scale
+    assert np.abs(out[0][:200] - lo).max() <= 1e-4 * scale
+    assert np.abs(out[0] - out[1]).max() <= 1e-4 * np.abs(out[1]).max()
