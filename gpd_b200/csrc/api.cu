@@ -190,6 +190,19 @@ static int fill_dev_params(gpdb_ctx *ctx) {
   d.shadow_length = r_img;
   d.vox_mult = 1.0 / GPDB_SHADOW_VOXEL;
   d.nsp = (int)std::floor(d.shadow_length / GPDB_SHADOW_VOXEL);
+  if (d.nsp > GPDB_MAX_NSP) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image volume too large: %d shadow draws per point (max %d)", d.nsp, GPDB_MAX_NSP);
+    return GPDB_ERR_INVALID;
+  }
+  {  // closed-form skip-ahead of HandSet::fastrand (hand_set.cpp:263-266), mod 2^32
+    unsigned A = 1u, Cc = 0u;
+    for (int t = 0; t < GPDB_MAX_NSP; t++) {
+      Cc = 214013u * Cc + 2531011u;
+      A = 214013u * A;
+      d.lcgA[t] = A;
+      d.lcgC[t] = Cc;
+    }
+  }
   double diag = std::sqrt(p.volume_depth * p.volume_depth + p.volume_width * p.volume_width +
                           4.0 * p.volume_height * p.volume_height);
   d.bm_dim = (int)std::ceil((diag + 2.0 * 3.2 * GPDB_SHADOW_VOXEL * 0.3) / GPDB_SHADOW_VOXEL) + 4;

@@ -20,6 +20,7 @@
 #define GPDB_MAX_ORIENT 32
 #define GPDB_MAX_SLOTS 32   // 2 * num_finger_placements
 #define GPDB_MAX_DEEPEN 64  // deepen steps
+#define GPDB_MAX_NSP 128    // shadow draws per point
 
 // Everything the kernels need, resident in global memory (uniform, L1/L2-cached loads).
 struct DevParams {
@@ -48,6 +49,7 @@ struct DevParams {
   double shadow_length, vox_mult;
   int nsp;                     // num_shadow_points
   int bm_dim;                  // bitmap edge (voxels)
+  unsigned lcgA[GPDB_MAX_NSP], lcgC[GPDB_MAX_NSP];  // LCG skip-ahead: seed after t+1 steps = lcgA[t]*seed0 + lcgC[t]
   // radii: float32 predicates (dist < r2) and search extents
   float r2_lrf, r2_hs, r2_img;
   float rf_lrf, rf_hs, rf_img;

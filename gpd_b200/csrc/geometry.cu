@@ -789,6 +789,7 @@ struct ImgSmem {
   int cam_or;
   int n_img;
   int box_n;
+  int wl_n;
   int bm_org[3], bm_dims[3];
   float fred[NT_IMG / 32][2];
   float a, b;
@@ -846,20 +847,41 @@ __device__ __forceinline__ void block_minmax(float &mn, float &mx, float (*red)[
 // [choff, choff+CH) of the C-channel HWC uint8 image (image_strategy.cpp:145-153,179-187,222-230).
 template <int CH>
 __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int choff, ImgSmem &sm) {
+  // separable 3x3 max: one thread owns an 8-row strip of one column; the dilated values stay in registers
+  // between the min/max reduction and the quantisation (the image is read once).
+  const int strips = (S + 7) >> 3;
+  const bool active = (int)threadIdx.x < S * strips;
+  const int c = threadIdx.x % S, r0 = (threadIdx.x / S) << 3;
+  float m[8][CH];
   float mn = FLT_MAX, mx = -FLT_MAX;
-  for (int pix = threadIdx.x; pix < S * S; pix += NT_IMG) {
-    int r = pix / S, c = pix - r * S;
-    float m[CH];
+  if (active) {
+    const int cl = max(c - 1, 0), cr = min(c + 1, S - 1);
+    float h0[CH], h1[CH], h2[CH];  // horizontal maxima of rows r-1, r, r+1 (sliding)
+    auto hrow = [&](int rr, float *h) {
+      if (rr < 0 || rr >= S) {
 #pragma unroll
-    for (int k = 0; k < CH; k++) m[k] = -FLT_MAX;
-    for (int rr = max(r - 1, 0); rr <= min(r + 1, S - 1); rr++)
-      for (int c2 = max(c - 1, 0); c2 <= min(c + 1, S - 1); c2++)
+        for (int k = 0; k < CH; k++) h[k] = -FLT_MAX;
+      } else {
+        const float *p = src + (size_t)rr * S * CH;
 #pragma unroll
-        for (int k = 0; k < CH; k++) m[k] = fmaxf(m[k], src[(rr * S + c2) * CH + k]);
+        for (int k = 0; k < CH; k++) h[k] = fmaxf(fmaxf(p[cl * CH + k], p[c * CH + k]), p[cr * CH + k]);
+      }
+    };
+    hrow(r0 - 1, h0);
+    hrow(r0, h1);
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-      mn = fminf(mn, m[k]);
-      mx = fmaxf(mx, m[k]);
+    for (int i = 0; i < 8; i++) {
+      hrow(r0 + i + 1, h2);
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        m[i][k] = fmaxf(fmaxf(h0[k], h1[k]), h2[k]);
+        if (r0 + i < S) {
+          mn = fminf(mn, m[i][k]);
+          mx = fmaxf(mx, m[i][k]);
+        }
+        h0[k] = h1[k];
+        h1[k] = h2[k];
+      }
     }
   }
   block_minmax<NT_IMG>(mn, mx, sm.fred);
@@ -867,21 +889,18 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
   double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
   double shift = 0.0 - smin * scale;
   const float a = (float)scale, b = (float)shift;
-  for (int pix = threadIdx.x; pix < S * S; pix += NT_IMG) {
-    int r = pix / S, c = pix - r * S;
-    float m[CH];
+  if (active) {
 #pragma unroll
-    for (int k = 0; k < CH; k++) m[k] = -FLT_MAX;
-    for (int rr = max(r - 1, 0); rr <= min(r + 1, S - 1); rr++)
-      for (int c2 = max(c - 1, 0); c2 <= min(c + 1, S - 1); c2++)
+    for (int i = 0; i < 8; i++) {
+      if (r0 + i < S) {
+        uint8_t *o = gimg + (size_t)((r0 + i) * S + c) * C + choff;
 #pragma unroll
-        for (int k = 0; k < CH; k++) m[k] = fmaxf(m[k], src[(rr * S + c2) * CH + k]);
-#pragma unroll
-    for (int k = 0; k < CH; k++) {
-      float v = fmaf(m[k], a, b);
-      int q = __float2int_rn(v * 255.0f);
-      q = min(max(q, 0), 255);
-      gimg[(size_t)pix * C + choff + k] = (uint8_t)q;
+        for (int k = 0; k < CH; k++) {
+          float v = fmaf(m[i][k], a, b);
+          int q = __float2int_rn(v * 255.0f);
+          o[k] = (uint8_t)min(max(q, 0), 255);
+        }
+      }
     }
   }
   __syncthreads();
@@ -1130,43 +1149,68 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         return in_image_box(P, h, x, y, z);
       };
       const int cam_set = sm.cam_or;
-      for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
+      // Shadow casting is load-balanced in two steps per camera: (1) the ball scan appends the points whose
+      // shadow segment can reach the bitmap to a work list (float4: x, y, z, LCG seed) living in the idle tile
+      // region; (2) the (point, draw) pairs are spread evenly over all threads — draw t of a point comes from
+      // the closed-form LCG skip-ahead seed_t = A^(t+1) seed_0 + C_(t+1) (mod 2^32).
+      float4 *wl = reinterpret_cast<float4 *>(tileA);
+      const int WL_CAP = (3 * SS * 8) / 16;
+      auto cast_draw = [&](double px, double py, double pz, unsigned seed, int k, unsigned *bm) {
+        const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
+        double u = (double)((seed >> 16) & 0x7FFFu) * mxu;
+        int v0 = (int)((px + u * s0) * P.vox_mult);
+        int v1 = (int)((py + u * s1) * P.vox_mult);
+        int v2 = (int)((pz + u * s2) * P.vox_mult);
+        int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
+        if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) return;
+        double x, y, z;
+        if (!voxel_point_in_box(v0, v1, v2, x, y, z)) return;
+        int bit = (b2 * d1 + b1) * d0 + b0;
+        atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+      };
+      for (int k = 0; k < K; k++) {
+        if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
+        unsigned *bm = bitmap + (size_t)k * bm_words;
+        const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
         __syncthreads();
-        int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
-        for (int c = tid; c < total; c += NT_IMG) {
-          float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
-          float d = l2_simple(q, p.x, p.y, p.z);
-          if (!(d < P.r2_img)) continue;
-          const int idx = __float_as_int(p.w);
-          const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-          for (int k = 0; k < K; k++) {
-            if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
-            const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
+        if (tid == 0) sm.wl_n = 0;
+        for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
+          __syncthreads();
+          int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
+          for (int c = tid; c < total; c += NT_IMG) {
+            float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
+            float d = l2_simple(q, p.x, p.y, p.z);
+            if (!(d < P.r2_img)) continue;
+            const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
             // quick reject: per-axis voxel range of the segment p .. p + sv vs the bitmap AABB
-            {
-              int a, e;
-              a = (int)(px * P.vox_mult); e = (int)((px + s0) * P.vox_mult);
-              if (max(a, e) < o0 - 1 || min(a, e) > o0 + d0) continue;
-              a = (int)(py * P.vox_mult); e = (int)((py + s1) * P.vox_mult);
-              if (max(a, e) < o1 - 1 || min(a, e) > o1 + d1) continue;
-              a = (int)(pz * P.vox_mult); e = (int)((pz + s2) * P.vox_mult);
-              if (max(a, e) < o2 - 1 || min(a, e) > o2 + d2) continue;
-            }
-            unsigned seed = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)idx, (unsigned)k);
-            unsigned *bm = bitmap + (size_t)k * bm_words;
-            for (int t = 0; t < P.nsp; t++) {
-              double u = (double)gpdb_fastrand(&seed) * mxu;
-              int v0 = (int)((px + u * s0) * P.vox_mult);
-              int v1 = (int)((py + u * s1) * P.vox_mult);
-              int v2 = (int)((pz + u * s2) * P.vox_mult);
-              int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
-              if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) continue;
-              double x, y, z;
-              if (!voxel_point_in_box(v0, v1, v2, x, y, z)) continue;
-              int bit = (b2 * d1 + b1) * d0 + b0;
-              atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+            int a, e;
+            a = (int)(px * P.vox_mult); e = (int)((px + s0) * P.vox_mult);
+            if (max(a, e) < o0 - 1 || min(a, e) > o0 + d0) continue;
+            a = (int)(py * P.vox_mult); e = (int)((py + s1) * P.vox_mult);
+            if (max(a, e) < o1 - 1 || min(a, e) > o1 + d1) continue;
+            a = (int)(pz * P.vox_mult); e = (int)((pz + s2) * P.vox_mult);
+            if (max(a, e) < o2 - 1 || min(a, e) > o2 + d2) continue;
+            unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
+            int pos = atomicAdd(&sm.wl_n, 1);
+            if (pos < WL_CAP) {
+              wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
+            } else {  // work list full (very dense neighbourhood): cast this point's draws in place
+              unsigned seed = seed0;
+              for (int t = 0; t < P.nsp; t++) {
+                gpdb_fastrand(&seed);
+                cast_draw(px, py, pz, seed, k, bm);
+              }
             }
           }
+        }
+        __syncthreads();
+        const int nw = min(sm.wl_n, WL_CAP);
+        const int nsp = P.nsp;
+        for (int w = tid; w < nw * nsp; w += NT_IMG) {
+          int item = w / nsp, t = w - item * nsp;
+          float4 e = wl[item];
+          unsigned seed = P.lcgA[t] * __float_as_uint(e.w) + P.lcgC[t];
+          cast_draw((double)e.x, (double)e.y, (double)e.z, seed, k, bm);
         }
       }
       __syncthreads();

@@ -44,11 +44,13 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
 constexpr int C1_N = 96, C1_BCHUNK = C1_N * 16;
 
-__global__ void __launch_bounds__(128, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C, int npl,
-                                                     const uint8_t *__restrict__ wblob, int nch, const float *__restrict__ bias,
-                                                     int relu, float *__restrict__ p1) {
+constexpr int C1_NT = 256;  // warps 0-3: TMEM epilogue (one lane quarter each); warps 4-7 help convert / pool
+
+__global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C, int npl,
+                                                       const uint8_t *__restrict__ wblob, int nch, const float *__restrict__ bias,
+                                                       int relu, float *__restrict__ p1) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar[2];
   __shared__ uint32_t tmem_base;
   __shared__ MmaTab tab[32];
   __shared__ float sbias[NF1];
@@ -56,10 +58,10 @@ __global__ void __launch_bounds__(128, 1) k_conv1_tc(const uint8_t *__restrict__
   uint8_t *sB = smem;                                  // nch(+1) chunks x 96 rows x 16 B
   uint8_t *sPl = sB + (size_t)(2 * nmma) * C1_BCHUNK;  // npl planes
   float *stage = reinterpret_cast<float *>(sPl + (size_t)npl * C1_PLANE);  // 2 x [60][20]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
 
-  for (int i = tid; i < (2 * nmma) * C1_BCHUNK / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
-  for (int i = tid; i < npl * C1_PLANE / 16; i += 128) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (2 * nmma) * C1_BCHUNK / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
+  for (int i = tid; i < npl * C1_PLANE / 16; i += C1_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
   if (tid < NF1) sbias[tid] = bias[tid];
   if (tid < nmma) {
     // chunk order c = (p*5 + kh)*5 + kw ; address of row 0: p*PLANE + (kh*60 + kw)*16 (monotonic in c)
@@ -73,96 +75,94 @@ __global__ void __launch_bounds__(128, 1) k_conv1_tc(const uint8_t *__restrict__
     tab[tid].a_lbo = (2 * tid + 1 >= nch) ? 16u : (a1 - a0);
   }
   if (tid == 0) {
-    umma::mbar_init(&mbar, 1);
+    umma::mbar_init(&mbar[0], 1);
+    umma::mbar_init(&mbar[1], 1);
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
   const uint32_t idesc = umma::instr_desc(128, C1_N, umma::BF16);
   const uint32_t sB_u = umma::smem_u32(sB), sPl_u = umma::smem_u32(sPl);
-  uint32_t phase = 0;
-  int stage_sel = 0;
+  uint32_t phase[2] = {0, 0};
+
+  // tile t accumulates into TMEM columns [128 (t&1), +96): the tensor pipe runs tile t+1 while the
+  // epilogue warps drain tile t
+  auto issue_tile = [&](int t) {
+    umma::fence_after_sync();
+    const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
+    const uint32_t dcol = tb + (uint32_t)(t & 1) * 128;
+    for (int i = 0; i < nmma; i++) {
+      uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
+      uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128);
+      umma::mma_f16(dcol, da, db, idesc, i > 0);
+    }
+    umma::commit(&mbar[t & 1]);
+  };
 
   for (int im = blockIdx.x; im < n; im += gridDim.x) {
-    // ---- uint8 HWC -> bf16 channel planes (exact). 16-byte coalesced global reads, 2-byte smem scatter.
+    // ---- uint8 HWC -> bf16 channel planes (exact): one thread per (pixel, plane), one 16-byte store each
     const uint8_t *g = images + (size_t)im * (C1_W * C1_W) * C;
-    const int nbytes = C1_W * C1_W * C;
-    for (int v = tid; v < nbytes / 16; v += 128) {
-      uint4 q = __ldg(reinterpret_cast<const uint4 *>(g) + v);
-      const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
-      int j = v * 16;
-      int pix = j / C, ch = j - pix * C;
+    for (int it = tid; it < C1_W * C1_W * npl; it += C1_NT) {
+      const int pix = it / npl, p = it - pix * npl;
+      const uint8_t *src = g + (size_t)pix * C + p * 8;
+      const int nc = min(8, C - p * 8);
+      __nv_bfloat16 v[8];
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        __nv_bfloat16 val = __float2bfloat16((float)qb[e]);
-        *reinterpret_cast<__nv_bfloat16 *>(sPl + (size_t)(ch >> 3) * C1_PLANE + (size_t)pix * 16 + (ch & 7) * 2) = val;
-        if (++ch == C) { ch = 0; pix++; }
-      }
-    }
-    for (int j = (nbytes / 16) * 16 + tid; j < nbytes; j += 128) {
-      int pix = j / C, ch = j - pix * C;
-      *reinterpret_cast<__nv_bfloat16 *>(sPl + (size_t)(ch >> 3) * C1_PLANE + (size_t)pix * 16 + (ch & 7) * 2) =
-          __float2bfloat16((float)g[j]);
+      for (int e = 0; e < 8; e++) v[e] = __float2bfloat16(e < nc ? (float)__ldg(src + e) : 0.0f);
+      *reinterpret_cast<uint4 *>(sPl + (size_t)p * C1_PLANE + (size_t)pix * 16) = *reinterpret_cast<uint4 *>(v);
     }
     umma::fence_async_smem();
     __syncthreads();
     float *out = p1 + (size_t)im * 784 * NF1;
+    if (tid == 0) issue_tile(0);
     for (int t = 0; t < C1_TILES; t++) {
-      if (tid == 0) {
+      if (tid == 0 && t + 1 < C1_TILES) issue_tile(t + 1);  // buffer (t+1)&1 was drained before the last barrier
+      float *stg = stage + (t & 1) * (60 * NF1);
+      if (warp < 4) {
+        umma::mbar_wait(&mbar[t & 1], phase[t & 1]);
         umma::fence_after_sync();
-        const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
-        for (int i = 0; i < nmma; i++) {
-          uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
-          uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128);
-          umma::mma_f16(tb, da, db, idesc, i > 0);
+        // ---- epilogue: row r = tid of the tile; sum the three weight terms; x-pair max; stage
+        const uint32_t trow = tb + (uint32_t)(t & 1) * 128 + ((uint32_t)(warp * 32) << 16);
+        const int r = tid;
+        float v[32];
+#pragma unroll
+        for (int hb = 0; hb < 2; hb++) {
+          float a[16], b[16], c[16];
+          umma::tmem_ld16(trow + hb * 16, a);
+          umma::tmem_ld16(trow + 32 + hb * 16, b);
+          umma::tmem_ld16(trow + 64 + hb * 16, c);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[hb * 16 + j] = (a[j] + b[j]) + c[j];
         }
-        umma::commit(&mbar);
-      }
-      umma::mbar_wait(&mbar, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
-      // ---- epilogue: row r = tid of the tile; sum the three weight terms; x-pair max; stage
-      float *stg = stage + stage_sel * (60 * NF1);
-      const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
-      const int r = tid;
-      float v[32];
 #pragma unroll
-      for (int hb = 0; hb < 2; hb++) {
-        float a[16], b[16], c[16];
-        umma::tmem_ld16(trow + hb * 16, a);
-        umma::tmem_ld16(trow + 32 + hb * 16, b);
-        umma::tmem_ld16(trow + 64 + hb * 16, c);
-        umma::tmem_ld_wait();
+        for (int j = 0; j < NF1; j++) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+        if ((r & 1) == 0 && r < C1_TILE_ROWS) {
+          int rr = r >> 1;  // 0..59: [dy][x/2]
+          if ((rr % 30) < 28) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[hb * 16 + j] = (a[j] + b[j]) + c[j];
-      }
-#pragma unroll
-      for (int j = 0; j < NF1; j++) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-      if ((r & 1) == 0 && r < C1_TILE_ROWS) {
-        int rr = r >> 1;  // 0..59: [dy][x/2]
-        if ((rr % 30) < 28) {
-#pragma unroll
-          for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
+            for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
+          }
         }
+        umma::fence_before_sync();
       }
-      umma::fence_before_sync();
+      phase[t & 1] ^= 1;
       __syncthreads();
-      for (int i = tid; i < 28 * NF1; i += 128) {
+      for (int i = tid; i < 28 * NF1; i += C1_NT) {
         int px = i / NF1, ch = i - px * NF1;
         float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
         if (relu) m = fmaxf(m, 0.0f);
         out[(size_t)(t * 28 + px) * NF1 + ch] = m;
       }
-      stage_sel ^= 1;
     }
     __syncthreads();  // planes are rewritten by the next image
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, 128);
+  if (warp == 0) umma::tmem_dealloc(tb, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -383,7 +383,7 @@ int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, flo
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
-  k_conv1_tc<<<std::min(n, ctx->sm_count), 128, sm1, ctx->stream>>>(d_images, n, C, t.npl, (const uint8_t *)t.b1, t.nch1,
+  k_conv1_tc<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, t.npl, (const uint8_t *)t.b1, t.nch1,
                                                                      ctx->w.c1b, relu, p1);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 5, e1);
