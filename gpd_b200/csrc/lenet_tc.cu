@@ -11,8 +11,8 @@
 //
 // Precision: the reference computes in float32 on raw 0..255 inputs (logits ~1e3), tolerance 1e-4 relative.
 //   conv1: activations are uint8 -> exact in bf16; weights are split w = w1 + w2 + w3 (bf16 each, 24 bits);
-//          the three terms are stacked along N (N = 3 x 32) so ONE instruction stream with N = 96 reads A once;
-//          the epilogue adds the three 32-column groups in float32.
+//          the three terms are stacked along N (rows 0..19 | 20..39 | 40..59 of a N = 64 B operand) so ONE
+//          instruction stream reads A once; the epilogue adds the three 20-column groups in float32.
 //   conv2: activations a and weights w are scaled by powers of two (exact) and split in two fp16 terms each;
 //          D[:, 0:64] += a_hi w_hi + a_lo w_hi, D[:, 64:128] += a_hi w_lo  (error ~2^-22), summed in the epilogue.
 // Output pixels with x beyond the valid width are computed and discarded (7 % / 14 % of the rows).
@@ -42,104 +42,123 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 // tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
-constexpr int C1_N = 96, C1_BCHUNK = C1_N * 16;
-
+constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: term0 0..19 | term1 20..39 | term2 40..59 | 4 zero rows
 constexpr int C1_NT = 256;  // warps 0-3: TMEM epilogue (one lane quarter each); warps 4-7 help convert / pool
 
-__global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C, int npl,
-                                                       const uint8_t *__restrict__ wblob, int nch, const float *__restrict__ bias,
+// chunk c = (p*5 + kh)*5 + kw -> byte offset of row 0 inside the plane set (monotonic in c)
+__host__ __device__ constexpr uint32_t c1_off(int c, int nch) {
+  return (uint32_t)(((c >= nch ? nch - 1 : c) / 25) * C1_PLANE +
+                    ((((c >= nch ? nch - 1 : c) / 5) % 5) * C1_W + (c >= nch ? nch - 1 : c) % 5) * 16);
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C,
+                                                       const uint8_t *__restrict__ wblob, const float *__restrict__ bias,
                                                        int relu, float *__restrict__ p1) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mbar[2];
+  constexpr int npl = NPL, nch = NPL * 25;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[2], empty[2], mbar_img;
   __shared__ uint32_t tmem_base;
-  __shared__ MmaTab tab[32];
   __shared__ float sbias[NF1];
-  const int nmma = (nch + 1) / 2;
-  uint8_t *sB = smem;                                  // nch(+1) chunks x 96 rows x 16 B
+  constexpr int nmma = (nch + 1) / 2;
+  const int img_bytes = C1_W * C1_W * C;
+  uint8_t *sB = smem;                                  // nch(+1) chunks x 64 rows x 16 B
   uint8_t *sPl = sB + (size_t)(2 * nmma) * C1_BCHUNK;  // npl planes
   float *stage = reinterpret_cast<float *>(sPl + (size_t)npl * C1_PLANE);  // 2 x [60][20]
-  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t *sRaw = reinterpret_cast<uint8_t *>(stage + 2 * 60 * NF1);           // next image, raw HWC bytes
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
 
   for (int i = tid; i < (2 * nmma) * C1_BCHUNK / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
   for (int i = tid; i < npl * C1_PLANE / 16; i += C1_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
   if (tid < NF1) sbias[tid] = bias[tid];
-  if (tid < nmma) {
-    // chunk order c = (p*5 + kh)*5 + kw ; address of row 0: p*PLANE + (kh*60 + kw)*16 (monotonic in c)
-    auto off = [&](int c) {
-      if (c >= nch) c = nch - 1;  // dummy chunk (zero weights): any valid address
-      int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
-      return (uint32_t)(p * C1_PLANE + (kh * C1_W + kw) * 16);
-    };
-    uint32_t a0 = off(2 * tid), a1 = off(2 * tid + 1);
-    tab[tid].a_off = a0;
-    tab[tid].a_lbo = (2 * tid + 1 >= nch) ? 16u : (a1 - a0);
-  }
   if (tid == 0) {
-    umma::mbar_init(&mbar[0], 1);
-    umma::mbar_init(&mbar[1], 1);
+    for (int b = 0; b < 2; b++) {
+      umma::mbar_init(&full[b], 1);   // tcgen05.commit of the MMA warp
+      umma::mbar_init(&empty[b], 4);  // one arrival per epilogue warp
+    }
+    umma::mbar_init(&mbar_img, 1);
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
   const uint32_t idesc = umma::instr_desc(128, C1_N, umma::BF16);
-  const uint32_t sB_u = umma::smem_u32(sB), sPl_u = umma::smem_u32(sPl);
-  uint32_t phase[2] = {0, 0};
+  uint32_t phase_img = 0;
+  int gt = 0;  // running tile counter of this role: TMEM buffer = gt & 1, use count = gt >> 1
 
-  // tile t accumulates into TMEM columns [128 (t&1), +96): the tensor pipe runs tile t+1 while the
-  // epilogue warps drain tile t
-  auto issue_tile = [&](int t) {
-    umma::fence_after_sync();
-    const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
-    const uint32_t dcol = tb + (uint32_t)(t & 1) * 128;
-    for (int i = 0; i < nmma; i++) {
-      uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
-      uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128);
-      umma::mma_f16(dcol, da, db, idesc, i > 0);
-    }
-    umma::commit(&mbar[t & 1]);
-  };
-
+  if (tid == 0 && (int)blockIdx.x < n) {
+    umma::mbar_expect_tx(&mbar_img, img_bytes);
+    umma::bulk_g2s(sRaw, images + (size_t)blockIdx.x * img_bytes, img_bytes, &mbar_img);
+  }
   for (int im = blockIdx.x; im < n; im += gridDim.x) {
-    // ---- uint8 HWC -> bf16 channel planes (exact): one thread per (pixel, plane), one 16-byte store each
-    const uint8_t *g = images + (size_t)im * (C1_W * C1_W) * C;
+    // ---- raw uint8 HWC (prefetched by the bulk-copy engine) -> bf16 channel planes (exact)
+    umma::mbar_wait(&mbar_img, phase_img);
+    phase_img ^= 1;
     for (int it = tid; it < C1_W * C1_W * npl; it += C1_NT) {
       const int pix = it / npl, p = it - pix * npl;
-      const uint8_t *src = g + (size_t)pix * C + p * 8;
+      const uint8_t *src = sRaw + (size_t)pix * C + p * 8;
       const int nc = min(8, C - p * 8);
       __nv_bfloat16 v[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) v[e] = __float2bfloat16(e < nc ? (float)__ldg(src + e) : 0.0f);
+      for (int e = 0; e < 8; e++) v[e] = __float2bfloat16(e < nc ? (float)src[e] : 0.0f);
       *reinterpret_cast<uint4 *>(sPl + (size_t)p * C1_PLANE + (size_t)pix * 16) = *reinterpret_cast<uint4 *>(v);
     }
     umma::fence_async_smem();
     __syncthreads();
+    if (tid == 0 && im + (int)gridDim.x < n) {  // prefetch the next image of this CTA behind the MMAs
+      umma::mbar_expect_tx(&mbar_img, img_bytes);
+      umma::bulk_g2s(sRaw, images + (size_t)(im + gridDim.x) * img_bytes, img_bytes, &mbar_img);
+    }
     float *out = p1 + (size_t)im * 784 * NF1;
-    if (tid == 0) issue_tile(0);
-    for (int t = 0; t < C1_TILES; t++) {
-      if (tid == 0 && t + 1 < C1_TILES) issue_tile(t + 1);  // buffer (t+1)&1 was drained before the last barrier
-      float *stg = stage + (t & 1) * (60 * NF1);
-      if (warp < 4) {
-        umma::mbar_wait(&mbar[t & 1], phase[t & 1]);
+    if (warp == 4) {
+      // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt&1), +64) as soon as the epilogue warps
+      // have drained that buffer. The whole warp runs the (fully unrolled) loop so that every descriptor is a
+      // uniform-register expression base + compile-time constant; one elected lane issues the instructions.
+      const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
+      for (int t = 0; t < C1_TILES; t++, gt++) {
+        const int b = gt & 1;
+        umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
         umma::fence_after_sync();
-        // ---- epilogue: row r = tid of the tile; sum the three weight terms; x-pair max; stage
-        const uint32_t trow = tb + (uint32_t)(t & 1) * 128 + ((uint32_t)(warp * 32) << 16);
-        const int r = tid;
-        float v[32];
+        const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
+        const uint32_t dcol = tb + (uint32_t)b * 64;
+        if (umma::elect_one()) {
 #pragma unroll
-        for (int hb = 0; hb < 2; hb++) {
-          float a[16], b[16], c[16];
-          umma::tmem_ld16(trow + hb * 16, a);
-          umma::tmem_ld16(trow + 32 + hb * 16, b);
-          umma::tmem_ld16(trow + 64 + hb * 16, c);
-          umma::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; j++) v[hb * 16 + j] = (a[j] + b[j]) + c[j];
+          for (int i = 0; i < nmma; i++) {
+            constexpr uint32_t dummy = 0;
+            (void)dummy;
+            const uint32_t a0 = c1_off(2 * i, nch), a1 = c1_off(2 * i + 1, nch);
+            const uint32_t lbo = (2 * i + 1 >= nch) ? 16u : (a1 - a0);
+            umma::mma_f16(dcol, umma::desc_from(arow + a0, lbo, 128), umma::desc_from(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128),
+                          idesc, i > 0);
+          }
+          umma::commit(&full[b]);
         }
+        __syncwarp();
+      }
+    } else if (warp < 4) {
+      // ===== epilogue warps: TMEM -> registers (sum of the three weight terms) -> x-pair max -> stage -> y-pair max
+      for (int t = 0; t < C1_TILES; t++, gt++) {
+        const int b = gt & 1;
+        umma::mbar_wait(&full[b], (gt >> 1) & 1);
+        umma::fence_after_sync();
+        const uint32_t trow = tb + (uint32_t)b * 64 + ((uint32_t)(warp * 32) << 16);
+        const int r = tid;
+        float d[64];
 #pragma unroll
-        for (int j = 0; j < NF1; j++) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+        for (int cb = 0; cb < 4; cb++) umma::tmem_ld16(trow + cb * 16, d + cb * 16);
+        umma::tmem_ld_wait();
+        umma::fence_before_sync();
+        __syncwarp();
+        if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);  // the buffer may be overwritten by tile t+2
+        float *stg = stage + b * (60 * NF1);
+        float v[NF1];
+#pragma unroll
+        for (int j = 0; j < NF1; j++) {
+          v[j] = (d[j] + d[NF1 + j]) + d[2 * NF1 + j];
+          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+        }
         if ((r & 1) == 0 && r < C1_TILE_ROWS) {
           int rr = r >> 1;  // 0..59: [dy][x/2]
           if ((rr % 30) < 28) {
@@ -147,22 +166,20 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
             for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
           }
         }
-        umma::fence_before_sync();
-      }
-      phase[t & 1] ^= 1;
-      __syncthreads();
-      for (int i = tid; i < 28 * NF1; i += C1_NT) {
-        int px = i / NF1, ch = i - px * NF1;
-        float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
-        if (relu) m = fmaxf(m, 0.0f);
-        out[(size_t)(t * 28 + px) * NF1 + ch] = m;
+        umma::named_bar_sync(1, 128);
+        for (int i = tid; i < 28 * NF1; i += 128) {
+          int px = i / NF1, ch = i - px * NF1;
+          float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
+          if (relu) m = fmaxf(m, 0.0f);
+          out[(size_t)(t * 28 + px) * NF1 + ch] = m;
+        }
       }
     }
-    __syncthreads();  // planes are rewritten by the next image
+    __syncthreads();  // every tile of this image has completed: the planes may be rewritten
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, 256);
+  if (warp == 0) umma::tmem_dealloc(tb, 128);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -173,59 +190,56 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
 constexpr int C2_W = 28, C2_NPIX = 472, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
 constexpr int C2_BCHUNK = 128 * 16;
 
-__global__ void __launch_bounds__(128, 1) k_conv2_tc(const float *__restrict__ p1, int n, const uint8_t *__restrict__ wblob,
-                                                     const float *__restrict__ bias, float a_scale, float out_scale, int relu,
-                                                     float *__restrict__ p2) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mbar;
+constexpr int C2_NT = 256;
+__host__ __device__ constexpr uint32_t c2_off(int c) {
+  return (uint32_t)(((c >= C2_NCH ? C2_NCH - 1 : c) / 25) * C2_PLANE +
+                    ((((c >= C2_NCH ? C2_NCH - 1 : c) / 5) % 5) * C2_W + (c >= C2_NCH ? C2_NCH - 1 : c) % 5) * 16);
+}
+
+__global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__ p1, int n, const uint8_t *__restrict__ wblob,
+                                                       const float *__restrict__ bias, float a_scale, float out_scale, int relu,
+                                                       float *__restrict__ p2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[2], empty[2];
   __shared__ uint32_t tmem_base;
-  __shared__ MmaTab tab[C2_NMMA];
   __shared__ float sbias[64];
   uint8_t *sB = smem;                                      // 76 chunks x 128 rows x 16 B
   uint8_t *sPl = sB + (size_t)(2 * C2_NMMA) * C2_BCHUNK;   // 6 planes: hi p0..2, lo p0..2
   float *stage = reinterpret_cast<float *>(sPl + 6 * C2_PLANE);  // 2 x [56][50]
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-  for (int i = tid; i < (2 * C2_NMMA) * C2_BCHUNK / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
-  for (int i = tid; i < 6 * C2_PLANE / 16; i += 128) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (2 * C2_NMMA) * C2_BCHUNK / 16; i += C2_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
+  for (int i = tid; i < 6 * C2_PLANE / 16; i += C2_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 64) sbias[tid] = tid < NF2 ? bias[tid] : 0.0f;
-  if (tid < C2_NMMA) {
-    auto off = [&](int c) {
-      if (c >= C2_NCH) c = C2_NCH - 1;
-      int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
-      return (uint32_t)(p * C2_PLANE + (kh * C2_W + kw) * 16);
-    };
-    uint32_t a0 = off(2 * tid), a1 = off(2 * tid + 1);
-    tab[tid].a_off = a0;
-    tab[tid].a_lbo = (2 * tid + 1 >= C2_NCH) ? 16u : (a1 - a0);
-  }
   if (tid == 0) {
-    umma::mbar_init(&mbar, 1);
+    for (int b = 0; b < 2; b++) {
+      umma::mbar_init(&full[b], 1);
+      umma::mbar_init(&empty[b], 4);
+    }
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
   const uint32_t idesc_hi = umma::instr_desc(128, 128, umma::F16), idesc_lo = umma::instr_desc(128, 64, umma::F16);
-  const uint32_t sB_u = umma::smem_u32(sB), sPl_u = umma::smem_u32(sPl);
-  uint32_t phase = 0;
-  int stage_sel = 0;
+  int gt = 0;  // running tile counter of this role
 
   for (int im = blockIdx.x; im < n; im += gridDim.x) {
     const float *g = p1 + (size_t)im * 784 * NF1;
     float *out = p2 + (size_t)im * 7200;
     for (int h = 0; h < 2; h++) {
       // ---- float32 -> scaled fp16 hi/lo channel planes for input rows 12h .. 12h+15 (448 px)
-      for (int i = tid; i < 448 * 3; i += 128) {
+#pragma unroll 2
+      for (int i = tid; i < 448 * 3; i += C2_NT) {
         int lp = i / 3, p = i - lp * 3;
         const float *src = g + (size_t)(12 * h * C2_W + lp) * NF1 + p * 8;
         float x[8];
-        float4 q0 = *reinterpret_cast<const float4 *>(src);
+        float4 q0 = __ldg(reinterpret_cast<const float4 *>(src));
         x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w;
         if (p < 2) {
-          float4 q1 = *reinterpret_cast<const float4 *>(src + 4);
+          float4 q1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
           x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
         } else {
           x[4] = x[5] = x[6] = x[7] = 0.0f;
@@ -242,60 +256,77 @@ __global__ void __launch_bounds__(128, 1) k_conv2_tc(const float *__restrict__ p
       }
       umma::fence_async_smem();
       __syncthreads();
-      for (int t = 0; t < 3; t++) {
-        if (tid == 0) {
+      if (warp == 4) {
+        const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
+        for (int t = 0; t < 3; t++, gt++) {
+          const int b = gt & 1;
+          umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
           umma::fence_after_sync();
           const uint32_t arow = sPl_u + (uint32_t)(t * 112) * 16;
-          for (int i = 0; i < C2_NMMA; i++) {  // a_hi x [w_hi | w_lo]
-            uint64_t da = umma::smem_desc(arow + tab[i].a_off, tab[i].a_lbo, 128);
-            uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128);
-            umma::mma_f16(tb, da, db, idesc_hi, i > 0);
-          }
-          for (int i = 0; i < C2_NMMA; i++) {  // a_lo x w_hi
-            uint64_t da = umma::smem_desc(arow + 3 * C2_PLANE + tab[i].a_off, tab[i].a_lbo, 128);
-            uint64_t db = umma::smem_desc(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128);
-            umma::mma_f16(tb, da, db, idesc_lo, true);
-          }
-          umma::commit(&mbar);
-        }
-        umma::mbar_wait(&mbar, phase);
-        phase ^= 1;
-        umma::fence_after_sync();
-        float *stg = stage + stage_sel * (56 * NF2);
-        const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
-        const int r = tid;
-        const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
-        const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
+          const uint32_t dcol = tb + (uint32_t)b * 128;
+          if (umma::elect_one()) {
 #pragma unroll
-        for (int cb = 0; cb < 4; cb++) {
-          float a[16], b[16];
-          umma::tmem_ld16(trow + cb * 16, a);
-          umma::tmem_ld16(trow + 64 + cb * 16, b);
-          umma::tmem_ld_wait();
+            for (int i = 0; i < C2_NMMA; i++) {  // a_hi x [w_hi | w_lo]
+              const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
+              const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
+              umma::mma_f16(dcol, umma::desc_from(arow + a0, lbo, 128),
+                            umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_hi, i > 0);
+            }
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            float v = (a[j] + b[j]) * out_scale;
-            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-            if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
+            for (int i = 0; i < C2_NMMA; i++) {  // a_lo x w_hi
+              const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
+              const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
+              umma::mma_f16(dcol, umma::desc_from(arow + 3 * C2_PLANE + a0, lbo, 128),
+                            umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_lo, true);
+            }
+            umma::commit(&full[b]);
+          }
+          __syncwarp();
+        }
+      } else if (warp < 4) {
+        for (int t = 0; t < 3; t++, gt++) {
+          const int b = gt & 1;
+          umma::mbar_wait(&full[b], (gt >> 1) & 1);
+          umma::fence_after_sync();
+          float *stg = stage + b * (56 * NF2);
+          const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)(warp * 32) << 16);
+          const int r = tid;
+          const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
+          const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
+#pragma unroll
+          for (int cb = 0; cb < 4; cb++) {
+            float a[16], bq[16];
+            umma::tmem_ld16(trow + cb * 16, a);
+            umma::tmem_ld16(trow + 64 + cb * 16, bq);
+            umma::tmem_ld_wait();
+            if (cb == 3) {
+              umma::fence_before_sync();
+              __syncwarp();
+              if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              float v = (a[j] + bq[j]) * out_scale;
+              v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+              if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
+            }
+          }
+          umma::named_bar_sync(1, 128);
+          for (int i = tid; i < 2 * 12 * NF2; i += 128) {
+            int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
+            float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
+            if (relu) m = fmaxf(m, 0.0f);
+            int j = (6 * h + 2 * t + q) * 12 + px;
+            out[(size_t)j * NF2 + ch] = m;
           }
         }
-        umma::fence_before_sync();
-        __syncthreads();
-        for (int i = tid; i < 2 * 12 * NF2; i += 128) {
-          int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
-          float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
-          if (relu) m = fmaxf(m, 0.0f);
-          int j = (6 * h + 2 * t + q) * 12 + px;
-          out[(size_t)j * NF2 + ch] = m;
-        }
-        stage_sel ^= 1;
       }
-      __syncthreads();  // planes are rewritten by the next half
+      __syncthreads();  // planes are rewritten by the next half; every tile of this half has completed
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, 128);
+  if (warp == 0) umma::tmem_dealloc(tb, 256);
 }
 
 }  // namespace
@@ -322,7 +353,7 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   t.npl = (C + 7) / 8;
   t.nch1 = t.npl * 25;
   const int nmma1 = (t.nch1 + 1) / 2;
-  // conv1 blob: [chunk c][row n = term*32 + o][8 x bf16], c = (p*5+kh)*5+kw, channel = 8p + e
+  // conv1 blob: [chunk c][row n = term*20 + o][8 x bf16], c = (p*5+kh)*5+kw, channel = 8p + e
   std::vector<__nv_bfloat16> b1((size_t)(2 * nmma1) * C1_N * 8, __float2bfloat16(0.0f));
   for (int c = 0; c < t.nch1; c++) {
     int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
@@ -337,7 +368,7 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
         float r2 = r1 - __bfloat162float(w2);
         __nv_bfloat16 w3 = __float2bfloat16(r2);
         __nv_bfloat16 terms[3] = {w1, w2, w3};
-        for (int tm = 0; tm < 3; tm++) b1[((size_t)c * C1_N + tm * 32 + o) * 8 + e] = terms[tm];
+        for (int tm = 0; tm < 3; tm++) b1[((size_t)c * C1_N + tm * NF1 + o) * 8 + e] = terms[tm];
       }
   }
   // conv2 blob: [chunk c][row n: 0..63 = w_hi (50 used), 64..127 = w_lo][8 x fp16], weights scaled by 2^k
@@ -378,17 +409,20 @@ int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, flo
   const LenetTc &t = ctx->tc;
   const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
   const int nmma1 = (t.nch1 + 1) / 2;
-  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + 1024;
-  size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float) + 1024;
-  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C;
+  size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
-  k_conv1_tc<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, t.npl, (const uint8_t *)t.b1, t.nch1,
-                                                                     ctx->w.c1b, relu, p1);
+  if (t.npl == 2)
+    k_conv1_tc<2><<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
+  else
+    k_conv1_tc<1><<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 5, e1);
   cudaEvent_t e2 = gpdb_st_begin(ctx);
-  k_conv2_tc<<<std::min(n, ctx->sm_count), 128, sm2, ctx->stream>>>(p1, n, (const uint8_t *)t.b2, ctx->w.c2b, t.a2_scale,
+  k_conv2_tc<<<std::min(n, ctx->sm_count), C2_NT, sm2, ctx->stream>>>(p1, n, (const uint8_t *)t.b2, ctx->w.c2b, t.a2_scale,
                                                                      1.0f / (t.a2_scale * t.w2_scale), relu, p2);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 6, e2);

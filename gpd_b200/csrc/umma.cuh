@@ -38,6 +38,26 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
       : "memory");
 }
 
+// elect one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor from its two 32-bit halves: lo = (addr >> 4) | (lbo >> 4) << 16 ; hi = (sbo >> 4) | 1 << 14 (version)
+__device__ __forceinline__ uint64_t desc_from(uint32_t addr_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint32_t lo = (addr_bytes >> 4) | ((lbo_bytes >> 4) << 16);
+  uint32_t hi = (sbo_bytes >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when complete
 __device__ __forceinline__ void commit(uint64_t *mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
@@ -60,6 +80,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(mbar)),
       "r"(parity)
       : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+// named barrier among a subset of the CTA's warps (id 1..15)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core reads)
