@@ -246,7 +246,8 @@ void gpdb_params_default(gpdb_params *p) {
 
 const char *gpdb_build_info(void) {
   return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images (fp64, -fmad=false), lenet: conv1/conv2 tcgen05 "
-         "implicit GEMM (bf16x3 / fp16x2 split, fp32 accumulate in TMEM) + ip1/ip2 simt-fp32; lenet_impl=1 forces simt";
+         "implicit GEMM + ip1 TMA-fed tcgen05 GEMM (bf16x3 / fp16x2 split operands, fp32 accumulate in TMEM), ip2 simt; "
+         "lenet_impl=1 forces the simt-fp32 kernels";
 }
 
 const char *gpdb_last_error(const gpdb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -324,6 +325,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   for (float *p : w) cudaFree(p);
   cudaFree(ctx->tc.b1);
   cudaFree(ctx->tc.b2);
+  cudaFree(ctx->tc.b3);
   for (int i = 0; i < 16; i++) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -92,9 +92,9 @@ struct LenetWeights {  // device pointers, layouts documented in lenet_simt.cu
 };
 
 struct LenetTc {  // tensor-core (tcgen05) weight blobs, lenet_tc.cu
-  void *b1, *b2;
+  void *b1, *b2, *b3;
   int npl, nch1;
-  float w2_scale, a2_scale;
+  float w2_scale, a2_scale, w3_scale, x3_scale;
   bool ready;
 };
 
@@ -157,4 +157,6 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
 
 // lenet_tc.cu (tcgen05 conv1 / conv2)
 int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]);
-int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, float *p2);
+struct __half;
+int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, __half *xc, float *h3);
+size_t lenet_tc_xc_bytes(int n);

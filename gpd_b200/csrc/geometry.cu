@@ -786,6 +786,7 @@ struct ImgSmem {
   double red[NT_IMG / 32][4];
   double center[3];
   double sv[GPDB_MAX_CAMERAS][3];
+  double svh[GPDB_MAX_CAMERAS][3];
   int cam_or;
   int n_img;
   int box_n;
@@ -898,7 +899,7 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
         for (int k = 0; k < CH; k++) {
           float v = fmaf(m[i][k], a, b);
           int q = __float2int_rn(v * 255.0f);
-          o[k] = (uint8_t)min(max(q, 0), 255);
+          o[k] = (uint8_t)min(max(q, 0), 255);  // shared-memory staging of the HWC image
         }
       }
     }
@@ -909,7 +910,7 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
 // dynamic smem layout (bytes): tiles 3 * 8*S*S | box list: keys 8*CAP, q 3*4*CAP, cells 4*CAP, nrm 3*4*CAP
 // (the shadow bitmaps alias the box list)
 __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
-                                                   uint8_t *images, const double *qtab, int *err) {
+                                                   uint8_t *images, const double *qtab, int *err, int img_off) {
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ ImgSmem sm;
@@ -925,6 +926,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
   float *nrmT = reinterpret_cast<float *>(tileB);                 // float[3*SS] over tileB..tileC
   float *depF = nrmT + 3 * SS;                                    // float[SS]
+  uint8_t *simg = dyn + img_off;                                  // uint8[SS*C] HWC staging of the output image
   const int tid = threadIdx.x, lane = tid & 31;
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
@@ -943,7 +945,8 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     }
     __syncthreads();
     const gpdb_pose &h = sm.h;
-    uint8_t *gimg = images + (size_t)b * SS * C;
+    uint8_t *gout = images + (size_t)b * SS * C;
+    uint8_t *gimg = simg;  // channels are written to the shared-memory staging image, flushed once at the end
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
     SegRange sr = seg_range(P, q, P.rf_img);
     // ---- ball scan 1: neighbourhood centre + camera set (HandSet::calculateShadow, hand_set.cpp:131-136)
@@ -1134,6 +1137,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         sm.sv[tid][0] = P.shadow_length * s0 / nn;
         sm.sv[tid][1] = P.shadow_length * s1 / nn;
         sm.sv[tid][2] = P.shadow_length * s2 / nn;
+        to_frame(h.frame, sm.sv[tid][0], sm.sv[tid][1], sm.sv[tid][2], sm.svh[tid][0], sm.svh[tid][1], sm.svh[tid][2]);
       }
       for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
       __syncthreads();
@@ -1154,7 +1158,12 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       // region; (2) the (point, draw) pairs are spread evenly over all threads — draw t of a point comes from
       // the closed-form LCG skip-ahead seed_t = A^(t+1) seed_0 + C_(t+1) (mod 2^32).
       float4 *wl = reinterpret_cast<float4 *>(tileA);
-      const int WL_CAP = (3 * SS * 8) / 16;
+      const int WL_CAP = (3 * SS * 8) / 20;
+      unsigned *wrange = reinterpret_cast<unsigned *>(wl + WL_CAP);
+      // image box in the hand frame, widened by voxel truncation (<= 0.003 sqrt 3) + jitter (<= gmax 0.0009 sqrt 3)
+      const double wm = 0.0105;
+      const double bx_lo[3] = {h.bottom - wm, h.center - P.vol_w / 2.0 - wm, -P.vol_h - wm};
+      const double bx_hi[3] = {h.bottom + P.vol_d + wm, h.center + P.vol_w / 2.0 + wm, P.vol_h + wm};
       auto cast_draw = [&](double px, double py, double pz, unsigned seed, int k, unsigned *bm) {
         const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
         double u = (double)((seed >> 16) & 0x7FFFu) * mxu;
@@ -1171,7 +1180,6 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       for (int k = 0; k < K; k++) {
         if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
         unsigned *bm = bitmap + (size_t)k * bm_words;
-        const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
         __syncthreads();
         if (tid == 0) sm.wl_n = 0;
         for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
@@ -1182,23 +1190,39 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
             float d = l2_simple(q, p.x, p.y, p.z);
             if (!(d < P.r2_img)) continue;
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-            // quick reject: per-axis voxel range of the segment p .. p + sv vs the bitmap AABB
-            int a, e;
-            a = (int)(px * P.vox_mult); e = (int)((px + s0) * P.vox_mult);
-            if (max(a, e) < o0 - 1 || min(a, e) > o0 + d0) continue;
-            a = (int)(py * P.vox_mult); e = (int)((py + s1) * P.vox_mult);
-            if (max(a, e) < o1 - 1 || min(a, e) > o1 + d1) continue;
-            a = (int)(pz * P.vox_mult); e = (int)((pz + s2) * P.vox_mult);
-            if (max(a, e) < o2 - 1 || min(a, e) > o2 + d2) continue;
+            // exact cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame) widened
+            // by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG value falls
+            // in [r0, r1] can produce a voxel point inside the box.
+            double ox, oy, oz;
+            to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], ox, oy, oz);
+            double tmin = 0.0, tmax = 1.0;
+            bool hit = true;
+            {
+              const double lo3[3] = {bx_lo[0], bx_lo[1], bx_lo[2]}, hi3[3] = {bx_hi[0], bx_hi[1], bx_hi[2]};
+              const double o3[3] = {ox, oy, oz}, d3[3] = {sm.svh[k][0], sm.svh[k][1], sm.svh[k][2]};
+#pragma unroll
+              for (int a = 0; a < 3; a++) {
+                if (fabs(d3[a]) < 1e-12) {
+                  hit = hit && o3[a] >= lo3[a] && o3[a] <= hi3[a];
+                } else {
+                  double t1 = (lo3[a] - o3[a]) / d3[a], t2 = (hi3[a] - o3[a]) / d3[a];
+                  tmin = fmax(tmin, fmin(t1, t2));
+                  tmax = fmin(tmax, fmax(t1, t2));
+                }
+              }
+            }
+            if (!hit || tmin > tmax) continue;
+            const int r0 = max((int)floor(tmin * 32767.0) - 1, 0), r1 = min((int)ceil(tmax * 32767.0) + 1, 32767);
             unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
             int pos = atomicAdd(&sm.wl_n, 1);
             if (pos < WL_CAP) {
               wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
+              wrange[pos] = (unsigned)r0 | ((unsigned)r1 << 16);
             } else {  // work list full (very dense neighbourhood): cast this point's draws in place
               unsigned seed = seed0;
               for (int t = 0; t < P.nsp; t++) {
-                gpdb_fastrand(&seed);
-                cast_draw(px, py, pz, seed, k, bm);
+                int r = (int)gpdb_fastrand(&seed);
+                if (r >= r0 && r <= r1) cast_draw(px, py, pz, seed, k, bm);
               }
             }
           }
@@ -1210,6 +1234,9 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
           int item = w / nsp, t = w - item * nsp;
           float4 e = wl[item];
           unsigned seed = P.lcgA[t] * __float_as_uint(e.w) + P.lcgC[t];
+          unsigned rg = wrange[item];
+          int r = (int)((seed >> 16) & 0x7FFFu);
+          if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) continue;
           cast_draw((double)e.x, (double)e.y, (double)e.z, seed, k, bm);
         }
       }
@@ -1280,6 +1307,13 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         __syncthreads();
         postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
       }
+    }
+    // ---- flush the staged image with coalesced 16-byte stores
+    __syncthreads();
+    {
+      const int nb = SS * C, nv = nb >> 4;
+      for (int v = tid; v < nv; v += NT_IMG) reinterpret_cast<uint4 *>(gout)[v] = reinterpret_cast<const uint4 *>(simg)[v];
+      for (int v = (nv << 4) + tid; v < nb; v += NT_IMG) gout[v] = simg[v];
     }
   }
 }
@@ -1408,19 +1442,22 @@ static size_t images_smem_bytes(const DevParams &hp) {
   size_t tiles = (size_t)3 * 8 * hp.S * hp.S;
   size_t list = (size_t)BOX_CAP * (8 + 12 + 4 + 12);
   size_t bm = (size_t)hp.K * (((size_t)hp.bm_dim * hp.bm_dim * hp.bm_dim + 31) / 32) * 4;
-  return tiles + std::max(list, hp.C == 15 ? bm : (size_t)0);
+  size_t work = tiles + std::max(list, hp.C == 15 ? bm : (size_t)0);
+  return (work + 15) / 16 * 16;
 }
 
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images) {
   if (nc <= 0) return GPDB_OK;
-  size_t smem = images_smem_bytes(ctx->hp);
-  if (smem > 200 * 1024) {
-    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 204800)", smem);
+  const size_t img_off = images_smem_bytes(ctx->hp);
+  size_t smem = img_off + ((size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C + 15) / 16 * 16;
+  if (smem > 215 * 1024) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 220160)", smem);
     return GPDB_ERR_INVALID;
   }
   CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(nc, ctx->sm_count * 64);
-  k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err);
+  k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
+                                                (int)img_off);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

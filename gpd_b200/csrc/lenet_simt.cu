@@ -9,11 +9,13 @@
 //   ip2 (500->2), score = y1 - y0    : one warp per image
 // Input is the reference's cv::Mat layout (HWC uint8), raw 0..255 values, no scaling
 // (imageToArray, eigen_classifier.cpp:130-149).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int NF1 = 20, NF2 = 50, KS = 5, NH = 500;
+constexpr int NF1 = 20, NF2 = 50, NH = 500;
 
 // ---- conv1 + pool --------------------------------------------------------------------------------
 // grid: persistent over images; block 224 threads; dyn smem: float w[C*25*20] | uint8 img[C*S*S]
@@ -285,8 +287,9 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
     return GPDB_ERR_INVALID;
   }
   const LenetWeights &w = ctx->w;
+  const bool use_tc = ctx->tc.ready && ctx->prm.lenet_impl != 1;
   float *p1 = (float *)gpdb_scratch(ctx, 4, sizeof(float) * (size_t)n * NF1 * P1 * P1);
-  float *p2 = (float *)gpdb_scratch(ctx, 5, sizeof(float) * (size_t)n * K);
+  float *p2 = (float *)gpdb_scratch(ctx, 5, use_tc ? lenet_tc_xc_bytes(n) : sizeof(float) * (size_t)n * K);
   float *h3 = (float *)gpdb_scratch(ctx, 6, sizeof(float) * (size_t)n * NH);
   if (!p1 || !p2 || !h3) return GPDB_ERR_CUDA;
   const int relu = ctx->prm.relu_after_conv;
@@ -294,10 +297,14 @@ int lenet_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *d_scores
   size_t sm2 = sizeof(float) * (NF1 * 25 * NF2 + NF1 * P1 * P1);
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-  const bool use_tc = ctx->tc.ready && ctx->prm.lenet_impl != 1;
   if (use_tc) {
-    int rc = lenet_tc_convs(ctx, d_images, n, p1, p2);
+    int rc = lenet_tc_forward(ctx, d_images, n, p1, reinterpret_cast<__half *>(p2), h3);
     if (rc != GPDB_OK) return rc;
+    cudaEvent_t e4 = gpdb_st_begin(ctx);
+    k_ip2<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(h3, n, w.i2w, w.i2b, d_scores, d_logits);
+    LAUNCH_CHECK();
+    gpdb_st_end(ctx, 7, e4);
+    return GPDB_OK;
   } else {
   cudaEvent_t e1 = gpdb_st_begin(ctx);
   k_conv1_pool<<<std::min(n, ctx->sm_count * 2), 224, sm1, ctx->stream>>>(d_images, n, S, C, w.c1w, w.c1b, relu, p1);

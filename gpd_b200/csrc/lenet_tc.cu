@@ -191,6 +191,7 @@ constexpr int C2_W = 28, C2_NPIX = 472, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2
 constexpr int C2_BCHUNK = 128 * 16;
 
 constexpr int C2_NT = 256;
+constexpr int IP_K = 7200, IP_KCH = IP_K / 8;  // ip1 reduction length, in 8-element chunks
 __host__ __device__ constexpr uint32_t c2_off(int c) {
   return (uint32_t)(((c >= C2_NCH ? C2_NCH - 1 : c) / 25) * C2_PLANE +
                     ((((c >= C2_NCH ? C2_NCH - 1 : c) / 5) % 5) * C2_W + (c >= C2_NCH ? C2_NCH - 1 : c) % 5) * 16);
@@ -198,7 +199,7 @@ __host__ __device__ constexpr uint32_t c2_off(int c) {
 
 __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__ p1, int n, const uint8_t *__restrict__ wblob,
                                                        const float *__restrict__ bias, float a_scale, float out_scale, int relu,
-                                                       float *__restrict__ p2) {
+                                                       float *__restrict__ p2, __half *__restrict__ xc, float x_scale) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2];
   __shared__ uint32_t tmem_base;
@@ -317,7 +318,16 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
             float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
             if (relu) m = fmaxf(m, 0.0f);
             int j = (6 * h + 2 * t + q) * 12 + px;
-            out[(size_t)j * NF2 + ch] = m;
+            if (p2) out[(size_t)j * NF2 + ch] = m;
+            if (xc) {  // ip1's A operand: [tile im/128][hi|lo][k/8][row im%128][k%8] fp16, scaled by 2^-8
+              const int k = ch + NF2 * j;
+              const float a = m * x_scale;
+              const __half hi = __float2half_rn(a);
+              const __half lo = __float2half_rn(a - __half2float(hi));
+              const size_t base = ((size_t)(im >> 7) * 2 * IP_KCH + (size_t)(k >> 3)) * 128 * 8 + (size_t)(im & 127) * 8 + (k & 7);
+              xc[base] = hi;
+              xc[base + (size_t)IP_KCH * 128 * 8] = lo;
+            }
           }
         }
       }
@@ -325,6 +335,106 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
     }
   }
   umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 256);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// ip1: H3[n x 500] = relu(X[n x 7200] W[7200 x 500] + b) as a TMA-fed tcgen05 GEMM.
+// CTA tile: 128 images x 128 outputs; X arrives as fp16 hi/lo in the canonical K-major layout written by conv2's
+// epilogue, W as a host-prepared fp16 hi/lo blob — both are plain contiguous byte ranges per K-block, so the
+// operand ring is filled by 1-D bulk copies (no tensor map needed).
+// D[:, 0:128] += x_hi w_hi + x_lo w_hi ; D[:, 128:256] += x_hi w_lo ; summed and rescaled in the epilogue.
+// warp 4: MMA issuer, warp 5: bulk-copy producer, warps 0-3: epilogue.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int IP_KB_CH = 6, IP_NKB = IP_KCH / IP_KB_CH, IP_STAGES = 4;     // 48-element K-blocks, 150 of them
+constexpr int IP_A_BYTES = IP_KB_CH * 128 * 16, IP_B_BYTES = IP_KB_CH * 256 * 16;
+constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + IP_B_BYTES;                 // 49152
+constexpr int IP_NT = 192;
+
+__global__ void __launch_bounds__(IP_NT, 1) k_ip1_tc(const __half *__restrict__ xc, int n, const uint8_t *__restrict__ wblob,
+                                                     const float *__restrict__ bias, float out_scale, float *__restrict__ h3) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[IP_STAGES], empty[IP_STAGES], done;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int mt = blockIdx.x, ob = blockIdx.y;
+  if (tid == 0) {
+    for (int s = 0; s < IP_STAGES; s++) {
+      umma::mbar_init(&full[s], 1);
+      umma::mbar_init(&empty[s], 1);
+    }
+    umma::mbar_init(&done, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (warp == 5) {
+    // ===== producer: one elected lane streams the K-blocks through the ring
+    if (umma::elect_one()) {
+      const uint8_t *xa_hi = reinterpret_cast<const uint8_t *>(xc) + (size_t)mt * 2 * IP_KCH * 128 * 16;
+      const uint8_t *xa_lo = xa_hi + (size_t)IP_KCH * 128 * 16;
+      const uint8_t *wb = wblob + (size_t)ob * IP_NKB * IP_B_BYTES;
+      for (int kb = 0; kb < IP_NKB; kb++) {
+        const int s = kb % IP_STAGES;
+        umma::mbar_wait(&empty[s], ((kb / IP_STAGES) & 1) ^ 1);
+        uint8_t *st = smem + (size_t)s * IP_STAGE_BYTES;
+        umma::mbar_expect_tx(&full[s], IP_STAGE_BYTES);
+        umma::bulk_g2s(st, xa_hi + (size_t)kb * IP_A_BYTES, IP_A_BYTES, &full[s]);
+        umma::bulk_g2s(st + IP_A_BYTES, xa_lo + (size_t)kb * IP_A_BYTES, IP_A_BYTES, &full[s]);
+        umma::bulk_g2s(st + 2 * IP_A_BYTES, wb + (size_t)kb * IP_B_BYTES, IP_B_BYTES, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // ===== MMA issuer
+    const uint32_t idesc_hi = umma::instr_desc(128, 256, umma::F16), idesc_lo = umma::instr_desc(128, 128, umma::F16);
+    const uint32_t sm_u = umma::smem_u32(smem);
+    for (int kb = 0; kb < IP_NKB; kb++) {
+      const int s = kb % IP_STAGES;
+      umma::mbar_wait(&full[s], (kb / IP_STAGES) & 1);
+      umma::fence_after_sync();
+      const uint32_t st = sm_u + (uint32_t)s * IP_STAGE_BYTES;
+      if (umma::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < IP_KB_CH / 2; ks++) {
+          const uint64_t da_hi = umma::desc_from(st + (uint32_t)(2 * ks) * 128 * 16, 128 * 16, 128);
+          const uint64_t da_lo = umma::desc_from(st + IP_A_BYTES + (uint32_t)(2 * ks) * 128 * 16, 128 * 16, 128);
+          const uint64_t db = umma::desc_from(st + 2 * IP_A_BYTES + (uint32_t)(2 * ks) * 256 * 16, 256 * 16, 128);
+          umma::mma_f16(tb, da_hi, db, idesc_hi, (kb | ks) != 0);  // x_hi x [w_hi | w_lo]
+          umma::mma_f16(tb, da_lo, db, idesc_lo, true);            // x_lo x w_hi
+        }
+        umma::commit(&empty[s]);                    // the stage may be refilled once these MMAs have read it
+        if (kb == IP_NKB - 1) umma::commit(&done);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: rows = images of this M-tile
+    umma::mbar_wait(&done, 0);
+    umma::fence_after_sync();
+    const int im = mt * 128 + tid;
+    const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int cb = 0; cb < 8; cb++) {
+      float a[16], b[16];
+      umma::tmem_ld16(trow + cb * 16, a);
+      umma::tmem_ld16(trow + 128 + cb * 16, b);
+      umma::tmem_ld_wait();
+      if (im < n) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int o = ob * 128 + cb * 16 + j;
+          if (o < NH) h3[(size_t)im * NH + o] = fmaxf((a[j] + b[j]) * out_scale + __ldg(bias + o), 0.0f);
+        }
+      }
+    }
+    umma::fence_before_sync();
+  }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tb, 256);
 }
@@ -390,13 +500,38 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
         b2[((size_t)c * 128 + 64 + o) * 8 + e] = lo;
       }
   }
+  // ip1 blob: [o-block 4][K-block 150][chunk 6][row 256: 0..127 w_hi(o), 128..255 w_lo(o)][8 x fp16], W(o,k) = w[4][o + 500 k]
+  mx = 0.0f;
+  for (size_t i = 0; i < (size_t)NH * IP_K; i++) mx = std::fmax(mx, std::fabs(w[4][i]));
+  t.w3_scale = pow2_scale(mx, 16.0f);
+  t.x3_scale = 1.0f / 256.0f;
+  std::vector<__half> b3((size_t)4 * IP_NKB * IP_KB_CH * 256 * 8, __float2half(0.0f));
+  for (int ob = 0; ob < 4; ob++)
+    for (int kc = 0; kc < IP_KCH; kc++) {
+      const int kb = kc / IP_KB_CH, c = kc % IP_KB_CH;
+      __half *dst = b3.data() + (((size_t)ob * IP_NKB + kb) * IP_KB_CH + c) * 256 * 8;
+      for (int ol = 0; ol < 128; ol++) {
+        const int o = ob * 128 + ol;
+        if (o >= NH) continue;
+        for (int e = 0; e < 8; e++) {
+          float wv = w[4][(size_t)o + (size_t)NH * (kc * 8 + e)] * t.w3_scale;
+          __half hi = __float2half_rn(wv);
+          __half lo = __float2half_rn(wv - __half2float(hi));
+          dst[(size_t)ol * 8 + e] = hi;
+          dst[(size_t)(128 + ol) * 8 + e] = lo;
+        }
+      }
+    }
   cudaFree(t.b1);
   cudaFree(t.b2);
-  t.b1 = t.b2 = nullptr;
+  cudaFree(t.b3);
+  t.b1 = t.b2 = t.b3 = nullptr;
   t.ready = false;
   if (cudaMalloc(&t.b1, b1.size() * 2) != cudaSuccess || cudaMalloc(&t.b2, b2.size() * 2) != cudaSuccess ||
       cudaMemcpy(t.b1, b1.data(), b1.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(t.b2, b2.data(), b2.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(t.b2, b2.data(), b2.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&t.b3, b3.size() * 2) != cudaSuccess ||
+      cudaMemcpy(t.b3, b3.data(), b3.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
     gpdb_set_error(ctx, GPDB_ERR_CUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return GPDB_ERR_CUDA;
   }
@@ -404,16 +539,18 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   return GPDB_OK;
 }
 
-// conv1 + pool and conv2 + pool on tcgen05; p1 [n][784][20], p2 [n][7200]
-int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, float *p2) {
+// conv1 + pool, conv2 + pool and ip1 + ReLU on tcgen05; p1 [n][784][20] f32, xc = fp16 hi/lo ip1 operand, h3 [n][500]
+int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, __half *xc, float *h3) {
   const LenetTc &t = ctx->tc;
   const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
   const int nmma1 = (t.nch1 + 1) / 2;
   size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C;
   size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
+  size_t sm3 = (size_t)IP_STAGES * IP_STAGE_BYTES;
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  CUDA_TRY(cudaFuncSetAttribute(k_ip1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
   if (t.npl == 2)
     k_conv1_tc<2><<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
@@ -423,8 +560,16 @@ int lenet_tc_convs(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, flo
   gpdb_st_end(ctx, 5, e1);
   cudaEvent_t e2 = gpdb_st_begin(ctx);
   k_conv2_tc<<<std::min(n, ctx->sm_count), C2_NT, sm2, ctx->stream>>>(p1, n, (const uint8_t *)t.b2, ctx->w.c2b, t.a2_scale,
-                                                                     1.0f / (t.a2_scale * t.w2_scale), relu, p2);
+                                                                       1.0f / (t.a2_scale * t.w2_scale), relu, nullptr, xc,
+                                                                       t.x3_scale);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 6, e2);
+  cudaEvent_t e3 = gpdb_st_begin(ctx);
+  dim3 g3((n + 127) / 128, 4);
+  k_ip1_tc<<<g3, IP_NT, sm3, ctx->stream>>>(xc, n, (const uint8_t *)t.b3, ctx->w.i1b, 1.0f / (t.x3_scale * t.w3_scale), h3);
+  LAUNCH_CHECK();
+  gpdb_st_end(ctx, 7, e3);
   return GPDB_OK;
 }
+
+size_t lenet_tc_xc_bytes(int n) { return (size_t)((n + 127) / 128) * 2 * IP_KCH * 128 * 16; }
