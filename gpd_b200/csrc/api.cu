@@ -206,6 +206,10 @@ static int fill_dev_params(gpdb_ctx *ctx) {
   double diag = std::sqrt(p.volume_depth * p.volume_depth + p.volume_width * p.volume_width +
                           4.0 * p.volume_height * p.volume_height);
   d.bm_dim = (int)std::ceil((diag + 2.0 * 3.2 * GPDB_SHADOW_VOXEL * 0.3) / GPDB_SHADOW_VOXEL) + 4;
+  if (d.bm_dim > 64 && d.C == 15) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image volume too large for the shadow bitmap (%d > 64 voxels across)", d.bm_dim);
+    return GPDB_ERR_INVALID;
+  }
   d.relu_after_conv = p.relu_after_conv;
   d.K = 1;
   d.dim[0] = d.dim[1] = d.dim[2] = 1;
@@ -315,6 +319,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dp);
   cudaFree(ctx->d_err);
+  cudaFree(ctx->d_prof);
   cudaFree(ctx->d_qtab);
   cudaFree(ctx->d_pts4);
   cudaFree(ctx->d_xyz);
@@ -715,6 +720,21 @@ void gpdb_free_result(gpdb_result *r) {
   free(r->candidates);
   free(r->images);
   memset(r, 0, sizeof(*r));
+}
+
+int gpdb_debug_phase_cycles(gpdb_ctx *ctx, int enable, uint64_t cycles_out[16]) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_prof && cycles_out)
+    CUDA_TRY(cudaMemcpy(cycles_out, ctx->d_prof, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+  if (enable && !ctx->d_prof) CUDA_TRY(cudaMalloc(&ctx->d_prof, sizeof(uint64_t) * 16));
+  if (enable) CUDA_TRY(cudaMemset(ctx->d_prof, 0, sizeof(uint64_t) * 16));
+  if (!enable && ctx->d_prof) {
+    cudaFree(ctx->d_prof);
+    ctx->d_prof = nullptr;
+  }
+  return GPDB_OK;
 }
 
 int gpdb_last_timings(const gpdb_ctx *ctx, double ms_out[8]) {

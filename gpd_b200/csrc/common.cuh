@@ -127,6 +127,7 @@ struct gpdb_ctx {
   void *scratch[16];
   size_t scratch_sz[16];
   int *d_err;
+  unsigned long long *d_prof;  // optional phase counters (gpdb_debug_phase_cycles), nullptr = off
   int64_t launches;
   double last_ms[8];
   cudaEvent_t ev[8];

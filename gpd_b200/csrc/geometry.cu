@@ -101,6 +101,34 @@ __device__ __forceinline__ void seg_row(const DevParams &P, const int *cell_star
   len = __ldg(cell_start + base + s.c1[0] + 1) - start;
 }
 
+// Ball scan, one warp per grid row: lanes stride over the row's contiguous point segment (coalesced float4 loads).
+// body(in_range, point) is called by all 32 lanes together, so it may use warp collectives.
+template <int NT, class F>
+__device__ __forceinline__ void scan_rows(const DevParams &P, const DevCloud &cl, const SegRange &sr, F &&body) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = NT / 32;
+  // this warp owns rows warp, warp + NW, ...; the bounds of 32 of them are fetched at once (one lane each) so that
+  // the dependent cell_start -> point loads cost one round trip per 32 rows, and empty rows are skipped by ballot
+  for (int j0 = 0; warp + NW * j0 < sr.nrows; j0 += 32) {
+    const int myrow = warp + NW * (j0 + lane);
+    int st = 0, len = 0;
+    if (myrow < sr.nrows) seg_row(P, cl.cell_start, sr, myrow, st, len);
+    unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+    while (nonempty) {
+      const int j = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const int rs = __shfl_sync(0xffffffffu, st, j), rl = __shfl_sync(0xffffffffu, len, j);
+      for (int k0 = 0; k0 < rl; k0 += 32) {
+        const int k = k0 + lane;
+        const bool in = k < rl;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) p = __ldg(cl.pts4 + rs + k);
+        body(in, p);
+      }
+    }
+  }
+}
+
 template <int NT>
 struct SegScan {
   typedef cub::BlockScan<int, NT> Scan;
@@ -379,32 +407,32 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
 // ------------------------------------------------------------------------------------------------
 // k_hands
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned slot_mask(const DevParams &P, double y) {
+__device__ __forceinline__ unsigned slot_mask(const DevParams &P, const double *sfs, const double *sfsw, double y) {
   unsigned m = 0;
   const int F = 2 * P.nfp;
   if (P.slots_disjoint) {
     // slots within each half are disjoint and ascending: find the last slot starting below y
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-      const double *fs = P.fs + half * P.nfp;
+      const double *fs = sfs + half * P.nfp;
       if (y > fs[0]) {
         int lo = 0, hi = P.nfp;
         while (hi - lo > 1) {
           int mid = (lo + hi) >> 1;
           if (y > fs[mid]) lo = mid; else hi = mid;
         }
-        if (y < P.fsw[half * P.nfp + lo]) m |= 1u << (half * P.nfp + lo);
+        if (y < sfsw[half * P.nfp + lo]) m |= 1u << (half * P.nfp + lo);
       }
     }
   } else {
     for (int f = 0; f < F; f++)
-      if (y > P.fs[f] && y < P.fsw[f]) m |= 1u << f;
+      if (y > sfs[f] && y < sfsw[f]) m |= 1u << f;
   }
   return m;
 }
 
 struct HandsSmem {
-  SegScan<NT_HANDS> seg;
+  double fs[GPDB_MAX_SLOTS], fsw[GPDB_MAX_SLOTS];  // finger slot tables (copied from DevParams)
   int count;      // staged (slab) points
   int n_ball;     // all points of the r ball
   unsigned long long nb0_key;
@@ -425,6 +453,10 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
   __shared__ HandsSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int work_n = list_mode ? *ovf_count : n;
+  if (tid < 2 * P.nfp) {
+    S.fs[tid] = P.fs[tid];
+    S.fsw[tid] = P.fsw[tid];
+  }
   for (int w = blockIdx.x; w < work_n; w += gridDim.x) {
     const int i = list_mode ? ovf_list[w] : w;
     const int si = sidx[i];
@@ -461,38 +493,31 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
     const double hz = P.hand_height * 1.001 + 1e-9;
     unsigned long long best = ~0ull;
     int nball = 0;
-    for (int row0 = 0; row0 < sr.nrows; row0 += NT_HANDS) {
-      __syncthreads();
-      int total = seg_batch<NT_HANDS>(P, cl.cell_start, sr, row0, S.seg);
-      for (int c0 = 0; c0 < total; c0 += NT_HANDS) {
-        int c = c0 + tid;
-        bool keep = false;
-        float4 p;
-        if (c < total) {
-          p = __ldg(cl.pts4 + seg_lookup<NT_HANDS>(S.seg, c));
-          float d = l2_simple(q, p.x, p.y, p.z);
-          if (d < P.r2_hs) {
-            nball++;
-            unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-            best = key < best ? key : best;
-            keep = true;
-            if (P.all_axes_z) {
-              double z0 = (S.T[6] * ((double)p.x - S.sample[0]) + S.T[7] * ((double)p.y - S.sample[1])) +
-                          S.T[8] * ((double)p.z - S.sample[2]);
-              keep = fabs(z0) < hz;
-            }
+    scan_rows<NT_HANDS>(P, cl, sr, [&](bool in, const float4 &p) {
+      bool keep = false;
+      if (in) {
+        float d = l2_simple(q, p.x, p.y, p.z);
+        if (d < P.r2_hs) {
+          nball++;
+          unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+          best = key < best ? key : best;
+          keep = true;
+          if (P.all_axes_z) {
+            double z0 = (S.T[6] * ((double)p.x - S.sample[0]) + S.T[7] * ((double)p.y - S.sample[1])) +
+                        S.T[8] * ((double)p.z - S.sample[2]);
+            keep = fabs(z0) < hz;
           }
         }
-        unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-          int leader = __ffs(m) - 1, base = 0;
-          if (lane == leader) base = atomicAdd(&S.count, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          int pos = base + __popc(m & ((1u << lane) - 1));
-          if (keep && pos < cap) list[pos] = p;
-        }
       }
-    }
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        int leader = __ffs(m) - 1, base = 0;
+        if (lane == leader) base = atomicAdd(&S.count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        int pos = base + __popc(m & ((1u << lane) - 1));
+        if (keep && pos < cap) list[pos] = p;
+      }
+    });
     nball = warp_sum(nball);
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -557,7 +582,7 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
             if (x < b0) {
               anyA = 1;
               if (x < bot0) anyB = 1;
-              fmask |= slot_mask(P, y);
+              fmask |= slot_mask(P, S.fs, S.fsw, y);
             }
           }
         }
@@ -566,7 +591,7 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
         if (npad > 0 && x0 < b0) {
           anyA = 1;
           if (x0 < bot0) anyB = 1;
-          fmask |= slot_mask(P, y0);
+          fmask |= slot_mask(P, S.fs, S.fsw, y0);
         }
         anyA = __reduce_or_sync(0xffffffffu, anyA);
         anyB = __reduce_or_sync(0xffffffffu, anyB);
@@ -781,7 +806,6 @@ __global__ void k_scatter_scores(const gpdb_pose *cand, const float *scores, int
 // k_images
 // ------------------------------------------------------------------------------------------------
 struct ImgSmem {
-  SegScan<NT_IMG> seg;
   gpdb_pose h;
   double red[NT_IMG / 32][4];
   double center[3];
@@ -809,6 +833,21 @@ __device__ __forceinline__ void unit_coords(const DevParams &P, const gpdb_pose 
   u0 = (x - h.bottom) / P.vol_d;
   u1 = (y - (h.center - half_od)) / P.vol_w;
   u2 = (z + P.vol_h) / double_height;
+}
+// unit coordinate + cell of one axis without the two float64 divisions of the reference formulas
+// ((v - lo) / extent, floor(u / (1.0 / S))) in the common case: a reciprocal multiply gives u to ~2 ulp, and the cell is
+// floor(u * S) unless u * S lies within 1e-9 of an integer — only then are the exact divisions evaluated, so the
+// cell index is always the reference's. u feeds the per-cell MEAN only (float32 result, 2 ulp of float64 are invisible).
+__device__ __forceinline__ void unit_axis(double v, double lo, double extent, double inv_extent, int S, double &u, int &cell) {
+  u = (v - lo) * inv_extent;
+  double q = u * (double)S;
+  double fq = floor(q);
+  if (q - fq < 1e-9 || fq + 1.0 - q < 1e-9) {
+    u = (v - lo) / extent;
+    double cellsize = 1.0 / (double)S;
+    fq = floor(u / cellsize);
+  }
+  cell = min((int)fq, S - 1);
 }
 // findCellIndices (image_strategy.cpp:92-102)
 __device__ __forceinline__ int unit_cell(double u, int S) {
@@ -909,8 +948,20 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
 
 // dynamic smem layout (bytes): tiles 3 * 8*S*S | box list: keys 8*CAP, q 3*4*CAP, cells 4*CAP, nrm 3*4*CAP
 // (the shadow bitmaps alias the box list)
+// optional phase timing (development aid, gpdb_debug_phase_cycles): thread 0 accumulates clock64() deltas
+#define PHASE(i)                                                        \
+  do {                                                                  \
+    if (prof && threadIdx.x == 0) {                                     \
+      long long now__ = clock64();                                      \
+      if ((i) > 1) atomicAdd(prof + (i), (unsigned long long)(now__ - t_phase)); \
+      t_phase = now__;                                                  \
+    }                                                                   \
+  } while (0)
+
 __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
-                                                   uint8_t *images, const double *qtab, int *err, int img_off) {
+                                                   uint8_t *images, const double *qtab, int *err, int img_off,
+                                                   unsigned long long *prof) {
+  long long t_phase = 0;
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ ImgSmem sm;
@@ -944,65 +995,63 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       sm.box_n = 0;
     }
     __syncthreads();
+    PHASE(1);   // image start
     const gpdb_pose &h = sm.h;
     uint8_t *gout = images + (size_t)b * SS * C;
     uint8_t *gimg = simg;  // channels are written to the shared-memory staging image, flushed once at the end
+    const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
     SegRange sr = seg_range(P, q, P.rf_img);
     // ---- ball scan 1: neighbourhood centre + camera set (HandSet::calculateShadow, hand_set.cpp:131-136)
     //      and the list of points inside the image box (ImageStrategy::transformToUnitImage)
     double sx = 0, sy = 0, sz = 0;
     int cnt = 0, cam_or = 0;
-    for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
-      __syncthreads();
-      int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
-      for (int c0 = 0; c0 < total; c0 += NT_IMG) {
-        int c = c0 + tid;
-        bool inb = false;
-        unsigned long long key = 0;
-        double u0 = 0, u1 = 0, u2 = 0;
-        int idx = 0;
-        if (c < total) {
-          float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
-          float d = l2_simple(q, p.x, p.y, p.z);
-          if (d < P.r2_img) {
-            idx = __float_as_int(p.w);
-            sx += (double)p.x;
-            sy += (double)p.y;
-            sz += (double)p.z;
-            cnt++;
-            cam_or |= cl.cam[idx];
-            double x, y, z;
-            to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
-            if (in_image_box(P, h, x, y, z)) {
-              inb = true;
-              unit_coords(P, h, x, y, z, u0, u1, u2);
-              key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
-            }
-          }
-        }
-        unsigned mk = __ballot_sync(0xffffffffu, inb);
-        if (mk) {
-          int leader = __ffs(mk) - 1, base = 0;
-          if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          int pos = base + __popc(mk & ((1u << lane) - 1));
-          if (inb && pos < BOX_CAP) {
-            bkeys[pos] = key;
-            bq[pos] = unit_q32(u0);
-            bq[BOX_CAP + pos] = unit_q32(u1);
-            bq[2 * BOX_CAP + pos] = unit_q32(u2);
-            bcell[pos] = (unsigned)unit_cell(u0, S) | ((unsigned)unit_cell(u1, S) << 8) | ((unsigned)unit_cell(u2, S) << 16);
-            const double *nn = cl.nrm + 3 * (size_t)idx;
-            double n0, n1, n2;
-            to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
-            bnrm[pos] = (float)fabs(n0);
-            bnrm[BOX_CAP + pos] = (float)fabs(n1);
-            bnrm[2 * BOX_CAP + pos] = (float)fabs(n2);
+    scan_rows<NT_IMG>(P, cl, sr, [&](bool in, const float4 &p) {
+      bool inb = false;
+      unsigned long long key = 0;
+      double u0 = 0, u1 = 0, u2 = 0;
+      int idx = 0, c0 = 0, c1 = 0, c2 = 0;
+      if (in) {
+        float d = l2_simple(q, p.x, p.y, p.z);
+        if (d < P.r2_img) {
+          idx = __float_as_int(p.w);
+          sx += (double)p.x;
+          sy += (double)p.y;
+          sz += (double)p.z;
+          cnt++;
+          cam_or |= cl.cam[idx];
+          double x, y, z;
+          to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
+          if (in_image_box(P, h, x, y, z)) {
+            inb = true;
+            unit_axis(x, h.bottom, P.vol_d, inv_d, S, u0, c0);
+            unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
+            unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
+            key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
           }
         }
       }
-    }
+      unsigned mk = __ballot_sync(0xffffffffu, inb);
+      if (mk) {
+        int leader = __ffs(mk) - 1, base = 0;
+        if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        int pos = base + __popc(mk & ((1u << lane) - 1));
+        if (inb && pos < BOX_CAP) {
+          bkeys[pos] = key;
+          bq[pos] = unit_q32(u0);
+          bq[BOX_CAP + pos] = unit_q32(u1);
+          bq[2 * BOX_CAP + pos] = unit_q32(u2);
+          bcell[pos] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
+          const double *nn = cl.nrm + 3 * (size_t)idx;
+          double n0, n1, n2;
+          to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
+          bnrm[pos] = (float)fabs(n0);
+          bnrm[BOX_CAP + pos] = (float)fabs(n1);
+          bnrm[2 * BOX_CAP + pos] = (float)fabs(n2);
+        }
+      }
+    });
     // block reduce centre sums
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -1038,6 +1087,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       }
     }
     __syncthreads();
+    PHASE(2);  // scan 1 + reductions done
     const int bn = sm.box_n;
 
     // ---- points phase: per projection rasterise normals (arg-max key = last writer in (dist, index)
@@ -1101,11 +1151,12 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       }
     }
 
+    PHASE(3);  // points phase (3 projections) done
     // ---- shadow phase (15 channels): HandSet::calculateShadow, deterministic variant
     if (C == 15) {
       const int K = P.K;
       const int bmd = P.bm_dim;
-      const int bm_words = (bmd * bmd * bmd + 31) / 32;
+      const int bm_words = 2 * bmd * bmd;  // rows of 64 bits along x (bm_dim <= 64)
       const double gmax = qtab[GPDB_QTAB_SIZE - 1];
       const double voxel = GPDB_SHADOW_VOXEL;
       if (tid == 0) {
@@ -1141,6 +1192,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       }
       for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
       __syncthreads();
+      PHASE(4);  // shadow setup done
       const int o0 = sm.bm_org[0], o1 = sm.bm_org[1], o2 = sm.bm_org[2];
       const int d0 = sm.bm_dims[0], d1 = sm.bm_dims[1], d2 = sm.bm_dims[2];
       const double mxu = 1.0 / 32767.0;
@@ -1164,6 +1216,14 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       const double wm = 0.0105;
       const double bx_lo[3] = {h.bottom - wm, h.center - P.vol_w / 2.0 - wm, -P.vol_h - wm};
       const double bx_hi[3] = {h.bottom + P.vol_d + wm, h.center + P.vol_w / 2.0 + wm, P.vol_h + wm};
+      // float32 copies for the pre-test: frame, sample, box widened by jitter (gmax 0.0009 sqrt 3) + 2e-5 slack
+      float fR[9];
+#pragma unroll
+      for (int e = 0; e < 9; e++) fR[e] = (float)h.frame[e];
+      const float fsx = (float)h.sample[0], fsy = (float)h.sample[1], fsz = (float)h.sample[2];
+      const float jm = (float)(gmax * voxel * 0.3 * 1.7320508075688772 + 2e-5);
+      const float fbx_lo[3] = {(float)h.bottom - jm, (float)(h.center - P.vol_w / 2.0) - jm, (float)(-P.vol_h) - jm};
+      const float fbx_hi[3] = {(float)(h.bottom + P.vol_d) + jm, (float)(h.center + P.vol_w / 2.0) + jm, (float)P.vol_h + jm};
       auto cast_draw = [&](double px, double py, double pz, unsigned seed, int k, unsigned *bm) {
         const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
         double u = (double)((seed >> 16) & 0x7FFFu) * mxu;
@@ -1172,9 +1232,17 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         int v2 = (int)((pz + u * s2) * P.vox_mult);
         int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
         if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) return;
-        double x, y, z;
-        if (!voxel_point_in_box(v0, v1, v2, x, y, z)) return;
-        int bit = (b2 * d1 + b1) * d0 + b0;
+        // conservative float32 pre-test of the voxel's lattice point against the image box widened by the largest
+        // jitter (+ rounding slack): rejects most out-of-box voxels for ~20 instructions. The exact float64 test
+        // (jitter + frame transform, the oracle's operation order) runs once per UNIQUE surviving voxel below.
+        {
+          const float wx = fmaf((float)v0, 0.003f, -fsx), wy = fmaf((float)v1, 0.003f, -fsy), wz = fmaf((float)v2, 0.003f, -fsz);
+          const float hx = fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz));
+          const float hy = fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz));
+          const float hz = fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz));
+          if (hx < fbx_lo[0] || hx > fbx_hi[0] || hy < fbx_lo[1] || hy > fbx_hi[1] || hz < fbx_lo[2] || hz > fbx_hi[2]) return;
+        }
+        int bit = ((b2 * d1 + b1) << 6) + b0;
         atomicOr(bm + (bit >> 5), 1u << (bit & 31));
       };
       for (int k = 0; k < K; k++) {
@@ -1182,13 +1250,11 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         unsigned *bm = bitmap + (size_t)k * bm_words;
         __syncthreads();
         if (tid == 0) sm.wl_n = 0;
-        for (int row0 = 0; row0 < sr.nrows; row0 += NT_IMG) {
-          __syncthreads();
-          int total = seg_batch<NT_IMG>(P, cl.cell_start, sr, row0, sm.seg);
-          for (int c = tid; c < total; c += NT_IMG) {
-            float4 p = __ldg(cl.pts4 + seg_lookup<NT_IMG>(sm.seg, c));
-            float d = l2_simple(q, p.x, p.y, p.z);
-            if (!(d < P.r2_img)) continue;
+        __syncthreads();
+        scan_rows<NT_IMG>(P, cl, sr, [&](bool in, const float4 &p) {
+          if (!in) return;
+          float d = l2_simple(q, p.x, p.y, p.z);
+          if (!(d < P.r2_img)) return;
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
             // exact cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame) widened
             // by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG value falls
@@ -1211,7 +1277,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
                 }
               }
             }
-            if (!hit || tmin > tmax) continue;
+            if (!hit || tmin > tmax) return;
             const int r0 = max((int)floor(tmin * 32767.0) - 1, 0), r1 = min((int)ceil(tmax * 32767.0) + 1, 32767);
             unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
             int pos = atomicAdd(&sm.wl_n, 1);
@@ -1225,8 +1291,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
                 if (r >= r0 && r <= r1) cast_draw(px, py, pz, seed, k, bm);
               }
             }
-          }
-        }
+                  });
         __syncthreads();
         const int nw = min(sm.wl_n, WL_CAP);
         const int nsp = P.nsp;
@@ -1241,6 +1306,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         }
       }
       __syncthreads();
+      PHASE(5);  // S1 (casting) done
       // set intersection over the cameras that see the neighbourhood, starting from camera 0's
       // set even when it is empty (hand_set.cpp:153-176)
       if (K > 1) {
@@ -1253,28 +1319,58 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       }
       for (int k = tid; k < 3 * SS; k += NT_IMG) tileA[k] = 0ull;
       __syncthreads();
-      const int nbits = d0 * d1 * d2;
-      for (int wd = tid; wd * 32 < nbits; wd += NT_IMG) {
-        unsigned bits = bitmap[wd];
+      // compact the set bits into a list (behind bitmap 0, in the dead box-list region) so that the per-voxel work
+      // is spread evenly: shadow voxels are spatially clustered, a thread-per-word loop would be badly unbalanced
+      const int nbits = 64 * d1 * d2;
+      unsigned *blist = bitmap + bm_words;
+      const int BL_CAP = (img_off - 3 * SS * 8) / 4 - bm_words;
+      auto eval_voxel = [&](unsigned packed) {  // b0 | b1 << 8 | b2 << 16
+        int b0 = packed & 255, b1 = (packed >> 8) & 255, b2 = packed >> 16;
+        double x, y, z;
+        if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) return;
+        double u[3];
+        int cellv[3];
+        unit_axis(x, h.bottom, P.vol_d, inv_d, S, u[0], cellv[0]);
+        unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u[1], cellv[1]);
+        unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u[2], cellv[2]);
+#pragma unroll
+        for (int pj = 0; pj < 3; pj++) {
+          const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
+          int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
+          atomicAdd(tileA + (size_t)pj * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
+        }
+      };
+      if (tid == 0) sm.wl_n = 0;
+      __syncthreads();
+      for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
+        const int wd = wd0 + tid;
+        unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
+        int cntb = __popc(bits);
+        int incl = cntb;  // warp-aggregated reservation of list slots
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
+        if (lane == 31 && total) base = atomicAdd(&sm.wl_n, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cntb;
+        const int rowi = wd >> 1;  // (b2 * d1 + b1)
+        const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
         while (bits) {
           int bi = __ffs(bits) - 1;
           bits &= bits - 1;
-          int bit = wd * 32 + bi;
-          int b0 = bit % d0, b1 = (bit / d0) % d1, b2 = bit / (d0 * d1);
-          double x, y, z;
-          if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) continue;
-          double u[3];
-          unit_coords(P, h, x, y, z, u[0], u[1], u[2]);
-          int cellv[3] = {unit_cell(u[0], S), unit_cell(u[1], S), unit_cell(u[2], S)};
-#pragma unroll
-          for (int pj = 0; pj < 3; pj++) {
-            const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
-            int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
-            atomicAdd(tileA + (size_t)pj * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
-          }
+          if (pos < BL_CAP) blist[pos] = hi | (unsigned)bi;
+          else eval_voxel(hi | (unsigned)bi);  // list full: evaluate in place
+          pos++;
         }
       }
       __syncthreads();
+      const int nset = min(sm.wl_n, BL_CAP);
+      for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i]);
+      __syncthreads();
+      PHASE(6);  // S2 bitmap pass done
       // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
       for (int pj = 0; pj < 3; pj++) {
         unsigned long long *tile = tileA + (size_t)pj * SS;
@@ -1310,11 +1406,13 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     }
     // ---- flush the staged image with coalesced 16-byte stores
     __syncthreads();
+    PHASE(7);  // shadow images done
     {
       const int nb = SS * C, nv = nb >> 4;
       for (int v = tid; v < nv; v += NT_IMG) reinterpret_cast<uint4 *>(gout)[v] = reinterpret_cast<const uint4 *>(simg)[v];
       for (int v = (nv << 4) + tid; v < nb; v += NT_IMG) gout[v] = simg[v];
     }
+    PHASE(8);  // flush done
   }
 }
 
@@ -1441,7 +1539,7 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
 static size_t images_smem_bytes(const DevParams &hp) {
   size_t tiles = (size_t)3 * 8 * hp.S * hp.S;
   size_t list = (size_t)BOX_CAP * (8 + 12 + 4 + 12);
-  size_t bm = (size_t)hp.K * (((size_t)hp.bm_dim * hp.bm_dim * hp.bm_dim + 31) / 32) * 4;
+  size_t bm = (size_t)hp.K * (2 * (size_t)hp.bm_dim * hp.bm_dim) * 4;
   size_t work = tiles + std::max(list, hp.C == 15 ? bm : (size_t)0);
   return (work + 15) / 16 * 16;
 }
@@ -1457,7 +1555,7 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images
   CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(nc, ctx->sm_count * 64);
   k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
-                                                (int)img_off);
+                                                (int)img_off, ctx->d_prof);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

@@ -19,7 +19,7 @@ EXPORTS = [
     "gpdb_params_default", "gpdb_create", "gpdb_destroy", "gpdb_last_error", "gpdb_load_weights_dir",
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
     "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
-    "gpdb_set_stream",
+    "gpdb_set_stream", "gpdb_debug_phase_cycles",
 ]
 
 
@@ -57,6 +57,7 @@ def lib():
     L.gpdb_build_info.restype = C.c_char_p
     L.gpdb_detect_resident.argtypes = [vp, vp, C.c_int32, vp, vp, C.POINTER(abi.Result)]
     L.gpdb_set_stream.argtypes = [vp, vp]
+    L.gpdb_debug_phase_cycles.argtypes = [vp, C.c_int, vp]
     _LIB = L
     return L
 
@@ -179,6 +180,11 @@ class Context:
         logits = np.zeros((n, 2), np.float32)
         self._check(lib().gpdb_classify(self.h, _p(images), n, _p(scores), _p(logits)))
         return scores, logits
+
+    def phase_cycles(self, enable=1):
+        out = np.zeros(16, np.uint64)
+        self._check(lib().gpdb_debug_phase_cycles(self.h, enable, _p(out)))
+        return out
 
     def last_timings(self):
         ms = np.zeros(8)

@@ -219,6 +219,12 @@ void gpdb_free_result(gpdb_result *r);
  * ms[0] frames, ms[1] hand search + compaction, ms[2] images, ms[3] LeNet, ms[4] whole call,
  * ms[5] conv1+pool, ms[6] conv2+pool, ms[7] ip1+ip2. */
 int gpdb_last_timings(const gpdb_ctx *ctx, double ms_out[8]);
+/* Development aid: per-phase SM-cycle counters of the image kernel (thread 0 of every CTA, summed over CTAs).
+ * enable != 0 allocates / clears the counters, enable == 0 frees them; cycles_out (may be NULL) receives the
+ * counters accumulated so far: [2] ball scan, [3] point channels, [4] shadow setup, [5] shadow casting,
+ * [6] shadow bitmap pass, [7] shadow channels, [8] output flush. */
+int gpdb_debug_phase_cycles(gpdb_ctx *ctx, int enable, uint64_t cycles_out[16]);
+
 /* Version / build info string (arch, lenet implementation). */
 const char *gpdb_build_info(void);
 
