@@ -289,19 +289,27 @@ def main():
         }
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         kd = kernels[dom]
+        # measured DRAM traffic (ncu --set full capture, profiles/traffic.json: bytes per image / per sample) scaled to
+        # the units of one step, like `achieved` (which sums all launches of the kernel in the step)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            if tj:
+                traffic = tj["bytes_per_unit"] * (n if tj["unit"] == "sample" else ncand)
         except Exception:
             pass
         if kd["bound"] == "hbm":
             ach = kd["bytes"] / (kd["ms"] * 1e-3) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src}
+                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "per": "step: all launches of the kernel summed (algorithmic bytes, CUDA-event time, ncu DRAM bytes)",
+                    "algorithmic_bytes": kd["bytes"]}
         else:
             ach = kd["flops"] / (kd["ms"] * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": traffic, "peak_source": peak_src}
+                    "frac": ach / tf_peak, "traffic": traffic, "peak_source": peak_src,
+                    "per": "step: all launches of the kernel summed (algorithmic flops, CUDA-event time, ncu DRAM bytes)",
+                    "algorithmic_flops": kd["flops"]}
         per_kernel = {}
         for k, v in kernels.items():
             if v["bound"] == "hbm":
