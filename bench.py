@@ -163,6 +163,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (the version banner goes to stdout)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cloud, sidx_all = make_workload(n_gpus, args.samples)
