@@ -1,0 +1,235 @@
+// gpd.h — C++ host shims that keep the reference's class names, namespaces and call signatures for the hot path
+// and forward to the C-ABI of libgpd_b200.so (include/gpd_b200.h). Dependency-free (no PCL / Eigen / OpenCV): where
+// the reference passes Eigen / PCL / cv types these shims use plain std containers with the same memory layout
+// (3 x N column-major doubles, HWC uint8 images). See INTEGRATION.md for the drop-in bindings into upstream GPD.
+//
+// reference interfaces mirrored (paths relative to /root/reference):
+//   util::ConfigFile        include/gpd/util/config_file.h:60-140, src/gpd/util/config_file.cpp
+//   util::Cloud (subset)    include/gpd/util/cloud.h:300-366 (accessors the path reads), cloud.cpp:643-660 (file loading)
+//   candidate::HandGeometry include/gpd/candidate/hand_geometry.h, hand_geometry.cpp:25-30
+//   candidate::Hand         include/gpd/candidate/hand.h
+//   candidate::HandSet      include/gpd/candidate/hand_set.h (getHands / getIsValid / getSample / getFrame)
+//   candidate::HandSearch   include/gpd/candidate/hand_search.h:107-108
+//   descriptor::ImageGeometry / ImageGenerator   include/gpd/descriptor/image_generator.h:92-96
+//   net::Classifier         include/gpd/net/classifier.h:52-81
+//   GraspDetector           include/gpd/grasp_detector.h:66-226
+#ifndef GPD_B200_HOST_GPD_H_
+#define GPD_B200_HOST_GPD_H_
+
+#include <array>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "gpd_b200.h"
+
+namespace gpd {
+
+namespace util {
+
+// `key = value` per line, '#' comments, first occurrence of a key wins (config_file.cpp:6-61)
+class ConfigFile {
+ public:
+  explicit ConfigFile(const std::string &fName);
+  bool ExtractKeys();
+  bool keyExists(const std::string &key) const;
+  template <typename ValueType>
+  ValueType getValueOfKey(const std::string &key, ValueType const &defaultValue) const {
+    if (!keyExists(key)) return defaultValue;
+    std::istringstream istr(contents.find(key)->second);
+    ValueType v;
+    if (!(istr >> v)) return defaultValue;
+    return v;
+  }
+  std::string getValueOfKeyAsString(const std::string &key, const std::string &defaultValue) const;
+  std::vector<double> getValueOfKeyAsStdVectorDouble(const std::string &key, const std::string &defaultValue) const;
+  std::vector<int> getValueOfKeyAsStdVectorInt(const std::string &key, const std::string &defaultValue) const;
+
+ private:
+  std::map<std::string, std::string> contents;
+  std::string fName;
+};
+
+// The part of util::Cloud the hot path reads. Points are the *processed* cloud (already voxelised, with normals):
+// preprocessing (cloud.cpp:286-604) is outside the accelerated path.
+class Cloud {
+ public:
+  Cloud() {}
+  // ASCII / binary .pcd with fields x y z [normal_x normal_y normal_z]; view_points 3 x k column-major
+  Cloud(const std::string &filename, const std::vector<double> &view_points);
+  Cloud(const std::vector<float> &xyz, const std::vector<double> &normals, const std::vector<int> &camera_source,
+        const std::vector<double> &view_points);
+  bool loadPointCloudFromFile(const std::string &filename);
+  void setNormalsFromFile(const std::string &filename);  // CSV, one normal per row or 3 x N (cloud.cpp:607-641)
+  void setNormals(const std::vector<double> &normals) { normals_ = normals; }
+  void setSampleIndices(const std::vector<int> &idx) { sample_indices_ = idx; }
+  void subsample(int num_samples);  // uniform draw of sample indices (cloud.cpp:350-405), seeded rand()
+  const std::vector<float> &getPoints() const { return points_; }       // packed x,y,z
+  const std::vector<double> &getNormals() const { return normals_; }    // 3 x N column-major
+  const std::vector<int> &getCameraSource() const { return camera_source_; }  // k x N column-major
+  const std::vector<double> &getViewPoints() const { return view_points_; }   // 3 x k column-major
+  const std::vector<int> &getSampleIndices() const { return sample_indices_; }
+  size_t size() const { return points_.size() / 3; }
+  int numCameras() const { return (int)(view_points_.size() / 3); }
+
+ private:
+  std::vector<float> points_;
+  std::vector<double> normals_;
+  std::vector<int> camera_source_;
+  std::vector<double> view_points_;
+  std::vector<int> sample_indices_;
+};
+
+}  // namespace util
+
+namespace candidate {
+
+struct HandGeometry {
+  double finger_width_{0.01}, outer_diameter_{0.12}, depth_{0.06}, height_{0.02}, init_bite_{0.01};
+  HandGeometry() {}
+  explicit HandGeometry(const std::string &filepath);  // hand_geometry.cpp:20-31
+};
+
+class Hand {
+ public:
+  Hand() {}
+  explicit Hand(const gpdb_pose &p) : p_(p) {}
+  std::array<double, 3> getApproach() const { return {p_.frame[0], p_.frame[1], p_.frame[2]}; }
+  std::array<double, 3> getBinormal() const { return {p_.frame[3], p_.frame[4], p_.frame[5]}; }
+  std::array<double, 3> getAxis() const { return {p_.frame[6], p_.frame[7], p_.frame[8]}; }
+  std::array<double, 3> getPosition() const { return {p_.position[0], p_.position[1], p_.position[2]}; }
+  std::array<double, 3> getSample() const { return {p_.sample[0], p_.sample[1], p_.sample[2]}; }
+  const double *getFrame() const { return p_.frame; }  // 3 x 3 column-major (Hand::orientation_)
+  double getGraspWidth() const { return p_.width; }
+  double getScore() const { return p_.score; }
+  void setScore(double s) { p_.score = (float)s; }
+  bool isFullAntipodal() const { return p_.full_antipodal != 0; }
+  bool isHalfAntipodal() const { return p_.half_antipodal != 0; }
+  double getTop() const { return p_.top; }
+  double getBottom() const { return p_.bottom; }
+  double getCenter() const { return p_.center; }
+  int getFingerPlacementIndex() const { return p_.finger_idx; }
+  const gpdb_pose &raw() const { return p_; }
+  void print() const;
+
+ private:
+  gpdb_pose p_{};
+};
+
+class HandSet {
+ public:
+  const std::vector<std::unique_ptr<Hand>> &getHands() const { return hands_; }
+  std::vector<std::unique_ptr<Hand>> &getHands() { return hands_; }
+  const std::vector<bool> &getIsValid() const { return is_valid_; }
+  void setIsValid(const std::vector<bool> &v) { is_valid_ = v; }
+  std::array<double, 3> getSample() const { return sample_; }
+  const std::array<double, 9> &getFrame() const { return frame_; }  // normal | binormal | curvature axis
+  std::vector<std::unique_ptr<Hand>> hands_;
+  std::vector<bool> is_valid_;
+  std::array<double, 3> sample_{};
+  std::array<double, 9> frame_{};
+};
+
+class HandSearch {
+ public:
+  struct Parameters {  // hand_search.h:60-80
+    double nn_radius_frames_{0.01};
+    int num_orientations_{8}, num_samples_{1000}, num_threads_{1}, num_finger_placements_{10};
+    std::vector<int> hand_axes_{2};
+    bool deepen_hand_{true};
+    double friction_coeff_{20.0};
+    int min_viable_{6};
+    HandGeometry hand_geometry_;
+  };
+  explicit HandSearch(Parameters params);
+  ~HandSearch();
+  // HandSearch::searchHands (hand_search.cpp:24-64): one HandSet per sample with a local frame
+  std::vector<std::unique_ptr<HandSet>> searchHands(const util::Cloud &cloud_cam) const;
+  const Parameters &getParams() const { return params_; }
+
+ private:
+  Parameters params_;
+  gpdb_ctx *ctx_{nullptr};
+};
+
+}  // namespace candidate
+
+namespace descriptor {
+
+struct ImageGeometry {
+  double outer_diameter_{0.10}, depth_{0.06}, height_{0.02};
+  int size_{60}, num_channels_{15};
+  ImageGeometry() {}
+  explicit ImageGeometry(const std::string &filepath);  // image_geometry.cpp:19-29
+};
+
+// stand-in for cv::Mat(size, size, CV_8UC(channels)): continuous HWC uint8
+struct Image {
+  int rows{0}, cols{0}, channels{0};
+  std::vector<uint8_t> data;
+  bool isContinuous() const { return true; }
+};
+
+class ImageGenerator {
+ public:
+  ImageGenerator(const ImageGeometry &image_geometry, int num_threads, int num_orientations, bool is_plotting,
+                 bool remove_plane);
+  ~ImageGenerator();
+  // image_generator.cpp:17-70: images of the valid hands, in (hand set, hand) order; the hands are moved to hands_out
+  void createImages(const util::Cloud &cloud_cam, const std::vector<std::unique_ptr<candidate::HandSet>> &hand_set_list,
+                    std::vector<std::unique_ptr<Image>> &images_out,
+                    std::vector<std::unique_ptr<candidate::Hand>> &hands_out) const;
+
+ private:
+  ImageGeometry image_params_;
+  gpdb_ctx *ctx_{nullptr};
+};
+
+}  // namespace descriptor
+
+namespace net {
+
+class Classifier {
+ public:
+  enum class Device : uint8_t { eCPU = 0, eGPU = 1, eVPU = 2, eFPGA = 3 };
+  // classifier.cpp:46-62; `weights_file` is the .bin parameter directory EigenClassifier reads
+  static std::shared_ptr<Classifier> create(const std::string &model_file, const std::string &weights_file,
+                                            Device device = Device::eGPU, int batch_size = 1, int num_channels = 15);
+  virtual ~Classifier() {}
+  virtual std::vector<float> classifyImages(const std::vector<std::unique_ptr<descriptor::Image>> &image_list) = 0;
+  virtual int getBatchSize() const = 0;
+};
+
+}  // namespace net
+
+class GraspDetector {
+ public:
+  explicit GraspDetector(const std::string &config_filename);
+  ~GraspDetector();
+  // grasp_detector.cpp:192-328: candidates -> filter -> images -> classify (one gpdb_detect) -> select -> sort
+  std::vector<std::unique_ptr<candidate::Hand>> detectGrasps(const util::Cloud &cloud);
+  void preprocessPointCloud(util::Cloud &cloud);  // only the subsample step; the rest is outside the path
+  std::vector<std::unique_ptr<candidate::Hand>> selectGrasps(std::vector<std::unique_ptr<candidate::Hand>> &hands) const;
+  const gpdb_params &getParams() const { return params_; }
+  const candidate::HandSearch::Parameters &getHandSearchParameters() const { return hand_search_params_; }
+  int getNumSamples() const { return num_samples_; }
+  double last_ms_candidates{0}, last_ms_images{0}, last_ms_classify{0};
+
+ private:
+  gpdb_params params_{};
+  gpdb_ctx *ctx_{nullptr};
+  candidate::HandSearch::Parameters hand_search_params_;
+  int num_selected_{100}, num_samples_{1000};
+  bool cluster_grasps_{false};
+  bool has_classifier_{false};
+};
+
+// fills gpdb_params from the reference's cfg keys (grasp_detector.cpp:22-185); returns false if the file is missing
+bool paramsFromConfig(const std::string &config_filename, gpdb_params &p, std::string &weights_file, int &num_selected,
+                      int &num_samples, int &min_inliers);
+
+}  // namespace gpd
+
+#endif  // GPD_B200_HOST_GPD_H_

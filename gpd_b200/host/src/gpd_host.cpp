@@ -1,0 +1,547 @@
+// gpd_host.cpp — implementation of the C++ host shims (include/gpd/gpd.h) over the C-ABI of libgpd_b200.so.
+#include "gpd/gpd.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+namespace gpd {
+
+// ------------------------------------------------------------------------------------------------ util::ConfigFile
+namespace util {
+
+ConfigFile::ConfigFile(const std::string &fName) : fName(fName) {}
+
+bool ConfigFile::ExtractKeys() {
+  std::ifstream file(fName.c_str());
+  if (!file) {
+    std::cout << "Config file " + fName + " could not be found!\n";
+    return false;
+  }
+  std::string line;
+  size_t lineNo = 0;
+  while (std::getline(file, line)) {
+    lineNo++;
+    if (line.empty()) continue;
+    if (line.find('#') != line.npos) line.erase(line.find('#'));          // removeComment
+    if (line.find_first_not_of(" \t\r") == line.npos) continue;            // onlyWhitespace
+    size_t sep = line.find('=');
+    if (sep == line.npos) {
+      std::cout << "CFG: Couldn't find separator on line: " << lineNo << "\n";
+      continue;
+    }
+    std::string temp = line;
+    temp.erase(0, temp.find_first_not_of("\t "));
+    sep = temp.find('=');
+    std::string key = temp.substr(0, sep);
+    if (key.find_first_of("\t ") != key.npos) key.erase(key.find_first_of("\t "));
+    std::string value = temp.substr(sep + 1);
+    value.erase(0, value.find_first_not_of("\t "));
+    size_t last = value.find_last_not_of("\t \r");
+    value.erase(last == value.npos ? 0 : last + 1);
+    if (key.empty() || value.empty()) {
+      std::cout << "CFG: Bad format for line: " << lineNo << "\n";
+      continue;
+    }
+    if (!keyExists(key)) contents.insert(std::make_pair(key, value));
+    else std::cout << "CFG: Can only have unique key names!\n";
+  }
+  return true;
+}
+
+bool ConfigFile::keyExists(const std::string &key) const { return contents.find(key) != contents.end(); }
+
+std::string ConfigFile::getValueOfKeyAsString(const std::string &key, const std::string &defaultValue) const {
+  if (!keyExists(key)) return defaultValue;
+  return contents.find(key)->second;
+}
+
+std::vector<double> ConfigFile::getValueOfKeyAsStdVectorDouble(const std::string &key, const std::string &defaultValue) const {
+  std::stringstream ss(getValueOfKeyAsString(key, defaultValue));
+  std::vector<double> v;
+  double x;
+  while (ss >> x) v.push_back(x);
+  return v;
+}
+
+std::vector<int> ConfigFile::getValueOfKeyAsStdVectorInt(const std::string &key, const std::string &defaultValue) const {
+  std::vector<int> v;
+  for (double x : getValueOfKeyAsStdVectorDouble(key, defaultValue)) v.push_back((int)x);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ util::Cloud
+Cloud::Cloud(const std::string &filename, const std::vector<double> &view_points) : view_points_(view_points) {
+  if (view_points_.empty()) view_points_ = {0.0, 0.0, 0.0};
+  loadPointCloudFromFile(filename);
+  camera_source_.assign((size_t)numCameras() * size(), 0);
+  for (size_t i = 0; i < size(); i++) camera_source_[i * numCameras()] = 1;  // single view: all points seen by camera 0
+  if (numCameras() > 1) std::fill(camera_source_.begin(), camera_source_.end(), 1);
+}
+
+Cloud::Cloud(const std::vector<float> &xyz, const std::vector<double> &normals, const std::vector<int> &camera_source,
+             const std::vector<double> &view_points)
+    : points_(xyz), normals_(normals), camera_source_(camera_source), view_points_(view_points) {}
+
+// .pcd reader: header fields FIELDS/SIZE/TYPE/COUNT/POINTS/DATA (ascii | binary); NaN points are dropped
+// (Cloud::removeNans). Replaces pcl::io::loadPCDFile in cloud.cpp:643-660.
+bool Cloud::loadPointCloudFromFile(const std::string &filename) {
+  std::ifstream f(filename.c_str(), std::ios::binary);
+  if (!f) {
+    std::cout << "Couldn't read .pcd file: " << filename << "\n";
+    return false;
+  }
+  std::vector<std::string> fields, types;
+  std::vector<int> sizes, counts;
+  size_t npoints = 0;
+  std::string data_kind, line;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::istringstream ss(line);
+    std::string tag;
+    ss >> tag;
+    std::string tok;
+    if (tag == "FIELDS") while (ss >> tok) fields.push_back(tok);
+    else if (tag == "SIZE") while (ss >> tok) sizes.push_back(std::atoi(tok.c_str()));
+    else if (tag == "TYPE") while (ss >> tok) types.push_back(tok);
+    else if (tag == "COUNT") while (ss >> tok) counts.push_back(std::atoi(tok.c_str()));
+    else if (tag == "POINTS") ss >> npoints;
+    else if (tag == "DATA") { ss >> data_kind; break; }
+  }
+  if (counts.empty()) counts.assign(fields.size(), 1);
+  if (fields.empty() || sizes.size() != fields.size() || types.size() != fields.size()) {
+    std::cout << "Bad .pcd header: " << filename << "\n";
+    return false;
+  }
+  auto idx_of = [&](const char *n) { for (size_t i = 0; i < fields.size(); i++) if (fields[i] == n) return (int)i; return -1; };
+  const int ix = idx_of("x"), iy = idx_of("y"), iz = idx_of("z");
+  const int inx = idx_of("normal_x"), iny = idx_of("normal_y"), inz = idx_of("normal_z");
+  if (ix < 0 || iy < 0 || iz < 0) {
+    std::cout << "No x/y/z fields in: " << filename << "\n";
+    return false;
+  }
+  points_.clear();
+  normals_.clear();
+  std::vector<double> row(fields.size());
+  auto push = [&]() {
+    if (!std::isfinite(row[ix]) || !std::isfinite(row[iy]) || !std::isfinite(row[iz])) return;
+    points_.push_back((float)row[ix]); points_.push_back((float)row[iy]); points_.push_back((float)row[iz]);
+    if (inx >= 0 && iny >= 0 && inz >= 0) {  // PCL normals are float32
+      normals_.push_back((double)(float)row[inx]); normals_.push_back((double)(float)row[iny]); normals_.push_back((double)(float)row[inz]);
+    }
+  };
+  if (data_kind == "ascii") {
+    while (std::getline(f, line)) {
+      std::istringstream ss(line);
+      bool ok = true;
+      for (size_t i = 0; i < fields.size() && ok; i++) {
+        std::string tok;
+        for (int c = 0; c < counts[i]; c++) {
+          if (!(ss >> tok)) { ok = false; break; }
+          if (c == 0) row[i] = (tok == "nan" || tok == "NaN") ? NAN : std::atof(tok.c_str());
+        }
+      }
+      if (ok) push();
+    }
+  } else if (data_kind == "binary") {
+    size_t stride = 0;
+    std::vector<size_t> off(fields.size());
+    for (size_t i = 0; i < fields.size(); i++) { off[i] = stride; stride += (size_t)sizes[i] * counts[i]; }
+    std::vector<char> buf(stride);
+    for (size_t p = 0; p < npoints && f.read(buf.data(), stride); p++) {
+      for (size_t i = 0; i < fields.size(); i++) {
+        const char *src = buf.data() + off[i];
+        if (types[i] == "F" && sizes[i] == 4) { float v; std::memcpy(&v, src, 4); row[i] = v; }
+        else if (types[i] == "F" && sizes[i] == 8) { double v; std::memcpy(&v, src, 8); row[i] = v; }
+        else if (sizes[i] == 4) { int32_t v; std::memcpy(&v, src, 4); row[i] = v; }
+        else if (sizes[i] == 2) { int16_t v; std::memcpy(&v, src, 2); row[i] = v; }
+        else { row[i] = (double)(unsigned char)src[0]; }
+      }
+      push();
+    }
+  } else {
+    std::cout << "Unsupported .pcd DATA kind '" << data_kind << "' (ascii and binary are supported)\n";
+    return false;
+  }
+  printf("Loaded point cloud with %zu points\n", size());
+  return true;
+}
+
+void Cloud::setNormalsFromFile(const std::string &filename) {
+  std::ifstream f(filename.c_str());
+  std::vector<std::vector<double>> rows;
+  std::string line;
+  while (std::getline(f, line)) {
+    for (char &c : line) if (c == ',') c = ' ';
+    std::istringstream ss(line);
+    std::vector<double> r;
+    double v;
+    while (ss >> v) r.push_back(v);
+    if (!r.empty()) rows.push_back(r);
+  }
+  const size_t n = size();
+  normals_.assign(3 * n, 0.0);
+  if (rows.size() == 3 && rows[0].size() == n) {  // 3 x N
+    for (size_t i = 0; i < n; i++) for (int r = 0; r < 3; r++) normals_[3 * i + r] = rows[r][i];
+  } else if (rows.size() == n && rows[0].size() >= 3) {  // N x 3
+    for (size_t i = 0; i < n; i++) for (int r = 0; r < 3; r++) normals_[3 * i + r] = rows[i][r];
+  } else {
+    std::cout << "ERROR: normals file does not match the cloud (" << rows.size() << " rows for " << n << " points)\n";
+    normals_.clear();
+  }
+}
+
+void Cloud::subsample(int num_samples) {
+  const int n = (int)size();
+  sample_indices_.clear();
+  if (num_samples <= 0 || n == 0) return;
+  if (num_samples >= n) {  // pcl::RandomSample returns every index (cloud.cpp:364-370)
+    for (int i = 0; i < n; i++) sample_indices_.push_back(i);
+    return;
+  }
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; i++) perm[i] = i;
+  unsigned s = 42u;
+  for (int i = 0; i < num_samples; i++) {  // partial Fisher-Yates with a fixed-seed LCG
+    s = s * 1664525u + 1013904223u;
+    int j = i + (int)(s % (unsigned)(n - i));
+    std::swap(perm[i], perm[j]);
+  }
+  sample_indices_.assign(perm.begin(), perm.begin() + num_samples);
+}
+
+}  // namespace util
+
+// ------------------------------------------------------------------------------------------------ geometry cfg
+namespace candidate {
+HandGeometry::HandGeometry(const std::string &filepath) {
+  util::ConfigFile c(filepath);
+  c.ExtractKeys();
+  finger_width_ = c.getValueOfKey<double>("finger_width", 0.01);
+  outer_diameter_ = c.getValueOfKey<double>("hand_outer_diameter", 0.12);
+  depth_ = c.getValueOfKey<double>("hand_depth", 0.06);
+  height_ = c.getValueOfKey<double>("hand_height", 0.02);
+  init_bite_ = c.getValueOfKey<double>("init_bite", 0.01);
+}
+void Hand::print() const {
+  auto v = [](const std::array<double, 3> &a) { printf("%g %g %g\n", a[0], a[1], a[2]); };
+  printf("position: "); v(getPosition());
+  printf("approach: "); v(getApproach());
+  printf("binormal: "); v(getBinormal());
+  printf("axis: "); v(getAxis());
+  printf("score: %g\nfull-antipodal: %d\nhalf-antipodal: %d\nclosing box:\n bottom: %g\n top: %g\n center: %g\n", getScore(),
+         (int)isFullAntipodal(), (int)isHalfAntipodal(), getBottom(), getTop(), getCenter());
+}
+}  // namespace candidate
+namespace descriptor {
+ImageGeometry::ImageGeometry(const std::string &filepath) {
+  util::ConfigFile c(filepath);
+  c.ExtractKeys();
+  outer_diameter_ = c.getValueOfKey<double>("volume_width", 0.10);
+  depth_ = c.getValueOfKey<double>("volume_depth", 0.06);
+  height_ = c.getValueOfKey<double>("volume_height", 0.02);
+  size_ = c.getValueOfKey<int>("image_size", 60);
+  num_channels_ = c.getValueOfKey<int>("image_num_channels", 15);
+}
+}  // namespace descriptor
+
+// ------------------------------------------------------------------------------------------------ helpers
+static void fill_hand_search(gpdb_params &p, const candidate::HandSearch::Parameters &hs) {
+  p.finger_width = hs.hand_geometry_.finger_width_;
+  p.hand_outer_diameter = hs.hand_geometry_.outer_diameter_;
+  p.hand_depth = hs.hand_geometry_.depth_;
+  p.hand_height = hs.hand_geometry_.height_;
+  p.init_bite = hs.hand_geometry_.init_bite_;
+  p.nn_radius = hs.nn_radius_frames_;
+  p.num_orientations = hs.num_orientations_;
+  p.num_finger_placements = hs.num_finger_placements_;
+  p.num_hand_axes = (int32_t)std::min<size_t>(hs.hand_axes_.size(), GPDB_MAX_HAND_AXES);
+  for (int i = 0; i < p.num_hand_axes; i++) p.hand_axes[i] = hs.hand_axes_[i];
+  p.deepen_hand = hs.deepen_hand_;
+  p.friction_coeff = hs.friction_coeff_;
+  p.min_viable = hs.min_viable_;
+}
+static void fill_image_geometry(gpdb_params &p, const descriptor::ImageGeometry &g) {
+  p.volume_width = g.outer_diameter_;
+  p.volume_depth = g.depth_;
+  p.volume_height = g.height_;
+  p.image_size = g.size_;
+  p.image_num_channels = g.num_channels_;
+}
+static gpdb_ctx *make_ctx(const gpdb_params &p) {
+  gpdb_ctx *ctx = nullptr;
+  if (gpdb_create(&p, &ctx) != GPDB_OK) {
+    printf("ERROR: %s\n", gpdb_last_error(nullptr));
+    return nullptr;
+  }
+  return ctx;
+}
+static int upload_cloud(gpdb_ctx *ctx, const util::Cloud &cloud) {
+  if (cloud.getNormals().size() != 3 * cloud.size()) {
+    printf("ERROR: the cloud has no surface normals (normal estimation is outside the accelerated path)\n");
+    return GPDB_ERR_INVALID;
+  }
+  return gpdb_set_cloud(ctx, cloud.getPoints().data(), cloud.getNormals().data(),
+                        cloud.getCameraSource().empty() ? nullptr : cloud.getCameraSource().data(), (int)cloud.size(),
+                        cloud.getViewPoints().data(), cloud.numCameras());
+}
+
+bool paramsFromConfig(const std::string &config_filename, gpdb_params &p, std::string &weights_file, int &num_selected,
+                      int &num_samples, int &min_inliers) {
+  util::ConfigFile config_file(config_filename);
+  if (!config_file.ExtractKeys()) return false;
+  gpdb_params_default(&p);
+  std::string hand_geometry_filename = config_file.getValueOfKeyAsString("hand_geometry_filename", "");
+  if (hand_geometry_filename == "0" || hand_geometry_filename.empty()) hand_geometry_filename = config_filename;
+  std::string image_geometry_filename = config_file.getValueOfKeyAsString("image_geometry_filename", "");
+  if (image_geometry_filename == "0" || image_geometry_filename.empty()) image_geometry_filename = config_filename;
+  candidate::HandSearch::Parameters hs;
+  hs.hand_geometry_ = candidate::HandGeometry(hand_geometry_filename);
+  hs.nn_radius_frames_ = config_file.getValueOfKey<double>("nn_radius", 0.01);
+  hs.num_samples_ = config_file.getValueOfKey<int>("num_samples", 1000);
+  hs.num_threads_ = config_file.getValueOfKey<int>("num_threads", 1);
+  hs.num_orientations_ = config_file.getValueOfKey<int>("num_orientations", 8);
+  hs.num_finger_placements_ = config_file.getValueOfKey<int>("num_finger_placements", 10);
+  hs.deepen_hand_ = config_file.getValueOfKey<bool>("deepen_hand", true);
+  hs.hand_axes_ = config_file.getValueOfKeyAsStdVectorInt("hand_axes", "2");
+  hs.friction_coeff_ = config_file.getValueOfKey<double>("friction_coeff", 20.0);
+  hs.min_viable_ = config_file.getValueOfKey<int>("min_viable", 6);
+  fill_hand_search(p, hs);
+  fill_image_geometry(p, descriptor::ImageGeometry(image_geometry_filename));
+  weights_file = config_file.getValueOfKeyAsString("weights_file", "");
+  p.device = 0;  // the cfg `device` key selects the reference's CPU/GPU/VPU backend; here: CUDA device 0
+  p.batch_size = 0;
+  std::vector<double> ws = config_file.getValueOfKeyAsStdVectorDouble("workspace_grasps", "-1 1 -1 1 -1 1");
+  for (size_t i = 0; i < 6 && i < ws.size(); i++) p.workspace_grasps[i] = ws[i];
+  p.min_aperture = config_file.getValueOfKey<double>("min_aperture", 0.0);
+  p.max_aperture = config_file.getValueOfKey<double>("max_aperture", 0.085);
+  p.filter_approach_direction = config_file.getValueOfKey<bool>("filter_approach_direction", false);
+  std::vector<double> dir = config_file.getValueOfKeyAsStdVectorDouble("direction", "1 0 0");
+  for (size_t i = 0; i < 3 && i < dir.size(); i++) p.direction[i] = dir[i];
+  p.thresh_rad = config_file.getValueOfKey<double>("thresh_rad", 2.3);
+  min_inliers = config_file.getValueOfKey<int>("min_inliers", 1);
+  num_selected = config_file.getValueOfKey<int>("num_selected", 100);
+  num_samples = hs.num_samples_;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ HandSearch
+namespace candidate {
+HandSearch::HandSearch(Parameters params) : params_(params) {
+  gpdb_params p;
+  gpdb_params_default(&p);
+  fill_hand_search(p, params_);
+  // HandSearch::searchHands does not filter (the workspace / aperture filters belong to GraspDetector): open them
+  p.min_aperture = -1e300;
+  p.max_aperture = 1e300;
+  for (int i = 0; i < 3; i++) {
+    p.workspace_grasps[2 * i] = -1e300;
+    p.workspace_grasps[2 * i + 1] = 1e300;
+  }
+  ctx_ = make_ctx(p);
+}
+HandSearch::~HandSearch() { gpdb_destroy(ctx_); }
+
+std::vector<std::unique_ptr<HandSet>> HandSearch::searchHands(const util::Cloud &cloud_cam) const {
+  std::vector<std::unique_ptr<HandSet>> out;
+  const std::vector<int> &idx = cloud_cam.getSampleIndices();
+  if (!ctx_ || idx.empty()) {
+    std::cout << "Error: No samples or no indices!\n";
+    return out;
+  }
+  if (upload_cloud(ctx_, cloud_cam) != GPDB_OK) return out;
+  gpdb_result r;
+  if (gpdb_hand_search(ctx_, idx.data(), (int)idx.size(), &r) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return out;
+  }
+  const int P = r.poses_per_sample;
+  int c = 0;
+  for (int i = 0; i < r.n_samples; i++) {
+    if (!r.frame_valid[i]) continue;  // frames without neighbours are dropped (frame_estimator.cpp:24-29)
+    auto hs = std::make_unique<HandSet>();
+    for (int k = 0; k < 9; k++) hs->frame_[k] = r.frames[9 * (size_t)i + k];
+    hs->hands_.resize(P);
+    hs->is_valid_.assign(P, false);
+    for (int j = 0; j < P; j++) {
+      const uint8_t fl = r.pose_flags[(size_t)i * P + j];
+      hs->is_valid_[j] = (fl & GPDB_POSE_VALID) != 0;
+      if ((fl & 3) == 3) {
+        hs->hands_[j] = std::make_unique<Hand>(r.candidates[c]);
+        for (int k = 0; k < 3; k++) hs->sample_[k] = r.candidates[c].sample[k];
+        c++;
+      } else {
+        hs->hands_[j] = std::make_unique<Hand>();  // invalid pose: no record (the reference keeps a stale pre-deepen box)
+      }
+    }
+    out.push_back(std::move(hs));
+  }
+  gpdb_free_result(&r);
+  printf("Found %d hand sets\n", (int)out.size());
+  return out;
+}
+}  // namespace candidate
+
+// ------------------------------------------------------------------------------------------------ ImageGenerator
+namespace descriptor {
+ImageGenerator::ImageGenerator(const ImageGeometry &image_geometry, int, int, bool, bool) : image_params_(image_geometry) {
+  gpdb_params p;
+  gpdb_params_default(&p);
+  fill_image_geometry(p, image_params_);
+  ctx_ = make_ctx(p);
+}
+ImageGenerator::~ImageGenerator() { gpdb_destroy(ctx_); }
+
+void ImageGenerator::createImages(const util::Cloud &cloud_cam,
+                                  const std::vector<std::unique_ptr<candidate::HandSet>> &hand_set_list,
+                                  std::vector<std::unique_ptr<Image>> &images_out,
+                                  std::vector<std::unique_ptr<candidate::Hand>> &hands_out) const {
+  if (!ctx_ || upload_cloud(ctx_, cloud_cam) != GPDB_OK) return;
+  std::vector<gpdb_pose> poses;
+  for (const auto &hs : hand_set_list)
+    for (size_t j = 0; j < hs->getHands().size(); j++)
+      if (hs->getIsValid()[j]) poses.push_back(hs->getHands()[j]->raw());
+  const size_t isz = (size_t)image_params_.size_ * image_params_.size_ * image_params_.num_channels_;
+  std::vector<uint8_t> buf(isz * poses.size());
+  if (gpdb_images(ctx_, poses.data(), (int)poses.size(), buf.data()) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return;
+  }
+  size_t k = 0;
+  for (const auto &hs : hand_set_list)
+    for (size_t j = 0; j < hs->getHands().size(); j++)
+      if (hs->getIsValid()[j]) {
+        auto im = std::make_unique<Image>();
+        im->rows = im->cols = image_params_.size_;
+        im->channels = image_params_.num_channels_;
+        im->data.assign(buf.begin() + isz * k, buf.begin() + isz * (k + 1));
+        images_out.push_back(std::move(im));
+        hands_out.push_back(std::move(const_cast<std::unique_ptr<candidate::Hand> &>(hs->getHands()[j])));
+        k++;
+      }
+  printf("Created %zu images\n", images_out.size());
+}
+}  // namespace descriptor
+
+// ------------------------------------------------------------------------------------------------ Classifier
+namespace net {
+namespace {
+class CudaClassifier : public Classifier {
+ public:
+  CudaClassifier(const std::string &weights_file, int batch_size, int num_channels) : batch_size_(batch_size) {
+    gpdb_params p;
+    gpdb_params_default(&p);
+    p.image_num_channels = num_channels;
+    p.batch_size = batch_size > 1 ? batch_size : 0;
+    ctx_ = make_ctx(p);
+    if (ctx_ && gpdb_load_weights_dir(ctx_, weights_file.c_str()) != GPDB_OK) printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    isz_ = (size_t)p.image_size * p.image_size * num_channels;
+  }
+  ~CudaClassifier() override { gpdb_destroy(ctx_); }
+  std::vector<float> classifyImages(const std::vector<std::unique_ptr<descriptor::Image>> &image_list) override {
+    std::vector<float> predictions(image_list.size(), 0.0f);
+    if (!ctx_ || image_list.empty()) return predictions;
+    std::vector<uint8_t> packed(isz_ * image_list.size(), 0);
+    for (size_t i = 0; i < image_list.size(); i++)
+      if (image_list[i]->isContinuous() && image_list[i]->data.size() == isz_)
+        std::memcpy(&packed[i * isz_], image_list[i]->data.data(), isz_);
+    if (gpdb_classify(ctx_, packed.data(), (int)image_list.size(), predictions.data(), nullptr) < 0)
+      printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return predictions;
+  }
+  int getBatchSize() const override { return batch_size_; }
+
+ private:
+  gpdb_ctx *ctx_{nullptr};
+  int batch_size_;
+  size_t isz_{0};
+};
+}  // namespace
+std::shared_ptr<Classifier> Classifier::create(const std::string &, const std::string &weights_file, Device, int batch_size,
+                                               int num_channels) {
+  return std::make_shared<CudaClassifier>(weights_file, batch_size, num_channels);
+}
+}  // namespace net
+
+// ------------------------------------------------------------------------------------------------ GraspDetector
+GraspDetector::GraspDetector(const std::string &config_filename) {
+  std::string weights_file;
+  int min_inliers = 0;
+  if (!paramsFromConfig(config_filename, params_, weights_file, num_selected_, num_samples_, min_inliers)) return;
+  cluster_grasps_ = min_inliers > 0;
+  ctx_ = make_ctx(params_);
+  if (ctx_ && !weights_file.empty()) {
+    if (gpdb_load_weights_dir(ctx_, weights_file.c_str()) == GPDB_OK) has_classifier_ = true;
+    else printf("ERROR: %s\n", gpdb_last_error(ctx_));
+  }
+  printf("============ CLASSIFIER ======================\nweights_file: %s\n==============================================\n",
+         weights_file.c_str());
+}
+GraspDetector::~GraspDetector() { gpdb_destroy(ctx_); }
+
+void GraspDetector::preprocessPointCloud(util::Cloud &cloud) {
+  // removeNans happens at load time; workspace filtering, voxelisation and normal estimation are outside the
+  // accelerated path (candidates_generator.cpp:14-37): the cloud must arrive processed. Only the sampling step:
+  if (cloud.getSampleIndices().empty()) cloud.subsample(num_samples_);
+}
+
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::selectGrasps(
+    std::vector<std::unique_ptr<candidate::Hand>> &hands) const {
+  printf("Selecting the %d highest scoring grasps ...\n", num_selected_);
+  int middle = std::min((int)hands.size(), num_selected_);
+  std::partial_sort(hands.begin(), hands.begin() + middle, hands.end(),
+                    [](const std::unique_ptr<candidate::Hand> &a, const std::unique_ptr<candidate::Hand> &b) {
+                      return a->getScore() > b->getScore();
+                    });
+  std::vector<std::unique_ptr<candidate::Hand>> out;
+  for (int i = 0; i < middle; i++) out.push_back(std::move(hands[i]));
+  return out;
+}
+
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const util::Cloud &cloud) {
+  std::vector<std::unique_ptr<candidate::Hand>> hands_out;
+  if (cloud.size() == 0) {
+    printf("ERROR: Point cloud is empty!");
+    return hands_out;
+  }
+  if (!ctx_ || !has_classifier_) {
+    printf("ERROR: detector not initialised (%s)\n", ctx_ ? "no classifier weights" : gpdb_last_error(nullptr));
+    return hands_out;
+  }
+  if (upload_cloud(ctx_, cloud) != GPDB_OK) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return hands_out;
+  }
+  const std::vector<int> &idx = cloud.getSampleIndices();
+  gpdb_result r;
+  int n = gpdb_detect(ctx_, idx.data(), (int)idx.size(), &r);
+  if (n < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return hands_out;
+  }
+  printf("Generated %d hand sets.\n", r.n_samples);
+  printf("Number of grasp candidates within workspace and gripper width: %d\n", n);
+  std::vector<std::unique_ptr<candidate::Hand>> hands;
+  for (int i = 0; i < n; i++) hands.push_back(std::make_unique<candidate::Hand>(r.candidates[i]));
+  last_ms_candidates = r.ms_candidates;
+  last_ms_images = r.ms_images;
+  last_ms_classify = r.ms_classify;
+  gpdb_free_result(&r);
+  hands = selectGrasps(hands);
+  if (cluster_grasps_) printf("(clustering requested by min_inliers > 0 is outside the accelerated path: skipped)\n");
+  std::sort(hands.begin(), hands.end(), [](const std::unique_ptr<candidate::Hand> &a, const std::unique_ptr<candidate::Hand> &b) {
+    return a->getScore() > b->getScore();
+  });
+  printf("======== Selected grasps ========\n");
+  for (size_t i = 0; i < hands.size(); i++) std::cout << "Grasp " << i << ": " << hands[i]->getScore() << "\n";
+  printf("======== RUNTIMES (device) ========\n 1. Candidate generation: %3.4fs\n 2. Descriptor extraction: %3.4fs\n"
+         " 3. Classification: %3.4fs\n==========\n",
+         last_ms_candidates * 1e-3, last_ms_images * 1e-3, last_ms_classify * 1e-3);
+  return hands;
+}
+
+}  // namespace gpd

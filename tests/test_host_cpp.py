@@ -1,0 +1,95 @@
+"""C++ host shims (gpd_b200/host: the reference's class names over the C-ABI) and the detect_grasps command line.
+CPU: cfg and PCD parsing (the reference's caller-side formats). GPU: the whole CLI against the ctypes path."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from gpd_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "gpd_b200", "host")
+CLI = os.path.join(HOST, "detect_grasps")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    subprocess.check_call(["make", "-C", HOST, "-s"], env={**os.environ, "CXX": "g++"})
+    return CLI
+
+
+def write_pcd(path, xyz, normals=None, binary=False):
+    n = len(xyz)
+    fields = "x y z" + (" normal_x normal_y normal_z" if normals is not None else "")
+    k = 6 if normals is not None else 3
+    hdr = (f"# .PCD v.7 - Point Cloud Data file format\nVERSION .7\nFIELDS {fields}\nSIZE {' '.join(['4'] * k)}\n"
+           f"TYPE {' '.join(['F'] * k)}\nCOUNT {' '.join(['1'] * k)}\nWIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\n"
+           f"DATA {'binary' if binary else 'ascii'}\n")
+    rows = np.hstack([xyz, normals]).astype(np.float32) if normals is not None else np.asarray(xyz, np.float32)
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if binary:
+            f.write(rows.tobytes())
+        else:
+            for r in rows:
+                f.write((" ".join(repr(float(v)) for v in r) + "\n").encode())
+
+
+def test_cfg_and_pcd_parsing(cli, tmp_path):
+    (tmp_path / "hand.cfg").write_text("# hand geometry\nfinger_width = 0.012   # comment\nhand_outer_diameter=0.13\nhand_depth = 0.07\n"
+                                       "hand_height\t=\t0.025\ninit_bite = 0.015\n")
+    (tmp_path / "main.cfg").write_text(
+        f"hand_geometry_filename = {tmp_path}/hand.cfg\nimage_geometry_filename = 0\n"
+        "volume_width = 0.11\nimage_num_channels = 12\n# defaults for the rest of the image geometry\n"
+        "weights_file = /some/where/params/\nnum_samples = 77\nnum_samples = 99\nnum_orientations = 6\nhand_axes = 0 2\n"
+        "deepen_hand = 0\nworkspace_grasps = -0.5 0.5 -0.4 0.4 0.1 1.1\nmax_aperture = 0.07\n"
+        "filter_approach_direction = 1\ndirection = 0 0 1\nthresh_rad = 1.5\nmin_inliers = 0\nnum_selected = 7\n"
+        "this line has no separator\n")
+    xyz = np.array([[0.1, 0.2, 0.3], [np.nan, 0, 0], [1.5, -2.5, 3.25]], np.float32)
+    nrm = np.array([[0, 0, 1], [0, 1, 0], [1, 0, 0]], np.float32)
+    for binary in (False, True):
+        write_pcd(tmp_path / "c.pcd", xyz, nrm, binary=binary)
+        out = subprocess.check_output([cli, "--dump-config", str(tmp_path / "main.cfg"), str(tmp_path / "c.pcd")]).decode()
+        d = json.loads(out[out.index("{"):out.rindex("}") + 1])
+        assert (d["finger_width"], d["hand_outer_diameter"], d["hand_depth"], d["hand_height"], d["init_bite"]) == (0.012, 0.13, 0.07, 0.025, 0.015)
+        assert (d["volume_width"], d["volume_depth"], d["volume_height"], d["image_size"], d["image_num_channels"]) == (0.11, 0.06, 0.02, 60, 12)
+        assert d["num_samples"] == 77  # first occurrence wins (config_file.cpp:44-50)
+        assert (d["num_orientations"], d["num_hand_axes"], d["hand_axes0"], d["deepen_hand"]) == (6, 2, 0, 0)
+        assert d["workspace_grasps"] == [-0.5, 0.5, -0.4, 0.4, 0.1, 1.1] and d["max_aperture"] == 0.07 and d["min_aperture"] == 0.0
+        assert d["filter_approach_direction"] == 1 and d["direction"] == [0, 0, 1] and d["thresh_rad"] == 1.5
+        assert d["weights_file"] == "/some/where/params/" and d["num_selected"] == 7 and d["min_inliers"] == 0
+        assert d["nn_radius"] == 0.01 and d["num_finger_placements"] == 10 and d["friction_coeff"] == 20 and d["min_viable"] == 6
+        assert d["cloud_points"] == 2 and d["cloud_has_normals"] == 1  # the NaN point is removed
+        assert np.allclose(d["first_point"], [0.1, 0.2, 0.3], atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_detect_grasps_cli_matches_library(cli, tmp_path):
+    from conftest import load_weights
+    from gpd_b200 import lib
+    k = scenes.krylon_cloud()
+    write_pcd(tmp_path / "krylon.pcd", k["xyz"], k["normals"], binary=True)
+    w, _ = load_weights(15)
+    os.makedirs(tmp_path / "params")
+    names = ["conv1_weights", "conv1_biases", "conv2_weights", "conv2_biases", "ip1_weights", "ip1_biases", "ip2_weights", "ip2_biases"]
+    for n, a in zip(names, w):
+        a.astype(np.float32).tofile(tmp_path / "params" / (n + ".bin"))
+    (tmp_path / "main.cfg").write_text(f"hand_geometry_filename = 0\nimage_geometry_filename = 0\nweights_file = {tmp_path}/params/\n"
+                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 10\nimage_num_channels = 15\n")
+    out = subprocess.check_output([cli, str(tmp_path / "main.cfg"), str(tmp_path / "krylon.pcd")]).decode()
+    res = [l for l in out.splitlines() if l.startswith("RESULT")][0]
+    n_grasps = int(res.split("n_grasps=")[1].split()[0])
+    best = float(res.split("best_score=")[1])
+    # num_samples >= N: every point is a sample (cloud.cpp:364-370)
+    p = lib.default_params(channels=15)
+    ctx = lib.Context(p)
+    ctx.set_weights(w)
+    ctx.set_cloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    r = ctx.detect(np.arange(len(k["xyz"]), dtype=np.int32))
+    assert n_grasps == 10
+    assert abs(best - r["candidates"]["score"].max()) <= 1e-3 * abs(best)
+    assert f"gripper width: {r['n_candidates']}" in out
+    ctx.close()
