@@ -431,7 +431,9 @@ __device__ __forceinline__ unsigned slot_mask(const DevParams &P, const double *
   return m;
 }
 
+constexpr int SURV_CAP = 1024;
 struct HandsSmem {
+  unsigned short surv[NT_HANDS / 32][SURV_CAP];  // per-warp closing-region member indices
   double fs[GPDB_MAX_SLOTS], fsw[GPDB_MAX_SLOTS];  // finger slot tables (copied from DevParams)
   int count;      // staged (slab) points
   int n_ball;     // all points of the r ball
@@ -648,16 +650,31 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
           center = 0.5 * (left + right);
           int cnt = 0;
           double mny = DBL_MAX, mxy = -DBL_MAX;
-          for (int a = lane; a < m; a += 32) {
-            float4 p = list[a];
-            double x, y, z;
-            to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
-            if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right) {
-              cnt++;
-              mny = fmin(mny, y);
-              mxy = fmax(mxy, y);
+          // the closing-region members (~10 % of the slab) are remembered per warp so that the two Antipodal passes
+          // below visit only them instead of re-transforming the whole slab
+          unsigned short *surv = S.surv[warp];
+          int nsurv = 0;
+          for (int a0 = 0; a0 < m; a0 += 32) {
+            const int a = a0 + lane;
+            bool inr = false;
+            if (a < m) {
+              float4 p = list[a];
+              double x, y, z;
+              to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+              if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right) {
+                inr = true;
+                cnt++;
+                mny = fmin(mny, y);
+                mxy = fmax(mxy, y);
+              }
             }
+            const unsigned mk = __ballot_sync(0xffffffffu, inr);
+            const int pos = nsurv + __popc(mk & ((1u << lane) - 1));
+            if (inr && pos < SURV_CAP) surv[pos] = (unsigned short)a;
+            nsurv += __popc(mk);
           }
+          const bool surv_ok = nsurv <= SURV_CAP && m <= 65535;
+          __syncwarp();
           const bool nb_in = npad > 0 && x0 > bottom && x0 < top && y0 > left && y0 < right;
           cnt = warp_sum(cnt) + (nb_in ? npad : 0);
           mny = warp_min(mny);
@@ -689,12 +706,21 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
                 rmaxx = fmax(rmaxx, x); rminx = fmin(rminx, x); rmaxz = fmax(rmaxz, z); rminz = fmin(rminz, z);
               }
             };
-            for (int a = lane; a < m; a += 32) {
-              float4 p = list[a];
-              double x, y, z;
-              to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
-              if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+            if (surv_ok) {
+              for (int sidx_ = lane; sidx_ < nsurv; sidx_ += 32) {
+                float4 p = list[surv[sidx_]];
+                double x, y, z;
+                to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
                 visitD(x, y, z, __float_as_int(p.w), 1);
+              }
+            } else {
+              for (int a = lane; a < m; a += 32) {
+                float4 p = list[a];
+                double x, y, z;
+                to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+                if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+                  visitD(x, y, z, __float_as_int(p.w), 1);
+              }
             }
             if (nb_in && lane == 0) visitD(x0, y0, z0, nb0, npad);
             cl_ = warp_sum(cl_);
@@ -716,12 +742,21 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
                 if (ldot > P.cosf && y < min_x && inw) nl += wgt;
                 if (rdot > P.cosf && y > max_x && inw) nr += wgt;
               };
-              for (int a = lane; a < m; a += 32) {
-                float4 p = list[a];
-                double x, y, z;
-                to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
-                if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+              if (surv_ok) {
+                for (int sidx_ = lane; sidx_ < nsurv; sidx_ += 32) {
+                  float4 p = list[surv[sidx_]];
+                  double x, y, z;
+                  to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
                   visitE(x, y, z, __float_as_int(p.w), 1);
+                }
+              } else {
+                for (int a = lane; a < m; a += 32) {
+                  float4 p = list[a];
+                  double x, y, z;
+                  to_frame(R, (double)p.x - S.sample[0], (double)p.y - S.sample[1], (double)p.z - S.sample[2], x, y, z);
+                  if (z > -1.0 * hh && z < hh && x > bottom && x < top && y > left && y < right)
+                    visitE(x, y, z, __float_as_int(p.w), 1);
+                }
               }
               if (nb_in && lane == 0) visitE(x0, y0, z0, nb0, npad);
               nl = warp_sum(nl);

@@ -43,7 +43,7 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 // ---------------------------------------------------------------------------------------------------------
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
 constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: term0 0..19 | term1 20..39 | term2 40..59 | 4 zero rows
-constexpr int C1_NT = 256;  // warps 0-3: TMEM epilogue (one lane quarter each); warps 4-7 help convert / pool
+constexpr int C1_NT = 288;  // warps 0-3 / 4-7: two epilogue groups (alternate tiles), warp 8: MMA issuer
 
 // chunk c = (p*5 + kh)*5 + kw -> byte offset of row 0 inside the plane set (monotonic in c)
 __host__ __device__ constexpr uint32_t c1_off(int c, int nch) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
       umma::bulk_g2s(sRaw, images + (size_t)(im + gridDim.x) * img_bytes, img_bytes, &mbar_img);
     }
     float *out = p1 + (size_t)im * 784 * NF1;
-    if (warp == 4) {
+    if (warp == 8) {
       // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt&1), +64) as soon as the epilogue warps
       // have drained that buffer. The whole warp runs the (fully unrolled) loop so that every descriptor is a
       // uniform-register expression base + compile-time constant; one elected lane issues the instructions.
@@ -137,14 +137,17 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
         }
         __syncwarp();
       }
-    } else if (warp < 4) {
-      // ===== epilogue warps: TMEM -> registers (sum of the three weight terms) -> x-pair max -> stage -> y-pair max
+    } else {
+      // ===== two epilogue groups (warps 0-3 and 4-7) drain alternate tiles: TMEM -> registers (sum of the three weight
+      // terms) -> x-pair max -> stage -> y-pair max -> global. Group g owns TMEM buffer g, stage g and named barrier 1+g.
+      const int grp = warp >> 2, r = tid & 127;
+      float *stg = stage + grp * (60 * NF1);
       for (int t = 0; t < C1_TILES; t++, gt++) {
         const int b = gt & 1;
+        if (b != grp) continue;
         umma::mbar_wait(&full[b], (gt >> 1) & 1);
         umma::fence_after_sync();
-        const uint32_t trow = tb + (uint32_t)b * 64 + ((uint32_t)(warp * 32) << 16);
-        const int r = tid;
+        const uint32_t trow = tb + (uint32_t)b * 64 + ((uint32_t)((warp & 3) * 32) << 16);
         float d[64];
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) umma::tmem_ld16(trow + cb * 16, d + cb * 16);
@@ -152,13 +155,13 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
         umma::fence_before_sync();
         __syncwarp();
         if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);  // the buffer may be overwritten by tile t+2
-        float *stg = stage + b * (60 * NF1);
         float v[NF1];
 #pragma unroll
         for (int j = 0; j < NF1; j++) {
           v[j] = (d[j] + d[NF1 + j]) + d[2 * NF1 + j];
           v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
         }
+        umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
         if ((r & 1) == 0 && r < C1_TILE_ROWS) {
           int rr = r >> 1;  // 0..59: [dy][x/2]
           if ((rr % 30) < 28) {
@@ -166,8 +169,8 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
             for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
           }
         }
-        umma::named_bar_sync(1, 128);
-        for (int i = tid; i < 28 * NF1; i += 128) {
+        umma::named_bar_sync(1 + grp, 128);
+        for (int i = r; i < 28 * NF1; i += 128) {
           int px = i / NF1, ch = i - px * NF1;
           float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
           if (relu) m = fmaxf(m, 0.0f);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
 constexpr int C2_W = 28, C2_NPIX = 472, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
 constexpr int C2_BCHUNK = 128 * 16;
 
-constexpr int C2_NT = 256;
+constexpr int C2_NT = 288;  // two epilogue groups + MMA issuer warp 8
 constexpr int IP_K = 7200, IP_KCH = IP_K / 8;  // ip1 reduction length, in 8-element chunks
 __host__ __device__ constexpr uint32_t c2_off(int c) {
   return (uint32_t)(((c >= C2_NCH ? C2_NCH - 1 : c) / 25) * C2_PLANE +
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
       }
       umma::fence_async_smem();
       __syncthreads();
-      if (warp == 4) {
+      if (warp == 8) {
         const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
         for (int t = 0; t < 3; t++, gt++) {
           const int b = gt & 1;
@@ -284,16 +287,18 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
           }
           __syncwarp();
         }
-      } else if (warp < 4) {
+      } else {
+        const int grp = warp >> 2, r = tid & 127;
+        float *stg = stage + grp * (56 * NF2);
         for (int t = 0; t < 3; t++, gt++) {
           const int b = gt & 1;
+          if (b != grp) continue;
           umma::mbar_wait(&full[b], (gt >> 1) & 1);
           umma::fence_after_sync();
-          float *stg = stage + b * (56 * NF2);
-          const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)(warp * 32) << 16);
-          const int r = tid;
+          const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)((warp & 3) * 32) << 16);
           const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
           const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
+          umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
 #pragma unroll
           for (int cb = 0; cb < 4; cb++) {
             float a[16], bq[16];
@@ -312,8 +317,8 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
               if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
             }
           }
-          umma::named_bar_sync(1, 128);
-          for (int i = tid; i < 2 * 12 * NF2; i += 128) {
+          umma::named_bar_sync(1 + grp, 128);
+          for (int i = r; i < 2 * 12 * NF2; i += 128) {
             int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
             float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
             if (relu) m = fmaxf(m, 0.0f);
