@@ -141,7 +141,8 @@ static int fill_dev_params(gpdb_ctx *ctx) {
     d.fs[d.nfp + i] = h;
   }
   for (int i = 0; i < 2 * d.nfp; i++) d.fsw[i] = d.fs[i] + p.finger_width;
-  d.slots_disjoint = 1;
+  d.slots_disjoint = d.nfp >= 3 ? 1 : 0;  // the arithmetic slot lookup needs >= 3 equally spaced slots; else linear scan
+  d.inv_slot_step = d.nfp >= 2 ? 1.0 / (d.fs[1] - d.fs[0]) : 0.0;
   for (int i = 0; i + 1 < d.nfp; i++)
     if (!(d.fsw[i] <= d.fs[i + 1]) || !(d.fsw[d.nfp + i] <= d.fs[d.nfp + i + 1])) d.slots_disjoint = 0;
   // deepenHand steps (finger_hand.cpp:118-121): repeated += 0.005 in double
@@ -457,7 +458,7 @@ int check_device_errors(gpdb_ctx *ctx) {
     gpdb_set_error(ctx, GPDB_ERR_CAPACITY,
                    "neighbourhood exceeded an on-chip tile (frame ball: %d samples, hand-search ball: %d samples, "
                    "image box: %d images): the cloud is denser than the supported %d / %d / %d points",
-                   e[0], e[1], e[2], 512, 13312, 1024);
+                   e[0], e[1], e[2], 512, 12800, 1024);
     return GPDB_ERR_CAPACITY;
   }
   return GPDB_OK;

@@ -29,6 +29,7 @@ struct DevParams {
   int P, n_axes, n_orient, nfp;
   int axes[GPDB_MAX_HAND_AXES];
   int deepen, slots_disjoint, all_axes_z;
+  double inv_slot_step;        // 1 / spacing of the finger slots (index estimate in slot_mask)
   double fs[GPDB_MAX_SLOTS];   // FingerHand::finger_spacing_ (finger_hand.cpp:12-19)
   double fsw[GPDB_MAX_SLOTS];  // fs + finger_width
   int J;                       // deepen steps d_j = init_bite + j*0.005 accumulated in double (finger_hand.cpp:120-121)

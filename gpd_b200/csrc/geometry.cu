@@ -150,6 +150,61 @@ __device__ __forceinline__ int seg_batch(const DevParams &P, const int *cell_sta
   __syncthreads();
   return total;
 }
+// Ball scan with exact load balance: the row bounds are fetched once (one thread per row), prefix-summed across
+// the CTA, and every warp walks an equal share [T w / NW, T (w+1) / NW) of the flattened candidate range, row by row
+// (rows are contiguous segments of the cell-sorted point array -> coalesced float4 loads, no per-candidate search).
+// body(in_range, point) is called by all 32 lanes together. Contains __syncthreads: call from uniform control flow.
+template <int NT, class F>
+__device__ __forceinline__ void scan_balanced(const DevParams &P, const DevCloud &cl, const SegRange &sr, SegScan<NT> &seg,
+                                              F &&body) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = NT / 32;
+  for (int row0 = 0; row0 < sr.nrows; row0 += NT) {
+    __syncthreads();
+    const int total = seg_batch<NT>(P, cl.cell_start, sr, row0, seg);  // fills seg.start / seg.prefix, syncs
+    const int nr = min(NT, sr.nrows - row0);
+    const int c_begin = (int)(((long long)total * warp) / NW), c_end = (int)(((long long)total * (warp + 1)) / NW);
+    if (c_begin >= c_end) continue;
+    int lo = 0, hi = nr;  // largest r with prefix[r] <= c_begin
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (seg.prefix[mid] <= c_begin) lo = mid; else hi = mid;
+    }
+    // software pipeline: the load of chunk i+1 is issued before chunk i is processed (the scan is latency bound:
+    // ~10 short row segments per warp, each a dependent L2 round trip)
+    int r = lo, c = c_begin;
+    auto fetch = [&](bool &have, bool &in, float4 &p) {
+      have = false;
+      in = false;
+      p = make_float4(0.f, 0.f, 0.f, 0.f);
+      while (c < c_end) {
+        const int pe = (r + 1 < nr) ? seg.prefix[r + 1] : total;
+        const int seg_end = min(pe, c_end);
+        if (c >= seg_end) {  // row exhausted (or empty): next row
+          r++;
+          continue;
+        }
+        const int k = c + lane;
+        in = k < seg_end;
+        if (in) p = __ldg(cl.pts4 + (seg.start[r] - seg.prefix[r]) + k);
+        c = min(c + 32, seg_end);
+        have = true;
+        return;
+      }
+    };
+    bool have0, in0, have1, in1;
+    float4 p0, p1;
+    fetch(have0, in0, p0);
+    while (have0) {
+      fetch(have1, in1, p1);
+      body(in0, p0);
+      have0 = have1;
+      in0 = in1;
+      p0 = p1;
+    }
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ int seg_lookup(const SegScan<NT> &seg, int c) {
   // largest r with prefix[r] <= c
@@ -411,17 +466,17 @@ __device__ __forceinline__ unsigned slot_mask(const DevParams &P, const double *
   unsigned m = 0;
   const int F = 2 * P.nfp;
   if (P.slots_disjoint) {
-    // slots within each half are disjoint and ascending: find the last slot starting below y
+    // slots within each half are disjoint, ascending and (nearly) equally spaced: estimate the slot index
+    // arithmetically and test the estimate and its two neighbours with the exact table values
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-      const double *fs = sfs + half * P.nfp;
-      if (y > fs[0]) {
-        int lo = 0, hi = P.nfp;
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (y > fs[mid]) lo = mid; else hi = mid;
-        }
-        if (y < sfsw[half * P.nfp + lo]) m |= 1u << (half * P.nfp + lo);
+      const double *fs = sfs + half * P.nfp, *fsw = sfsw + half * P.nfp;
+      int e = (int)((y - fs[0]) * P.inv_slot_step);
+      e = min(max(e, 1), P.nfp - 2 > 1 ? P.nfp - 2 : 1);
+#pragma unroll
+      for (int d = -1; d <= 1; d++) {
+        const int i = e + d;
+        if (i >= 0 && i < P.nfp && y > fs[i] && y < fsw[i]) m |= 1u << (half * P.nfp + i);
       }
     }
   } else {
@@ -433,6 +488,7 @@ __device__ __forceinline__ unsigned slot_mask(const DevParams &P, const double *
 
 constexpr int SURV_CAP = 1024;
 struct HandsSmem {
+  SegScan<NT_HANDS> seg;
   unsigned short surv[NT_HANDS / 32][SURV_CAP];  // per-warp closing-region member indices
   double fs[GPDB_MAX_SLOTS], fsw[GPDB_MAX_SLOTS];  // finger slot tables (copied from DevParams)
   int count;      // staged (slab) points
@@ -495,7 +551,7 @@ __global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevClou
     const double hz = P.hand_height * 1.001 + 1e-9;
     unsigned long long best = ~0ull;
     int nball = 0;
-    scan_rows<NT_HANDS>(P, cl, sr, [&](bool in, const float4 &p) {
+    scan_balanced<NT_HANDS>(P, cl, sr, S.seg, [&](bool in, const float4 &p) {
       bool keep = false;
       if (in) {
         float d = l2_simple(q, p.x, p.y, p.z);
@@ -841,6 +897,7 @@ __global__ void k_scatter_scores(const gpdb_pose *cand, const float *scores, int
 // k_images
 // ------------------------------------------------------------------------------------------------
 struct ImgSmem {
+  SegScan<NT_IMG> seg;
   gpdb_pose h;
   double red[NT_IMG / 32][4];
   double center[3];
@@ -1041,15 +1098,15 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     //      and the list of points inside the image box (ImageStrategy::transformToUnitImage)
     double sx = 0, sy = 0, sz = 0;
     int cnt = 0, cam_or = 0;
-    scan_rows<NT_IMG>(P, cl, sr, [&](bool in, const float4 &p) {
+    scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p) {
+      // the scan only APPENDS the raw box points (few lanes qualify: doing the per-point work here would run it at
+      // ~6 % lane utilisation); unit coordinates, cells and normals are computed densely after the scan
       bool inb = false;
       unsigned long long key = 0;
-      double u0 = 0, u1 = 0, u2 = 0;
-      int idx = 0, c0 = 0, c1 = 0, c2 = 0;
       if (in) {
         float d = l2_simple(q, p.x, p.y, p.z);
         if (d < P.r2_img) {
-          idx = __float_as_int(p.w);
+          const int idx = __float_as_int(p.w);
           sx += (double)p.x;
           sy += (double)p.y;
           sz += (double)p.z;
@@ -1059,9 +1116,6 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
           to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
           if (in_image_box(P, h, x, y, z)) {
             inb = true;
-            unit_axis(x, h.bottom, P.vol_d, inv_d, S, u0, c0);
-            unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
-            unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
             key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
           }
         }
@@ -1074,16 +1128,9 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         int pos = base + __popc(mk & ((1u << lane) - 1));
         if (inb && pos < BOX_CAP) {
           bkeys[pos] = key;
-          bq[pos] = unit_q32(u0);
-          bq[BOX_CAP + pos] = unit_q32(u1);
-          bq[2 * BOX_CAP + pos] = unit_q32(u2);
-          bcell[pos] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
-          const double *nn = cl.nrm + 3 * (size_t)idx;
-          double n0, n1, n2;
-          to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
-          bnrm[pos] = (float)fabs(n0);
-          bnrm[BOX_CAP + pos] = (float)fabs(n1);
-          bnrm[2 * BOX_CAP + pos] = (float)fabs(n2);
+          bq[pos] = __float_as_uint(p.x);  // raw coordinates, replaced by the fixed-point unit coordinates below
+          bq[BOX_CAP + pos] = __float_as_uint(p.y);
+          bq[2 * BOX_CAP + pos] = __float_as_uint(p.z);
         }
       }
     });
@@ -1124,6 +1171,28 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     __syncthreads();
     PHASE(2);  // scan 1 + reductions done
     const int bn = sm.box_n;
+    // dense pass over the box points: hand-frame coordinates -> unit cube, cell indices, |R^T n| (all lanes busy)
+    for (int k = tid; k < bn; k += NT_IMG) {
+      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP + k]),
+                   pz = (double)__uint_as_float(bq[2 * BOX_CAP + k]);
+      double x, y, z, u0, u1, u2;
+      int c0, c1, c2;
+      to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], x, y, z);
+      unit_axis(x, h.bottom, P.vol_d, inv_d, S, u0, c0);
+      unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
+      unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
+      bq[k] = unit_q32(u0);
+      bq[BOX_CAP + k] = unit_q32(u1);
+      bq[2 * BOX_CAP + k] = unit_q32(u2);
+      bcell[k] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
+      const double *nn = cl.nrm + 3 * (size_t)(unsigned)(bkeys[k] & 0xffffffffull);
+      double n0, n1, n2;
+      to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
+      bnrm[k] = (float)fabs(n0);
+      bnrm[BOX_CAP + k] = (float)fabs(n1);
+      bnrm[2 * BOX_CAP + k] = (float)fabs(n2);
+    }
+    __syncthreads();
 
     // ---- points phase: per projection rasterise normals (arg-max key = last writer in (dist, index)
     // order, createNormalsImage :124-143) and depth (per-cell mean, createDepthImage :158-176)
@@ -1259,26 +1328,28 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       const float jm = (float)(gmax * voxel * 0.3 * 1.7320508075688772 + 2e-5);
       const float fbx_lo[3] = {(float)h.bottom - jm, (float)(h.center - P.vol_w / 2.0) - jm, (float)(-P.vol_h) - jm};
       const float fbx_hi[3] = {(float)(h.bottom + P.vol_d) + jm, (float)(h.center + P.vol_w / 2.0) + jm, (float)P.vol_h + jm};
-      auto cast_draw = [&](double px, double py, double pz, unsigned seed, int k, unsigned *bm) {
+      // one shadow draw -> bit index in camera k's bitmap, or -1 (outside the bitmap AABB / fails the pre-test)
+      auto draw_bit = [&](double px, double py, double pz, unsigned seed, int k) -> int {
         const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
         double u = (double)((seed >> 16) & 0x7FFFu) * mxu;
         int v0 = (int)((px + u * s0) * P.vox_mult);
         int v1 = (int)((py + u * s1) * P.vox_mult);
         int v2 = (int)((pz + u * s2) * P.vox_mult);
         int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
-        if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) return;
+        if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) return -1;
         // conservative float32 pre-test of the voxel's lattice point against the image box widened by the largest
         // jitter (+ rounding slack): rejects most out-of-box voxels for ~20 instructions. The exact float64 test
         // (jitter + frame transform, the oracle's operation order) runs once per UNIQUE surviving voxel below.
-        {
-          const float wx = fmaf((float)v0, 0.003f, -fsx), wy = fmaf((float)v1, 0.003f, -fsy), wz = fmaf((float)v2, 0.003f, -fsz);
-          const float hx = fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz));
-          const float hy = fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz));
-          const float hz = fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz));
-          if (hx < fbx_lo[0] || hx > fbx_hi[0] || hy < fbx_lo[1] || hy > fbx_hi[1] || hz < fbx_lo[2] || hz > fbx_hi[2]) return;
-        }
-        int bit = ((b2 * d1 + b1) << 6) + b0;
-        atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+        const float wx = fmaf((float)v0, 0.003f, -fsx), wy = fmaf((float)v1, 0.003f, -fsy), wz = fmaf((float)v2, 0.003f, -fsz);
+        const float hx = fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz));
+        const float hy = fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz));
+        const float hz = fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz));
+        if (hx < fbx_lo[0] || hx > fbx_hi[0] || hy < fbx_lo[1] || hy > fbx_hi[1] || hz < fbx_lo[2] || hz > fbx_hi[2]) return -1;
+        return ((b2 * d1 + b1) << 6) + b0;
+      };
+      auto cast_draw = [&](double px, double py, double pz, unsigned seed, int k, unsigned *bm) {
+        int bit = draw_bit(px, py, pz, seed, k);
+        if (bit >= 0) atomicOr(bm + (bit >> 5), 1u << (bit & 31));
       };
       for (int k = 0; k < K; k++) {
         if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
@@ -1286,7 +1357,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         __syncthreads();
         if (tid == 0) sm.wl_n = 0;
         __syncthreads();
-        scan_rows<NT_IMG>(P, cl, sr, [&](bool in, const float4 &p) {
+        scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p) {
           if (!in) return;
           float d = l2_simple(q, p.x, p.y, p.z);
           if (!(d < P.r2_img)) return;
@@ -1329,15 +1400,23 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
                   });
         __syncthreads();
         const int nw = min(sm.wl_n, WL_CAP);
+        if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
         const int nsp = P.nsp;
-        for (int w = tid; w < nw * nsp; w += NT_IMG) {
+        // two independent (point, draw) pairs per iteration: the float64 chains of the two draws interleave
+        auto work_bit = [&](int w) -> int {
+          if (w >= nw * nsp) return -1;
           int item = w / nsp, t = w - item * nsp;
           float4 e = wl[item];
           unsigned seed = P.lcgA[t] * __float_as_uint(e.w) + P.lcgC[t];
           unsigned rg = wrange[item];
           int r = (int)((seed >> 16) & 0x7FFFu);
-          if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) continue;
-          cast_draw((double)e.x, (double)e.y, (double)e.z, seed, k, bm);
+          if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) return -1;
+          return draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
+        };
+        for (int w = tid; w < nw * nsp; w += 2 * NT_IMG) {
+          const int bit_a = work_bit(w), bit_b = work_bit(w + NT_IMG);
+          if (bit_a >= 0) atomicOr(bm + (bit_a >> 5), 1u << (bit_a & 31));
+          if (bit_b >= 0) atomicOr(bm + (bit_b >> 5), 1u << (bit_b & 31));
         }
       }
       __syncthreads();
@@ -1403,6 +1482,11 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       }
       __syncthreads();
       const int nset = min(sm.wl_n, BL_CAP);
+      if (prof && tid == 0) {
+        atomicAdd(prof + 11, (unsigned long long)sm.wl_n);
+        atomicAdd(prof + 12, (unsigned long long)bn);
+        atomicAdd(prof + 13, (unsigned long long)sm.n_img);
+      }
       for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i]);
       __syncthreads();
       PHASE(6);  // S2 bitmap pass done
@@ -1523,7 +1607,7 @@ int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_
   return GPDB_OK;
 }
 
-static const int HANDS_CAP1 = 4096, HANDS_CAP2 = 13312;
+static const int HANDS_CAP1 = 4096, HANDS_CAP2 = 12800;
 
 int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
               gpdb_pose *d_poses, uint8_t *d_flags) {

@@ -16,7 +16,10 @@ ctx.phase_cycles(1)
 r = ctx.detect(sidx)
 c = ctx.phase_cycles(1).astype(np.float64)
 names = {2: "ball scan 1", 3: "point channels", 4: "shadow setup", 5: "shadow casting", 6: "shadow bitmap pass", 7: "shadow channels", 8: "flush"}
-tot = c.sum()
+tot = c[2:9].sum()
 print("candidates", r["n_candidates"], "cycles per image", tot / r["n_candidates"])
 for k, v in names.items():
     print(f"  {v:20s} {c[k] / tot:6.1%}  {c[k] / r['n_candidates']:10.0f} cycles/image")
+nc = r["n_candidates"]
+print(f"per image: ball points {c[13]/nc:.0f}, box points {c[12]/nc:.0f}, shadow work-list points {c[9]/nc:.0f}, "
+      f"draws passing the window {c[10]/nc:.0f} of {33*c[9]/nc:.0f}, unique voxels evaluated {c[11]/nc:.0f}")
