@@ -231,3 +231,92 @@ def test_tensor_core_lenet_matches_simt_and_oracle_on_many_images(ch):
     assert np.abs(out[1][:200] - lo).max() <= 1e-4 * scale
     assert np.abs(out[0][:200] - lo).max() <= 1e-4 * scale
     assert np.abs(out[0] - out[1]).max() <= 1e-4 * np.abs(out[1]).max()
+
+
+def test_capacity_error_is_reported_not_crashed():
+    """A cloud far denser than a voxelised one overflows the on-chip neighbourhood tiles: the call must fail with
+    GPDB_ERR_CAPACITY (-5) and the context must stay usable."""
+    rng = np.random.default_rng(0)
+    xyz = (rng.random((150000, 3)) * 0.1).astype(np.float32)  # 150 k points in a 10 cm cube: ~630 points per r=1 cm ball
+    nrm = rng.standard_normal((150000, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    p = lib.default_params(channels=3)
+    ctx = lib.Context(p)
+    ctx.set_cloud(xyz, nrm.astype(np.float32).astype(np.float64), None, np.zeros((1, 3)))
+    with pytest.raises(lib.GpdbError) as e:
+        ctx.frames(np.arange(2000, dtype=np.int32))
+    assert e.value.code == -5 and "denser" in str(e.value)
+    k = scenes.krylon_cloud()
+    ctx.set_cloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    f, v = ctx.frames(np.arange(10, dtype=np.int32))
+    assert v.all()
+    ctx.close()
+
+
+def test_dense_cloud_uses_the_large_tile_tier():
+    """1.2 mm lattice (6x the density of a 3 mm voxelised cloud): the hand-search slab exceeds the 4 096-point tile
+    and goes through the 12 800-point pass; results must still equal the oracle."""
+    g = np.arange(-0.09, 0.09, 0.0012)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    Z = 0.6 + 0.01 * np.sin(40 * X) * np.cos(30 * Y)
+    xyz = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    rng = np.random.default_rng(1)
+    nrm = np.tile([0.0, 0.0, -1.0], (len(xyz), 1)) + rng.normal(0, 0.05, (len(xyz), 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    cloud = {"xyz": xyz, "normals": nrm.astype(np.float32).astype(np.float64), "cam_source": None, "view_points": np.zeros((1, 3))}
+    p, ctx, oc, w = make(cloud, 3)
+    center = np.argsort(np.linalg.norm(xyz[:, :2], axis=1))[:2000]
+    sidx = center[rng.choice(2000, 16, replace=False)].astype(np.int32)
+    idx, _ = oc.radius_search(xyz[sidx[0]], 0.11)
+    assert len(idx) > 12000  # ~6x a voxelised neighbourhood
+    # (the image stage is not exercised here: such a cloud also exceeds the 1 024-point image-box list)
+    fo, vo = oc.frames(p, sidx)
+    po, flo = oc.hand_search(p, sidx, fo, vo)
+    rg = ctx.hand_search(sidx)
+    assert np.array_equal(rg["frames"], fo) and np.array_equal(rg["pose_flags"], flo)
+    co = po[(flo & 3) == 3]
+    assert len(co) == rg["n_candidates"] > 0
+    for f in ("position", "frame", "top", "bottom", "center", "width"):
+        assert np.allclose(co[f], rg["candidates"][f], atol=1e-9, rtol=0), f
+    assert np.array_equal(co["finger_idx"], rg["candidates"]["finger_idx"])
+    ctx.close()
+
+
+def test_config2_krylon_with_replacement():
+    """BASELINE config 2: krylon, 10 000 samples drawn with replacement, 15 channels."""
+    k = scenes.krylon_cloud()
+    p, ctx, oc, w = make(k, 15)
+    sidx = scenes.sample_indices(2, len(k["xyz"]))
+    assert len(sidx) == 10000
+    r = ctx.detect(sidx)
+    # duplicated sample indices must give identical rows
+    order = np.argsort(sidx, kind="stable")
+    s_sorted = sidx[order]
+    dup = np.where(s_sorted[1:] == s_sorted[:-1])[0]
+    assert len(dup) > 1000
+    a, b = order[dup], order[dup + 1]
+    assert np.array_equal(r["pose_flags"][a], r["pose_flags"][b])
+    assert np.array_equal(r["pose_scores"][a], r["pose_scores"][b], equal_nan=True)
+    pick = np.random.default_rng(2).choice(len(sidx), 200, replace=False)
+    ro = oc.detect(p, w, sidx[pick])
+    assert np.array_equal(ro["pose_flags"], r["pose_flags"][pick])
+    m = ~np.isnan(ro["pose_scores"])
+    assert np.abs(ro["pose_scores"][m] - r["pose_scores"][pick][m]).max() <= 1e-4 * np.abs(ro["pose_scores"][m]).max()
+    ctx.close()
+
+
+def test_config5_two_view_12ch_full_cloud():
+    """BASELINE config 5 cloud (300 k points, two cameras, 12-channel ReLU net): 20 000 samples on the GPU,
+    exact parity on a subset."""
+    s = scenes.synthetic_table_scene(5, two_cameras=True)
+    p, ctx, oc, w = make(s, 12)
+    sidx = scenes.sample_indices(5, len(s["xyz"]), 20000)
+    r = ctx.detect(sidx)
+    assert r["n_candidates"] > 5000
+    pick = np.random.default_rng(3).choice(len(sidx), 250, replace=False)
+    ro = oc.detect(p, w, sidx[pick])
+    assert np.array_equal(ro["pose_flags"], r["pose_flags"][pick])
+    m = ~np.isnan(ro["pose_scores"])
+    assert m.sum() > 50
+    assert np.abs(ro["pose_scores"][m] - r["pose_scores"][pick][m]).max() <= 1e-4 * np.abs(ro["pose_scores"][m]).max()
+    ctx.close()
