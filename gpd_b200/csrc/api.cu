@@ -458,7 +458,7 @@ int check_device_errors(gpdb_ctx *ctx) {
     gpdb_set_error(ctx, GPDB_ERR_CAPACITY,
                    "neighbourhood exceeded an on-chip tile (frame ball: %d samples, hand-search ball: %d samples, "
                    "image box: %d images): the cloud is denser than the supported %d / %d / %d points",
-                   e[0], e[1], e[2], 512, 12800, 1024);
+                   e[0], e[1], e[2], 1024, 12800, 2048);
     return GPDB_ERR_CAPACITY;
   }
   return GPDB_OK;

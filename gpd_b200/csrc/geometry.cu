@@ -31,8 +31,8 @@ namespace {
 constexpr int NT_HANDS = 256;
 constexpr int NT_IMG = 512;
 constexpr int LRF_WARPS = 4;
-constexpr int LRF_CAP = 512;
-constexpr int BOX_CAP = 1024;
+constexpr int LRF_CAP = 1024;  // points of the r = nn_radius ball (dynamic shared memory: 2 x 8 B x LRF_CAP per warp)
+constexpr int BOX_CAP = 2048;  // points inside one image box
 constexpr int MAXPIX = 64 * 64;  // image_size <= 64
 
 __device__ __forceinline__ int cell_of(const DevParams &P, float v, int a) {
@@ -372,8 +372,9 @@ __device__ void eigen3(const double *Min, double *eval, double *Q) {
 __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, DevCloud cl, const int *sidx, int n,
                                                             double *frames, uint8_t *valid, int *err) {
   const DevParams &P = *Pp;
-  __shared__ unsigned long long s_keys[LRF_WARPS][LRF_CAP];
-  __shared__ unsigned long long s_sorted[LRF_WARPS][LRF_CAP];
+  extern __shared__ __align__(16) unsigned char lrf_dyn[];
+  unsigned long long(*s_keys)[LRF_CAP] = reinterpret_cast<unsigned long long(*)[LRF_CAP]>(lrf_dyn);
+  unsigned long long(*s_sorted)[LRF_CAP] = s_keys + LRF_WARPS;
   __shared__ double s_acc[LRF_WARPS][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * LRF_WARPS + warp;
@@ -1601,7 +1602,9 @@ int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N) {
 
 int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_t *d_valid) {
   if (n <= 0) return GPDB_OK;
-  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, 0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
+  const size_t lrf_smem = (size_t)2 * LRF_WARPS * LRF_CAP * sizeof(unsigned long long);
+  CUDA_TRY(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrf_smem));
+  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, lrf_smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
                                                                                   d_valid, ctx->d_err);
   LAUNCH_CHECK();
   return GPDB_OK;
@@ -1667,8 +1670,8 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images
   if (nc <= 0) return GPDB_OK;
   const size_t img_off = images_smem_bytes(ctx->hp);
   size_t smem = img_off + ((size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C + 15) / 16 * 16;
-  if (smem > 215 * 1024) {
-    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 220160)", smem);
+  if (smem > 219 * 1024) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem);
     return GPDB_ERR_INVALID;
   }
   CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

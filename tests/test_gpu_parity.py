@@ -237,8 +237,8 @@ def test_capacity_error_is_reported_not_crashed():
     """A cloud far denser than a voxelised one overflows the on-chip neighbourhood tiles: the call must fail with
     GPDB_ERR_CAPACITY (-5) and the context must stay usable."""
     rng = np.random.default_rng(0)
-    xyz = (rng.random((150000, 3)) * 0.1).astype(np.float32)  # 150 k points in a 10 cm cube: ~630 points per r=1 cm ball
-    nrm = rng.standard_normal((150000, 3))
+    xyz = (rng.random((500000, 3)) * 0.1).astype(np.float32)  # 500 k points in a 10 cm cube: ~2 100 points per r=1 cm ball
+    nrm = rng.standard_normal((500000, 3))
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     p = lib.default_params(channels=3)
     ctx = lib.Context(p)
@@ -269,7 +269,7 @@ def test_dense_cloud_uses_the_large_tile_tier():
     sidx = center[rng.choice(2000, 16, replace=False)].astype(np.int32)
     idx, _ = oc.radius_search(xyz[sidx[0]], 0.11)
     assert len(idx) > 12000  # ~6x a voxelised neighbourhood
-    # (the image stage is not exercised here: such a cloud also exceeds the 1 024-point image-box list)
+    # (the image stage is not exercised here: such a cloud also exceeds the 2 048-point image-box list)
     fo, vo = oc.frames(p, sidx)
     po, flo = oc.hand_search(p, sidx, fo, vo)
     rg = ctx.hand_search(sidx)
