@@ -162,3 +162,27 @@ def test_shadow_variant_is_deterministic_and_documented():
         assert np.array_equal(ia[key], ib[key])
     # shadow channels are populated
     assert any(im.reshape(-1, 15)[:, 4].max() > 0 for im in a["images"])
+
+
+def test_config1_krylon_500_samples_3ch_cpu_plumbing():
+    """BASELINE config 1: tutorials/krylon.pcd (voxelised fixture), num_samples = 500 without replacement, 3-channel
+    images, the reference's 3-channel LeNet weights — the CPU-only plumbing case, run through the oracle with the
+    reference's three stage timers (grasp_detector.cpp:313-320)."""
+    k = scenes.krylon_cloud()
+    assert len(k["xyz"]) == 2373
+    sidx = scenes.sample_indices(1, len(k["xyz"]))
+    assert len(sidx) == 500 and len(np.unique(sidx)) == 500
+    w, relu = load_weights(3)
+    p = abi.default_params(3, relu_after_conv=relu)
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    r = oc.detect(p, oracle.WeightPack(w), sidx)
+    assert r["frame_valid"].all()
+    assert r["n_candidates"] == ((r["pose_flags"] & 3) == 3).sum() > 1000
+    assert np.isfinite(r["candidates"]["score"]).all()
+    assert np.array_equal(np.isnan(r["pose_scores"]), (r["pose_flags"] & 3) != 3)
+    assert (r["stage_seconds"][:3] > 0).all() and abs(r["stage_seconds"][:3].sum() - r["stage_seconds"][3]) < 0.05
+    # top-5 selection as GraspDetector::selectGrasps would do it (grasp_detector.cpp:405-420)
+    top = np.sort(r["candidates"]["score"])[::-1][:5]
+    assert (np.diff(top) <= 0).all()
+    r2 = oc.detect(p, oracle.WeightPack(w), sidx, nthreads=1)
+    assert np.array_equal(r2["pose_flags"], r["pose_flags"]) and np.array_equal(r2["candidates"]["score"], r["candidates"]["score"])
