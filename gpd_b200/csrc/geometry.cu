@@ -472,12 +472,20 @@ __device__ __forceinline__ unsigned slot_mask(const DevParams &P, const double *
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       const double *fs = sfs + half * P.nfp, *fsw = sfsw + half * P.nfp;
-      int e = (int)((y - fs[0]) * P.inv_slot_step);
-      e = min(max(e, 1), P.nfp - 2 > 1 ? P.nfp - 2 : 1);
-#pragma unroll
-      for (int d = -1; d <= 1; d++) {
-        const int i = e + d;
+      const double tq = (y - fs[0]) * P.inv_slot_step;
+      const double tf = floor(tq);
+      if (tq - tf > 1e-9 && tf + 1.0 - tq > 1e-9) {
+        // clearly inside one slot pitch: only that slot can contain y (one exact test)
+        const int i = (int)tf;
         if (i >= 0 && i < P.nfp && y > fs[i] && y < fsw[i]) m |= 1u << (half * P.nfp + i);
+      } else {
+        // within rounding distance of a pitch boundary: test the estimate and both neighbours exactly
+        const int e = min(max((int)tf, 1), P.nfp - 2 > 1 ? P.nfp - 2 : 1);
+#pragma unroll
+        for (int d = -1; d <= 1; d++) {
+          const int i = e + d;
+          if (i >= 0 && i < P.nfp && y > fs[i] && y < fsw[i]) m |= 1u << (half * P.nfp + i);
+        }
       }
     }
   } else {

@@ -98,11 +98,28 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
     phase_img ^= 1;
     for (int it = tid; it < C1_W * C1_W * npl; it += C1_NT) {
       const int pix = it / npl, p = it - pix * npl;
-      const uint8_t *src = sRaw + (size_t)pix * C + p * 8;
-      const int nc = min(8, C - p * 8);
+      // the 8 channel bytes of this (pixel, plane) start at an arbitrary byte offset of the HWC stream: fetch the
+      // three aligned 32-bit words covering them and funnel-shift (3 wide loads instead of 8 byte loads: the shared
+      // memory pipe is shared with the tensor core's operand reads and is the bottleneck of this kernel)
+      const int off = pix * C + p * 8, nc = min(8, C - p * 8);
+      const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(sRaw) + (off >> 2);
+      const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2];
+      const int sh = (off & 3) * 8;
+      uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+      if (nc < 8) {
+        if (nc <= 4) {
+          hi = 0;
+          lo &= (nc == 4) ? 0xffffffffu : ((1u << (8 * nc)) - 1);
+        } else {
+          hi &= (1u << (8 * (nc - 4))) - 1;
+        }
+      }
       __nv_bfloat16 v[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) v[e] = __float2bfloat16(e < nc ? (float)src[e] : 0.0f);
+      for (int e = 0; e < 4; e++) {
+        v[e] = __float2bfloat16((float)((lo >> (8 * e)) & 255u));
+        v[4 + e] = __float2bfloat16((float)((hi >> (8 * e)) & 255u));
+      }
       *reinterpret_cast<uint4 *>(sPl + (size_t)p * C1_PLANE + (size_t)pix * 16) = *reinterpret_cast<uint4 *>(v);
     }
     umma::fence_async_smem();
@@ -549,7 +566,7 @@ int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, _
   const LenetTc &t = ctx->tc;
   const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
   const int nmma1 = (t.nch1 + 1) / 2;
-  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C;
+  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C + 16;
   size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
   size_t sm3 = (size_t)IP_STAGES * IP_STAGE_BYTES;
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
