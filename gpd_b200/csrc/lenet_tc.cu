@@ -38,131 +38,155 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// conv1: image 60x60xC uint8 (HWC) -> P1 [784 px][20] float32 (pixel-major), 2x2 max-pooled
+// conv1: image 60x60xC uint8 (HWC) -> P1 [784 px][20] float32 (pixel-major), 2x2 max-pooled.
+// Integer tensor-core path (tcgen05.mma kind::i8, int32 accumulators in TMEM): the uint8 image IS the A operand —
+// one pixel = one 16-byte K-chunk (C <= 16 channels, zero padded), so an instruction (K = 32) covers two filter taps.
+// Weights: w = s_o * W, W a 24-bit signed integer (s_o = max|w_o| / 8.3e6 per filter), W = 65536 d0 + 256 d1 + d2 with
+// balanced int8 digits; the three digit planes are stacked along N (rows 0..19 | 20..39 | 40..59 of N = 64). The
+// dot products are EXACT integers; the epilogue recombines them in float32 (error ~1e-7 relative, like float32 itself).
 // tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
+// warps [0, 4 NG): NG epilogue groups (tile t -> group t % NG, TMEM buffer t % NG); warp 4 NG: MMA issuer;
+// warps 4 NG + 1 .. + 4: converters (raw HWC bytes of the NEXT image -> 16-byte pixels, double-buffered plane).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
-constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: term0 0..19 | term1 20..39 | term2 40..59 | 4 zero rows
-constexpr int C1_NT = 288;  // warps 0-3 / 4-7: two epilogue groups (alternate tiles), warp 8: MMA issuer
+constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: digit0 0..19 | digit1 20..39 | digit2 40..59 | 4 zero rows
+constexpr int C1_NCH = 25, C1_NMMA = 13;         // chunk c = kh*5 + kw (+1 zero-weight chunk)
+constexpr int C1_NG = 4;                         // epilogue groups = TMEM accumulator buffers
+constexpr int C1_MMA_WARP = 4 * C1_NG, C1_CONV_WARP0 = C1_MMA_WARP + 1, C1_NT = (C1_CONV_WARP0 + 4) * 32;
+constexpr int C1_B_BYTES = 2 * C1_NMMA * C1_BCHUNK;
 
-// chunk c = (p*5 + kh)*5 + kw -> byte offset of row 0 inside the plane set (monotonic in c)
-__host__ __device__ constexpr uint32_t c1_off(int c, int nch) {
-  return (uint32_t)(((c >= nch ? nch - 1 : c) / 25) * C1_PLANE +
-                    ((((c >= nch ? nch - 1 : c) / 5) % 5) * C1_W + (c >= nch ? nch - 1 : c) % 5) * 16);
+// chunk c -> byte offset of row 0 inside the plane (monotonic in c)
+__host__ __device__ constexpr uint32_t c1_off(int c) {
+  return (uint32_t)((((c >= C1_NCH ? C1_NCH - 1 : c) / 5) * C1_W + (c >= C1_NCH ? C1_NCH - 1 : c) % 5) * 16);
+}
+__host__ __device__ constexpr uint32_t instr_desc_i8(int M, int N) {  // D = s32, A = u8, B = s8, K-major both
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict__ images, int n, int C,
+__global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict__ images, int n, int C,
                                                        const uint8_t *__restrict__ wblob, const float *__restrict__ bias,
                                                        int relu, float *__restrict__ p1) {
-  constexpr int npl = NPL, nch = NPL * 25;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], empty[2], mbar_img;
+  __shared__ uint64_t full[C1_NG], empty[C1_NG], pl_full[2], pl_empty[2], raw_full;
   __shared__ uint32_t tmem_base;
-  __shared__ float sbias[NF1];
-  constexpr int nmma = (nch + 1) / 2;
+  __shared__ float sbias[NF1], sscale[NF1];
   const int img_bytes = C1_W * C1_W * C;
-  uint8_t *sB = smem;                                  // nch(+1) chunks x 64 rows x 16 B
-  uint8_t *sPl = sB + (size_t)(2 * nmma) * C1_BCHUNK;  // npl planes
-  float *stage = reinterpret_cast<float *>(sPl + (size_t)npl * C1_PLANE);  // 2 x [60][20]
-  uint8_t *sRaw = reinterpret_cast<uint8_t *>(stage + 2 * 60 * NF1);           // next image, raw HWC bytes
+  uint8_t *sB = smem;                                   // 26 chunks x 64 rows x 16 B (int8)
+  uint8_t *sPl = sB + C1_B_BYTES;                       // 2 planes of 3616 px x 16 B (uint8)
+  float *stage = reinterpret_cast<float *>(sPl + 2 * C1_PLANE);        // NG x [60][20]
+  uint8_t *sRaw = reinterpret_cast<uint8_t *>(stage + C1_NG * 60 * NF1);  // next image, raw HWC bytes
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
 
-  for (int i = tid; i < (2 * nmma) * C1_BCHUNK / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
-  for (int i = tid; i < npl * C1_PLANE / 16; i += C1_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < NF1) sbias[tid] = bias[tid];
+  for (int i = tid; i < C1_B_BYTES / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
+  for (int i = tid; i < 2 * C1_PLANE / 16; i += C1_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < NF1) {
+    sbias[tid] = bias[tid];
+    sscale[tid] = reinterpret_cast<const float *>(wblob + C1_B_BYTES)[tid];
+  }
   if (tid == 0) {
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < C1_NG; b++) {
       umma::mbar_init(&full[b], 1);   // tcgen05.commit of the MMA warp
       umma::mbar_init(&empty[b], 4);  // one arrival per epilogue warp
     }
-    umma::mbar_init(&mbar_img, 1);
+    for (int b = 0; b < 2; b++) {
+      umma::mbar_init(&pl_full[b], 4);   // one arrival per converter warp
+      umma::mbar_init(&pl_empty[b], 1);  // tcgen05.commit after the image's last tile
+    }
+    umma::mbar_init(&raw_full, 1);
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 64 * C1_NG);
+  umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
-  const uint32_t idesc = umma::instr_desc(128, C1_N, umma::BF16);
-  uint32_t phase_img = 0;
-  int gt = 0;  // running tile counter of this role: TMEM buffer = gt & 1, use count = gt >> 1
 
-  if (tid == 0 && (int)blockIdx.x < n) {
-    umma::mbar_expect_tx(&mbar_img, img_bytes);
-    umma::bulk_g2s(sRaw, images + (size_t)blockIdx.x * img_bytes, img_bytes, &mbar_img);
-  }
-  for (int im = blockIdx.x; im < n; im += gridDim.x) {
-    // ---- raw uint8 HWC (prefetched by the bulk-copy engine) -> bf16 channel planes (exact)
-    umma::mbar_wait(&mbar_img, phase_img);
-    phase_img ^= 1;
-    for (int it = tid; it < C1_W * C1_W * npl; it += C1_NT) {
-      const int pix = it / npl, p = it - pix * npl;
-      // the 8 channel bytes of this (pixel, plane) start at an arbitrary byte offset of the HWC stream: fetch the
-      // three aligned 32-bit words covering them and funnel-shift (3 wide loads instead of 8 byte loads: the shared
-      // memory pipe is shared with the tensor core's operand reads and is the bottleneck of this kernel)
-      const int off = pix * C + p * 8, nc = min(8, C - p * 8);
-      const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(sRaw) + (off >> 2);
-      const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2];
-      const int sh = (off & 3) * 8;
-      uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-      if (nc < 8) {
-        if (nc <= 4) {
-          hi = 0;
-          lo &= (nc == 4) ? 0xffffffffu : ((1u << (8 * nc)) - 1);
-        } else {
-          hi &= (1u << (8 * (nc - 4))) - 1;
-        }
-      }
-      __nv_bfloat16 v[8];
+  if (warp >= C1_CONV_WARP0) {
+    // ===== converters: raw HWC stream -> one 16-byte group per pixel (channels C..15 zero) in plane (it & 1)
+    const int ct = tid - C1_CONV_WARP0 * 32;  // 0..127
+    if (ct == 0 && (int)blockIdx.x < n) {
+      umma::mbar_expect_tx(&raw_full, img_bytes);
+      umma::bulk_g2s(sRaw, images + (size_t)blockIdx.x * img_bytes, img_bytes, &raw_full);
+    }
+    uint32_t msk[4];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        v[e] = __float2bfloat16((float)((lo >> (8 * e)) & 255u));
-        v[4 + e] = __float2bfloat16((float)((hi >> (8 * e)) & 255u));
+    for (int q = 0; q < 4; q++) {
+      const int nb = min(max(C - 4 * q, 0), 4);
+      msk[q] = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
+    }
+    int it = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x, it++) {
+      const int buf = it & 1;
+      umma::mbar_wait(&pl_empty[buf], ((it >> 1) & 1) ^ 1);  // the MMAs of image it-2 have read this plane
+      umma::mbar_wait(&raw_full, it & 1);
+      uint8_t *pl = sPl + (size_t)buf * C1_PLANE;
+      for (int pix = ct; pix < C1_W * C1_W; pix += 128) {
+        // the C channel bytes of this pixel start at an arbitrary byte offset: fetch the aligned 32-bit words covering
+        // them and funnel-shift
+        const int off = pix * C;
+        const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(sRaw) + (off >> 2);
+        const int sh = (off & 3) * 8;
+        const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, sh) & msk[0];
+        o.y = __funnelshift_r(w1, w2, sh) & msk[1];
+        o.z = __funnelshift_r(w2, w3, sh) & msk[2];
+        o.w = __funnelshift_r(w3, w4, sh) & msk[3];
+        *reinterpret_cast<uint4 *>(pl + (size_t)pix * 16) = o;
       }
-      *reinterpret_cast<uint4 *>(sPl + (size_t)p * C1_PLANE + (size_t)pix * 16) = *reinterpret_cast<uint4 *>(v);
+      umma::fence_async_smem();
+      umma::named_bar_sync(1 + C1_NG, 128);  // all four converter warps are done with sRaw
+      if (ct == 0 && im + (int)gridDim.x < n) {
+        umma::mbar_expect_tx(&raw_full, img_bytes);
+        umma::bulk_g2s(sRaw, images + (size_t)(im + gridDim.x) * img_bytes, img_bytes, &raw_full);
+      }
+      if ((tid & 31) == 0) umma::mbar_arrive(&pl_full[buf]);
     }
-    umma::fence_async_smem();
-    __syncthreads();
-    if (tid == 0 && im + (int)gridDim.x < n) {  // prefetch the next image of this CTA behind the MMAs
-      umma::mbar_expect_tx(&mbar_img, img_bytes);
-      umma::bulk_g2s(sRaw, images + (size_t)(im + gridDim.x) * img_bytes, img_bytes, &mbar_img);
-    }
-    float *out = p1 + (size_t)im * 784 * NF1;
-    if (warp == 8) {
-      // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt&1), +64) as soon as the epilogue warps
-      // have drained that buffer. The whole warp runs the (fully unrolled) loop so that every descriptor is a
-      // uniform-register expression base + compile-time constant; one elected lane issues the instructions.
-      const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
+  } else if (warp == C1_MMA_WARP) {
+    // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt % NG), +64) as soon as that buffer has been
+    // drained. The whole warp runs the (fully unrolled) loop so that every descriptor is a uniform-register
+    // expression base + compile-time constant; one elected lane issues the instructions.
+    const uint32_t sB_u = umma::smem_u32(sB);
+    constexpr uint32_t idesc = instr_desc_i8(128, C1_N);
+    int gt = 0, it = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x, it++) {
+      const int buf = it & 1;
+      umma::mbar_wait(&pl_full[buf], (it >> 1) & 1);
+      umma::fence_after_sync();
+      const uint32_t sPl_u = umma::smem_u32(sPl) + (uint32_t)buf * C1_PLANE;
       for (int t = 0; t < C1_TILES; t++, gt++) {
-        const int b = gt & 1;
-        umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
+        const int b = gt % C1_NG;
+        umma::mbar_wait(&empty[b], ((gt / C1_NG) & 1) ^ 1);
         umma::fence_after_sync();
         const uint32_t arow = sPl_u + (uint32_t)(t * C1_TILE_ROWS) * 16;
         const uint32_t dcol = tb + (uint32_t)b * 64;
         if (umma::elect_one()) {
 #pragma unroll
-          for (int i = 0; i < nmma; i++) {
-            constexpr uint32_t dummy = 0;
-            (void)dummy;
-            const uint32_t a0 = c1_off(2 * i, nch), a1 = c1_off(2 * i + 1, nch);
-            const uint32_t lbo = (2 * i + 1 >= nch) ? 16u : (a1 - a0);
-            umma::mma_f16(dcol, umma::desc_from(arow + a0, lbo, 128), umma::desc_from(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128),
-                          idesc, i > 0);
+          for (int i = 0; i < C1_NMMA; i++) {
+            const uint32_t a0 = c1_off(2 * i), a1 = c1_off(2 * i + 1);
+            const uint32_t lbo = (2 * i + 1 >= C1_NCH) ? 16u : (a1 - a0);
+            umma::mma_i8(dcol, umma::desc_from(arow + a0, lbo, 128), umma::desc_from(sB_u + (uint32_t)(2 * i) * C1_BCHUNK, C1_BCHUNK, 128),
+                         idesc, i > 0);
           }
           umma::commit(&full[b]);
+          if (t == C1_TILES - 1) umma::commit(&pl_empty[buf]);  // every MMA that reads this plane has completed
         }
         __syncwarp();
       }
-    } else {
-      // ===== two epilogue groups (warps 0-3 and 4-7) drain alternate tiles: TMEM -> registers (sum of the three weight
-      // terms) -> x-pair max -> stage -> y-pair max -> global. Group g owns TMEM buffer g, stage g and named barrier 1+g.
-      const int grp = warp >> 2, r = tid & 127;
-      float *stg = stage + grp * (60 * NF1);
+    }
+  } else {
+    // ===== epilogue groups drain the tiles round-robin: TMEM -> registers (recombine the three digit planes) ->
+    // x-pair max -> stage -> y-pair max -> scale, bias -> global. Group g owns TMEM buffer g, stage g, named barrier 1+g.
+    const int grp = warp >> 2, r = tid & 127;
+    float *stg = stage + grp * (60 * NF1);
+    int gt = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x) {
+      float *out = p1 + (size_t)im * 784 * NF1;
       for (int t = 0; t < C1_TILES; t++, gt++) {
-        const int b = gt & 1;
+        const int b = gt % C1_NG;
         if (b != grp) continue;
-        umma::mbar_wait(&full[b], (gt >> 1) & 1);
+        umma::mbar_wait(&full[b], (gt / C1_NG) & 1);
         umma::fence_after_sync();
         const uint32_t trow = tb + (uint32_t)b * 64 + ((uint32_t)((warp & 3) * 32) << 16);
         float d[64];
@@ -171,11 +195,12 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
         umma::tmem_ld_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);  // the buffer may be overwritten by tile t+2
+        if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);  // the buffer may be overwritten by tile t + NG
         float v[NF1];
 #pragma unroll
         for (int j = 0; j < NF1; j++) {
-          v[j] = (d[j] + d[NF1 + j]) + d[2 * NF1 + j];
+          const float f0 = (float)__float_as_int(d[j]), f1 = (float)__float_as_int(d[NF1 + j]), f2 = (float)__float_as_int(d[2 * NF1 + j]);
+          v[j] = fmaf(f0, 65536.0f, fmaf(f1, 256.0f, f2));
           v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
         }
         umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
@@ -189,17 +214,16 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_tc(const uint8_t *__restrict
         umma::named_bar_sync(1 + grp, 128);
         for (int i = r; i < 28 * NF1; i += 128) {
           int px = i / NF1, ch = i - px * NF1;
-          float m = fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]) + sbias[ch];
+          float m = fmaf(fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]), sscale[ch], sbias[ch]);
           if (relu) m = fmaxf(m, 0.0f);
           out[(size_t)(t * 28 + px) * NF1 + ch] = m;
         }
       }
     }
-    __syncthreads();  // every tile of this image has completed: the planes may be rewritten
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, 128);
+  if (warp == 0) umma::tmem_dealloc(tb, 64 * C1_NG);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -482,26 +506,33 @@ static float pow2_scale(float maxabs, float target) {
 int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   const int C = ctx->prm.image_num_channels;
   LenetTc &t = ctx->tc;
-  t.npl = (C + 7) / 8;
-  t.nch1 = t.npl * 25;
-  const int nmma1 = (t.nch1 + 1) / 2;
-  // conv1 blob: [chunk c][row n = term*20 + o][8 x bf16], c = (p*5+kh)*5+kw, channel = 8p + e
-  std::vector<__nv_bfloat16> b1((size_t)(2 * nmma1) * C1_N * 8, __float2bfloat16(0.0f));
-  for (int c = 0; c < t.nch1; c++) {
-    int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
-    for (int o = 0; o < NF1; o++)
-      for (int e = 0; e < 8; e++) {
-        int ch = p * 8 + e;
-        if (ch >= C) continue;
-        float wv = w[0][(((size_t)o * C + ch) * 5 + kh) * 5 + kw];
-        __nv_bfloat16 w1 = __float2bfloat16(wv);
-        float r1 = wv - __bfloat162float(w1);
-        __nv_bfloat16 w2 = __float2bfloat16(r1);
-        float r2 = r1 - __bfloat162float(w2);
-        __nv_bfloat16 w3 = __float2bfloat16(r2);
-        __nv_bfloat16 terms[3] = {w1, w2, w3};
-        for (int tm = 0; tm < 3; tm++) b1[((size_t)c * C1_N + tm * NF1 + o) * 8 + e] = terms[tm];
-      }
+  t.npl = 1;
+  t.nch1 = C1_NCH;
+  // conv1 blob: [chunk c = kh*5+kw (26, last zero)][row n = digit*20 + o (64)][16 x int8: channel e], then 20 float scales
+  std::vector<int8_t> b1((size_t)C1_B_BYTES + NF1 * sizeof(float), 0);
+  {
+    float *scales = reinterpret_cast<float *>(b1.data() + C1_B_BYTES);
+    for (int o = 0; o < NF1; o++) {
+      float mxo = 0.0f;
+      for (size_t i = 0; i < (size_t)C * 25; i++) mxo = std::fmax(mxo, std::fabs(w[0][(size_t)o * C * 25 + i]));
+      const double so = mxo > 0.0f ? (double)mxo / 8300000.0 : 1.0;
+      scales[o] = (float)so;
+      for (int ch = 0; ch < C && ch < 16; ch++)
+        for (int kh = 0; kh < 5; kh++)
+          for (int kw = 0; kw < 5; kw++) {
+            const double wv = w[0][(((size_t)o * C + ch) * 5 + kh) * 5 + kw];
+            long W = std::lround(wv / (double)scales[o]);
+            int dg[3];
+            for (int k = 2; k >= 1; k--) {  // balanced base-256 digits, least significant first
+              long d = ((W + 128) % 256 + 256) % 256 - 128;
+              dg[k] = (int)d;
+              W = (W - d) / 256;
+            }
+            dg[0] = (int)std::max(-128L, std::min(127L, W));
+            const int c = kh * 5 + kw;
+            for (int tm = 0; tm < 3; tm++) b1[((size_t)c * C1_N + tm * NF1 + o) * 16 + ch] = (int8_t)dg[tm];
+          }
+    }
   }
   // conv2 blob: [chunk c][row n: 0..63 = w_hi (50 used), 64..127 = w_lo][8 x fp16], weights scaled by 2^k
   float mx = 0.0f;
@@ -549,15 +580,15 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   cudaFree(t.b3);
   t.b1 = t.b2 = t.b3 = nullptr;
   t.ready = false;
-  if (cudaMalloc(&t.b1, b1.size() * 2) != cudaSuccess || cudaMalloc(&t.b2, b2.size() * 2) != cudaSuccess ||
-      cudaMemcpy(t.b1, b1.data(), b1.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+  if (cudaMalloc(&t.b1, b1.size()) != cudaSuccess || cudaMalloc(&t.b2, b2.size() * 2) != cudaSuccess ||
+      cudaMemcpy(t.b1, b1.data(), b1.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(t.b2, b2.data(), b2.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc(&t.b3, b3.size() * 2) != cudaSuccess ||
       cudaMemcpy(t.b3, b3.data(), b3.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
     gpdb_set_error(ctx, GPDB_ERR_CUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return GPDB_ERR_CUDA;
   }
-  t.ready = ctx->prm.image_size == 60;
+  t.ready = ctx->prm.image_size == 60 && C <= 16;
   return GPDB_OK;
 }
 
@@ -565,19 +596,14 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
 int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, __half *xc, float *h3) {
   const LenetTc &t = ctx->tc;
   const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
-  const int nmma1 = (t.nch1 + 1) / 2;
-  size_t sm1 = (size_t)(2 * nmma1) * C1_BCHUNK + (size_t)t.npl * C1_PLANE + 2 * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C + 16;
+  size_t sm1 = (size_t)C1_B_BYTES + 2 * (size_t)C1_PLANE + C1_NG * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C + 32;
   size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
   size_t sm3 = (size_t)IP_STAGES * IP_STAGE_BYTES;
-  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  CUDA_TRY(cudaFuncSetAttribute(k_conv1_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv1_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   CUDA_TRY(cudaFuncSetAttribute(k_ip1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
-  if (t.npl == 2)
-    k_conv1_tc<2><<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
-  else
-    k_conv1_tc<1><<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
+  k_conv1_i8<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 5, e1);
   cudaEvent_t e2 = gpdb_st_begin(ctx);
