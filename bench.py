@@ -123,6 +123,48 @@ def cpu_baseline(cloud, sidx, weights, target_seconds=15.0, nthreads=0):
                       f"{r['stage_seconds'][0]:.2f}/{r['stage_seconds'][1]:.2f}/{r['stage_seconds'][2]:.2f}"}, r
 
 
+def bench_preprocess(ctx, hbm_peak, with_cpu):
+    """Secondary measurement (SURVEY.md 8(f).1): CandidatesGenerator::preprocessPointCloud on the device —
+    NaN / workspace filter, voxelisation at 0.003, normal estimation r = 0.03 — for the RAW cloud of the same scene
+    family (seed 3, ~0.9 M points -> ~0.5 M voxels), through gpdb_preprocess with HOST buffers."""
+    from gpd_b200 import lib
+    raw = scenes.synthetic_raw_scene(3)
+    pp = lib.preprocess_params()
+    n_out = 0
+    for _ in range(2):
+        n_out = ctx.preprocess(raw["xyz"], raw["cam_source"], raw["view_points"], pp, read_back=False)
+    reps, wall, dev_ms = 3, 0.0, np.zeros(6)
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ctx.preprocess(raw["xyz"], raw["cam_source"], raw["view_points"], pp, read_back=False)
+        wall += time.perf_counter() - t0
+        dev_ms += ctx.preprocess_timings()
+    wall /= reps
+    dev_ms /= reps
+    m = len(raw["xyz"])
+    out = {"metric": "raw points preprocessed / s (filter + voxelise 0.003 + normals r=0.03), host buffers in, processed cloud resident",
+           "value": m / wall, "unit": "raw points/s", "raw_points": m, "processed_points": int(n_out),
+           "ms_per_call_wall": round(wall * 1e3, 3),
+           "device_ms": {k: round(float(v), 3) for k, v in zip(["upload", "filter", "voxelise", "grid", "normals", "total"], dev_ms)},
+           "h2d_bytes_per_call": int(m * (12 + 1))}
+    cloud = ctx.get_cloud()
+    from oracle import oracle
+    oc = oracle.OracleCloud(cloud["xyz"], cloud["normals"], cloud["cam_source"], raw["view_points"])
+    probe = np.arange(0, n_out, max(1, n_out // 256))[:256]
+    n_nb = float(np.mean([len(oc.radius_search(cloud["xyz"][i], pp.normals_radius)[0]) for i in probe]))
+    alg = n_out * (n_nb * 16 + 24)  # float4 gather per neighbour + one float64 normal out
+    ach = alg / (dev_ms[4] * 1e-3) / 1e9
+    out["k_normals"] = {"ms": round(float(dev_ms[4]), 3), "mean_neighbours": n_nb, "algorithmic_bytes": alg, "GB/s": round(ach, 1),
+                        "frac_hbm": round(ach / hbm_peak, 4)}
+    if with_cpu:
+        t0 = time.perf_counter()
+        ro = oracle.preprocess(raw["xyz"], raw["cam_source"], raw["view_points"], pp)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "raw points/s", "cores": oracle.num_threads(), "kind": "port",
+                               "sample": f"the same {m} raw points, once: {dt:.2f} s (voxelise {ro['seconds'][0]:.2f} s, normals {ro['seconds'][1]:.2f} s)"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,6 +200,7 @@ def main():
     ap.add_argument("--samples", type=int, default=SAMPLES_PER_GPU, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lenet-impl", type=int, default=0)
+    ap.add_argument("--no-preprocess", action="store_true", help="skip the secondary gpdb_preprocess measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -356,6 +399,8 @@ def main():
         if not args.no_cpu_baseline:
             cb, _ = cpu_baseline(cloud, sidx, weights)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_preprocess:
+            line["preprocess"] = bench_preprocess(ctx, hbm_peak, not args.no_cpu_baseline)
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -114,6 +114,35 @@ class Result(C.Structure):
     ]
 
 
+class PreprocessParams(C.Structure):
+    """gpdb_preprocess_params — cfg keys of CandidatesGenerator::preprocessPointCloud
+    (candidates_generator.cpp:14-37, grasp_detector.cpp:50-66)."""
+
+    _fields_ = [
+        ("workspace", C.c_double * 6),
+        ("voxel_size", C.c_double),
+        ("normals_radius", C.c_double),
+        ("voxelize", C.c_int32),
+        ("estimate_normals", C.c_int32),
+    ]
+
+
+def default_preprocess_params(**over):
+    """Reference defaults (cfg/eigen_params.cfg:16-21, grasp_detector.cpp:56-66)."""
+    p = PreprocessParams()
+    p.workspace[:] = [-1.0, 1.0, -1.0, 1.0, -1.0, 1.0]
+    p.voxel_size = 0.003
+    p.normals_radius = 0.03
+    p.voxelize = 1
+    p.estimate_normals = 1
+    for k, v in over.items():
+        if k == "workspace":
+            p.workspace[:] = list(v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
 def default_params(channels=15, **over):
     """The reference defaults (gpdb_params_default in C), restated for the oracle loader.
 

@@ -1,6 +1,7 @@
 // api.cu — the C-ABI of libgpd_b200.so (include/gpd_b200.h): context, cloud upload, the chunked
 // detect pipeline and the stage-level entry points. Host-side logic only; kernels live in
 // geometry.cu / lenet_simt.cu / lenet_tc.cu. There is no CPU fallback anywhere in this library.
+#include <cfloat>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -326,6 +327,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   cudaFree(ctx->d_xyz);
   cudaFree(ctx->d_nrm);
   cudaFree(ctx->d_cam);
+  cudaFree(ctx->d_src);
   cudaFree(ctx->d_cell_start);
   float *w[8] = {ctx->w.c1w, ctx->w.c1b, ctx->w.c2w, ctx->w.c2b, ctx->w.i1w, ctx->w.i1b, ctx->w.i2w, ctx->w.i2b};
   for (float *p : w) cudaFree(p);
@@ -383,6 +385,31 @@ int gpdb_load_weights_dir(gpdb_ctx *ctx, const char *dir) {
                           bufs[5].data(), bufs[6].data(), bufs[7].data());
 }
 
+}  // extern "C"
+
+// Cloud arrays are an arena: grown when a larger cloud arrives, never shrunk, so that repeated gpdb_set_cloud /
+// gpdb_preprocess calls (one per camera frame) do not pay cudaMalloc / cudaFree.
+int gpdb_cloud_reserve(gpdb_ctx *ctx, size_t n) {
+  if (n <= ctx->cloud_cap) return GPDB_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_pts4); ctx->d_pts4 = nullptr;
+  cudaFree(ctx->d_xyz); ctx->d_xyz = nullptr;
+  cudaFree(ctx->d_nrm); ctx->d_nrm = nullptr;
+  cudaFree(ctx->d_cam); ctx->d_cam = nullptr;
+  cudaFree(ctx->d_src); ctx->d_src = nullptr;
+  ctx->cloud_cap = 0;
+  const size_t cap = n + n / 8 + 1024;
+  CUDA_TRY(cudaMalloc(&ctx->d_pts4, sizeof(float4) * cap));
+  CUDA_TRY(cudaMalloc(&ctx->d_xyz, sizeof(float) * 3 * cap));
+  CUDA_TRY(cudaMalloc(&ctx->d_nrm, sizeof(double) * 3 * cap));
+  CUDA_TRY(cudaMalloc(&ctx->d_cam, cap));
+  CUDA_TRY(cudaMalloc(&ctx->d_src, sizeof(int) * cap));
+  ctx->cloud_cap = cap;
+  return GPDB_OK;
+}
+
+extern "C" {
+
 int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const int32_t *cam_source, int32_t N,
                    const double *view_points, int32_t K) {
   if (!ctx) return GPDB_ERR_INVALID;
@@ -394,14 +421,11 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const
   CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->cloud_set = false;
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->d_pts4); ctx->d_pts4 = nullptr;
-  cudaFree(ctx->d_xyz); ctx->d_xyz = nullptr;
-  cudaFree(ctx->d_nrm); ctx->d_nrm = nullptr;
-  cudaFree(ctx->d_cam); ctx->d_cam = nullptr;
-  CUDA_TRY(cudaMalloc(&ctx->d_pts4, sizeof(float4) * (size_t)N));
-  CUDA_TRY(cudaMalloc(&ctx->d_xyz, sizeof(float) * 3 * (size_t)N));
-  CUDA_TRY(cudaMalloc(&ctx->d_nrm, sizeof(double) * 3 * (size_t)N));
-  CUDA_TRY(cudaMalloc(&ctx->d_cam, (size_t)N));
+  {
+    int rc = gpdb_cloud_reserve(ctx, (size_t)N);
+    if (rc != GPDB_OK) return rc;
+  }
+  ctx->has_src = false;
   std::vector<uint8_t> cam((size_t)N, (uint8_t)((1u << K) - 1));
   if (cam_source)
     for (int i = 0; i < N; i++) {
@@ -423,9 +447,147 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const
   ctx->cloud.xyz = ctx->d_xyz;
   ctx->cloud.nrm = ctx->d_nrm;
   ctx->cloud.cam = ctx->d_cam;
-  int rc = geo_build_grid(ctx, xyz, N);
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = 0; i < N; i++)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], xyz[3 * (size_t)i + a]);
+      hi[a] = fmaxf(hi[a], xyz[3 * (size_t)i + a]);
+    }
+  int rc = geo_build_grid(ctx, lo, hi, N);
   if (rc != GPDB_OK) return rc;
   ctx->cloud_set = true;
+  return GPDB_OK;
+}
+
+void gpdb_preprocess_params_default(gpdb_preprocess_params *p) {
+  memset(p, 0, sizeof(*p));
+  const double ws[6] = {-1, 1, -1, 1, -1, 1};
+  for (int i = 0; i < 6; i++) p->workspace[i] = ws[i];
+  p->voxel_size = 0.003;
+  p->normals_radius = 0.03;
+  p->voxelize = 1;
+  p->estimate_normals = 1;
+}
+
+int gpdb_preprocess(gpdb_ctx *ctx, const float *xyz, const double *normals, const int32_t *cam_source, int32_t M,
+                    const double *view_points, int32_t K, const gpdb_preprocess_params *pp) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  if (!xyz || !view_points || !pp || M <= 0 || K <= 0 || K > GPDB_MAX_CAMERAS) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_preprocess: need xyz, view_points, params, n_points > 0, 1 <= cameras <= %d",
+                   GPDB_MAX_CAMERAS);
+    return GPDB_ERR_INVALID;
+  }
+  if (!pp->estimate_normals && !normals) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_preprocess: estimate_normals = 0 needs the caller's normals");
+    return GPDB_ERR_INVALID;
+  }
+  if ((pp->voxelize && !(pp->voxel_size > 0.0)) || (pp->estimate_normals && !(pp->normals_radius > 0.0))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_preprocess: voxel_size and normals_radius must be positive");
+    return GPDB_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->cloud_set = false;
+  cudaEvent_t ev[6];
+  for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+  auto drop_events = [&]() { for (auto &e : ev) cudaEventDestroy(e); };
+  // ---- upload the raw cloud (camera source packed to one bit per camera, as gpdb_set_cloud does)
+  std::vector<uint8_t> cam((size_t)M, (uint8_t)((1u << K) - 1));
+  if (cam_source)
+    for (int i = 0; i < M; i++) {
+      uint8_t m = 0;
+      for (int k = 0; k < K; k++)
+        if (cam_source[(size_t)i * K + k] > 0) m |= (uint8_t)(1u << k);
+      cam[i] = m;
+    }
+  const size_t raw_bytes = sizeof(float) * 3 * (size_t)M + (size_t)M + 16 + (normals ? sizeof(double) * 3 * (size_t)M : 0);
+  unsigned char *raw = (unsigned char *)gpdb_scratch(ctx, 7, raw_bytes);
+  if (!raw) { drop_events(); return GPDB_ERR_CUDA; }
+  double *d_nrm_raw = normals ? (double *)raw : nullptr;
+  float *d_xyz_raw = (float *)(raw + (normals ? sizeof(double) * 3 * (size_t)M : 0));
+  uint8_t *d_cam_raw = (uint8_t *)(d_xyz_raw + 3 * (size_t)M);
+  cudaEventRecord(ev[0], ctx->stream);
+  CUDA_TRY(cudaMemcpyAsync(d_xyz_raw, xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_cam_raw, cam.data(), (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  if (normals) CUDA_TRY(cudaMemcpyAsync(d_nrm_raw, normals, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  cudaEventRecord(ev[1], ctx->stream);
+  // ---- removeNans + filterWorkspace + voxelizeCloud
+  int N = 0;
+  int rc = pre_filter_voxelize(ctx, d_xyz_raw, d_cam_raw, d_nrm_raw, M, *pp, &N, ev[2]);
+  if (rc != GPDB_OK) { drop_events(); return rc; }
+  cudaEventRecord(ev[3], ctx->stream);
+  // ---- install as the context's cloud (the arrays were written in place)
+  ctx->N = N;
+  ctx->K = K;
+  ctx->hp.K = K;
+  for (int k = 0; k < K; k++)
+    for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];
+  memset(ctx->pre_ms, 0, sizeof(ctx->pre_ms));
+  if (N == 0) { drop_events(); return 0; }
+  ctx->has_src = true;
+  ctx->cloud.pts4 = ctx->d_pts4;
+  ctx->cloud.xyz = ctx->d_xyz;
+  ctx->cloud.nrm = ctx->d_nrm;
+  ctx->cloud.cam = ctx->d_cam;
+  float lo[3], hi[3];
+  int *d_bounds = (int *)gpdb_scratch(ctx, 4, sizeof(double) * 6 + sizeof(int) * 8);
+  if (!d_bounds) { drop_events(); return GPDB_ERR_CUDA; }
+  rc = pre_bounds(ctx, ctx->d_xyz, N, d_bounds, lo, hi);
+  if (rc == GPDB_OK) rc = geo_build_grid(ctx, lo, hi, N);
+  if (rc != GPDB_OK) { drop_events(); return rc; }
+  cudaEventRecord(ev[4], ctx->stream);
+  // ---- calculateNormalsOMP + reverseNormals
+  if (pp->estimate_normals) {
+    rc = pre_normals(ctx, pp->normals_radius);
+    if (rc != GPDB_OK) { drop_events(); return rc; }
+  }
+  cudaEventRecord(ev[5], ctx->stream);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float t;
+  const int a[5] = {0, 1, 2, 3, 4}, b[5] = {1, 2, 3, 4, 5};
+  for (int i = 0; i < 5; i++)
+    if (cudaEventElapsedTime(&t, ev[a[i]], ev[b[i]]) == cudaSuccess) ctx->pre_ms[i] = t;
+  if (cudaEventElapsedTime(&t, ev[0], ev[5]) == cudaSuccess) ctx->pre_ms[5] = t;
+  drop_events();
+  ctx->cloud_set = true;
+  return N;
+}
+
+int gpdb_get_cloud(gpdb_ctx *ctx, float *xyz_out, double *normals_out, int32_t *cam_source_out) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  if (!ctx->cloud_set) {
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "no point cloud: call gpdb_set_cloud / gpdb_preprocess first");
+    return GPDB_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t N = (size_t)ctx->N;
+  if (xyz_out) CUDA_TRY(cudaMemcpyAsync(xyz_out, ctx->d_xyz, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (normals_out) CUDA_TRY(cudaMemcpyAsync(normals_out, ctx->d_nrm, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cam_source_out) {
+    int *d = (int *)gpdb_scratch(ctx, 5, sizeof(int) * N * ctx->K);
+    if (!d) return GPDB_ERR_CUDA;
+    int rc = pre_cam_expand(ctx, d);
+    if (rc != GPDB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cam_source_out, d, sizeof(int) * N * ctx->K, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ctx->N;
+}
+
+int gpdb_get_cloud_source_index(gpdb_ctx *ctx, int32_t *src_out) {
+  if (!ctx || !src_out) return GPDB_ERR_INVALID;
+  if (!ctx->cloud_set || !ctx->has_src) {
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "no preprocessed cloud: call gpdb_preprocess first");
+    return GPDB_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMemcpyAsync(src_out, ctx->d_src, sizeof(int) * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return ctx->N;
+}
+
+int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]) {
+  if (!ctx || !ms_out) return GPDB_ERR_INVALID;
+  for (int i = 0; i < 6; i++) ms_out[i] = ctx->pre_ms[i];
   return GPDB_OK;
 }
 

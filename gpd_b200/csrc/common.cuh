@@ -73,7 +73,7 @@ struct DevCloud {
 };
 
 // device error counters: [0] LRF capacity, [1] hand-search capacity (final tier), [2] image box list,
-// [3] hand-search tier-1 overflow count (informational)
+// [3] hand-search tier-1 overflow count (informational), [4] normal-estimation capacity (final tier)
 #define GPDB_NERR 8
 
 #define CUDA_TRY(expr)                                                                        \
@@ -118,6 +118,8 @@ struct gpdb_ctx {
   double *d_nrm;
   uint8_t *d_cam;
   int *d_cell_start;
+  size_t cloud_cap;       // capacity (points) of pts4 / xyz / nrm / cam / src: grown, never shrunk
+  size_t cell_cap;        // capacity (ints) of cell_start
   int N, K;
   bool cloud_set;
   double *d_qtab;
@@ -131,6 +133,9 @@ struct gpdb_ctx {
   unsigned long long *d_prof;  // optional phase counters (gpdb_debug_phase_cycles), nullptr = off
   int64_t launches;
   double last_ms[8];
+  double pre_ms[6];   // gpdb_preprocess stage timings
+  int *d_src;         // raw index of each processed point (valid after gpdb_preprocess: has_src)
+  bool has_src;
   cudaEvent_t ev[8];
 };
 
@@ -142,7 +147,8 @@ void gpdb_st_end(gpdb_ctx *ctx, int stage, cudaEvent_t begin);
 void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes);  // returns nullptr on failure (error set)
 
 // geometry.cu
-int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N);
+// builds the neighbour grid over ctx->d_xyz (N points) whose per-axis bounds are lo / hi
+int geo_build_grid(gpdb_ctx *ctx, const float lo[3], const float hi[3], int N);
 int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_t *d_valid);
 int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
               gpdb_pose *d_poses, uint8_t *d_flags);
@@ -152,6 +158,16 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images);
 int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
                        float *d_pose_scores, gpdb_pose *d_cand_out);
+
+// preprocess.cu (cloud preprocessing)
+// (re)allocates the context's cloud arrays for at least n points (api.cu)
+int gpdb_cloud_reserve(gpdb_ctx *ctx, size_t n);
+int pre_bounds(gpdb_ctx *ctx, const float *d_xyz, int n, int *d_bounds, float lo[3], float hi[3]);
+// filters + voxelises the raw arrays into the context's cloud arrays (reserved inside); *n_out = processed points
+int pre_filter_voxelize(gpdb_ctx *ctx, const float *d_xyz_raw, const uint8_t *d_cam_raw, const double *d_nrm_raw, int M,
+                        const gpdb_preprocess_params &pp, int *n_out, cudaEvent_t ev_filter_done);
+int pre_normals(gpdb_ctx *ctx, double radius);
+int pre_cam_expand(gpdb_ctx *ctx, int *d_out);
 
 // lenet_simt.cu
 int lenet_upload(gpdb_ctx *ctx, const float *const w[8]);

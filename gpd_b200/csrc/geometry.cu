@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace {
 
@@ -34,20 +35,6 @@ constexpr int LRF_WARPS = 4;
 constexpr int LRF_CAP = 1024;  // points of the r = nn_radius ball (dynamic shared memory: 2 x 8 B x LRF_CAP per warp)
 constexpr int BOX_CAP = 2048;  // points inside one image box
 constexpr int MAXPIX = 64 * 64;  // image_size <= 64
-
-__device__ __forceinline__ int cell_of(const DevParams &P, float v, int a) {
-  int c = (int)floorf((v - P.lo[a]) * P.inv_cell);
-  return min(max(c, 0), P.dim[a] - 1);
-}
-
-// FLANN L2_Simple<float> (float32, accumulated x,y,z in order)
-__device__ __forceinline__ float l2_simple(const float q[3], float x, float y, float z) {
-  float dx = q[0] - x, dy = q[1] - y, dz = q[2] - z;
-  float d = dx * dx;
-  d += dy * dy;
-  d += dz * dz;
-  return d;
-}
 
 // o = frame^T v, frame column-major, summed left to right (PointList::transformToHandFrame, point_list.cpp:22-33)
 __device__ __forceinline__ void to_frame(const double *F, double v0, double v1, double v2, double &o0, double &o1,
@@ -74,60 +61,6 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
-
-// ------------------------------------------------------------------------------------------------
-// Row segments of the grid cube around q: rows (cy,cz), each one contiguous run [start, start+len).
-// Block-wide; NT threads; at most NT rows per batch. Returns total candidates of the batch.
-// ------------------------------------------------------------------------------------------------
-struct SegRange {
-  int c0[3], c1[3], ny, nrows;
-};
-__device__ __forceinline__ SegRange seg_range(const DevParams &P, const float q[3], float rf) {
-  SegRange s;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    s.c0[a] = cell_of(P, q[a] - rf, a);
-    s.c1[a] = cell_of(P, q[a] + rf, a);
-  }
-  s.ny = s.c1[1] - s.c0[1] + 1;
-  s.nrows = s.ny * (s.c1[2] - s.c0[2] + 1);
-  return s;
-}
-__device__ __forceinline__ void seg_row(const DevParams &P, const int *cell_start, const SegRange &s, int row, int &start,
-                                        int &len) {
-  int cy = s.c0[1] + row % s.ny, cz = s.c0[2] + row / s.ny;
-  size_t base = ((size_t)cz * P.dim[1] + cy) * P.dim[0];
-  start = __ldg(cell_start + base + s.c0[0]);
-  len = __ldg(cell_start + base + s.c1[0] + 1) - start;
-}
-
-// Ball scan, one warp per grid row: lanes stride over the row's contiguous point segment (coalesced float4 loads).
-// body(in_range, point) is called by all 32 lanes together, so it may use warp collectives.
-template <int NT, class F>
-__device__ __forceinline__ void scan_rows(const DevParams &P, const DevCloud &cl, const SegRange &sr, F &&body) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = NT / 32;
-  // this warp owns rows warp, warp + NW, ...; the bounds of 32 of them are fetched at once (one lane each) so that
-  // the dependent cell_start -> point loads cost one round trip per 32 rows, and empty rows are skipped by ballot
-  for (int j0 = 0; warp + NW * j0 < sr.nrows; j0 += 32) {
-    const int myrow = warp + NW * (j0 + lane);
-    int st = 0, len = 0;
-    if (myrow < sr.nrows) seg_row(P, cl.cell_start, sr, myrow, st, len);
-    unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
-    while (nonempty) {
-      const int j = __ffs(nonempty) - 1;
-      nonempty &= nonempty - 1;
-      const int rs = __shfl_sync(0xffffffffu, st, j), rl = __shfl_sync(0xffffffffu, len, j);
-      for (int k0 = 0; k0 < rl; k0 += 32) {
-        const int k = k0 + lane;
-        const bool in = k < rl;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) p = __ldg(cl.pts4 + rs + k);
-        body(in, p);
-      }
-    }
-  }
-}
 
 template <int NT>
 struct SegScan {
@@ -1559,14 +1492,8 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     }                                                    \
   } while (0)
 
-int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N) {
+int geo_build_grid(gpdb_ctx *ctx, const float lo[3], const float hi[3], int N) {
   DevParams &hp = ctx->hp;
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = 0; i < N; i++)
-    for (int a = 0; a < 3; a++) {
-      lo[a] = fminf(lo[a], h_xyz[3 * (size_t)i + a]);
-      hi[a] = fmaxf(hi[a], h_xyz[3 * (size_t)i + a]);
-    }
   float cell = 0.02f;
   size_t ncell;
   for (;;) {
@@ -1582,9 +1509,14 @@ int geo_build_grid(gpdb_ctx *ctx, const float *h_xyz, int N) {
   hp.inv_cell = 1.0f / cell;
   hp.N = N;
   CUDA_TRY(cudaMemcpyAsync(ctx->dp, &hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
-  cudaFree(ctx->d_cell_start);
-  ctx->d_cell_start = nullptr;
-  CUDA_TRY(cudaMalloc(&ctx->d_cell_start, sizeof(int) * (ncell + 1)));
+  if (ncell + 1 > ctx->cell_cap) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_cell_start);
+    ctx->d_cell_start = nullptr;
+    ctx->cell_cap = 0;
+    CUDA_TRY(cudaMalloc(&ctx->d_cell_start, sizeof(int) * (ncell + 1 + ncell / 4)));
+    ctx->cell_cap = ncell + 1 + ncell / 4;
+  }
   CUDA_TRY(cudaMemsetAsync(ctx->d_cell_start, 0, sizeof(int) * (ncell + 1), ctx->stream));
   int *cid = (int *)gpdb_scratch(ctx, 0, sizeof(int) * (size_t)N * 4);
   if (!cid) return GPDB_ERR_CUDA;

@@ -52,8 +52,8 @@ class ConfigFile {
   std::string fName;
 };
 
-// The part of util::Cloud the hot path reads. Points are the *processed* cloud (already voxelised, with normals):
-// preprocessing (cloud.cpp:286-604) is outside the accelerated path.
+// The part of util::Cloud the hot path reads. A cloud loaded without normals is RAW: GraspDetector::preprocessPointCloud
+// filters, voxelises and estimates normals on the device (gpdb_preprocess) and stores the processed cloud back here.
 class Cloud {
  public:
   Cloud() {}
@@ -63,8 +63,13 @@ class Cloud {
         const std::vector<double> &view_points);
   bool loadPointCloudFromFile(const std::string &filename);
   void setNormalsFromFile(const std::string &filename);  // CSV, one normal per row or 3 x N (cloud.cpp:607-641)
-  void setNormals(const std::vector<double> &normals) { normals_ = normals; }
+  void setNormals(const std::vector<double> &normals) { normals_ = normals; touch(); }
   void setSampleIndices(const std::vector<int> &idx) { sample_indices_ = idx; }
+  // replaces cloud_processed_ / normals_ / camera_source_ (what Cloud::filterWorkspace / voxelizeCloud /
+  // calculateNormals leave behind, cloud.cpp:207-348,458-535); sample indices are invalidated
+  void setProcessed(std::vector<float> points, std::vector<double> normals, std::vector<int> camera_source);
+  bool hasNormals() const { return normals_.size() == points_.size() && !points_.empty(); }
+  unsigned revision() const { return revision_; }  // process-unique, renewed by every mutation of points / normals
   void subsample(int num_samples);  // uniform draw of sample indices (cloud.cpp:350-405), seeded rand()
   const std::vector<float> &getPoints() const { return points_; }       // packed x,y,z
   const std::vector<double> &getNormals() const { return normals_; }    // 3 x N column-major
@@ -80,6 +85,8 @@ class Cloud {
   std::vector<int> camera_source_;
   std::vector<double> view_points_;
   std::vector<int> sample_indices_;
+  unsigned revision_{0};
+  void touch();
 };
 
 }  // namespace util
@@ -210,7 +217,10 @@ class GraspDetector {
   ~GraspDetector();
   // grasp_detector.cpp:192-328: candidates -> filter -> images -> classify (one gpdb_detect) -> select -> sort
   std::vector<std::unique_ptr<candidate::Hand>> detectGrasps(const util::Cloud &cloud);
-  void preprocessPointCloud(util::Cloud &cloud);  // only the subsample step; the rest is outside the path
+  // CandidatesGenerator::preprocessPointCloud (candidates_generator.cpp:14-37) on the device: removeNans,
+  // filterWorkspace, voxelizeCloud, calculateNormals (skipped when the cloud brings normals), then subsample
+  void preprocessPointCloud(util::Cloud &cloud);
+  const gpdb_preprocess_params &getPreprocessParams() const { return pre_params_; }
   std::vector<std::unique_ptr<candidate::Hand>> selectGrasps(std::vector<std::unique_ptr<candidate::Hand>> &hands) const;
   const gpdb_params &getParams() const { return params_; }
   const candidate::HandSearch::Parameters &getHandSearchParameters() const { return hand_search_params_; }
@@ -219,7 +229,10 @@ class GraspDetector {
 
  private:
   gpdb_params params_{};
+  gpdb_preprocess_params pre_params_{};
   gpdb_ctx *ctx_{nullptr};
+  const util::Cloud *installed_cloud_{nullptr};  // cloud whose processed arrays are resident on the device
+  unsigned installed_revision_{0};
   candidate::HandSearch::Parameters hand_search_params_;
   int num_selected_{100}, num_samples_{1000};
   bool cluster_grasps_{false};
@@ -229,6 +242,9 @@ class GraspDetector {
 // fills gpdb_params from the reference's cfg keys (grasp_detector.cpp:22-185); returns false if the file is missing
 bool paramsFromConfig(const std::string &config_filename, gpdb_params &p, std::string &weights_file, int &num_selected,
                       int &num_samples, int &min_inliers);
+// cfg keys voxelize, voxel_size, workspace, normals_radius (grasp_detector.cpp:56-66); keys of steps that are not
+// implemented (remove_outliers, refine_normals_k, sample_above_plane) are reported and ignored
+bool preprocessParamsFromConfig(const std::string &config_filename, gpdb_preprocess_params &pp);
 
 }  // namespace gpd
 

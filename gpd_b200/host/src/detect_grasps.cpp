@@ -1,5 +1,7 @@
 // detect_grasps CONFIG_FILE PCD_FILE [NORMALS_FILE] — the reference's command line (src/detect_grasps.cpp:20-94) over
-// the B200 path. The cloud must already be processed (voxelised, with normals as PCD fields or a normals file).
+// the B200 path. A cloud without normals is preprocessed on the device (workspace filter, voxelisation, normal
+// estimation: GraspDetector::preprocessPointCloud -> gpdb_preprocess); normals given as PCD fields or as a
+// NORMALS_FILE are kept.
 // --dump-config prints the parsed parameters as JSON and exits (used by the CPU tests).
 #include <cstdio>
 #include <cstring>
@@ -41,7 +43,12 @@ int main(int argc, char *argv[]) {
     if (!paramsFromConfig(config_filename, p, weights, num_selected, num_samples, min_inliers)) return -1;
     util::Cloud cloud;
     if (args.size() >= 2) cloud = util::Cloud(args[1], {0.0, 0.0, 0.0});
-    printf("{\"finger_width\": %.17g, \"hand_outer_diameter\": %.17g, \"hand_depth\": %.17g, \"hand_height\": %.17g, "
+    gpdb_preprocess_params pp;
+    preprocessParamsFromConfig(config_filename, pp);
+    printf("{\"voxelize\": %d, \"voxel_size\": %.17g, \"normals_radius\": %.17g, \"workspace\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g], ",
+           pp.voxelize, pp.voxel_size, pp.normals_radius, pp.workspace[0], pp.workspace[1], pp.workspace[2], pp.workspace[3],
+           pp.workspace[4], pp.workspace[5]);
+    printf("\"finger_width\": %.17g, \"hand_outer_diameter\": %.17g, \"hand_depth\": %.17g, \"hand_height\": %.17g, "
            "\"init_bite\": %.17g, \"volume_width\": %.17g, \"volume_depth\": %.17g, \"volume_height\": %.17g, "
            "\"image_size\": %d, \"image_num_channels\": %d, \"nn_radius\": %.17g, \"num_orientations\": %d, "
            "\"num_finger_placements\": %d, \"num_hand_axes\": %d, \"hand_axes0\": %d, \"deepen_hand\": %d, "

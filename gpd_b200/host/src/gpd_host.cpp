@@ -81,11 +81,14 @@ Cloud::Cloud(const std::string &filename, const std::vector<double> &view_points
   camera_source_.assign((size_t)numCameras() * size(), 0);
   for (size_t i = 0; i < size(); i++) camera_source_[i * numCameras()] = 1;  // single view: all points seen by camera 0
   if (numCameras() > 1) std::fill(camera_source_.begin(), camera_source_.end(), 1);
+  touch();
 }
 
 Cloud::Cloud(const std::vector<float> &xyz, const std::vector<double> &normals, const std::vector<int> &camera_source,
              const std::vector<double> &view_points)
-    : points_(xyz), normals_(normals), camera_source_(camera_source), view_points_(view_points) {}
+    : points_(xyz), normals_(normals), camera_source_(camera_source), view_points_(view_points) {
+  touch();
+}
 
 // .pcd reader: header fields FIELDS/SIZE/TYPE/COUNT/POINTS/DATA (ascii | binary); NaN points are dropped
 // (Cloud::removeNans). Replaces pcl::io::loadPCDFile in cloud.cpp:643-660.
@@ -193,6 +196,20 @@ void Cloud::setNormalsFromFile(const std::string &filename) {
     std::cout << "ERROR: normals file does not match the cloud (" << rows.size() << " rows for " << n << " points)\n";
     normals_.clear();
   }
+  touch();
+}
+
+void Cloud::touch() {
+  static unsigned counter = 0;
+  revision_ = ++counter;
+}
+
+void Cloud::setProcessed(std::vector<float> points, std::vector<double> normals, std::vector<int> camera_source) {
+  points_ = std::move(points);
+  normals_ = std::move(normals);
+  camera_source_ = std::move(camera_source);
+  sample_indices_.clear();
+  touch();
 }
 
 void Cloud::subsample(int num_samples) {
@@ -473,6 +490,7 @@ GraspDetector::GraspDetector(const std::string &config_filename) {
   int min_inliers = 0;
   if (!paramsFromConfig(config_filename, params_, weights_file, num_selected_, num_samples_, min_inliers)) return;
   cluster_grasps_ = min_inliers > 0;
+  preprocessParamsFromConfig(config_filename, pre_params_);
   ctx_ = make_ctx(params_);
   if (ctx_ && !weights_file.empty()) {
     if (gpdb_load_weights_dir(ctx_, weights_file.c_str()) == GPDB_OK) has_classifier_ = true;
@@ -483,10 +501,50 @@ GraspDetector::GraspDetector(const std::string &config_filename) {
 }
 GraspDetector::~GraspDetector() { gpdb_destroy(ctx_); }
 
+bool preprocessParamsFromConfig(const std::string &config_filename, gpdb_preprocess_params &pp) {
+  util::ConfigFile config_file(config_filename);
+  gpdb_preprocess_params_default(&pp);
+  if (!config_file.ExtractKeys()) return false;
+  pp.voxelize = config_file.getValueOfKey<bool>("voxelize", true) ? 1 : 0;
+  pp.voxel_size = config_file.getValueOfKey<double>("voxel_size", 0.003);
+  pp.normals_radius = config_file.getValueOfKey<double>("normals_radius", 0.03);
+  std::vector<double> ws = config_file.getValueOfKeyAsStdVectorDouble("workspace", "-1 1 -1 1 -1 1");
+  for (size_t i = 0; i < 6 && i < ws.size(); i++) pp.workspace[i] = ws[i];
+  if (config_file.getValueOfKey<bool>("remove_outliers", false) || config_file.getValueOfKey<int>("refine_normals_k", 0) > 0 ||
+      config_file.getValueOfKey<bool>("sample_above_plane", false))
+    printf("NOTE: remove_outliers / refine_normals_k / sample_above_plane are not part of the accelerated preprocessing: ignored\n");
+  return true;
+}
+
 void GraspDetector::preprocessPointCloud(util::Cloud &cloud) {
-  // removeNans happens at load time; workspace filtering, voxelisation and normal estimation are outside the
-  // accelerated path (candidates_generator.cpp:14-37): the cloud must arrive processed. Only the sampling step:
-  if (cloud.getSampleIndices().empty()) cloud.subsample(num_samples_);
+  printf("Processing cloud with %zu points.\n", cloud.size());
+  if (!ctx_ || cloud.size() == 0) return;
+  gpdb_preprocess_params pp = pre_params_;
+  // the reference recomputes the normals unconditionally (cloud.cpp:458-484), which discards a NORMALS_FILE the
+  // caller supplied; here supplied normals are kept (voxel-averaged, cloud.cpp:307-311,331-333)
+  pp.estimate_normals = cloud.hasNormals() ? 0 : 1;
+  const int n = gpdb_preprocess(ctx_, cloud.getPoints().data(), cloud.hasNormals() ? cloud.getNormals().data() : nullptr,
+                                cloud.getCameraSource().empty() ? nullptr : cloud.getCameraSource().data(), (int)cloud.size(),
+                                cloud.getViewPoints().data(), cloud.numCameras(), &pp);
+  if (n < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return;
+  }
+  double ms[6];
+  gpdb_preprocess_timings(ctx_, ms);
+  if (pp.voxelize) printf("Voxelized cloud: %d\n", n);
+  if (pp.estimate_normals) printf("Calculated %d surface normals in %3.4fs (mode: B200).\n", n, ms[4] * 1e-3);
+  std::vector<float> xyz(3 * (size_t)n);
+  std::vector<double> nrm(3 * (size_t)n);
+  std::vector<int> cam((size_t)n * cloud.numCameras());
+  if (n > 0 && gpdb_get_cloud(ctx_, xyz.data(), nrm.data(), cam.data()) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return;
+  }
+  cloud.setProcessed(std::move(xyz), std::move(nrm), std::move(cam));
+  installed_cloud_ = n > 0 ? &cloud : nullptr;  // the processed cloud is already resident: detectGrasps skips the upload
+  installed_revision_ = cloud.revision();
+  cloud.subsample(num_samples_);
 }
 
 std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::selectGrasps(
@@ -512,9 +570,13 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
     printf("ERROR: detector not initialised (%s)\n", ctx_ ? "no classifier weights" : gpdb_last_error(nullptr));
     return hands_out;
   }
-  if (upload_cloud(ctx_, cloud) != GPDB_OK) {
-    printf("ERROR: %s\n", gpdb_last_error(ctx_));
-    return hands_out;
+  if (!(installed_cloud_ == &cloud && installed_revision_ == cloud.revision())) {
+    if (upload_cloud(ctx_, cloud) != GPDB_OK) {
+      printf("ERROR: %s\n", gpdb_last_error(ctx_));
+      return hands_out;
+    }
+    installed_cloud_ = &cloud;
+    installed_revision_ = cloud.revision();
   }
   const std::vector<int> &idx = cloud.getSampleIndices();
   gpdb_result r;

@@ -19,7 +19,8 @@ EXPORTS = [
     "gpdb_params_default", "gpdb_create", "gpdb_destroy", "gpdb_last_error", "gpdb_load_weights_dir",
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
     "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
-    "gpdb_set_stream", "gpdb_debug_phase_cycles",
+    "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
+    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings",
 ]
 
 
@@ -58,6 +59,11 @@ def lib():
     L.gpdb_detect_resident.argtypes = [vp, vp, C.c_int32, vp, vp, C.POINTER(abi.Result)]
     L.gpdb_set_stream.argtypes = [vp, vp]
     L.gpdb_debug_phase_cycles.argtypes = [vp, C.c_int, vp]
+    L.gpdb_preprocess_params_default.argtypes = [C.POINTER(abi.PreprocessParams)]
+    L.gpdb_preprocess.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(abi.PreprocessParams)]
+    L.gpdb_get_cloud.argtypes = [vp, vp, vp, vp]
+    L.gpdb_get_cloud_source_index.argtypes = [vp, vp]
+    L.gpdb_preprocess_timings.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -86,6 +92,18 @@ def default_params(**over):
         else:
             setattr(p, k, v)
     del q
+    return p
+
+
+def preprocess_params(**over):
+    """gpdb_preprocess_params with the reference defaults (cfg/eigen_params.cfg:16-21), overridden by keyword."""
+    p = abi.PreprocessParams()
+    lib().gpdb_preprocess_params_default(C.byref(p))
+    for k, v in over.items():
+        if k == "workspace":
+            p.workspace[:] = list(v)
+        else:
+            setattr(p, k, v)
     return p
 
 
@@ -129,6 +147,50 @@ class Context:
         vp = np.ascontiguousarray(view_points if view_points is not None else np.zeros((1, 3)), dtype=np.float64)
         cam = None if cam_source is None else np.ascontiguousarray(cam_source, dtype=np.int32)
         self._check(lib().gpdb_set_cloud(self.h, _p(xyz), _p(normals), _p(cam), xyz.shape[0], _p(vp), vp.shape[0]))
+
+    def preprocess(self, xyz, cam_source=None, view_points=None, pp=None, normals=None, read_back=True):
+        """CandidatesGenerator::preprocessPointCloud on the device (gpdb_preprocess): NaN / workspace filter,
+        voxelisation, normal estimation; installs the processed cloud. Returns the processed cloud as a dict
+        (xyz, normals, cam_source, view_points, src) or just N' when read_back is False."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        vp = np.ascontiguousarray(view_points if view_points is not None else np.zeros((1, 3)), dtype=np.float64)
+        cam = None if cam_source is None else np.ascontiguousarray(cam_source, dtype=np.int32)
+        nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64)
+        if pp is None:
+            pp = preprocess_params()
+        n = self._check(lib().gpdb_preprocess(self.h, _p(xyz), _p(nrm), _p(cam), xyz.shape[0], _p(vp), vp.shape[0],
+                                              C.byref(pp)))
+        if not read_back:
+            return n
+        out = self.get_cloud() if n > 0 else {"xyz": np.zeros((0, 3), np.float32), "normals": np.zeros((0, 3)),
+                                              "cam_source": np.zeros((0, vp.shape[0]), np.int32)}
+        out["view_points"] = vp
+        if n > 0:
+            src = np.zeros(n, np.int32)
+            self._check(lib().gpdb_get_cloud_source_index(self.h, _p(src)))
+            out["src"] = src
+        else:
+            out["src"] = np.zeros(0, np.int32)
+        return out
+
+    def get_cloud(self):
+        n = self._check(lib().gpdb_get_cloud(self.h, None, None, None))
+        xyz = np.zeros((n, 3), np.float32)
+        nrm = np.zeros((n, 3), np.float64)
+        self._check(lib().gpdb_get_cloud(self.h, _p(xyz), _p(nrm), None))
+        return {"xyz": xyz, "normals": nrm, "cam_source": self._cam_source(n)}
+
+    def _cam_source(self, n, kmax=8):
+        # the camera count is not exported separately: read k x N into a buffer sized for GPDB_MAX_CAMERAS
+        buf = np.full(n * kmax, -1, np.int32)
+        self._check(lib().gpdb_get_cloud(self.h, None, None, _p(buf)))
+        k = int(np.count_nonzero(buf >= 0)) // max(n, 1)
+        return buf[: n * k].reshape(n, k).copy()
+
+    def preprocess_timings(self):
+        ms = np.zeros(6)
+        lib().gpdb_preprocess_timings(self.h, _p(ms))
+        return ms
 
     def _result(self, fn, sample_idx):
         sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)

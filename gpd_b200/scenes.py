@@ -153,7 +153,21 @@ def _visible(points, cam, ang_res):
     return vis
 
 
-def synthetic_table_scene(seed, n_points=300000, two_cameras=False, step=0.003):
+def synthetic_raw_scene(seed, n_points=300000, two_cameras=False, step=0.002, nan_fraction=0.0):
+    """RAW (unprocessed) cloud of the same cluttered-table scene family: the hidden-surface-culled noisy surface
+    samples BEFORE voxelisation and normal estimation (several points per 3 mm voxel at the default 2 mm
+    lattice), i.e. what CandidatesGenerator::preprocessPointCloud receives (candidates_generator.cpp:14-37).
+    `n_points` sizes the scene like synthetic_table_scene (the voxelised cloud has roughly that many points);
+    `nan_fraction` of the points get a NaN coordinate (depth-camera dropouts, cloud.cpp:154-164)."""
+    d = synthetic_table_scene(seed, n_points=n_points, two_cameras=two_cameras, step=step, _raw=True)
+    if nan_fraction > 0:
+        rng = np.random.default_rng(seed + 1000)
+        bad = rng.random(len(d["xyz"])) < nan_fraction
+        d["xyz"][bad, rng.integers(0, 3, int(bad.sum()))] = np.nan
+    return d
+
+
+def synthetic_table_scene(seed, n_points=300000, two_cameras=False, step=0.003, _raw=False):
     """Config 3/4/5 cloud: a table plane at z ~ 0.9 m in front of a camera at the origin looking
     along +z, 30-60 boxes / cylinders / spheres (5-25 cm) resting on it, surfaces on a 3 mm
     lattice with sigma = 0.5 mm noise, hidden-surface culled per camera, voxelised at 0.003 and
@@ -182,6 +196,14 @@ def synthetic_table_scene(seed, n_points=300000, two_cameras=False, step=0.003):
         seen[:, k] = facing & _visible(pts, cam, 0.6 * step / tz)
     keep = seen.any(1)
     pts, nrm, seen = pts[keep], nrm[keep], seen[keep]
+    if _raw:
+        order = rng.permutation(len(pts))  # scan order is not voxel order
+        pts, seen = pts[order], seen[order]
+        firstcam = np.argmax(seen, axis=1)
+        cam_source = np.zeros((len(pts), len(cams)), np.int32)
+        cam_source[np.arange(len(pts)), firstcam] = 1
+        return {"xyz": np.ascontiguousarray(pts.astype(np.float32)), "cam_source": cam_source,
+                "view_points": np.array(cams, dtype=np.float64)}
     xyz, first = voxelize(pts.astype(np.float32), step)
     nrm, seen = nrm[first], seen[first]
     if len(xyz) < n_points:

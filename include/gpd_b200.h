@@ -211,6 +211,50 @@ int gpdb_images(gpdb_ctx *ctx, const gpdb_pose *poses, int32_t n_poses, uint8_t 
 int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n_images, float *scores_out,
                   float *logits_out);
 
+/* --- cloud preprocessing (the step immediately before the path) -------------- */
+
+/* Parameters of CandidatesGenerator::preprocessPointCloud (candidates_generator.cpp:14-37); field names are
+ * the reference's cfg keys (grasp_detector.cpp:50-66, cfg/eigen_params.cfg:16-21). */
+typedef struct gpdb_preprocess_params {
+  double workspace[6];      /* cfg `workspace`: min_x max_x min_y max_y min_z max_z, strict inequalities   */
+  double voxel_size;        /* cfg `voxel_size`; Cloud::voxelizeCloud(float cell_size) rounds it to float  */
+  double normals_radius;    /* cfg `normals_radius`                                                        */
+  int32_t voxelize;         /* cfg `voxelize`                                                              */
+  int32_t estimate_normals; /* 1: Cloud::calculateNormalsOMP + reverseNormals (cloud.cpp:497-535,573-604); */
+                            /* 0: keep the caller's normals (voxel-averaged, cloud.cpp:307-311,331-333)    */
+} gpdb_preprocess_params;
+
+/* Reference defaults: workspace -1..1, voxelize, voxel_size 0.003, normals_radius 0.03, estimate normals. */
+void gpdb_preprocess_params_default(gpdb_preprocess_params *p);
+
+/* Replaces: CandidatesGenerator::preprocessPointCloud steps removeNans -> filterWorkspace -> voxelizeCloud ->
+ * calculateNormals (candidates_generator.cpp:18-26; cloud.cpp:154-164,207-266,286-348,458-484,497-535,573-604)
+ * on the device, and installs the processed cloud in the context exactly as gpdb_set_cloud would (the neighbour
+ * grid is built from the device copy). Inputs as gpdb_set_cloud (raw cloud, n_points may be millions); `normals`
+ * may be NULL when estimate_normals = 1. Returns the number of processed points N' (>= 0) or a negative error.
+ * Not covered: refine_normals_k, remove_outliers, sample_above_plane (PCL filters outside the default cfg) and
+ * Cloud::subsample (host-side RNG; the sample indices are an input of gpdb_detect).
+ * Semantics that differ from the reference by specification (DESIGN.md "preprocessing"): the voxel set is an
+ * exact set (the reference's std::set comparator is not a strict weak order), output order = descending index
+ * of each voxel's first point (the reference's iteration order whenever its de-duplication succeeds). */
+int gpdb_preprocess(gpdb_ctx *ctx, const float *xyz, const double *normals, const int32_t *cam_source,
+                    int32_t n_points, const double *view_points, int32_t n_cams,
+                    const gpdb_preprocess_params *pp);
+
+/* Reads back the cloud currently installed in the context (after gpdb_preprocess or gpdb_set_cloud):
+ * xyz_out [3*N] float32, normals_out [3*N] float64 (3 x N column-major), cam_source_out [k*N] int32 (k x N
+ * column-major); any output may be NULL. Returns N. These are the util::Cloud members the reference's
+ * preprocessing leaves behind (cloud_processed_, normals_, camera_source_; cloud.h:300-333). */
+int gpdb_get_cloud(gpdb_ctx *ctx, float *xyz_out, double *normals_out, int32_t *cam_source_out);
+
+/* After gpdb_preprocess: src_out [N] = index into the RAW cloud of the point that represents each processed point
+ * (the first point of its voxel, cloud.cpp:304-310 `(*res.first)(3)`). Returns N. */
+int gpdb_get_cloud_source_index(gpdb_ctx *ctx, int32_t *src_out);
+
+/* Device time (ms, CUDA events) of the stages of the last gpdb_preprocess call:
+ * ms[0] upload, ms[1] NaN/workspace filter, ms[2] voxelise, ms[3] grid build, ms[4] normals, ms[5] whole call. */
+int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]);
+
 /* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). */
 void gpdb_free_result(gpdb_result *r);
 

@@ -1101,6 +1101,259 @@ void lenet_forward(const gpdb_params &pr, const Weights &w, const uint8_t *img_h
   logits2[1] = y[1] + w.i2b[1];
 }
 
+// ------------------------------------------------------------------------------------------
+// Cloud preprocessing: CandidatesGenerator::preprocessPointCloud
+// (candidates_generator.cpp:14-37) = removeNans -> filterWorkspace -> voxelizeCloud ->
+// calculateNormals(OMP) -> reverseNormals.
+//
+// PARITY UNPINNED: PCL (>= 1.9, unpinned, README.md:44) is absent from this image. The normal
+// estimation restates the published algorithm of PCL 1.9.1 (the minimum version the reference
+// names): pcl::NormalEstimationOMP::computeFeature -> computePointNormal ->
+// computeMeanAndCovarianceMatrix (float32 single pass, common/impl/centroid.hpp) ->
+// solvePlaneParameters -> pcl::eigen33 / computeRoots (common/impl/eigen.hpp, float32 closed
+// form) -> flipNormalTowardsViewpoint (features/normal_3d.h), with the neighbours in the
+// kd-tree's sorted (dist, index) order, which fixes the float32 summation order.
+// ------------------------------------------------------------------------------------------
+
+// pcl::computeRoots2 (common/impl/eigen.hpp)
+void pcl_roots2(float b, float c, float *roots) {
+  roots[0] = 0.0f;
+  float d = (float)((double)(b * b) - 4.0 * (double)c);  // Scalar (b * b - 4.0 * c): the subtraction is done in double
+  if (d < 0.0f) d = 0.0f;
+  float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+// pcl::computeRoots (common/impl/eigen.hpp), Scalar = float; m row-major symmetric
+void pcl_roots(const float m[3][3], float *roots) {
+  float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+             m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+             m[1][2] * m[1][2];
+  float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < FLT_EPSILON) {
+    pcl_roots2(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = std::sqrt(3.0f);
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  float rho = std::sqrt(-a_over_3);
+  float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  float cos_theta = std::cos(theta);
+  float sin_theta = std::sin(theta);
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    std::swap(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0.0f) pcl_roots2(c2, c1, roots);
+}
+// pcl::eigen33 (mat, eigenvalue, eigenvector): smallest eigenvalue and its eigenvector
+void pcl_eigen33_smallest(const float cov[3][3], float &eigenvalue, float *evec) {
+  float scale = 0.0f;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) scale = std::max(scale, std::fabs(cov[r][c]));
+  if (scale <= FLT_MIN) scale = 1.0f;
+  float sm[3][3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) sm[r][c] = cov[r][c] / scale;
+  float ev[3];
+  pcl_roots(sm, ev);
+  eigenvalue = ev[0] * scale;
+  for (int d = 0; d < 3; d++) sm[d][d] -= ev[0];
+  auto cross = [](const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  float v1[3], v2[3], v3[3];
+  cross(sm[0], sm[1], v1);
+  cross(sm[0], sm[2], v2);
+  cross(sm[1], sm[2], v3);
+  auto sq = [](const float *v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; };
+  float l1 = sq(v1), l2 = sq(v2), l3 = sq(v3);
+  const float *best;
+  float len;
+  if (l1 >= l2 && l1 >= l3) { best = v1; len = l1; }
+  else if (l2 >= l1 && l2 >= l3) { best = v2; len = l2; }
+  else { best = v3; len = l3; }
+  float sl = std::sqrt(len);
+  for (int k = 0; k < 3; k++) evec[k] = best[k] / sl;
+}
+
+struct PreOut {
+  std::vector<float> xyz;
+  std::vector<double> nrm;
+  std::vector<int32_t> cam;
+  std::vector<int32_t> src;  // index (into the raw cloud) of the point that represents each output point
+};
+
+// removeNans (cloud.cpp:154-164) + filterWorkspace (cloud.cpp:239-265): strict inequalities on float32 points
+// against the double workspace bounds; cam_source / normals are filtered consistently.
+// voxelizeCloud (cloud.cpp:286-348), exact-set variant (see include/gpd_b200.h gpdb_preprocess).
+void preprocess_points(const float *xyz, const double *nrm_in, const int32_t *cam, int M, int K,
+                       const gpdb_preprocess_params &pp, PreOut &o) {
+  std::vector<int> keep;
+  keep.reserve(M);
+  for (int i = 0; i < M; i++) {
+    const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    if (!(std::isfinite(x) && std::isfinite(y) && std::isfinite(z))) continue;
+    if (x > pp.workspace[0] && x < pp.workspace[1] && y > pp.workspace[2] && y < pp.workspace[3] && z > pp.workspace[4] &&
+        z < pp.workspace[5])
+      keep.push_back(i);
+  }
+  const int M1 = (int)keep.size();
+  auto cam_of = [&](int i, int j) { return cam ? cam[(size_t)i * K + j] : 1; };
+  if (!pp.voxelize || M1 == 0) {
+    o.xyz.resize(3 * (size_t)M1);
+    o.cam.resize((size_t)K * M1);
+    o.src = keep;
+    if (nrm_in) o.nrm.resize(3 * (size_t)M1);
+    for (int k = 0; k < M1; k++) {
+      const int i = keep[k];
+      for (int a = 0; a < 3; a++) o.xyz[3 * (size_t)k + a] = xyz[3 * (size_t)i + a];
+      for (int j = 0; j < K; j++) o.cam[(size_t)k * K + j] = cam_of(i, j);
+      if (nrm_in)
+        for (int a = 0; a < 3; a++) o.nrm[3 * (size_t)k + a] = nrm_in[3 * (size_t)i + a];
+    }
+    return;
+  }
+  const float cell = (float)pp.voxel_size;  // voxelizeCloud(float cell_size)
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};  // pcl::getMinMax3D
+  for (int k = 0; k < M1; k++)
+    for (int a = 0; a < 3; a++) mn[a] = std::min(mn[a], xyz[3 * (size_t)keep[k] + a]);
+  struct V { long long key; int pos; };
+  std::vector<V> v(M1);
+  std::vector<int> vox(3 * (size_t)M1);
+  for (int k = 0; k < M1; k++) {
+    long long key = 0;
+    for (int a = 0; a < 3; a++) {
+      float t = (xyz[3 * (size_t)keep[k] + a] - mn[a]) / cell;  // (pt - min_pt) / cell_size, float32
+      int c = (int)std::floor(t);                                // EigenUtils::floorVector
+      vox[3 * (size_t)k + a] = c;
+      key = (key << 21) | (long long)(c & 0x1FFFFF);
+    }
+    v[k] = {key, k};
+  }
+  std::stable_sort(v.begin(), v.end(), [](const V &a, const V &b) { return a.key < b.key; });
+  struct G { int first, begin, end; };
+  std::vector<G> groups;
+  for (int s = 0; s < M1;) {
+    int e = s;
+    while (e < M1 && v[e].key == v[s].key) e++;
+    groups.push_back({v[s].pos, s, e});
+    s = e;
+  }
+  // iteration order of the reference's set when its de-duplication succeeds: every new voxel is linked in at the
+  // leftmost position of the tree (comp(v, x) == "differs" sends the descent left), i.e. newest first
+  std::sort(groups.begin(), groups.end(), [](const G &a, const G &b) { return a.first > b.first; });
+  const int U = (int)groups.size();
+  o.xyz.resize(3 * (size_t)U);
+  o.cam.resize((size_t)K * U);
+  o.src.resize(U);
+  if (nrm_in) o.nrm.resize(3 * (size_t)U);
+  for (int g = 0; g < U; g++) {
+    const int k = groups[g].first, i = keep[k];
+    o.src[g] = i;
+    for (int a = 0; a < 3; a++) {
+      float t = cell * (float)vox[3 * (size_t)k + a];  // min_pt + cell_size * v.cast<float>()
+      o.xyz[3 * (size_t)g + a] = mn[a] + t;
+    }
+    for (int j = 0; j < K; j++) o.cam[(size_t)g * K + j] = (cam_of(i, j) == 1) ? 1 : 0;
+    if (nrm_in) {
+      double acc[3] = {0, 0, 0};
+      for (int s = groups[g].begin; s < groups[g].end; s++)  // avg_normals.col(idx) += normals_.col(i), index order
+        for (int a = 0; a < 3; a++) acc[a] += nrm_in[3 * (size_t)keep[v[s].pos] + a];
+      const double cnt = (double)(groups[g].end - groups[g].begin);
+      for (int a = 0; a < 3; a++) o.nrm[3 * (size_t)g + a] = acc[a] / cnt;
+    }
+  }
+}
+
+// Cloud::calculateNormalsOMP (cloud.cpp:497-535) + reverseNormals (cloud.cpp:573-604) on a built Cloud
+// (c.xyz, c.cam, c.vp set, grid built); writes c.nrm.
+void estimate_normals(Cloud &c, double radius) {
+  const int N = c.N, K = c.K;
+  c.nrm.assign(3 * (size_t)N, 0.0);
+#pragma omp parallel
+  {
+    std::vector<Nb> nn;
+#pragma omp for schedule(dynamic, 64)
+    for (int i = 0; i < N; i++) {
+      // convertCameraSourceMatrixToLists (cloud.cpp:606-621): the FIRST camera that sees the point
+      int camera = -1;
+      for (int j = 0; j < K; j++)
+        if (c.cam[(size_t)i * K + j] == 1) { camera = j; break; }
+      if (camera < 0) continue;  // the reference leaves such columns uninitialised; specified here as 0
+      const float q[3] = {c.xyz[3 * (size_t)i], c.xyz[3 * (size_t)i + 1], c.xyz[3 * (size_t)i + 2]};
+      radius_search(c, q, radius, nn);
+      float n[3];
+      if (nn.size() < 3) {  // computePointNormal returns false -> NaN normal (normal_3d_omp.hpp)
+        n[0] = n[1] = n[2] = std::numeric_limits<float>::quiet_NaN();
+      } else {
+        float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (const Nb &b : nn) {
+          const float x = c.xyz[3 * (size_t)b.i], y = c.xyz[3 * (size_t)b.i + 1], z = c.xyz[3 * (size_t)b.i + 2];
+          accu[0] += x * x;
+          accu[1] += x * y;
+          accu[2] += x * z;
+          accu[3] += y * y;
+          accu[4] += y * z;
+          accu[5] += z * z;
+          accu[6] += x;
+          accu[7] += y;
+          accu[8] += z;
+        }
+        const float cnt = (float)nn.size();
+        for (int k = 0; k < 9; k++) accu[k] /= cnt;
+        float cov[3][3];
+        cov[0][0] = accu[0] - accu[6] * accu[6];
+        cov[0][1] = accu[1] - accu[6] * accu[7];
+        cov[0][2] = accu[2] - accu[6] * accu[8];
+        cov[1][1] = accu[3] - accu[7] * accu[7];
+        cov[1][2] = accu[4] - accu[7] * accu[8];
+        cov[2][2] = accu[5] - accu[8] * accu[8];
+        cov[1][0] = cov[0][1];
+        cov[2][0] = cov[0][2];
+        cov[2][1] = cov[1][2];
+        float ev;
+        pcl_eigen33_smallest(cov, ev, n);
+        // flipNormalTowardsViewpoint (features/normal_3d.h), float32; setViewPoint takes floats
+        float vx = (float)c.vp[3 * camera] - q[0], vy = (float)c.vp[3 * camera + 1] - q[1], vz = (float)c.vp[3 * camera + 2] - q[2];
+        float cos_theta = vx * n[0] + vy * n[1] + vz * n[2];
+        if (cos_theta < 0) {
+          n[0] *= -1;
+          n[1] *= -1;
+          n[2] *= -1;
+        }
+      }
+      double nd[3] = {(double)n[0], (double)n[1], (double)n[2]};
+      // reverseNormals (cloud.cpp:573-604)
+      bool needs_reverse = true;
+      for (int j = 0; j < K; j++)
+        if (c.cam[(size_t)i * K + j] == 1) {
+          double d0 = (double)q[0] - c.vp[3 * j], d1 = (double)q[1] - c.vp[3 * j + 1], d2 = (double)q[2] - c.vp[3 * j + 2];
+          if (nd[0] * d0 + nd[1] * d1 + nd[2] * d2 < 0) {
+            needs_reverse = false;
+            break;
+          }
+        }
+      if (needs_reverse)
+        for (int a = 0; a < 3; a++) nd[a] *= -1.0;
+      for (int a = 0; a < 3; a++) c.nrm[3 * (size_t)i + a] = nd[a];
+    }
+  }
+}
+
 std::vector<double> g_qtab;
 const double *qtab() {
   if (g_qtab.empty()) {
@@ -1315,6 +1568,59 @@ int gpdo_detect(void *cloud, const gpdb_params *pr, const float *const *wts, con
     stage_seconds[3] = t3 - t0;
   }
   return nc;
+}
+
+void gpdb_preprocess_params_default_o(gpdb_preprocess_params *p) {
+  const double ws[6] = {-1, 1, -1, 1, -1, 1};
+  for (int i = 0; i < 6; i++) p->workspace[i] = ws[i];
+  p->voxel_size = 0.003;
+  p->normals_radius = 0.03;
+  p->voxelize = 1;
+  p->estimate_normals = 1;
+}
+
+// CandidatesGenerator::preprocessPointCloud restated (see the preprocessing block above). Outputs are caller
+// allocated for n_points entries; returns N'. ms_out[0..1]: seconds spent in voxelisation / normals.
+int gpdo_preprocess(const float *xyz, const double *normals, const int32_t *cam, int32_t M, const double *vp, int32_t K,
+                    const gpdb_preprocess_params *pp, float *xyz_out, double *nrm_out, int32_t *cam_out, int32_t *src_out,
+                    double *sec_out, int32_t num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0) omp_set_num_threads(num_threads);
+#endif
+  PreOut o;
+  double t0 = now_s();
+  preprocess_points(xyz, normals, cam, M, K, *pp, o);
+  double t1 = now_s();
+  const int N = (int)o.src.size();
+  Cloud c;
+  c.N = N;
+  c.K = K;
+  c.xyz = o.xyz;
+  c.cam = o.cam;
+  c.vp.assign(vp, vp + 3 * (size_t)K);
+  if (pp->estimate_normals) {
+    c.build();
+    estimate_normals(c, pp->normals_radius);
+  } else {
+    c.nrm = o.nrm;
+    if (c.nrm.size() != 3 * (size_t)N) return GPDB_ERR_INVALID;
+  }
+  double t2 = now_s();
+  if (xyz_out) std::memcpy(xyz_out, c.xyz.data(), sizeof(float) * 3 * (size_t)N);
+  if (nrm_out) std::memcpy(nrm_out, c.nrm.data(), sizeof(double) * 3 * (size_t)N);
+  if (cam_out) std::memcpy(cam_out, c.cam.data(), sizeof(int32_t) * (size_t)K * N);
+  if (src_out) std::memcpy(src_out, o.src.data(), sizeof(int32_t) * (size_t)N);
+  if (sec_out) {
+    sec_out[0] = t1 - t0;
+    sec_out[1] = t2 - t1;
+  }
+  return N;
+}
+void gpdo_pcl_eigen33(const float *cov9 /* row-major */, float *eigenvalue, float *evec) {
+  float m[3][3];
+  for (int r = 0; r < 3; r++)
+    for (int c2 = 0; c2 < 3; c2++) m[r][c2] = cov9[3 * r + c2];
+  pcl_eigen33_smallest(m, *eigenvalue, evec);
 }
 
 void gpdo_free_result(gpdb_result *r) {

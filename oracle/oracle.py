@@ -53,6 +53,9 @@ def lib():
     L.gpdo_angle_axis.argtypes = [C.c_double, vp, vp]
     L.gpdo_qtab.argtypes = [vp]
     L.gpdo_num_threads.restype = C.c_int
+    L.gpdo_preprocess.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(abi.PreprocessParams), vp, vp, vp, vp, vp,
+                                  C.c_int32]
+    L.gpdo_pcl_eigen33.argtypes = [vp, vp, vp]
     _LIB = L
     return L
 
@@ -187,3 +190,35 @@ def conv_forward(x, w, b, k):
     out = np.zeros((M, (H - k + 1) * (Wd - k + 1)), np.float32)
     lib().gpdo_conv_forward(_p(x), Cc, H, Wd, _p(w), _p(b), M, k, _p(out))
     return out
+
+
+def preprocess(xyz, cam_source, view_points, pp, normals=None, nthreads=0):
+    """CandidatesGenerator::preprocessPointCloud restated on the CPU (removeNans, filterWorkspace, voxelizeCloud,
+    calculateNormalsOMP, reverseNormals). Returns a cloud dict + `src` (raw index of each output point) +
+    `seconds` (voxelise, normals)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    M = len(xyz)
+    vp_ = np.ascontiguousarray(view_points, dtype=np.float64)
+    K = vp_.shape[0]
+    cam = None if cam_source is None else np.ascontiguousarray(cam_source, dtype=np.int32)
+    nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64)
+    xo = np.zeros((M, 3), np.float32)
+    no = np.zeros((M, 3), np.float64)
+    co = np.zeros((M, K), np.int32)
+    so = np.zeros(M, np.int32)
+    sec = np.zeros(2)
+    n = lib().gpdo_preprocess(_p(xyz), None if nrm is None else _p(nrm), None if cam is None else _p(cam), M, _p(vp_), K,
+                              C.byref(pp), _p(xo), _p(no), _p(co), _p(so), _p(sec), nthreads or num_threads())
+    if n < 0:
+        raise RuntimeError(f"gpdo_preprocess failed: {n}")
+    return {"xyz": xo[:n].copy(), "normals": no[:n].copy(), "cam_source": co[:n].copy(), "view_points": vp_,
+            "src": so[:n].copy(), "seconds": sec}
+
+
+def pcl_eigen33(cov):
+    """pcl::eigen33 (smallest eigenvalue + eigenvector) of a 3x3 float32 symmetric matrix."""
+    cov = np.ascontiguousarray(cov, dtype=np.float32)
+    ev = np.zeros(1, np.float32)
+    vec = np.zeros(3, np.float32)
+    lib().gpdo_pcl_eigen33(_p(cov), _p(ev), _p(vec))
+    return float(ev[0]), vec

@@ -47,7 +47,7 @@ def test_cfg_and_pcd_parsing(cli, tmp_path):
         "weights_file = /some/where/params/\nnum_samples = 77\nnum_samples = 99\nnum_orientations = 6\nhand_axes = 0 2\n"
         "deepen_hand = 0\nworkspace_grasps = -0.5 0.5 -0.4 0.4 0.1 1.1\nmax_aperture = 0.07\n"
         "filter_approach_direction = 1\ndirection = 0 0 1\nthresh_rad = 1.5\nmin_inliers = 0\nnum_selected = 7\n"
-        "this line has no separator\n")
+        "voxel_size = 0.004\nworkspace = -0.9 0.9 -0.8 0.8 -0.7 0.7\nnormals_radius = 0.025\nthis line has no separator\n")
     xyz = np.array([[0.1, 0.2, 0.3], [np.nan, 0, 0], [1.5, -2.5, 3.25]], np.float32)
     nrm = np.array([[0, 0, 1], [0, 1, 0], [1, 0, 0]], np.float32)
     for binary in (False, True):
@@ -62,6 +62,8 @@ def test_cfg_and_pcd_parsing(cli, tmp_path):
         assert d["filter_approach_direction"] == 1 and d["direction"] == [0, 0, 1] and d["thresh_rad"] == 1.5
         assert d["weights_file"] == "/some/where/params/" and d["num_selected"] == 7 and d["min_inliers"] == 0
         assert d["nn_radius"] == 0.01 and d["num_finger_placements"] == 10 and d["friction_coeff"] == 20 and d["min_viable"] == 6
+        assert (d["voxelize"], d["voxel_size"], d["normals_radius"]) == (1, 0.004, 0.025)
+        assert d["workspace"] == [-0.9, 0.9, -0.8, 0.8, -0.7, 0.7]
         assert d["cloud_points"] == 2 and d["cloud_has_normals"] == 1  # the NaN point is removed
         assert np.allclose(d["first_point"], [0.1, 0.2, 0.3], atol=1e-7)
 
@@ -78,7 +80,7 @@ def test_detect_grasps_cli_matches_library(cli, tmp_path):
     for n, a in zip(names, w):
         a.astype(np.float32).tofile(tmp_path / "params" / (n + ".bin"))
     (tmp_path / "main.cfg").write_text(f"hand_geometry_filename = 0\nimage_geometry_filename = 0\nweights_file = {tmp_path}/params/\n"
-                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 10\nimage_num_channels = 15\n")
+                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 10\nimage_num_channels = 15\nvoxelize = 0\n")
     out = subprocess.check_output([cli, str(tmp_path / "main.cfg"), str(tmp_path / "krylon.pcd")]).decode()
     res = [l for l in out.splitlines() if l.startswith("RESULT")][0]
     n_grasps = int(res.split("n_grasps=")[1].split()[0])
@@ -92,4 +94,35 @@ def test_detect_grasps_cli_matches_library(cli, tmp_path):
     assert n_grasps == 10
     assert abs(best - r["candidates"]["score"].max()) <= 1e-3 * abs(best)
     assert f"gripper width: {r['n_candidates']}" in out
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_detect_grasps_cli_preprocesses_a_raw_cloud(cli, tmp_path, golden_dir):
+    """Raw PCD without normals: the CLI filters, voxelises and estimates normals on the device
+    (GraspDetector::preprocessPointCloud -> gpdb_preprocess) and then runs the path; same result as the ctypes
+    calls on the same raw points."""
+    from conftest import load_weights
+    from gpd_b200 import lib
+    raw = np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))["raw"]
+    write_pcd(tmp_path / "raw.pcd", raw, None, binary=True)
+    w, _ = load_weights(15)
+    os.makedirs(tmp_path / "params")
+    names = ["conv1_weights", "conv1_biases", "conv2_weights", "conv2_biases", "ip1_weights", "ip1_biases", "ip2_weights", "ip2_biases"]
+    for n, a in zip(names, w):
+        a.astype(np.float32).tofile(tmp_path / "params" / (n + ".bin"))
+    (tmp_path / "main.cfg").write_text(f"hand_geometry_filename = 0\nimage_geometry_filename = 0\nweights_file = {tmp_path}/params/\n"
+                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 10\nimage_num_channels = 15\n"
+                                       "centered_at_origin = 1\n")
+    out = subprocess.check_output([cli, str(tmp_path / "main.cfg"), str(tmp_path / "raw.pcd")]).decode()
+    assert "Voxelized cloud: 2373" in out
+    res = [l for l in out.splitlines() if l.startswith("RESULT")][0]
+    best = float(res.split("best_score=")[1])
+    ctx = lib.Context(lib.default_params(channels=15))
+    ctx.set_weights(w)
+    c = ctx.preprocess(raw, None, np.zeros((1, 3)), lib.preprocess_params())
+    ctx.set_cloud(c["xyz"], -c["normals"], c["cam_source"], c["view_points"])  # centered_at_origin (detect_grasps.cpp:75-80)
+    r = ctx.detect(np.arange(len(c["xyz"]), dtype=np.int32))
+    assert int(res.split("n_grasps=")[1].split()[0]) == 10
+    assert abs(best - r["candidates"]["score"].max()) <= 1e-3 * abs(best)
     ctx.close()

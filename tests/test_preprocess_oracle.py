@@ -1,0 +1,93 @@
+"""CPU tests of the preprocessing restatement (oracle/gpd_oracle.cpp "Cloud preprocessing"): SURVEY.md 8(f).1,
+CandidatesGenerator::preprocessPointCloud (candidates_generator.cpp:14-37).
+
+PCL is absent from this image, so parity against upstream binaries is UNPINNED; what is pinned here: the committed
+golden (regression), an independent float64 PCA of the same neighbourhoods, the closed-form float32 eigen-solver
+against numpy.linalg.eigh, and the voxel-set semantics against numpy.unique.
+"""
+import os
+
+import numpy as np
+
+from gpd_b200 import abi, scenes
+from oracle import oracle
+
+
+def test_krylon_preprocess_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))
+    r = oracle.preprocess(g["raw"], None, np.zeros((1, 3)), abi.default_preprocess_params())
+    assert np.array_equal(r["xyz"], g["xyz"]) and np.array_equal(r["src"], g["src"])
+    assert np.array_equal(r["cam_source"], g["cam_source"])
+    # regression pin; libm's float atan2f / cosf / sinf may differ between hosts in the last bit
+    assert np.abs(r["normals"] - g["normals"]).max() <= 1e-6
+    # independent check: float64 PCA of the same balls (sign-free)
+    c = np.abs((r["normals"] * g["pca64"]).sum(1))
+    assert (1.0 - c).max() < 2e-4
+    # viewpoint flip + reverseNormals: every normal points towards the camera at the origin
+    assert ((r["xyz"].astype(np.float64) * r["normals"]).sum(1) < 0).all()
+    # and the committed voxelised fixture used by the path tests is the same point set
+    k = np.load(os.path.join(golden_dir, "krylon_voxel.npz"))
+    assert set(map(tuple, k["xyz"])) == set(map(tuple, r["xyz"]))
+
+
+def test_pcl_eigen33_is_the_smallest_eigenpair():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a = rng.standard_normal((3, 8)) * rng.uniform(1e-3, 1.0, (3, 1))
+        cov = (a @ a.T / 8).astype(np.float32)
+        ev, vec = oracle.pcl_eigen33(cov)
+        w, v = np.linalg.eigh(cov.astype(np.float64))
+        scale = np.abs(cov).max()
+        assert abs(ev - w[0]) <= 2e-5 * scale
+        gap = (w[1] - w[0]) / scale
+        if gap > 1e-2:
+            assert 1.0 - abs(float(vec @ v[:, 0])) < 1e-3 / gap
+        assert abs(np.linalg.norm(vec) - 1) < 1e-5
+
+
+def test_voxelise_is_an_exact_set_in_reverse_first_occurrence_order():
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-0.05, 0.05, (5000, 3)).astype(np.float32)
+    pts[100] = [np.nan, 0, 0]                      # removeNans
+    pts[200] = [0.9, 0, 0]                         # outside the workspace below
+    nrm = rng.standard_normal((5000, 3))
+    cam = np.zeros((5000, 2), np.int32)
+    cam[np.arange(5000), rng.integers(0, 2, 5000)] = 1
+    pp = abi.default_preprocess_params(workspace=[-0.5, 0.5, -0.5, 0.5, -0.5, 0.5], voxel_size=0.01, estimate_normals=0)
+    r = oracle.preprocess(pts, cam, np.zeros((2, 3)), pp, normals=nrm)
+    keep = np.array([i for i in range(5000) if i not in (100, 200)])
+    mn = pts[keep].min(0)
+    vox = np.floor((pts[keep] - mn) / np.float32(0.01)).astype(np.int64)
+    uniq, first, inv = np.unique(vox, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(-first)                      # newest first
+    assert np.array_equal(r["src"], keep[first[order]])
+    assert np.array_equal(r["xyz"], (mn + np.float32(0.01) * uniq[order].astype(np.float32)).astype(np.float32))
+    assert np.array_equal(r["cam_source"], cam[r["src"]])
+    inv = inv.ravel()
+    for o in (0, 7, len(order) - 1):               # voxel-averaged normals, summed in index order
+        members = keep[np.nonzero(inv == order[o])[0]]
+        acc = np.zeros(3)
+        for i in members:
+            acc += nrm[i]
+        assert np.array_equal(r["normals"][o], acc / len(members))
+    # no voxelisation: plain order-preserving filter
+    pp2 = abi.default_preprocess_params(workspace=[-0.5, 0.5, -0.5, 0.5, -0.5, 0.5], voxelize=0, estimate_normals=0)
+    r2 = oracle.preprocess(pts, cam, np.zeros((2, 3)), pp2, normals=nrm)
+    assert np.array_equal(r2["src"], keep) and np.array_equal(r2["xyz"], pts[keep]) and np.array_equal(r2["normals"], nrm[keep])
+
+
+def test_normals_two_cameras_and_degenerate_neighbourhoods():
+    s = scenes.synthetic_raw_scene(7, n_points=20000, two_cameras=True, nan_fraction=0.01)
+    r = oracle.preprocess(s["xyz"], s["cam_source"], s["view_points"], abi.default_preprocess_params())
+    n = r["normals"]
+    assert not np.isnan(r["xyz"]).any() and len(r["xyz"]) < len(s["xyz"])
+    ok = ~np.isnan(n).any(1)
+    assert ok.mean() > 0.999 and np.abs(np.linalg.norm(n[ok], axis=1) - 1).max() < 1e-5
+    # reverseNormals: the normal points towards at least one camera that sees the point
+    d = r["xyz"].astype(np.float64)[:, None, :] - s["view_points"][None]
+    toward = ((d * n[:, None, :]).sum(2) < 0) & (r["cam_source"] == 1)
+    assert toward.any(1)[ok].all()
+    # isolated points (< 3 neighbours) get NaN normals like pcl::computePointNormal
+    iso = np.array([[0.3, 0.3, 0.3], [0.0, 0.0, 0.5], [0.001, 0.0, 0.5], [0.0, 0.001, 0.5], [0.001, 0.001, 0.5]], np.float32)
+    r3 = oracle.preprocess(iso, None, np.zeros((1, 3)), abi.default_preprocess_params(voxelize=0))
+    assert np.isnan(r3["normals"][0]).all() and not np.isnan(r3["normals"][1:]).any()

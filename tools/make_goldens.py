@@ -10,6 +10,8 @@ independent ground truth the reference itself links against). The GPU box never 
   tests/golden/lenet_ir_12ch.npz     torch restatement of the OpenVINO IR 12-channel net
   tests/golden/krylon_oracle_15ch.npz     oracle outputs (regression pin of the oracle itself)
   gpd_b200/weights/lenet_{15,3,12}ch.npz  the reference weights in the .bin layout
+  tests/golden/krylon_preprocess.npz      raw tutorials/krylon.pcd points + the oracle's preprocessing outputs
+                                          + an independent float64 PCA normal per point (`--only preprocess`)
 """
 import os
 import re
@@ -157,9 +159,34 @@ def krylon_oracle():
     print("krylon oracle golden:", r["n_candidates"], "candidates")
 
 
+def krylon_preprocess():
+    """Raw tutorial cloud -> CandidatesGenerator::preprocessPointCloud (oracle restatement) with the defaults of
+    cfg/eigen_params.cfg:16-21; `pca64` = normal direction from numpy float64 eigh of the same r-ball (independent
+    of the float32 PCL restatement; agreement is limited by PCL's float32 single-pass covariance, ~1e-4)."""
+    from scipy.spatial import cKDTree
+    raw = scenes.load_pcd_ascii(f"{REF}/tutorials/krylon.pcd")
+    vp = np.zeros((1, 3))
+    pp = abi.default_preprocess_params()
+    r = oracle.preprocess(raw, None, vp, pp)
+    P = r["xyz"].astype(np.float64)
+    tree = cKDTree(P)
+    pca = np.zeros_like(P)
+    for i in range(len(P)):
+        d2 = ((P - P[i]) ** 2).sum(1)
+        nb = np.nonzero(d2 < 0.03 ** 2)[0]
+        w, v = np.linalg.eigh(np.cov(P[nb].T, bias=True))
+        pca[i] = v[:, 0]
+    np.savez_compressed(os.path.join(G, "krylon_preprocess.npz"), raw=raw, xyz=r["xyz"], normals=r["normals"],
+                        cam_source=r["cam_source"], src=r["src"], pca64=pca)
+    print("krylon_preprocess:", len(raw), "->", len(P))
+
+
 if __name__ == "__main__":
     os.makedirs(G, exist_ok=True)
     os.makedirs(W, exist_ok=True)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "preprocess":
+        krylon_preprocess()
+        sys.exit(0)
     krylon_oracle()
     cv_pins()
     lenet_caffe(15)
