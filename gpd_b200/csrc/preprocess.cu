@@ -373,14 +373,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, Dev
     const int ib = (lane == 1 || lane == 3) ? 1 : ((lane == 2 || lane == 4 || lane == 5) ? 2 : (lane == 0 ? 0 : -1));
     float acc = 0.0f;
     if (lane < 9) {
+      // one loop for all nine accumulators: lanes 6..8 (plain sums) multiply by 1.0f, which is exact
       const float *pa = pc + (size_t)ia * cap, *pb = pc + (size_t)max(ib, 0) * cap;
-      if (ib >= 0) {
-        for (int k = 0; k < cnt; k++) {
-          const int j = ord[k];
-          acc += pa[j] * pb[j];
-        }
-      } else {
-        for (int k = 0; k < cnt; k++) acc += pa[ord[k]];
+      const bool prod = ib >= 0;
+#pragma unroll 4
+      for (int k = 0; k < cnt; k++) {
+        const int j = ord[k];
+        const float f = prod ? pb[j] : 1.0f;
+        acc += pa[j] * f;
       }
     }
     const float fc = (float)cnt;
