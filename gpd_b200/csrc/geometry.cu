@@ -853,9 +853,6 @@ struct ImgSmem {
   float fred[NT_IMG / 32][2];
   float a, b;
   float smax;
-  unsigned long long occ[64];  // occupied cells of the current channel group, one 64-bit word per image row
-  unsigned long long dil[64];  // its 3x3 dilation (border ignored): the only pixels that can be non-zero
-  int nlist;
 };
 
 __device__ __forceinline__ bool in_image_box(const DevParams &P, const gpdb_pose &h, double x, double y, double z) {
@@ -919,67 +916,72 @@ __device__ __forceinline__ void block_minmax(float &mn, float &mx, float (*red)[
   }
 }
 
-// cv::dilate(3x3 rect, border ignored) -> cv::normalize(NORM_MINMAX over all channels) -> convertTo(CV_8U, 255)
-// (image_strategy.cpp:145-153,179-187,222-230), evaluated SPARSELY. Every source image of the path is >= 0 with
-// exact zeros on unoccupied cells (|n|, 1 - mean, max - mean), so after the 3x3 dilation only pixels within one cell
-// of an occupied cell can be non-zero (~10 % of the 60 x 60 image for the point channels, ~35 % for the shadow
-// channels). With the occupied cells as a bitmap (one 64-bit word per row):
-//   max over the dilated image  = max over the occupied source cells (dilation keeps the maximum),
-//   min over the dilated image  = 0 as soon as one pixel lies outside the dilated footprint; otherwise it is
-//                                 reduced over the footprint (= the whole image) explicitly,
-//   pixels outside the footprint quantise to round(255 * fmaf(0, a, -0 * a)) = 0: the staged image is zero-filled
-//   once and only the footprint pixels are computed (nine guarded neighbour reads each).
-// The arithmetic of each pixel is the dense formula's, so the result is bit-identical to it.
-__device__ __forceinline__ void norm_ab(float mn, float mx, float &a, float &b) {
-  const double smin = (double)mn, smax = (double)mx;
-  const double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
-  const double shift = 0.0 - smin * scale;
-  a = (float)scale;
-  b = (float)shift;
-}
-__device__ __forceinline__ uint8_t quant8(float m, float a, float b) {
-  const float v = fmaf(m, a, b);
-  const int q = __float2int_rn(v * 255.0f);
-  return (uint8_t)min(max(q, 0), 255);
-}
-// sm.occ -> sm.dil and the list of its set pixels, packed row << 6 | col. Block-wide (contains barriers); returns
-// the number of listed pixels.
-__device__ __forceinline__ int build_footprint(ImgSmem &sm, int S, unsigned short *list) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) sm.nlist = 0;
-  __syncthreads();
-  if (tid < S) {
-    const unsigned long long mask = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
-    unsigned long long acc = 0ull;
+// cv::dilate(3x3 rect, border ignored) -> cv::normalize(NORM_MINMAX over all channels) ->
+// convertTo(CV_8U, 255) of a CH-channel float image `src` (HWC, SxS), written into channels
+// [choff, choff+CH) of the C-channel HWC uint8 image (image_strategy.cpp:145-153,179-187,222-230).
+template <int CH>
+__device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int choff, ImgSmem &sm) {
+  // separable 3x3 max: one thread owns an 8-row strip of one column; the dilated values stay in registers
+  // between the min/max reduction and the quantisation (the image is read once).
+  const int strips = (S + 7) >> 3;
+  const bool active = (int)threadIdx.x < S * strips;
+  const int c = threadIdx.x % S, r0 = (threadIdx.x / S) << 3;
+  float m[8][CH];
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  if (active) {
+    const int cl = max(c - 1, 0), cr = min(c + 1, S - 1);
+    float h0[CH], h1[CH], h2[CH];  // horizontal maxima of rows r-1, r, r+1 (sliding)
+    auto hrow = [&](int rr, float *h) {
+      if (rr < 0 || rr >= S) {
 #pragma unroll
-    for (int dr = -1; dr <= 1; dr++) {
-      const int r = tid + dr;
-      if (r >= 0 && r < S) {
-        const unsigned long long o = sm.occ[r];
-        acc |= (o | (o << 1) | (o >> 1)) & mask;
+        for (int k = 0; k < CH; k++) h[k] = -FLT_MAX;
+      } else {
+        const float *p = src + (size_t)rr * S * CH;
+#pragma unroll
+        for (int k = 0; k < CH; k++) h[k] = fmaxf(fmaxf(p[cl * CH + k], p[c * CH + k]), p[cr * CH + k]);
+      }
+    };
+    hrow(r0 - 1, h0);
+    hrow(r0, h1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      hrow(r0 + i + 1, h2);
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        m[i][k] = fmaxf(fmaxf(h0[k], h1[k]), h2[k]);
+        if (r0 + i < S) {
+          mn = fminf(mn, m[i][k]);
+          mx = fmaxf(mx, m[i][k]);
+        }
+        h0[k] = h1[k];
+        h1[k] = h2[k];
       }
     }
-    sm.dil[tid] = acc;
   }
-  __syncthreads();
-  for (int id0 = 0; id0 < S * 64; id0 += NT_IMG) {
-    const int id = id0 + tid, row = id >> 6, col = id & 63;
-    const bool set = row < S && ((sm.dil[row] >> col) & 1ull);
-    const unsigned m = __ballot_sync(0xffffffffu, set);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(&sm.nlist, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (set) list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)id;
+  block_minmax<NT_IMG>(mn, mx, sm.fred);
+  double smin = (double)mn, smax = (double)mx;
+  double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
+  double shift = 0.0 - smin * scale;
+  const float a = (float)scale, b = (float)shift;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (r0 + i < S) {
+        uint8_t *o = gimg + (size_t)((r0 + i) * S + c) * C + choff;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+          float v = fmaf(m[i][k], a, b);
+          int q = __float2int_rn(v * 255.0f);
+          o[k] = (uint8_t)min(max(q, 0), 255);  // shared-memory staging of the HWC image
+        }
+      }
     }
   }
   __syncthreads();
-  return sm.nlist;
 }
 
 // dynamic smem layout (bytes): tiles 3 * 8*S*S | box list: keys 8*CAP, q 3*4*CAP, cells 4*CAP, nrm 3*4*CAP
-// (the shadow bitmaps alias the box list) | staged image S*S*C | footprint pixel list 2 * 64*S
+// (the shadow bitmaps alias the box list)
 // optional phase timing (development aid, gpdb_debug_phase_cycles): thread 0 accumulates clock64() deltas
 #define PHASE(i)                                                        \
   do {                                                                  \
@@ -1007,8 +1009,9 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
   unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
   float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
+  float *nrmT = reinterpret_cast<float *>(tileB);                 // float[3*SS] over tileB..tileC
+  float *depF = nrmT + 3 * SS;                                    // float[SS]
   uint8_t *simg = dyn + img_off;                                  // uint8[SS*C] HWC staging of the output image
-  unsigned short *plist = reinterpret_cast<unsigned short *>(simg + ((SS * C + 15) / 16) * 16);  // footprint pixel list
   const int tid = threadIdx.x, lane = tid & 31;
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
@@ -1025,16 +1028,11 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       sm.n_img = 0;
       sm.box_n = 0;
     }
-    if (tid < 64) sm.occ[tid] = 0ull;
-    {  // the staged image starts as zeros (pixels outside every footprint stay 0); tileA / tileB start clean
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      for (int v = tid; v < (SS * C + 15) / 16; v += NT_IMG) reinterpret_cast<uint4 *>(simg)[v] = z;
-      for (int v = tid; v < SS; v += NT_IMG) reinterpret_cast<uint4 *>(tileA)[v] = z;  // 2 * SS x 8 B
-    }
     __syncthreads();
     PHASE(1);   // image start
     const gpdb_pose &h = sm.h;
     uint8_t *gout = images + (size_t)b * SS * C;
+    uint8_t *gimg = simg;  // channels are written to the shared-memory staging image, flushed once at the end
     const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
     SegRange sr = seg_range(P, q, P.rf_img);
@@ -1139,109 +1137,65 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     __syncthreads();
 
     // ---- points phase: per projection rasterise normals (arg-max key = last writer in (dist, index)
-    // order, createNormalsImage :124-143) and depth (per-cell mean, createDepthImage :158-176), then the sparse
-    // dilate / normalise / quantise of both channel groups
-    const bool has_nrm = (C != 1), has_dep = (C == 1 || C >= 12);
+    // order, createNormalsImage :124-143) and depth (per-cell mean, createDepthImage :158-176)
     for (int pj = 0; pj < nproj; pj++) {
       // coordinate orders (x,y,z), (z,y,x), (z,x,y): rows cumulatively swapped {0<->2}, {1<->2}
       // (image_15_channels_strategy.cpp:57-64)
       const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
-      __syncthreads();  // tiles and occupancy words are clean (image start / sparse reset below)
+      for (int k = tid; k < 2 * SS; k += NT_IMG) tileA[k] = 0ull;  // tileA + tileB
+      __syncthreads();
       for (int k = tid; k < bn; k += NT_IMG) {
-        const unsigned cc = bcell[k];
-        const int row = S - 1 - (int)((cc >> (8 * a0)) & 255), col = (cc >> (8 * a1)) & 255;
-        const int pix = row * S + col;
+        unsigned cc = bcell[k];
+        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
+        int pix = (S - 1 - v) * S + hcol;
         atomicMax(tileA + pix, bkeys[k]);
         atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
-        atomicOr(&sm.occ[row], 1ull << col);
       }
       __syncthreads();
-      // winner pass: the point that owns a cell (largest key) turns the cell's accumulators into its values:
-      // tileA[pix] = marker | box index of the winner (its |R^T n| is bnrm[.][index]), tileB[pix] = float bits of
-      // 1 - mean. Keys never have bit 63 set (non-negative float32 distance), so losers keep failing the test.
-      float mxn = 0.0f, mxd = 0.0f;
-      for (int k = tid; k < bn; k += NT_IMG) {
-        const unsigned cc = bcell[k];
-        const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
-        if (tileA[pix] == bkeys[k]) {
-          const unsigned long long acc = tileB[pix];
-          const unsigned cntc = (unsigned)(acc >> 48);
-          const double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
-          const float avg = (float)mean;
-          const float val = (float)(1.0 - (double)avg);
-          tileB[pix] = (unsigned long long)__float_as_uint(val);
-          tileA[pix] = 0x8000000000000000ull | (unsigned long long)k;
-          mxn = fmaxf(mxn, fmaxf(fmaxf(bnrm[k], bnrm[BOX_CAP + k]), bnrm[2 * BOX_CAP + k]));
-          mxd = fmaxf(mxd, val);
-        }
+      unsigned long long dreg[(MAXPIX + NT_IMG - 1) / NT_IMG];
+#pragma unroll
+      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+        int pix = tid + t * NT_IMG;
+        dreg[t] = pix < SS ? tileB[pix] : 0ull;
       }
-      float neg_mxd = -mxd;
-      block_minmax<NT_IMG>(neg_mxd, mxn, sm.fred);  // block maxima of both groups (min of the negated depth maximum)
-      mxd = -neg_mxd;
-      const int nL = build_footprint(sm, S, plist);
-      // dilated values of one footprint pixel: max over the occupied in-bounds 3x3 neighbours (all values >= 0)
-      auto dilated = [&](int id, float &m0, float &m1, float &m2, float &md) {
-        const int row = id >> 6, col = id & 63;
-        m0 = m1 = m2 = md = 0.0f;
+      __syncthreads();
 #pragma unroll
-        for (int dr = -1; dr <= 1; dr++) {
-          const int r2 = row + dr;
-          if (r2 < 0 || r2 >= S) continue;
-          const unsigned long long o = sm.occ[r2];
-#pragma unroll
-          for (int dc = -1; dc <= 1; dc++) {
-            const int c2 = col + dc;
-            if (c2 < 0 || c2 >= S || !((o >> c2) & 1ull)) continue;
-            const int p2 = r2 * S + c2;
-            const unsigned kw = (unsigned)tileA[p2];
-            m0 = fmaxf(m0, bnrm[kw]);
-            m1 = fmaxf(m1, bnrm[BOX_CAP + kw]);
-            m2 = fmaxf(m2, bnrm[2 * BOX_CAP + kw]);
-            md = fmaxf(md, __uint_as_float((unsigned)tileB[p2]));
+      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+        int pix = tid + t * NT_IMG;
+        if (pix < SS) {
+          nrmT[pix * 3] = 0.0f;
+          nrmT[pix * 3 + 1] = 0.0f;
+          nrmT[pix * 3 + 2] = 0.0f;
+          unsigned long long acc = dreg[t];
+          unsigned cntc = (unsigned)(acc >> 48);
+          float val = 0.0f;
+          if (cntc) {
+            double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+            float avg = (float)mean;
+            val = (float)(1.0 - (double)avg);
           }
+          depF[pix] = val;
         }
-      };
-      float mnn = 0.0f, mnd = 0.0f;
-      if (nL == SS) {  // the footprint covers the whole image: the minimum is not the implicit zero
-        float vn = FLT_MAX, vd = FLT_MAX, dummy = 0.0f;
-        for (int e = tid; e < nL; e += NT_IMG) {
-          float m0, m1, m2, md;
-          dilated(plist[e], m0, m1, m2, md);
-          vn = fminf(vn, fminf(fminf(m0, m1), m2));
-          vd = fminf(vd, md);
-        }
-        block_minmax<NT_IMG>(vn, dummy, sm.fred);
-        block_minmax<NT_IMG>(vd, dummy, sm.fred);
-        mnn = vn;
-        mnd = vd;
-      }
-      float an, bn_, ad, bd;
-      norm_ab(mnn, mxn, an, bn_);
-      norm_ab(mnd, mxd, ad, bd);
-      const int ch_n = (C == 3) ? 0 : pj * per, ch_d = (C == 1) ? 0 : pj * per + 3;
-      for (int e = tid; e < nL; e += NT_IMG) {
-        const int id = plist[e];
-        float m0, m1, m2, md;
-        dilated(id, m0, m1, m2, md);
-        uint8_t *o = simg + (size_t)((id >> 6) * S + (id & 63)) * C;
-        if (has_nrm) {
-          o[ch_n] = quant8(m0, an, bn_);
-          o[ch_n + 1] = quant8(m1, an, bn_);
-          o[ch_n + 2] = quant8(m2, an, bn_);
-        }
-        if (has_dep) o[ch_d] = quant8(md, ad, bd);
       }
       __syncthreads();
-      // sparse reset of the touched cells for the next projection / the shadow phase
       for (int k = tid; k < bn; k += NT_IMG) {
-        const unsigned cc = bcell[k];
-        const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
-        tileA[pix] = 0ull;
-        tileB[pix] = 0ull;
+        unsigned cc = bcell[k];
+        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
+        int pix = (S - 1 - v) * S + hcol;
+        if (tileA[pix] == bkeys[k]) {
+          nrmT[pix * 3] = bnrm[k];
+          nrmT[pix * 3 + 1] = bnrm[BOX_CAP + k];
+          nrmT[pix * 3 + 2] = bnrm[2 * BOX_CAP + k];
+        }
       }
-      if (tid < 64) sm.occ[tid] = 0ull;
+      __syncthreads();
+      if (C == 1) {
+        postprocess<1>(depF, S, gimg, C, 0, sm);
+      } else {
+        postprocess<3>(nrmT, S, gimg, C, pj * per, sm);
+        if (C >= 12) postprocess<1>(depF, S, gimg, C, pj * per + 3, sm);
+      }
     }
-    __syncthreads();
 
     PHASE(3);  // points phase (3 projections) done
     // ---- shadow phase (15 channels): HandSet::calculateShadow, deterministic variant
@@ -1342,6 +1296,16 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       for (int k = 0; k < K; k++) {
         if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
         unsigned *bm = bitmap + (size_t)k * bm_words;
+        float cull_lo[3], cull_hi[3], cull_inv[3];
+        bool cull_par[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const float dv = (float)sm.svh[k][a];
+          cull_par[a] = fabsf(dv) < 1e-6f;  // moves the coordinate by < 1e-6 over the whole segment: below the margin
+          cull_inv[a] = cull_par[a] ? 0.0f : 1.0f / dv;
+          cull_lo[a] = (float)bx_lo[a] - 1e-5f;
+          cull_hi[a] = (float)bx_hi[a] + 1e-5f;
+        }
         __syncthreads();
         if (tid == 0) sm.wl_n = 0;
         __syncthreads();
@@ -1350,29 +1314,28 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
           float d = l2_simple(q, p.x, p.y, p.z);
           if (!(d < P.r2_img)) return;
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-            // exact cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame) widened
-            // by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG value falls
-            // in [r0, r1] can produce a voxel point inside the box.
-            double ox, oy, oz;
-            to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], ox, oy, oz);
-            double tmin = 0.0, tmax = 1.0;
+            // conservative cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame)
+            // widened by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG
+            // value falls in [r0, r1] can produce a voxel point inside the box. float32 is enough here: its rounding
+            // (~1e-7 of coordinates < 0.2 m, 3e-7 of t) is covered by the extra 1e-5 of box margin and by the +-1 of
+            // slack on r0 / r1 (1 / 32767 = 3e-5); the draws themselves are evaluated in the reference's float64.
+            const float wx = p.x - fsx, wy = p.y - fsy, wz = p.z - fsz;
+            const float o3[3] = {fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz)), fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz)),
+                                 fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz))};
+            float tmin = 0.0f, tmax = 1.0f;
             bool hit = true;
-            {
-              const double lo3[3] = {bx_lo[0], bx_lo[1], bx_lo[2]}, hi3[3] = {bx_hi[0], bx_hi[1], bx_hi[2]};
-              const double o3[3] = {ox, oy, oz}, d3[3] = {sm.svh[k][0], sm.svh[k][1], sm.svh[k][2]};
 #pragma unroll
-              for (int a = 0; a < 3; a++) {
-                if (fabs(d3[a]) < 1e-12) {
-                  hit = hit && o3[a] >= lo3[a] && o3[a] <= hi3[a];
-                } else {
-                  double t1 = (lo3[a] - o3[a]) / d3[a], t2 = (hi3[a] - o3[a]) / d3[a];
-                  tmin = fmax(tmin, fmin(t1, t2));
-                  tmax = fmin(tmax, fmax(t1, t2));
-                }
+            for (int a = 0; a < 3; a++) {
+              if (cull_par[a]) {  // segment (numerically) parallel to the slab: inside or outside for every u
+                hit = hit && o3[a] >= cull_lo[a] && o3[a] <= cull_hi[a];
+              } else {
+                const float t1 = (cull_lo[a] - o3[a]) * cull_inv[a], t2 = (cull_hi[a] - o3[a]) * cull_inv[a];
+                tmin = fmaxf(tmin, fminf(t1, t2));
+                tmax = fminf(tmax, fmaxf(t1, t2));
               }
             }
             if (!hit || tmin > tmax) return;
-            const int r0 = max((int)floor(tmin * 32767.0) - 1, 0), r1 = min((int)ceil(tmax * 32767.0) + 1, 32767);
+            const int r0 = max((int)floorf(tmin * 32767.0f) - 1, 0), r1 = min((int)ceilf(tmax * 32767.0f) + 1, 32767);
             unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
             int pos = atomicAdd(&sm.wl_n, 1);
             if (pos < WL_CAP) {
@@ -1390,10 +1353,12 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         const int nw = min(sm.wl_n, WL_CAP);
         if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
         const int nsp = P.nsp;
+        const unsigned nsp_magic = nsp > 1 ? (unsigned)((0x100000000ull + (unsigned)nsp - 1) / (unsigned)nsp) : 0u;  // ceil(2^32 / nsp)
         // two independent (point, draw) pairs per iteration: the float64 chains of the two draws interleave
         auto work_bit = [&](int w) -> int {
           if (w >= nw * nsp) return -1;
-          int item = w / nsp, t = w - item * nsp;
+          // w / nsp by multiply-high: exact for w < 2^32 / nsp (w < WL_CAP * nsp < 2^20)
+          int item = nsp > 1 ? (int)__umulhi((unsigned)w, nsp_magic) : w, t = w - item * nsp;
           float4 e = wl[item];
           unsigned seed = P.lcgA[t] * __float_as_uint(e.w) + P.lcgC[t];
           unsigned rg = wrange[item];
@@ -1478,76 +1443,37 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i]);
       __syncthreads();
       PHASE(6);  // S2 bitmap pass done
-      // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean; sparse
-      // dilate / normalise / quantise as above (the occupancy words come from the per-cell counts)
+      // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
       for (int pj = 0; pj < 3; pj++) {
         unsigned long long *tile = tileA + (size_t)pj * SS;
         float *srcF = reinterpret_cast<float *>(tile);
-        unsigned *occ32 = reinterpret_cast<unsigned *>(sm.occ);
         float avgr[(MAXPIX + NT_IMG - 1) / NT_IMG];
-        unsigned occm = 0;
+        unsigned occ = 0;
         float mn = FLT_MAX, mx = -FLT_MAX;
 #pragma unroll
         for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-          const int id = tid + t * NT_IMG, row = id >> 6, col = id & 63;  // a warp covers 32 columns of one row
+          int pix = tid + t * NT_IMG;
           avgr[t] = 0.0f;
-          bool occupied = false;
-          if (row < S && col < S) {
-            const unsigned long long acc = tile[row * S + col];
-            const unsigned cntc = (unsigned)(acc >> 48);
+          if (pix < SS) {
+            unsigned long long acc = tile[pix];
+            unsigned cntc = (unsigned)(acc >> 48);
             if (cntc) {
-              const double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+              double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
               avgr[t] = (float)mean;
-              occm |= 1u << t;
-              occupied = true;
+              occ |= 1u << t;
               mx = fmaxf(mx, avgr[t]);
-              mn = fminf(mn, avgr[t]);
             }
           }
-          const unsigned m = __ballot_sync(0xffffffffu, occupied);
-          if (lane == 0 && row < S) occ32[row * 2 + (col >> 5)] = m;
         }
-        block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between the tile reads and the writes below
+        block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between reads and writes
         const float maxf = (mx == -FLT_MAX) ? 0.0f : mx;
 #pragma unroll
         for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-          const int id = tid + t * NT_IMG;
-          if ((occm >> t) & 1) srcF[(id >> 6) * S + (id & 63)] = maxf - avgr[t];
-        }
-        // largest source value: x -> maxf - x is monotone, so it is attained at the smallest mean
-        const float smax = (mx == -FLT_MAX) ? 0.0f : maxf - mn;
-        const int nL = build_footprint(sm, S, plist);  // its first barrier also orders the srcF writes
-        auto dilated1 = [&](int id) -> float {
-          const int row = id >> 6, col = id & 63;
-          float m = 0.0f;
-#pragma unroll
-          for (int dr = -1; dr <= 1; dr++) {
-            const int r2 = row + dr;
-            if (r2 < 0 || r2 >= S) continue;
-            const unsigned long long o = sm.occ[r2];
-#pragma unroll
-            for (int dc = -1; dc <= 1; dc++) {
-              const int c2 = col + dc;
-              if (c2 < 0 || c2 >= S || !((o >> c2) & 1ull)) continue;
-              m = fmaxf(m, srcF[r2 * S + c2]);
-            }
-          }
-          return m;
-        };
-        float smin = 0.0f;
-        if (nL == SS) {
-          float v = FLT_MAX, dummy = 0.0f;
-          for (int e = tid; e < nL; e += NT_IMG) v = fminf(v, dilated1(plist[e]));
-          block_minmax<NT_IMG>(v, dummy, sm.fred);
-          smin = v;
-        }
-        float a, bsh;
-        norm_ab(smin, smax, a, bsh);
-        for (int e = tid; e < nL; e += NT_IMG) {
-          const int id = plist[e];
-          simg[(size_t)((id >> 6) * S + (id & 63)) * C + pj * 5 + 4] = quant8(dilated1(id), a, bsh);
+          int pix = tid + t * NT_IMG;
+          if (pix < SS) srcF[pix] = ((occ >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
         }
         __syncthreads();
+        postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
       }
     }
     // ---- flush the staged image with coalesced 16-byte stores
@@ -1694,8 +1620,7 @@ static size_t images_smem_bytes(const DevParams &hp) {
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images) {
   if (nc <= 0) return GPDB_OK;
   const size_t img_off = images_smem_bytes(ctx->hp);
-  size_t smem = img_off + ((size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C + 15) / 16 * 16 +
-                (size_t)2 * ctx->hp.S * 64;  // staged HWC image + footprint pixel list (uint16 per padded pixel)
+  size_t smem = img_off + ((size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C + 15) / 16 * 16;
   if (smem > 219 * 1024) {
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem);
     return GPDB_ERR_INVALID;

@@ -248,4 +248,28 @@ bool preprocessParamsFromConfig(const std::string &config_filename, gpdb_preproc
 
 }  // namespace gpd
 
+// ---- the reference's own C interface for Python callers (src/detect_grasps_python.cpp:49-65,431-475,598-601),
+// same names, argument order and struct layout, over the B200 path (exported by libgpd_host.so) -----------------
+extern "C" {
+struct Grasp {       // detect_grasps_python.cpp:49-56
+  double *pos;       // Hand position (3)
+  double *orient;    // Eigen::Quaterniond(hand frame) coefficients x, y, z, w (4)
+  double *sample;    // the sample the hand was found at (3); the reference allocates it and never fills it
+  double score;
+  bool label;        // Hand::isFullAntipodal
+  int *image;        // {-1}: no descriptor attached (the reference writes -1 into a zero-length array)
+};
+// points: packed x,y,z (3 * size); camera_index: num_view_points x size, column-major; view_points: 3 x
+// num_view_points. Preprocesses (GraspDetector::preprocessPointCloud) and detects. Returns the number of grasps
+// (>= 0) or -1; *grasps_out is allocated by the callee and released with freeMemoryGrasps.
+int detectGraspsInCloud(char *config_filename, float *points, int *camera_index, float *view_points, int size,
+                        int num_view_points, struct Grasp **grasps_out);
+int detectGraspsInCloudNormals(char *config_filename, float *points, float *normals, int *camera_index,
+                               float *view_points, int size, int num_view_points, struct Grasp **grasps_out);
+int freeMemoryGrasps(struct Grasp *in);  // unlike the reference (`delete[] in` only) this also frees the members
+// Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other,3,3>):
+// m column-major 3x3 -> q = x, y, z, w
+void gpdQuaternionFromMatrix(const double *m, double *q);
+}
+
 #endif  // GPD_B200_HOST_GPD_H_

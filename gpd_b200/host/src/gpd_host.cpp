@@ -607,3 +607,104 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
 }
 
 }  // namespace gpd
+
+// ------------------------------------------------------------------------------------------------
+// The reference's C interface for Python callers (src/detect_grasps_python.cpp)
+// ------------------------------------------------------------------------------------------------
+namespace {
+std::vector<Grasp *> g_grasp_arrays;  // arrays handed out, with their lengths, so that freeMemoryGrasps can free members
+std::vector<int> g_grasp_counts;
+
+gpd::util::Cloud make_cloud(float *points, float *normals, int *camera_index, float *view_points, int size, int nv) {
+  std::vector<float> xyz(points, points + 3 * (size_t)size);
+  std::vector<double> nrm;
+  if (normals) nrm.assign(normals, normals + 3 * (size_t)size);  // viewPointsToMatrix(normals, size): 3 x N
+  std::vector<int> cam(camera_index, camera_index + (size_t)nv * size);
+  std::vector<double> vp(view_points, view_points + 3 * (size_t)nv);
+  return gpd::util::Cloud(xyz, nrm, cam, vp);
+}
+
+int detect_to_structs(char *config_filename, gpd::util::Cloud &cloud, Grasp **grasps_out) {
+  if (!config_filename || !grasps_out) return -1;
+  *grasps_out = nullptr;
+  gpd::GraspDetector detector(config_filename);  // detect_grasps_python.cpp:298-308
+  detector.preprocessPointCloud(cloud);
+  std::vector<std::unique_ptr<gpd::candidate::Hand>> hands = detector.detectGrasps(cloud);
+  const int n = (int)hands.size();
+  Grasp *g = new Grasp[n > 0 ? n : 1];
+  for (int i = 0; i < n; i++) {  // handsToGraspsStruct (detect_grasps_python.cpp:251-268)
+    const gpdb_pose &p = hands[i]->raw();
+    g[i].pos = new double[3]{p.position[0], p.position[1], p.position[2]};
+    g[i].orient = new double[4];
+    gpdQuaternionFromMatrix(p.frame, g[i].orient);
+    g[i].sample = new double[3]{p.sample[0], p.sample[1], p.sample[2]};
+    g[i].score = hands[i]->getScore();
+    g[i].label = hands[i]->isFullAntipodal();
+    g[i].image = new int[1]{-1};
+  }
+  g_grasp_arrays.push_back(g);
+  g_grasp_counts.push_back(n);
+  *grasps_out = g;
+  return n;
+}
+}  // namespace
+
+extern "C" {
+
+void gpdQuaternionFromMatrix(const double *m, double *q) {
+  auto M = [&](int r, int c) { return m[c * 3 + r]; };
+  double t = M(0, 0) + M(1, 1) + M(2, 2);
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (M(2, 1) - M(1, 2)) * t;
+    q[1] = (M(0, 2) - M(2, 0)) * t;
+    q[2] = (M(1, 0) - M(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (M(1, 1) > M(0, 0)) i = 1;
+    if (M(2, 2) > M(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (M(k, j) - M(j, k)) * t;
+    q[j] = (M(j, i) + M(i, j)) * t;
+    q[k] = (M(k, i) + M(i, k)) * t;
+  }
+}
+
+int detectGraspsInCloud(char *config_filename, float *points, int *camera_index, float *view_points, int size,
+                        int num_view_points, struct Grasp **grasps_out) {
+  if (!points || !camera_index || !view_points || size <= 0 || num_view_points <= 0) return -1;
+  gpd::util::Cloud cloud = make_cloud(points, nullptr, camera_index, view_points, size, num_view_points);
+  return detect_to_structs(config_filename, cloud, grasps_out);
+}
+
+int detectGraspsInCloudNormals(char *config_filename, float *points, float *normals, int *camera_index,
+                               float *view_points, int size, int num_view_points, struct Grasp **grasps_out) {
+  if (!points || !normals || !camera_index || !view_points || size <= 0 || num_view_points <= 0) return -1;
+  gpd::util::Cloud cloud = make_cloud(points, normals, camera_index, view_points, size, num_view_points);
+  return detect_to_structs(config_filename, cloud, grasps_out);
+}
+
+int freeMemoryGrasps(struct Grasp *in) {
+  if (!in) return 0;
+  for (size_t a = 0; a < g_grasp_arrays.size(); a++)
+    if (g_grasp_arrays[a] == in) {
+      for (int i = 0; i < g_grasp_counts[a]; i++) {
+        delete[] in[i].pos;
+        delete[] in[i].orient;
+        delete[] in[i].sample;
+        delete[] in[i].image;
+      }
+      g_grasp_arrays.erase(g_grasp_arrays.begin() + a);
+      g_grasp_counts.erase(g_grasp_counts.begin() + a);
+      break;
+    }
+  delete[] in;
+  return 0;
+}
+
+}  // extern "C"

@@ -1190,6 +1190,63 @@ void pcl_eigen33_smallest(const float cov[3][3], float &eigenvalue, float *evec)
   for (int k = 0; k < 3; k++) evec[k] = best[k] / sl;
 }
 
+// Cloud::voxelizeCloud (cloud.cpp:286-348) LITERALLY, including the behaviour of
+// std::set<Eigen::Vector4i, Cloud::UniqueVector4First3Comparator> (cloud.h:105-122). The comparator returns
+// "a differs from b in one of the first three elements", which is not a strict weak ordering; with libstdc++'s
+// red-black tree (bits/stl_tree.h _M_get_insert_unique_pos, tree.cc _Rb_tree_insert_and_rebalance) this means:
+//   * the descent goes LEFT at every node that differs from the key and right at a node that equals it, so the
+//     search path is the left spine of the tree down to the first equal node;
+//   * an equal node on the left spine is recognised as a duplicate (the predecessor test finds it); if no node of
+//     the left spine equals the key, the key is linked in as the new leftmost node, even when an equal key sits
+//     elsewhere in the tree;
+//   * iteration (in-order) therefore visits the keys newest first.
+// Only the tree SHAPE matters for which old keys are still on the left spine, so the simulation keeps a real
+// red-black tree with libstdc++'s insert fix-up (the new node is always a left child of a left child: only the
+// "red uncle -> recolour" and "black uncle -> rotate right at the grandparent" cases occur).
+// Used only to quantify the difference to the exact-set variant the product implements (tests/test_preprocess_oracle.py).
+struct RbSim {
+  struct Node { int parent, left, right; bool red; int item; };
+  std::vector<Node> n;
+  int root = -1, leftmost = -1;
+  void rotate_right(int x) {
+    const int y = n[x].left;
+    n[x].left = n[y].right;
+    if (n[y].right >= 0) n[n[y].right].parent = x;
+    n[y].parent = n[x].parent;
+    if (x == root) root = y;
+    else if (x == n[n[x].parent].right) n[n[x].parent].right = y;
+    else n[n[x].parent].left = y;
+    n[y].right = x;
+    n[x].parent = y;
+  }
+  void insert_leftmost(int item) {
+    const int z = (int)n.size();
+    n.push_back({leftmost, -1, -1, true, item});
+    if (leftmost < 0) {
+      root = z;
+    } else {
+      n[leftmost].left = z;
+    }
+    leftmost = z;
+    int x = z;
+    while (x != root && n[n[x].parent].red) {
+      const int xp = n[x].parent, xpp = n[xp].parent;  // xp is red, so it is not the root: xpp exists
+      const int y = n[xpp].right;                       // xp == n[xpp].left always (leftmost insertions)
+      if (y >= 0 && n[y].red) {
+        n[xp].red = false;
+        n[y].red = false;
+        n[xpp].red = true;
+        x = xpp;
+      } else {
+        n[xp].red = false;
+        n[xpp].red = true;
+        rotate_right(xpp);
+      }
+    }
+    n[root].red = false;
+  }
+};
+
 struct PreOut {
   std::vector<float> xyz;
   std::vector<double> nrm;
@@ -1621,6 +1678,48 @@ void gpdo_pcl_eigen33(const float *cov9 /* row-major */, float *eigenvalue, floa
   for (int r = 0; r < 3; r++)
     for (int c2 = 0; c2 < 3; c2++) m[r][c2] = cov9[3 * r + c2];
   pcl_eigen33_smallest(m, *eigenvalue, evec);
+}
+
+// Literal voxel set of the reference (see RbSim): xyz = M finite points inside the workspace; src_out receives, in
+// the reference's iteration order, the index of the point kept for each set element (may contain several elements
+// per voxel); returns the number of elements. first_seen_dups_out (may be NULL): how many insertions were linked in
+// although an equal voxel was already in the set.
+int gpdo_voxelize_literal(const float *xyz, int32_t M, double voxel_size, int32_t *src_out, int32_t *missed_out) {
+  const float cell = (float)voxel_size;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+  for (int i = 0; i < M; i++)
+    for (int a = 0; a < 3; a++) mn[a] = std::min(mn[a], xyz[3 * (size_t)i + a]);
+  std::vector<long long> key(M);
+  for (int i = 0; i < M; i++) {
+    long long k = 0;
+    for (int a = 0; a < 3; a++) k = (k << 21) | (long long)((int)std::floor((xyz[3 * (size_t)i + a] - mn[a]) / cell) & 0x1FFFFF);
+    key[i] = k;
+  }
+  RbSim t;
+  std::unordered_set<long long> seen;
+  int missed = 0;
+  for (int i = 0; i < M; i++) {
+    bool dup = false;
+    for (int x = t.root; x >= 0; x = t.n[x].left)  // the search path: the left spine, top down
+      if (key[t.n[x].item] == key[i]) { dup = true; break; }
+    if (!dup) {
+      if (!seen.insert(key[i]).second) missed++;
+      t.insert_leftmost(i);
+    }
+  }
+  // in-order traversal = newest first: leftmost insertions only ever prepend
+  int cnt = 0;
+  std::vector<int> stack;
+  int x = t.root;
+  while (x >= 0 || !stack.empty()) {
+    while (x >= 0) { stack.push_back(x); x = t.n[x].left; }
+    x = stack.back();
+    stack.pop_back();
+    src_out[cnt++] = t.n[x].item;
+    x = t.n[x].right;
+  }
+  if (missed_out) *missed_out = missed;
+  return cnt;
 }
 
 void gpdo_free_result(gpdb_result *r) {

@@ -56,6 +56,7 @@ def lib():
     L.gpdo_preprocess.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(abi.PreprocessParams), vp, vp, vp, vp, vp,
                                   C.c_int32]
     L.gpdo_pcl_eigen33.argtypes = [vp, vp, vp]
+    L.gpdo_voxelize_literal.argtypes = [vp, C.c_int32, C.c_double, vp, vp]
     _LIB = L
     return L
 
@@ -222,3 +223,13 @@ def pcl_eigen33(cov):
     vec = np.zeros(3, np.float32)
     lib().gpdo_pcl_eigen33(_p(cov), _p(ev), _p(vec))
     return float(ev[0]), vec
+
+
+def voxelize_literal(xyz, voxel_size=0.003):
+    """Cloud::voxelizeCloud with the literal libstdc++ behaviour of its std::set (non-strict-weak comparator):
+    returns (src indices in the reference's iteration order, number of duplicate voxels that slipped in)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    src = np.zeros(len(xyz), np.int32)
+    missed = np.zeros(1, np.int32)
+    n = lib().gpdo_voxelize_literal(_p(xyz), len(xyz), float(voxel_size), _p(src), _p(missed))
+    return src[:n].copy(), int(missed[0])

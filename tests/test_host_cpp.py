@@ -126,3 +126,82 @@ def test_detect_grasps_cli_preprocesses_a_raw_cloud(cli, tmp_path, golden_dir):
     assert int(res.split("n_grasps=")[1].split()[0]) == 10
     assert abs(best - r["candidates"]["score"].max()) <= 1e-3 * abs(best)
     ctx.close()
+
+
+class GraspStruct(__import__("ctypes").Structure):
+    """struct Grasp of src/detect_grasps_python.cpp:49-56."""
+    import ctypes as _C
+    _fields_ = [("pos", _C.POINTER(_C.c_double)), ("orient", _C.POINTER(_C.c_double)), ("sample", _C.POINTER(_C.c_double)),
+                ("score", _C.c_double), ("label", _C.c_bool), ("image", _C.POINTER(_C.c_int))]
+
+
+def _host_lib(cli):
+    import ctypes as C
+    L = C.CDLL(os.path.join(HOST, "libgpd_host.so"))
+    L.detectGraspsInCloud.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(GraspStruct))]
+    L.detectGraspsInCloudNormals.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.POINTER(C.POINTER(GraspStruct))]
+    L.freeMemoryGrasps.argtypes = [C.POINTER(GraspStruct)]
+    L.gpdQuaternionFromMatrix.argtypes = [C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_python_c_interface_symbols_and_quaternion(cli):
+    """The reference's extern "C" interface for Python callers (detect_grasps_python.cpp:431-475,598-601) is exported
+    by libgpd_host.so; the quaternion is Eigen::Quaterniond(Matrix3d) (x, y, z, w; w >= 0 branch when trace > 0)."""
+    from scipy.spatial.transform import Rotation
+    L = _host_lib(cli)
+    rng = np.random.default_rng(0)
+    for R in Rotation.random(200, random_state=1).as_matrix():
+        m = np.asfortranarray(R)
+        q = np.zeros(4)
+        L.gpdQuaternionFromMatrix(m.ctypes.data, q.ctypes.data)
+        assert abs(np.linalg.norm(q) - 1) < 1e-12
+        assert np.allclose(Rotation.from_quat(q).as_matrix(), R, atol=1e-12)
+        if np.trace(R) > 0:
+            assert q[3] > 0
+        else:
+            assert q[int(np.argmax(np.diag(R)))] > 0
+    assert L.detectGraspsInCloud(None, None, None, None, 0, 0, None) == -1
+
+
+@pytest.mark.gpu
+def test_python_c_interface_detects_like_the_library(cli, tmp_path, golden_dir):
+    import ctypes as C
+    from conftest import load_weights
+    from gpd_b200 import lib
+    L = _host_lib(cli)
+    raw = np.ascontiguousarray(np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))["raw"], np.float32)
+    w, _ = load_weights(15)
+    os.makedirs(tmp_path / "params")
+    names = ["conv1_weights", "conv1_biases", "conv2_weights", "conv2_biases", "ip1_weights", "ip1_biases", "ip2_weights", "ip2_biases"]
+    for n, a in zip(names, w):
+        a.astype(np.float32).tofile(tmp_path / "params" / (n + ".bin"))
+    (tmp_path / "main.cfg").write_text(f"hand_geometry_filename = 0\nimage_geometry_filename = 0\nweights_file = {tmp_path}/params/\n"
+                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 25\nimage_num_channels = 15\n")
+    cam = np.ones((len(raw), 1), np.int32)
+    vp = np.zeros(3, np.float32)
+    out = C.POINTER(GraspStruct)()
+    n = L.detectGraspsInCloud(str(tmp_path / "main.cfg").encode(), raw.ctypes.data, cam.ctypes.data, vp.ctypes.data, len(raw), 1,
+                              C.byref(out))
+    assert n == 25
+    ctx = lib.Context(lib.default_params(channels=15))
+    ctx.set_weights(w)
+    c = ctx.preprocess(raw, cam, np.zeros((1, 3)), lib.preprocess_params())
+    r = ctx.detect(np.arange(len(c["xyz"]), dtype=np.int32))
+    cand = r["candidates"]
+    order = np.argsort(-cand["score"], kind="stable")[:25]
+    scores = np.array([out[i].score for i in range(n)])
+    assert np.allclose(scores, cand["score"][order], rtol=1e-6)
+    for i in (0, 7, 24):
+        j = order[i]
+        if i and scores[i] == scores[i - 1]:
+            continue  # ties may be ordered differently by partial_sort
+        assert np.allclose([out[i].pos[k] for k in range(3)], cand["position"][j])
+        assert np.allclose([out[i].sample[k] for k in range(3)], cand["sample"][j])
+        q = np.array([out[i].orient[k] for k in range(4)])
+        from scipy.spatial.transform import Rotation
+        assert np.allclose(Rotation.from_quat(q).as_matrix(), cand["frame"][j].reshape(3, 3).T, atol=1e-9)
+        assert bool(out[i].label) == bool(cand["full_antipodal"][j]) and out[i].image[0] == -1
+    assert L.freeMemoryGrasps(out) == 0
+    ctx.close()

@@ -91,3 +91,26 @@ def test_normals_two_cameras_and_degenerate_neighbourhoods():
     iso = np.array([[0.3, 0.3, 0.3], [0.0, 0.0, 0.5], [0.001, 0.0, 0.5], [0.0, 0.001, 0.5], [0.001, 0.001, 0.5]], np.float32)
     r3 = oracle.preprocess(iso, None, np.zeros((1, 3)), abi.default_preprocess_params(voxelize=0))
     assert np.isnan(r3["normals"][0]).all() and not np.isnan(r3["normals"][1:]).any()
+
+
+def test_literal_std_set_emulation_quantifies_the_upstream_quirk(golden_dir):
+    """The reference's voxel set uses a comparator that is not a strict weak ordering (cloud.h:105-122); emulating
+    libstdc++'s red-black tree literally (oracle RbSim) shows what upstream really computes: duplicates are only
+    recognised on the tree's left spine. The exact-set variant (product + oracle) equals the literal result whenever
+    no duplicate is missed, order included; on the tutorial cloud upstream keeps 993 duplicate voxels."""
+    raw = np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))["raw"]
+    pp = abi.default_preprocess_params(estimate_normals=0)
+    zeros = np.zeros((len(raw), 3))
+    exact = oracle.preprocess(raw, None, np.zeros((1, 3)), pp, normals=zeros)
+    src, missed = oracle.voxelize_literal(raw)
+    assert len(exact["src"]) == 2373 and len(src) == 2373 + missed and missed == 993
+    # every literal element is a voxel of the exact set, and every exact voxel appears
+    mn = raw.min(0)
+    vox = lambda idx: set(map(tuple, np.floor((raw[idx] - mn) / np.float32(0.003)).astype(np.int64)))
+    assert vox(src) == vox(exact["src"])
+    # duplicates adjacent in the input (voxel-sorted scan): nothing is missed and the two agree, order included
+    v = np.floor((raw - mn) / np.float32(0.003)).astype(np.int64)
+    rs = raw[np.lexsort((v[:, 2], v[:, 1], v[:, 0]))]
+    src2, missed2 = oracle.voxelize_literal(rs)
+    ex2 = oracle.preprocess(rs, None, np.zeros((1, 3)), pp, normals=zeros)
+    assert missed2 == 0 and np.array_equal(src2, ex2["src"])
