@@ -12,7 +12,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgpd_b200.so")
+# GPD_B200_LIB overrides the library path (A/B comparison of builds during development); default: the in-tree build
+SO_PATH = os.environ.get("GPD_B200_LIB") or os.path.join(_HERE, "libgpd_b200.so")
 _LIB = None
 
 EXPORTS = [
