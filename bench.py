@@ -319,6 +319,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = n * world / (t_e2e / args.steps)
+    # the reference-facing call of GraspDetector::detectGrasps proper returns the num_selected best grasps only
+    # (selectGrasps, cfg default 100): gpdb_detect_select picks them on the device (secondary number, N = 1)
+    e2e_select = None
+    if world == 1:
+        for _ in range(2):
+            ctx.detect_select_raw(h_np, 100, res)
+            lib.free_result(res)
+        t_sel = 0.0
+        for k in range(args.steps):
+            flush.fill_(k)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nsel = ctx.detect_select_raw(h_np, 100, res)
+            t_sel += time.perf_counter() - t0
+            lib.free_result(res)
+        e2e_select = {"value": n / (t_sel / args.steps), "unit": UNIT, "num_selected": 100, "h2d_bytes_per_step": int(n * 4),
+                      "d2h_bytes_per_step": int(nsel * ctypes.sizeof(abi.Pose)),
+                      "call": "gpdb_detect_select (detectGrasps + selectGrasps, top-100 picked on the device)"}
 
     if rank == 0:
         st = stage_ms / args.steps  # per step, this rank
@@ -393,6 +411,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(d2h),
                     "timing": "wall clock around gpdb_detect (host buffers, synchronous), max over ranks"},
+            "e2e_select": e2e_select,
             "gpu_launches": launches,
             "neighbourhood": {"mean_r0.11": n_hs, "mean_r0.10": n_img, "candidates_per_step": ncand_all},
         }

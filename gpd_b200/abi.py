@@ -111,6 +111,7 @@ class Result(C.Structure):
         ("ms_images", C.c_double),
         ("ms_classify", C.c_double),
         ("kernel_launches", C.c_int64),
+        ("n_total_candidates", C.c_int32),
     ]
 
 
@@ -190,14 +191,16 @@ def result_to_numpy(res, image_bytes):
     """Copy a gpdb_result into numpy arrays (so the C result can be freed)."""
     n, P = res.n_samples, res.poses_per_sample
     nc = res.n_candidates
+    full = bool(res.frames)  # gpdb_detect_select returns the selected pose records only
     out = {
         "n_samples": n,
         "poses_per_sample": P,
-        "frame_valid": np.ctypeslib.as_array(res.frame_valid, (n,)).copy() if n else np.zeros(0, np.uint8),
-        "frames": np.ctypeslib.as_array(res.frames, (n, 9)).copy() if n else np.zeros((0, 9)),
-        "pose_flags": np.ctypeslib.as_array(res.pose_flags, (n, P)).copy() if n else np.zeros((0, P), np.uint8),
-        "pose_scores": np.ctypeslib.as_array(res.pose_scores, (n, P)).copy() if n else np.zeros((0, P), np.float32),
+        "frame_valid": None if not full else np.ctypeslib.as_array(res.frame_valid, (n,)).copy() if n else np.zeros(0, np.uint8),
+        "frames": None if not full else np.ctypeslib.as_array(res.frames, (n, 9)).copy() if n else np.zeros((0, 9)),
+        "pose_flags": None if not full else np.ctypeslib.as_array(res.pose_flags, (n, P)).copy() if n else np.zeros((0, P), np.uint8),
+        "pose_scores": None if not full else np.ctypeslib.as_array(res.pose_scores, (n, P)).copy() if n else np.zeros((0, P), np.float32),
         "n_candidates": nc,
+        "n_total_candidates": res.n_total_candidates,
         "ms": (res.ms_candidates, res.ms_images, res.ms_classify),
         "kernel_launches": res.kernel_launches,
     }

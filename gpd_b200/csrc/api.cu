@@ -328,6 +328,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   cudaFree(ctx->d_nrm);
   cudaFree(ctx->d_cam);
   cudaFree(ctx->d_src);
+  cudaFree(ctx->d_sel);
   cudaFree(ctx->d_cell_start);
   float *w[8] = {ctx->w.c1w, ctx->w.c1b, ctx->w.c2w, ctx->w.c2b, ctx->w.i1w, ctx->w.i1b, ctx->w.i2w, ctx->w.i2b};
   for (float *p : w) cudaFree(p);
@@ -630,8 +631,11 @@ int check_device_errors(gpdb_ctx *ctx) {
 //   resident == false: sample_idx is a HOST array, every result is copied back to the host (out)
 //   resident == true : sample_idx, flags_ext, scores_ext are DEVICE arrays; nothing but the per-chunk
 //                      candidate count crosses PCIe (out receives counts and timings only)
+// select_k >= 0 (gpdb_detect_select): the classified candidates of all chunks stay on the device, the select_k best are
+// sorted out there and only they are copied back; no per-sample / per-pose array is returned.
 int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
-                 bool resident, uint8_t *flags_ext, float *scores_ext) {
+                 bool resident, uint8_t *flags_ext, float *scores_ext, int select_k = -1) {
+  const bool selecting = select_k >= 0;
   memset(out, 0, sizeof(*out));
   const int P = ctx->hp.P, S = ctx->hp.S, C = ctx->hp.C;
   const size_t isz = (size_t)S * S * C;
@@ -648,7 +652,7 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int chunk = ctx->prm.chunk_samples > 0 ? ctx->prm.chunk_samples : 16384;
   const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
-  const bool keep = with_images_and_scores && ctx->prm.keep_images && !resident;
+  const bool keep = with_images_and_scores && ctx->prm.keep_images && !resident && !selecting;
   const size_t nP = (size_t)n * P;
   int *d_sidx = resident ? const_cast<int *>(sample_idx) : (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
   double *d_frames = (double *)gpdb_scratch(ctx, 8, sizeof(double) * 9 * (size_t)n);
@@ -711,7 +715,20 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
         CUDA_TRY(cudaMemcpyAsync(images.data() + off, d_img, isz * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
       }
     }
-    if (nc > 0 && !resident) {
+    if (nc > 0 && selecting) {  // keep the chunk's scored candidates on the device
+      if ((size_t)total_nc > ctx->sel_cap) {
+        const size_t cap = std::max((size_t)total_nc * 2, (size_t)65536);
+        gpdb_pose *grown = nullptr;
+        CUDA_TRY(cudaMalloc(&grown, sizeof(gpdb_pose) * cap));
+        if (ctx->d_sel && total_nc > nc)
+          CUDA_TRY(cudaMemcpyAsync(grown, ctx->d_sel, sizeof(gpdb_pose) * (size_t)(total_nc - nc), cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_sel);
+        ctx->d_sel = grown;
+        ctx->sel_cap = cap;
+      }
+      CUDA_TRY(cudaMemcpyAsync(ctx->d_sel + (total_nc - nc), d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (nc > 0 && !resident) {
       size_t off = cands.size();
       cands.resize(off + nc);
       CUDA_TRY(cudaMemcpyAsync(cands.data() + off, d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToHost,
@@ -719,7 +736,18 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
       CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
   }
-  if (!resident) {
+  int n_sel = 0;
+  if (selecting) {
+    n_sel = std::min(select_k, total_nc);
+    if (n_sel > 0) {
+      gpdb_pose *d_top = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)std::max(n_sel, cmax * P));
+      if (!d_top) return GPDB_ERR_CUDA;
+      if ((rc = geo_select(ctx, ctx->d_sel, total_nc, n_sel, d_top)) != GPDB_OK) return rc;
+      cands.resize(n_sel);
+      CUDA_TRY(cudaMemcpyAsync(cands.data(), d_top, sizeof(gpdb_pose) * (size_t)n_sel, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (!resident && !selecting) {
     out->frame_valid = (uint8_t *)malloc((size_t)n + 1);
     out->frames = (double *)malloc(sizeof(double) * 9 * (size_t)n + 8);
     out->pose_flags = (uint8_t *)malloc(nP + 1);
@@ -738,7 +766,8 @@ int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_resul
     gpdb_free_result(out);
     return rc;
   }
-  out->n_candidates = total_nc;
+  out->n_candidates = selecting ? n_sel : total_nc;
+  out->n_total_candidates = total_nc;
   if (!resident) {
     out->candidates = (gpdb_pose *)malloc(sizeof(gpdb_pose) * cands.size() + 8);
     if (!cands.empty()) memcpy(out->candidates, cands.data(), sizeof(gpdb_pose) * cands.size());
@@ -767,6 +796,16 @@ int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result
     return GPDB_ERR_INVALID;
   }
   return run_pipeline(ctx, sample_idx, n, out, true, false, nullptr, nullptr);
+}
+
+int gpdb_detect_select(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, int32_t num_selected, gpdb_result *out) {
+  int rc = check_state(ctx, true, true);
+  if (rc != GPDB_OK) return rc;
+  if (!out || (n > 0 && !sample_idx) || n < 0 || num_selected < 0) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_detect_select: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  return run_pipeline(ctx, sample_idx, n, out, true, false, nullptr, nullptr, num_selected);
 }
 
 int gpdb_detect_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx, int32_t n, uint8_t *d_flags_out,

@@ -134,6 +134,8 @@ struct gpdb_ctx {
   int64_t launches;
   double last_ms[8];
   double pre_ms[6];   // gpdb_preprocess stage timings
+  gpdb_pose *d_sel;   // gpdb_detect_select: all classified candidates of a call (grown on demand)
+  size_t sel_cap;
   int *d_src;         // raw index of each processed point (valid after gpdb_preprocess: has_src)
   bool has_src;
   cudaEvent_t ev[8];
@@ -158,6 +160,9 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images);
 int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
                        float *d_pose_scores, gpdb_pose *d_cand_out);
+
+// the k highest-scoring of the n candidate records (scores filled), descending, stable -> d_out[k]
+int geo_select(gpdb_ctx *ctx, const gpdb_pose *d_cand, int n, int k, gpdb_pose *d_out);
 
 // preprocess.cu (cloud preprocessing)
 // (re)allocates the context's cloud arrays for at least n points (api.cu)

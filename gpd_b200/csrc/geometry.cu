@@ -302,20 +302,27 @@ __device__ void eigen3(const double *Min, double *eval, double *Q) {
 // (dist bits << 32 | index), rank-sorted so that N*N^T and sum(n) are accumulated in exactly the
 // (dist, index) order the reference's sorted radiusSearch yields -> bit-identical to the oracle.
 // ------------------------------------------------------------------------------------------------
+// Two tiers: tier 0 runs every sample with a small per-warp list (cap0 keys: 16 CTAs per SM instead of 3), samples
+// whose ball does not fit are appended to `ovf` and re-run by tier 1 with LRF_CAP keys (beyond that: err[0]).
 __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, DevCloud cl, const int *sidx, int n,
-                                                            double *frames, uint8_t *valid, int *err) {
+                                                            double *frames, uint8_t *valid, int *err, int cap, int *ovf,
+                                                            int *ovf_count, int tier) {
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char lrf_dyn[];
-  unsigned long long(*s_keys)[LRF_CAP] = reinterpret_cast<unsigned long long(*)[LRF_CAP]>(lrf_dyn);
-  unsigned long long(*s_sorted)[LRF_CAP] = s_keys + LRF_WARPS;
   __shared__ double s_acc[LRF_WARPS][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * LRF_WARPS + warp;
-  if (i >= n) return;
+  int i = blockIdx.x * LRF_WARPS + warp;
+  if (tier == 0) {
+    if (i >= n) return;
+  } else {
+    if (i >= *ovf_count) return;
+    i = ovf[i];
+  }
   const int si = sidx[i];
   float q[3] = {cl.xyz[3 * (size_t)si], cl.xyz[3 * (size_t)si + 1], cl.xyz[3 * (size_t)si + 2]};
   SegRange sr = seg_range(P, q, P.rf_lrf);
-  unsigned long long *keys = s_keys[warp], *sorted = s_sorted[warp];
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)warp * cap;
+  unsigned long long *sorted = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)(LRF_WARPS + warp) * cap;
   int cnt = 0;
   for (int row = 0; row < sr.nrows; row++) {
     int st, len;
@@ -332,13 +339,17 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
       int pos = cnt + __popc(m & ((1u << lane) - 1));
-      if (hit && pos < LRF_CAP) keys[pos] = key;
+      if (hit && pos < cap) keys[pos] = key;
       cnt += __popc(m);
     }
   }
-  if (cnt > LRF_CAP) {
+  if (cnt > cap) {
+    if (tier == 0) {  // re-run with the large list
+      if (lane == 0) ovf[atomicAdd(ovf_count, 1)] = i;
+      return;
+    }
     if (lane == 0) atomicAdd(err + 0, 1);
-    cnt = LRF_CAP;
+    cnt = cap;
   }
   __syncwarp();
   if (cnt == 0) {
@@ -443,7 +454,7 @@ struct HandsSmem {
 };
 
 // one CTA per sample; dynamic smem: float4 list[cap]
-__global__ void __launch_bounds__(NT_HANDS) k_hands(const DevParams *Pp, DevCloud cl, const int *sidx, int n, int slot0,
+__global__ void __launch_bounds__(NT_HANDS, 4) k_hands(const DevParams *Pp, DevCloud cl, const int *sidx, int n, int slot0,
                                                     const double *frames, const uint8_t *fvalid, gpdb_pose *poses,
                                                     uint8_t *flags, int cap, int *ovf_list, int *ovf_count,
                                                     int list_mode, int *err) {
@@ -833,6 +844,24 @@ __global__ void k_scatter_scores(const gpdb_pose *cand, const float *scores, int
   float s = scores[i];
   pose_scores[(size_t)(cand[i].sample_slot - slot0) * P + cand[i].pose_slot] = s;
   cand_out[i].score = s;
+}
+
+// selectGrasps (grasp_detector.cpp:405-420) on the device: sort key = descending score, stable in candidate order
+__global__ void k_select_keys(const gpdb_pose *cand, int n, unsigned *keys, int *vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned u = __float_as_uint(cand[i].score);
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // ascending float order as unsigned
+  keys[i] = ~u;                                // descending
+  vals[i] = i;
+}
+__global__ void k_gather_poses(const gpdb_pose *cand, const int *order, int k, gpdb_pose *out) {
+  // one warp per record: 176-byte pose = 44 words
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= k) return;
+  const int *src = reinterpret_cast<const int *>(cand + order[w]);
+  int *dst = reinterpret_cast<int *>(out + w);
+  for (int j = lane; j < (int)(sizeof(gpdb_pose) / 4); j += 32) dst[j] = src[j];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1553,15 +1582,26 @@ int geo_build_grid(gpdb_ctx *ctx, const float lo[3], const float hi[3], int N) {
 
 int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_t *d_valid) {
   if (n <= 0) return GPDB_OK;
-  const size_t lrf_smem = (size_t)2 * LRF_WARPS * LRF_CAP * sizeof(unsigned long long);
-  CUDA_TRY(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrf_smem));
-  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, lrf_smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
-                                                                                  d_valid, ctx->d_err);
+  const int cap0 = 128;  // ~44 points at the default nn_radius on a 3 mm cloud
+  const size_t smem0 = (size_t)2 * LRF_WARPS * cap0 * sizeof(unsigned long long);
+  const size_t smem1 = (size_t)2 * LRF_WARPS * LRF_CAP * sizeof(unsigned long long);
+  CUDA_TRY(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)n + 1));
+  if (!ovf) return GPDB_ERR_CUDA;
+  int *ovf_count = ovf + n;
+  CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
+  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, smem0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
+                                                                               d_valid, ctx->d_err, cap0, ovf, ovf_count, 0);
+  LAUNCH_CHECK();
+  // overflow tier over the (usually empty) list: the grid is sized for the worst case (every sample overflowed) so no
+  // host round trip is needed; warps beyond the list length exit at once
+  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, smem1, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
+                                                                               d_valid, ctx->d_err, LRF_CAP, ovf, ovf_count, 1);
   LAUNCH_CHECK();
   return GPDB_OK;
 }
 
-static const int HANDS_CAP1 = 4096, HANDS_CAP2 = 12800;
+static const int HANDS_CAP1 = 2176, HANDS_CAP2 = 12800;  // tier 1: 4 CTAs per SM (34 KB + 20 KB static each, <= 64 registers)
 
 int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
               gpdb_pose *d_poses, uint8_t *d_flags) {
@@ -1629,6 +1669,25 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images
   int grid = std::min(nc, ctx->sm_count * 64);
   k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
                                                 (int)img_off, ctx->d_prof);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+int geo_select(gpdb_ctx *ctx, const gpdb_pose *d_cand, int n, int k, gpdb_pose *d_out) {
+  if (n <= 0 || k <= 0) return GPDB_OK;
+  unsigned *keys = (unsigned *)gpdb_scratch(ctx, 3, sizeof(unsigned) * (size_t)n * 4);
+  if (!keys) return GPDB_ERR_CUDA;
+  unsigned *keys2 = keys + n;
+  int *vals = (int *)(keys2 + n), *vals2 = vals + n;
+  k_select_keys<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_cand, n, keys, vals);
+  LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, n, 0, 32, ctx->stream);
+  void *tmp = gpdb_scratch(ctx, 1, tmp_bytes);
+  if (!tmp) return GPDB_ERR_CUDA;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, n, 0, 32, ctx->stream));
+  ctx->launches += 4;
+  k_gather_poses<<<(k * 32 + 255) / 256, 256, 0, ctx->stream>>>(d_cand, vals2, k, d_out);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

@@ -580,20 +580,22 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
   }
   const std::vector<int> &idx = cloud.getSampleIndices();
   gpdb_result r;
-  int n = gpdb_detect(ctx_, idx.data(), (int)idx.size(), &r);
+  // steps 1-4 + selectGrasps in one call: the num_selected best hands are picked on the device and only they are
+  // copied back (grasp_detector.cpp:222-283,405-420)
+  int n = gpdb_detect_select(ctx_, idx.data(), (int)idx.size(), num_selected_, &r);
   if (n < 0) {
     printf("ERROR: %s\n", gpdb_last_error(ctx_));
     return hands_out;
   }
   printf("Generated %d hand sets.\n", r.n_samples);
-  printf("Number of grasp candidates within workspace and gripper width: %d\n", n);
+  printf("Number of grasp candidates within workspace and gripper width: %d\n", r.n_total_candidates);
+  printf("Selecting the %d highest scoring grasps ...\n", num_selected_);
   std::vector<std::unique_ptr<candidate::Hand>> hands;
   for (int i = 0; i < n; i++) hands.push_back(std::make_unique<candidate::Hand>(r.candidates[i]));
   last_ms_candidates = r.ms_candidates;
   last_ms_images = r.ms_images;
   last_ms_classify = r.ms_classify;
   gpdb_free_result(&r);
-  hands = selectGrasps(hands);
   if (cluster_grasps_) printf("(clustering requested by min_inliers > 0 is outside the accelerated path: skipped)\n");
   std::sort(hands.begin(), hands.end(), [](const std::unique_ptr<candidate::Hand> &a, const std::unique_ptr<candidate::Hand> &b) {
     return a->getScore() > b->getScore();

@@ -21,7 +21,7 @@ EXPORTS = [
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
     "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
     "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
-    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings",
+    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select",
 ]
 
 
@@ -51,6 +51,7 @@ def lib():
     L.gpdb_set_cloud.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32]
     L.gpdb_detect.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
     L.gpdb_hand_search.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
+    L.gpdb_detect_select.argtypes = [vp, vp, C.c_int32, C.c_int32, C.POINTER(abi.Result)]
     L.gpdb_frames.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.gpdb_images.argtypes = [vp, vp, C.c_int32, vp]
     L.gpdb_classify.argtypes = [vp, vp, C.c_int32, vp, vp]
@@ -204,6 +205,20 @@ class Context:
 
     def detect(self, sample_idx):
         return self._result(lib().gpdb_detect, sample_idx)
+
+    def detect_select(self, sample_idx, num_selected):
+        """detectGrasps + selectGrasps: the num_selected best candidates, sorted on the device (gpdb_detect_select)."""
+        sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        res = abi.Result()
+        self._check(lib().gpdb_detect_select(self.h, _p(sidx), len(sidx), int(num_selected), C.byref(res)))
+        S, Cc = self.params.image_size, self.params.image_num_channels
+        out = abi.result_to_numpy(res, S * S * Cc)
+        lib().gpdb_free_result(C.byref(res))
+        return out
+
+    def detect_select_raw(self, sidx_i32, num_selected, res):
+        """Timed path for bench.py; caller frees `res`."""
+        return self._check(lib().gpdb_detect_select(self.h, _p(sidx_i32), len(sidx_i32), int(num_selected), C.byref(res)))
 
     def detect_raw(self, sidx_i32, res):
         """Timed path for bench.py: no numpy conversion; caller frees `res`."""

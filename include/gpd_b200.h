@@ -137,6 +137,7 @@ typedef struct gpdb_result {
   double ms_images;         /*                "2. Descriptor extraction"                     */
   double ms_classify;       /*                "3. Classification"                            */
   int64_t kernel_launches;  /* CUDA kernels launched by this call                     */
+  int32_t n_total_candidates; /* all poses with VALID and FILTERED set (= n_candidates except after gpdb_detect_select) */
 } gpdb_result;
 
 typedef struct gpdb_ctx gpdb_ctx;
@@ -177,6 +178,14 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals,
 /* Replaces: GraspDetector::detectGrasps steps 1-4 (grasp_detector.cpp:222-273) for the
  * samples cloud.getSampleIndices() (cloud.h:345). Returns n_candidates or a negative error. */
 int gpdb_detect(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, gpdb_result *out);
+
+/* Replaces: GraspDetector::detectGrasps steps 1-4 followed by selectGrasps (grasp_detector.cpp:222-283,405-420): the
+ * `num_selected` highest-scoring candidates, sorted by descending score (ties: (sample slot, pose slot) order), selected
+ * ON THE DEVICE — only those pose records cross PCIe. out->candidates holds n_candidates = min(num_selected, total)
+ * records, out->n_total_candidates the number of classified candidates; the per-sample / per-pose arrays
+ * (frame_valid, frames, pose_flags, pose_scores, images) are NULL. Returns n_candidates or a negative error. */
+int gpdb_detect_select(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, int32_t num_selected,
+                       gpdb_result *out);
 
 /* Device-resident variant of gpdb_detect: d_sample_idx [n], d_flags_out [n*P] and d_scores_out [n*P]
  * are DEVICE pointers on the context's device; no input or result crosses PCIe (only the per-chunk

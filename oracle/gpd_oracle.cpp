@@ -1596,6 +1596,7 @@ int gpdo_detect(void *cloud, const gpdb_params *pr, const float *const *wts, con
     if ((out->pose_flags[i] & 3) == 3) nc++;
   }
   out->n_candidates = nc;
+  out->n_total_candidates = nc;
   out->candidates = (gpdb_pose *)std::malloc(sizeof(gpdb_pose) * (size_t)nc + 8);
   int k = 0;
   for (size_t i = 0; i < (size_t)n * P; i++)

@@ -41,6 +41,8 @@ int main(void) {
          offsetof(gpdb_pose, half_antipodal));
   printf("%zu %zu %zu\n", offsetof(gpdb_result, candidates), offsetof(gpdb_result, ms_candidates),
          offsetof(gpdb_result, kernel_launches));
+  printf("%zu %zu %zu\n", sizeof(gpdb_preprocess_params), offsetof(gpdb_preprocess_params, voxelize),
+         offsetof(gpdb_result, n_total_candidates));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -54,6 +56,8 @@ int main(void) {
     assert nums[7:11] == [abi.Pose.position.offset, abi.Pose.score.offset, abi.Pose.pose_slot.offset,
                           abi.Pose.half_antipodal.offset]
     assert nums[11:14] == [abi.Result.candidates.offset, abi.Result.ms_candidates.offset, abi.Result.kernel_launches.offset]
+    assert nums[14:17] == [C.sizeof(abi.PreprocessParams), abi.PreprocessParams.voxelize.offset,
+                           abi.Result.n_total_candidates.offset]
     assert abi.POSE_DTYPE.itemsize == C.sizeof(abi.Pose)
 
 

@@ -320,3 +320,25 @@ def test_config5_two_view_12ch_full_cloud():
     assert m.sum() > 50
     assert np.abs(ro["pose_scores"][m] - r["pose_scores"][pick][m]).max() <= 1e-4 * np.abs(ro["pose_scores"][m]).max()
     ctx.close()
+
+
+def test_detect_select_is_detect_plus_select_grasps():
+    """gpdb_detect_select = detectGrasps steps 1-4 + selectGrasps (grasp_detector.cpp:405-420): the k best candidate
+    records, descending score, ties in candidate order; bit-equal to sorting gpdb_detect's candidates on the host."""
+    s = scenes.synthetic_table_scene(7, n_points=60000)
+    p, ctx, oc, w = make(s, 15, chunk_samples=512)  # several chunks: candidates of all chunks compete
+    sidx = scenes.sample_indices(3, 60000, 3000)
+    full = ctx.detect(sidx)
+    cand = full["candidates"]
+    order = np.argsort(-cand["score"].astype(np.float64), kind="stable")
+    for k in (0, 1, 50, len(cand), len(cand) + 10):
+        r = ctx.detect_select(sidx, k)
+        kk = min(k, len(cand))
+        assert r["n_candidates"] == kk and r["n_total_candidates"] == len(cand) and r["frames"] is None
+        assert r["candidates"].tobytes() == cand[order[:kk]].tobytes()
+    # against the oracle's scores (selection is a pure sort, so the same tolerance as the scores applies)
+    ro = oc.detect(p, w, sidx)
+    oo = np.argsort(-ro["candidates"]["score"].astype(np.float64), kind="stable")[:20]
+    r = ctx.detect_select(sidx, 20)
+    assert np.abs(r["candidates"]["score"] - ro["candidates"]["score"][oo]).max() <= 1e-4 * np.abs(ro["candidates"]["score"]).max()
+    ctx.close()
