@@ -335,7 +335,8 @@ def test_detect_select_is_detect_plus_select_grasps():
         r = ctx.detect_select(sidx, k)
         kk = min(k, len(cand))
         assert r["n_candidates"] == kk and r["n_total_candidates"] == len(cand) and r["frames"] is None
-        assert r["candidates"].tobytes() == cand[order[:kk]].tobytes()
+        for f in cand.dtype.names:  # field by field: the struct's trailing padding bytes are not part of the contract
+            assert np.array_equal(r["candidates"][f], cand[order[:kk]][f]), (k, f)
     # against the oracle's scores (selection is a pure sort, so the same tolerance as the scores applies)
     ro = oc.detect(p, w, sidx)
     oo = np.argsort(-ro["candidates"]["score"].astype(np.float64), kind="stable")[:20]
