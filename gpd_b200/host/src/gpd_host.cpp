@@ -445,17 +445,42 @@ void ImageGenerator::createImages(const util::Cloud &cloud_cam,
 }  // namespace descriptor
 
 // ------------------------------------------------------------------------------------------------ Classifier
+// An OpenVINO IR (weights_file *.bin / *.xml, not a directory) may carry ReLU layers after the convolutions
+// (models/openvino/two_views_12_channels_curv_axis.xml): the context must be created with relu_after_conv = 1 then.
+static int relu_after_conv_of(const std::string &model_file, const std::string &weights_file, int num_channels) {
+  if (weights_file.empty() || weights_file.back() == '/') return 0;
+  const bool ir = weights_file.size() > 4 && (weights_file.compare(weights_file.size() - 4, 4, ".bin") == 0 ||
+                                               weights_file.compare(weights_file.size() - 4, 4, ".xml") == 0);
+  if (!ir) return 0;
+  const size_t sizes[8] = {(size_t)20 * num_channels * 25, 20, 50 * 20 * 25, 50, (size_t)500 * 7200, 500, 1000, 2};
+  std::vector<std::vector<float>> bufs(8);
+  float *ptrs[8];
+  for (int i = 0; i < 8; i++) {
+    bufs[i].resize(sizes[i]);
+    ptrs[i] = bufs[i].data();
+  }
+  int relu = -1;
+  char err[512];
+  if (gpdb_read_weights_file(model_file.empty() ? nullptr : model_file.c_str(), weights_file.c_str(), num_channels, ptrs, &relu, err,
+                             sizeof(err)) != GPDB_OK)
+    return 0;
+  return relu >= 3 ? 1 : 0;
+}
+
 namespace net {
 namespace {
 class CudaClassifier : public Classifier {
  public:
-  CudaClassifier(const std::string &weights_file, int batch_size, int num_channels) : batch_size_(batch_size) {
+  CudaClassifier(const std::string &model_file, const std::string &weights_file, int batch_size, int num_channels)
+      : batch_size_(batch_size) {
     gpdb_params p;
     gpdb_params_default(&p);
     p.image_num_channels = num_channels;
     p.batch_size = batch_size > 1 ? batch_size : 0;
+    p.relu_after_conv = relu_after_conv_of(model_file, weights_file, num_channels);
     ctx_ = make_ctx(p);
-    if (ctx_ && gpdb_load_weights_dir(ctx_, weights_file.c_str()) != GPDB_OK) printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    if (ctx_ && gpdb_load_weights_file(ctx_, model_file.empty() ? nullptr : model_file.c_str(), weights_file.c_str()) != GPDB_OK)
+      printf("ERROR: %s\n", gpdb_last_error(ctx_));
     isz_ = (size_t)p.image_size * p.image_size * num_channels;
   }
   ~CudaClassifier() override { gpdb_destroy(ctx_); }
@@ -478,9 +503,9 @@ class CudaClassifier : public Classifier {
   size_t isz_{0};
 };
 }  // namespace
-std::shared_ptr<Classifier> Classifier::create(const std::string &, const std::string &weights_file, Device, int batch_size,
-                                               int num_channels) {
-  return std::make_shared<CudaClassifier>(weights_file, batch_size, num_channels);
+std::shared_ptr<Classifier> Classifier::create(const std::string &model_file, const std::string &weights_file, Device,
+                                               int batch_size, int num_channels) {
+  return std::make_shared<CudaClassifier>(model_file, weights_file, batch_size, num_channels);
 }
 }  // namespace net
 
@@ -491,9 +516,17 @@ GraspDetector::GraspDetector(const std::string &config_filename) {
   if (!paramsFromConfig(config_filename, params_, weights_file, num_selected_, num_samples_, min_inliers)) return;
   cluster_grasps_ = min_inliers > 0;
   preprocessParamsFromConfig(config_filename, pre_params_);
+  std::string model_file;
+  {
+    util::ConfigFile config_file(config_filename);
+    if (config_file.ExtractKeys()) model_file = config_file.getValueOfKeyAsString("model_file", "");  // grasp_detector.cpp:130
+  }
+  if (relu_after_conv_of(model_file, weights_file, params_.image_num_channels)) params_.relu_after_conv = 1;
   ctx_ = make_ctx(params_);
   if (ctx_ && !weights_file.empty()) {
-    if (gpdb_load_weights_dir(ctx_, weights_file.c_str()) == GPDB_OK) has_classifier_ = true;
+    // .bin parameter directory (EigenClassifier), .caffemodel (Caffe backend) or OpenVINO IR (classifier.cpp:33-61)
+    if (gpdb_load_weights_file(ctx_, model_file.empty() ? nullptr : model_file.c_str(), weights_file.c_str()) == GPDB_OK)
+      has_classifier_ = true;
     else printf("ERROR: %s\n", gpdb_last_error(ctx_));
   }
   printf("============ CLASSIFIER ======================\nweights_file: %s\n==============================================\n",

@@ -21,7 +21,7 @@ EXPORTS = [
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
     "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
     "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
-    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select",
+    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select", "gpdb_load_weights_file", "gpdb_read_weights_file",
 ]
 
 
@@ -48,6 +48,8 @@ def lib():
     L.gpdb_last_error.argtypes = [vp]
     L.gpdb_load_weights_dir.argtypes = [vp, C.c_char_p]
     L.gpdb_set_weights.argtypes = [vp] + [vp] * 8
+    L.gpdb_load_weights_file.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.gpdb_read_weights_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, vp, vp, C.c_char_p, C.c_int32]
     L.gpdb_set_cloud.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32]
     L.gpdb_detect.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
     L.gpdb_hand_search.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
@@ -109,6 +111,21 @@ def preprocess_params(**over):
     return p
 
 
+def read_weights_file(weights_file, channels, model_file=None):
+    """Host-side import of a .caffemodel or an OpenVINO IR into the eight arrays of the .bin layout (no device needed).
+    Returns (arrays, relu_layers)."""
+    sizes = [20 * channels * 25, 20, 50 * 20 * 25, 50, 500 * 7200, 500, 1000, 2]
+    arrs = [np.zeros(s, np.float32) for s in sizes]
+    ptrs = (C.c_void_p * 8)(*[a.ctypes.data for a in arrs])
+    relu = C.c_int32(-1)
+    err = C.create_string_buffer(512)
+    rc = lib().gpdb_read_weights_file(None if model_file is None else model_file.encode(), weights_file.encode(), channels, ptrs,
+                                      C.byref(relu), err, 512)
+    if rc != 0:
+        raise GpdbError(rc, err.value.decode())
+    return arrs, relu.value
+
+
 class Context:
     """One gpdb_ctx: one CUDA device + stream (gpdb_create ... gpdb_destroy)."""
 
@@ -138,6 +155,10 @@ class Context:
         if not d.endswith("/"):
             d += "/"
         self._check(lib().gpdb_load_weights_dir(self.h, d.encode()))
+
+    def load_weights_file(self, weights_file, model_file=None):
+        """.bin directory, .caffemodel or OpenVINO IR (.bin + .xml), as Classifier::create's weights_file / model_file."""
+        self._check(lib().gpdb_load_weights_file(self.h, None if model_file is None else model_file.encode(), weights_file.encode()))
 
     def set_weights(self, arrays):
         arrs = [np.ascontiguousarray(a, dtype=np.float32).ravel() for a in arrays]

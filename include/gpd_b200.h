@@ -158,6 +158,17 @@ const char *gpdb_last_error(const gpdb_ctx *ctx);
  * {conv1,conv2,ip1,ip2}_{weights,biases}.bin in the reference's raw float32 layout. */
 int gpdb_load_weights_dir(gpdb_ctx *ctx, const char *dir);
 
+/* Replaces: Classifier::create(model_file, weights_file, ...) weight loading for the reference's other backends
+ * (classifier.cpp:33-61): `weights_file` may be a .bin parameter directory (trailing '/', as above), a Caffe
+ * `.caffemodel` (layers conv1, conv2, ip1, ip2; caffe_classifier.cpp) or an OpenVINO IR `.bin` whose `.xml` is
+ * `model_file` (or lies next to it; openvino_classifier.cpp:20-57). The blobs are converted to the .bin layout on the
+ * host. An IR with ReLU after the convolutions needs a context created with relu_after_conv = 1. */
+int gpdb_load_weights_file(gpdb_ctx *ctx, const char *model_file, const char *weights_file);
+/* The host-side conversion alone (no device): fills eight caller-allocated arrays (sizes as gpdb_set_weights) in the
+ * .bin layout; relu_layers_out = number of ReLU layers of an IR, -1 for a caffemodel; err_out receives the message. */
+int gpdb_read_weights_file(const char *model_file, const char *weights_file, int32_t channels, float *const out[8],
+                           int32_t *relu_layers_out, char *err_out, int32_t err_len);
+
 /* Same, from memory, in the layout of the .bin files (A14): conv = OIHW row-major,
  * ip = column-major (out, in). Sizes: conv1 20*C*25, conv2 50*20*25, ip1 500*7200, ip2 2*500. */
 int gpdb_set_weights(gpdb_ctx *ctx, const float *conv1_w, const float *conv1_b,
