@@ -112,6 +112,8 @@ class Hand {
   double getGraspWidth() const { return p_.width; }
   double getScore() const { return p_.score; }
   void setScore(double s) { p_.score = (float)s; }
+  void setPosition(const std::array<double, 3> &p) { for (int i = 0; i < 3; i++) p_.position[i] = p[i]; }
+  void setFullAntipodal(bool b) { p_.full_antipodal = b ? 1 : 0; }
   bool isFullAntipodal() const { return p_.full_antipodal != 0; }
   bool isHalfAntipodal() const { return p_.half_antipodal != 0; }
   double getTop() const { return p_.top; }
@@ -211,6 +213,21 @@ class Classifier {
 
 }  // namespace net
 
+// Clustering::findClusters (include/gpd/clustering.h:50-80, src/gpd/clustering.cpp:5-105): a grasp whose axis, position
+// and axis-orthogonal offset agree with at least min_inliers other grasps becomes a cluster: position = mean inlier
+// position, score = lower bound of the 99 % confidence interval of the inlier scores. O(n^2) over the SELECTED grasps
+// (n <= num_selected), host side.
+class Clustering {
+ public:
+  explicit Clustering(int min_inliers) : min_inliers_(min_inliers) {}
+  std::vector<std::unique_ptr<candidate::Hand>> findClusters(const std::vector<std::unique_ptr<candidate::Hand>> &hand_list,
+                                                             bool remove_inliers = false) const;
+  int getMinInliers() const { return min_inliers_; }
+
+ private:
+  int min_inliers_;
+};
+
 class GraspDetector {
  public:
   explicit GraspDetector(const std::string &config_filename);
@@ -236,6 +253,7 @@ class GraspDetector {
   candidate::HandSearch::Parameters hand_search_params_;
   int num_selected_{100}, num_samples_{1000};
   bool cluster_grasps_{false};
+  int min_inliers_{1};
   bool has_classifier_{false};
 };
 
@@ -270,6 +288,8 @@ int freeMemoryGrasps(struct Grasp *in);  // unlike the reference (`delete[] in` 
 // Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other,3,3>):
 // m column-major 3x3 -> q = x, y, z, w
 void gpdQuaternionFromMatrix(const double *m, double *q);
+// Clustering::findClusters over plain pose records (testing aid): out has room for n records; returns the cluster count
+int gpdFindClusters(const gpdb_pose *hands, int n, int min_inliers, int remove_inliers, gpdb_pose *out);
 }
 
 #endif  // GPD_B200_HOST_GPD_H_

@@ -509,12 +509,68 @@ std::shared_ptr<Classifier> Classifier::create(const std::string &model_file, co
 }
 }  // namespace net
 
+// ------------------------------------------------------------------------------------------------ Clustering
+std::vector<std::unique_ptr<candidate::Hand>> Clustering::findClusters(
+    const std::vector<std::unique_ptr<candidate::Hand>> &hand_list, bool remove_inliers) const {
+  const double AXIS_ALIGN_ANGLE_THRESH = 12.0 * M_PI / 180.0;  // clustering.cpp:9-13
+  const double AXIS_ALIGN_DIST_THRESH = 0.005;
+  const double MAX_DIST_THRESH = 0.05;
+  std::vector<std::unique_ptr<candidate::Hand>> hands_out;
+  const int n = (int)hand_list.size();
+  std::vector<bool> has_used(n, false);
+  for (int i = 0; i < n; i++) {
+    int num_inliers = 0;
+    double position_delta[3] = {0, 0, 0};
+    const std::array<double, 3> ai = hand_list[i]->getAxis(), pi = hand_list[i]->getPosition();
+    double outer[3][3];  // axis * axis^T
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) outer[r][c] = ai[r] * ai[c];
+    double mean = 0.0, standard_deviation = 0.0;
+    for (int j = 0; j < n; j++) {
+      if (i == j || (remove_inliers && has_used[j])) continue;
+      const std::array<double, 3> aj = hand_list[j]->getAxis(), pj = hand_list[j]->getPosition();
+      const double axis_aligned = ai[0] * aj[0] + ai[1] * aj[1] + ai[2] * aj[2];
+      const bool axis_aligned_binary = std::fabs(axis_aligned) > std::cos(AXIS_ALIGN_ANGLE_THRESH);
+      const double d[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
+      const bool delta_pos_mag_binary = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) <= MAX_DIST_THRESH;
+      double proj[3];  // (I - axis axis^T) * delta_pos
+      for (int r = 0; r < 3; r++)
+        proj[r] = ((r == 0 ? 1.0 : 0.0) - outer[r][0]) * d[0] + ((r == 1 ? 1.0 : 0.0) - outer[r][1]) * d[1] +
+                  ((r == 2 ? 1.0 : 0.0) - outer[r][2]) * d[2];
+      const bool delta_pos_proj_mag_binary =
+          std::sqrt(proj[0] * proj[0] + proj[1] * proj[1] + proj[2] * proj[2]) <= AXIS_ALIGN_DIST_THRESH;
+      if (axis_aligned_binary && delta_pos_mag_binary && delta_pos_proj_mag_binary) {
+        num_inliers++;
+        for (int r = 0; r < 3; r++) position_delta[r] += pj[r];
+        const double old_mean = mean, sj = hand_list[j]->getScore();
+        mean += (sj - mean) / (double)num_inliers;             // Welford update (clustering.cpp:66-70)
+        standard_deviation += (sj - mean) * (sj - old_mean);
+        if (remove_inliers) has_used[j] = true;
+      }
+    }
+    if (num_inliers >= min_inliers_) {
+      const double dn = (double)num_inliers;
+      for (int r = 0; r < 3; r++) position_delta[r] = position_delta[r] / dn - pi[r];
+      standard_deviation /= dn;
+      if (standard_deviation != 0) standard_deviation = std::sqrt(standard_deviation);
+      const double conf_lb = mean - 2.576 * standard_deviation / std::sqrt((double)num_inliers);
+      auto hand = std::make_unique<candidate::Hand>(*hand_list[i]);
+      hand->setPosition({pi[0] + position_delta[0], pi[1] + position_delta[1], pi[2] + position_delta[2]});
+      hand->setScore(conf_lb);
+      hand->setFullAntipodal(hand_list[i]->isFullAntipodal());
+      hands_out.push_back(std::move(hand));
+    }
+  }
+  return hands_out;
+}
+
 // ------------------------------------------------------------------------------------------------ GraspDetector
 GraspDetector::GraspDetector(const std::string &config_filename) {
   std::string weights_file;
   int min_inliers = 0;
   if (!paramsFromConfig(config_filename, params_, weights_file, num_selected_, num_samples_, min_inliers)) return;
   cluster_grasps_ = min_inliers > 0;
+  min_inliers_ = min_inliers;
   preprocessParamsFromConfig(config_filename, pre_params_);
   std::string model_file;
   {
@@ -629,7 +685,15 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
   last_ms_images = r.ms_images;
   last_ms_classify = r.ms_classify;
   gpdb_free_result(&r);
-  if (cluster_grasps_) printf("(clustering requested by min_inliers > 0 is outside the accelerated path: skipped)\n");
+  if (cluster_grasps_) {  // 6. Cluster the grasps (grasp_detector.cpp:283-301)
+    std::vector<std::unique_ptr<candidate::Hand>> clusters = Clustering(min_inliers_).findClusters(hands);
+    printf("Found %d clusters.\n", (int)clusters.size());
+    if (clusters.size() <= 3) {
+      printf("Not enough clusters found! Adding all grasps from previous step.");
+      for (auto &h : hands) clusters.push_back(std::move(h));
+    }
+    hands = std::move(clusters);
+  }
   std::sort(hands.begin(), hands.end(), [](const std::unique_ptr<candidate::Hand> &a, const std::unique_ptr<candidate::Hand> &b) {
     return a->getScore() > b->getScore();
   });
@@ -708,6 +772,14 @@ void gpdQuaternionFromMatrix(const double *m, double *q) {
     q[j] = (M(j, i) + M(i, j)) * t;
     q[k] = (M(k, i) + M(i, k)) * t;
   }
+}
+
+int gpdFindClusters(const gpdb_pose *hands, int n, int min_inliers, int remove_inliers, gpdb_pose *out) {
+  std::vector<std::unique_ptr<gpd::candidate::Hand>> list;
+  for (int i = 0; i < n; i++) list.push_back(std::make_unique<gpd::candidate::Hand>(hands[i]));
+  auto clusters = gpd::Clustering(min_inliers).findClusters(list, remove_inliers != 0);
+  for (size_t i = 0; i < clusters.size(); i++) out[i] = clusters[i]->raw();
+  return (int)clusters.size();
 }
 
 int detectGraspsInCloud(char *config_filename, float *points, int *camera_index, float *view_points, int size,

@@ -205,3 +205,59 @@ def test_python_c_interface_detects_like_the_library(cli, tmp_path, golden_dir):
         assert bool(out[i].label) == bool(cand["full_antipodal"][j]) and out[i].image[0] == -1
     assert L.freeMemoryGrasps(out) == 0
     ctx.close()
+
+
+def test_clustering_matches_a_python_restatement(cli):
+    """Clustering::findClusters (clustering.cpp:5-105) in the host shim against a line-by-line numpy restatement."""
+    import ctypes as C
+    from gpd_b200 import abi
+    L = C.CDLL(os.path.join(HOST, "libgpd_host.so"))
+    L.gpdFindClusters.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(4)
+    n = 120
+    hands = np.zeros(n, dtype=abi.POSE_DTYPE)
+    centers = rng.uniform(-0.1, 0.1, (6, 3))
+    axes = rng.standard_normal((6, 3))
+    axes /= np.linalg.norm(axes, axis=1, keepdims=True)
+    for i in range(n):
+        c = i % 6
+        a = axes[c] + rng.normal(0, 0.02, 3)
+        a /= np.linalg.norm(a)
+        hands["frame"][i][6:9] = a                                   # Hand::getAxis = third column
+        hands["position"][i] = centers[c] + a * rng.uniform(-0.03, 0.03) + rng.normal(0, 0.001, 3)
+        hands["score"][i] = rng.normal(100, 30)
+        hands["full_antipodal"][i] = i % 2
+
+    def restate(min_inliers, remove):
+        out, used = [], np.zeros(n, bool)
+        for i in range(n):
+            ai, pi = hands["frame"][i][6:9], hands["position"][i]
+            k, pos, mean, sd = 0, np.zeros(3), 0.0, 0.0
+            for j in range(n):
+                if i == j or (remove and used[j]):
+                    continue
+                aj, pj = hands["frame"][j][6:9], hands["position"][j]
+                d = pi - pj
+                proj = (np.eye(3) - np.outer(ai, ai)) @ d
+                if abs(ai @ aj) > np.cos(np.deg2rad(12.0)) and np.linalg.norm(d) <= 0.05 and np.linalg.norm(proj) <= 0.005:
+                    k += 1
+                    pos += pj
+                    old, sj = mean, float(hands["score"][j])
+                    mean += (sj - mean) / k
+                    sd += (sj - mean) * (sj - old)
+                    if remove:
+                        used[j] = True
+            if k >= min_inliers:
+                sd /= k
+                sd = np.sqrt(sd) if sd != 0 else sd
+                out.append((i, pi + (pos / k - pi), mean - 2.576 * sd / np.sqrt(k)))
+        return out
+
+    for min_inliers, remove in ((1, 0), (3, 0), (2, 1), (0, 0)):
+        got = np.zeros(n, dtype=abi.POSE_DTYPE)
+        m = L.gpdFindClusters(hands.ctypes.data, n, min_inliers, remove, got.ctypes.data)
+        exp = restate(min_inliers, remove)
+        assert m == len(exp)
+        for g, (i, pos, lb) in zip(got[:m], exp):
+            assert np.allclose(g["position"], pos, atol=1e-12) and abs(g["score"] - np.float32(lb)) <= 1e-4 * max(1, abs(lb))
+            assert np.array_equal(g["frame"], hands["frame"][i]) and g["full_antipodal"] == hands["full_antipodal"][i]
