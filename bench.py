@@ -191,6 +191,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _divert_stdout():
+    """Send everything written to file descriptor 1 (Python AND native libraries: NCCL prints its version banner to
+    stdout when NCCL_DEBUG >= VERSION) to stderr; the ONE JSON line is printed after _restore_stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _restore_stdout(saved):
+    sys.stdout.flush()
+    try:
+        ctypes.CDLL(None).fflush(None)  # flush C stdio buffers into the diverted descriptor first
+    except Exception:
+        pass
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,12 +232,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    saved_stdout = _divert_stdout()
+    final_line = None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (the version banner goes to stdout)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / warnings: not on stdout
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cloud, sidx_all = make_workload(n_gpus, args.samples)
@@ -420,11 +440,14 @@ def main():
             line["cpu_baseline"] = cb
         if world == 1 and not args.no_preprocess:
             line["preprocess"] = bench_preprocess(ctx, hbm_peak, not args.no_cpu_baseline)
-        print(json.dumps(line))
+        final_line = json.dumps(line)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    _restore_stdout(saved_stdout)
+    if final_line is not None:
+        print(final_line, flush=True)
 
 
 if __name__ == "__main__":

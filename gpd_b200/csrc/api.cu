@@ -251,8 +251,9 @@ void gpdb_params_default(gpdb_params *p) {
 }
 
 const char *gpdb_build_info(void) {
-  return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images (fp64, -fmad=false), lenet: conv1/conv2 tcgen05 "
-         "implicit GEMM + ip1 TMA-fed tcgen05 GEMM (bf16x3 / fp16x2 split operands, fp32 accumulate in TMEM), ip2 simt; "
+  return "gpd_b200 v1, sm_100a, kernels: k_frames k_hands k_images k_normals (fp64 / PCL-order fp32, -fmad=false), lenet: "
+         "conv1 tcgen05 kind::i8 implicit GEMM (uint8 image x 3 int8 weight digit planes, exact int32 in TMEM), conv2 tcgen05 "
+         "f16 implicit GEMM + ip1 TMA-fed tcgen05 GEMM (fp16 hi/lo split operands, fp32 accumulate in TMEM), ip2 simt; "
          "lenet_impl=1 forces the simt-fp32 kernels";
 }
 

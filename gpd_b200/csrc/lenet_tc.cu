@@ -10,9 +10,10 @@
 // No patch matrix is ever materialised; every tcgen05.mma reads the plane directly.
 //
 // Precision: the reference computes in float32 on raw 0..255 inputs (logits ~1e3), tolerance 1e-4 relative.
-//   conv1: activations are uint8 -> exact in bf16; weights are split w = w1 + w2 + w3 (bf16 each, 24 bits);
-//          the three terms are stacked along N (rows 0..19 | 20..39 | 40..59 of a N = 64 B operand) so ONE
-//          instruction stream reads A once; the epilogue adds the three 20-column groups in float32.
+//   conv1: integer path (kind::i8): the uint8 image is the A operand as it is; each weight is a 24-bit integer times
+//          a per-filter scale, split into three balanced int8 digits stacked along N (rows 0..19 | 20..39 | 40..59
+//          of a N = 64 B operand) so ONE instruction stream reads A once; the int32 dot products are exact and the
+//          epilogue recombines the three 20-column groups in float32 (see k_conv1_i8 below).
 //   conv2: activations a and weights w are scaled by powers of two (exact) and split in two fp16 terms each;
 //          D[:, 0:64] += a_hi w_hi + a_lo w_hi, D[:, 64:128] += a_hi w_lo  (error ~2^-22), summed in the epilogue.
 // Output pixels with x beyond the valid width are computed and discarded (7 % / 14 % of the rows).

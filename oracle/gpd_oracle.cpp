@@ -18,12 +18,13 @@
  *     dist < (float)(r*r), results sorted by (dist, index);
  *   - OpenCV >= 3.4: dilate(3x3 rect, border ignored), normalize(NORM_MINMAX), minMaxLoc(mask),
  *     convertTo(CV_8U, 255) — these restatements ARE pinned against the real library through
- *     Python cv2 in tests/test_oracle_pins.py;
+ *     Python cv2 in tests/test_oracle.py (fixtures: tools/make_goldens.py);
  *   - the LeNet restatement is pinned against cv2.dnn running the reference's own
  *     .prototxt/.caffemodel (tests/golden/, tools/make_goldens.py).
  * PARITY STATUS: the reference ships no golden vectors or asserting tests for this path
- * (SURVEY.md section 4), so the geometry stages are "parity unpinned" against upstream binaries;
- * what is pinned is listed above.
+ * (SURVEY.md section 4), so the geometry stages and the cloud preprocessing (PCL 1.9.1 normal
+ * estimation restated from its published algorithm, see "Cloud preprocessing" below) are
+ * "parity unpinned" against upstream binaries; what is pinned is listed above.
  *
  * The 15-channel shadow follows the deterministic variant specified in
  * include/gpd_b200_shadow.h (the reference's is racy and random by construction).
