@@ -69,3 +69,25 @@ def test_two_rank_gloo_allgather_matches_single_rank():
     assert np.array_equal(np.isnan(full), np.isnan(ref))
     m = ~np.isnan(ref)
     assert m.any() and np.array_equal(full[m], ref[m])
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores, no GPU): exactly one JSON line on stdout
+    with the keys of the bench contract."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[-400:] + out.stderr[-400:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("grasp candidates/sec") and d["unit"].startswith("samples/s")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank of a torchrun launch does no work and prints nothing
+    out2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                          capture_output=True, text=True, timeout=60, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert out2.returncode == 0 and out2.stdout.strip() == ""
