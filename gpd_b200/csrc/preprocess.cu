@@ -30,9 +30,9 @@
 namespace {
 
 constexpr int NRM_WARPS = 4;       // warps per CTA, tier 1
-constexpr int NRM_CAP1 = 1024;     // neighbours per point, tier 1 (4 warps x 24 B x 1024 = 96 KB per CTA, 2 CTAs per SM)
-constexpr int NRM_CAP2 = 8192;     // tier 2: one warp per CTA (192 KB)
-constexpr int NRM_BYTES_PER = 24;  // key 8 + xyz 12 + bucket group 2 + order 2
+constexpr int NRM_CAP1 = 1024;     // neighbours per point, tier 1 (4 warps x 26 B x 1024 = 104 KB per CTA, 2 CTAs per SM)
+constexpr int NRM_CAP2 = 8192;     // tier 2: one warp per CTA (208 KB)
+constexpr int NRM_BYTES_PER = 26;  // key 8 + xyz 12 + bucket group 2 + pad 2 + rank 2 (keys / group / pad are reused: sorted xyz)
 constexpr int NRM_NB1 = 32;        // distance buckets, tier 1
 constexpr int NRM_NB2 = 256;       // tier 2
 
@@ -251,8 +251,10 @@ __device__ void pcl_eigen33_smallest(const float cov[3][3], float *evec) {
 // Sorting the ball by (dist, index): the squared distance is quantised into NB monotone buckets (on a surface the
 // neighbour count grows linearly in d^2, so the buckets fill evenly), the arrival positions are grouped by
 // bucket with a counting pass, and each key is ranked inside its own bucket only: n^2 / NB comparisons, not n^2.
-// Per-warp shared memory, 24 B per neighbour: keys u64[cap] + pc float[3][cap] (arrival order), grp u16[cap]
-// (arrival positions grouped by bucket), ord u16[cap] (arrival positions in sorted order).
+// Per-warp shared memory, 26 B per neighbour: keys u64[cap] + pc float[3][cap] (arrival order), grp u16[cap]
+// (arrival positions grouped by bucket) + 2 B pad, rk u16[cap] (rank of each arrival position). Once the ranks are
+// known, keys / grp / pad are dead and receive the coordinates IN SORTED ORDER (sx, sy over the keys, sz over grp + pad),
+// so that the ordered accumulation reads three plain arrays sequentially (16-byte loads, no index chain).
 template <int WARPS, int NB>
 __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, DevCloud cl, int N, float r2, float rf,
                                                         int cap, double *nrm_out, int *ovf, int *ovf_count, int tier,
@@ -265,7 +267,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, Dev
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(base);
   float *pc = reinterpret_cast<float *>(keys + cap);  // [3][cap]
   unsigned short *grp = reinterpret_cast<unsigned short *>(pc + 3 * (size_t)cap);
-  unsigned short *ord = grp + cap;
+  unsigned short *rk = grp + 2 * (size_t)cap;                       // after grp[cap] and the pad[cap]
+  float *sxy = reinterpret_cast<float *>(keys);                     // sorted x [cap] | sorted y [cap] (over keys)
+  float *sz = reinterpret_cast<float *>(grp);                       // sorted z [cap] (over grp + pad)
   int *hist = s_hist[warp];      // [0..NB]: bucket starts after the scan
   int *fill = hist + NB + 1;     // [0..NB): per-bucket cursor of the grouping pass
   int i;
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, Dev
       grp[hist[b] + atomicAdd(fill + b, 1)] = (unsigned short)a;
     }
     __syncwarp();
-    // rank of every key inside its bucket -> ord[rank] = arrival position, ascending (dist, index)
+    // rank of every key inside its bucket -> rk[arrival position] = rank in ascending (dist, index) order
     for (int s = lane; s < cnt; s += 32) {
       const int a = grp[s];
       const unsigned long long ka = keys[a];
@@ -365,7 +369,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, Dev
       const int lo = hist[b], hi = hist[b + 1];
       int rank = lo;
       for (int t = lo; t < hi; t++) rank += (keys[grp[t]] < ka);
-      ord[rank] = (unsigned short)a;
+      rk[a] = (unsigned short)rank;
+    }
+    __syncwarp();
+    // keys / grp are dead: permute the coordinates into sorted order
+    for (int a = lane; a < cnt; a += 32) {
+      const int r = rk[a];
+      sxy[r] = pc[a];
+      sxy[cap + r] = pc[cap + a];
+      sz[r] = pc[2 * cap + a];
     }
     __syncwarp();
     // computeMeanAndCovarianceMatrix (float32, single pass, sorted order): lanes 0..8 own accu[0..8]
@@ -373,15 +385,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_normals(const DevParams *Pp, Dev
     const int ib = (lane == 1 || lane == 3) ? 1 : ((lane == 2 || lane == 4 || lane == 5) ? 2 : (lane == 0 ? 0 : -1));
     float acc = 0.0f;
     if (lane < 9) {
-      // one loop for all nine accumulators: lanes 6..8 (plain sums) multiply by 1.0f, which is exact
-      const float *pa = pc + (size_t)ia * cap, *pb = pc + (size_t)max(ib, 0) * cap;
+      // one loop for all nine accumulators: lanes 6..8 (plain sums) multiply by 1.0f, which is exact. Strictly
+      // ascending k; every product is rounded before it is added (-fmad=false): the reference's arithmetic.
+      const float *pa = ia == 2 ? sz : sxy + (size_t)ia * cap;
+      const float *pb = ib == 2 ? sz : sxy + (size_t)max(ib, 0) * cap;
       const bool prod = ib >= 0;
-#pragma unroll 4
-      for (int k = 0; k < cnt; k++) {
-        const int j = ord[k];
-        const float f = prod ? pb[j] : 1.0f;
-        acc += pa[j] * f;
+      int k = 0;
+      for (; k + 4 <= cnt; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(pa + k);
+        float4 b4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        if (prod) b4 = *reinterpret_cast<const float4 *>(pb + k);
+        acc += a4.x * b4.x;
+        acc += a4.y * b4.y;
+        acc += a4.z * b4.z;
+        acc += a4.w * b4.w;
       }
+      for (; k < cnt; k++) acc += pa[k] * (prod ? pb[k] : 1.0f);
     }
     const float fc = (float)cnt;
     acc = acc / fc;
