@@ -261,3 +261,21 @@ def test_clustering_matches_a_python_restatement(cli):
         for g, (i, pos, lb) in zip(got[:m], exp):
             assert np.allclose(g["position"], pos, atol=1e-12) and abs(g["score"] - np.float32(lb)) <= 1e-4 * max(1, abs(lb))
             assert np.array_equal(g["frame"], hands["frame"][i]) and g["full_antipodal"] == hands["full_antipodal"][i]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cfg"), reason="the reference's cfg files exist only in the build container")
+def test_shipped_cfg_files_parse_like_the_reference(cli):
+    """The reference's own cfg files (relative geometry / model paths resolved from the working directory, as upstream
+    does) through the shim's parser: cfg/eigen_params.cfg, cfg/vino_params_12channels.cfg, cfg/all_axes_vino_12channels.cfg."""
+    def dump(name):
+        out = subprocess.check_output([cli, "--dump-config", name], cwd="/root/reference/cfg").decode()
+        return json.loads(out[out.index("{"):out.rindex("}") + 1])
+    d = dump("eigen_params.cfg")
+    assert (d["image_num_channels"], d["num_samples"], d["num_selected"], d["min_inliers"]) == (15, 30, 5, 0)
+    assert d["weights_file"] == "../models/lenet/15channels/params/" and d["voxelize"] == 1 and d["voxel_size"] == 0.003
+    assert (d["finger_width"], d["hand_outer_diameter"], d["hand_depth"], d["hand_height"], d["init_bite"]) == (0.01, 0.12, 0.06, 0.02, 0.01)
+    d = dump("vino_params_12channels.cfg")
+    assert (d["image_num_channels"], d["num_hand_axes"], d["hand_axes0"], d["min_inliers"], d["num_selected"]) == (12, 1, 2, 1, 50)
+    assert d["weights_file"].endswith("two_views_12_channels_curv_axis.bin")
+    d = dump("all_axes_vino_12channels.cfg")
+    assert (d["image_num_channels"], d["num_hand_axes"], d["hand_axes0"]) == (12, 3, 0)
