@@ -1606,11 +1606,8 @@ static const int HANDS_CAP1 = 2176, HANDS_CAP2 = 12800;  // tier 1: 4 CTAs per S
 int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
               gpdb_pose *d_poses, uint8_t *d_flags) {
   if (n <= 0) return GPDB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_hands, cudaFuncAttributeMaxDynamicSharedMemorySize, HANDS_CAP2 * 16));
-    attr_set = true;
-  }
+  // per call, not once per process: function attributes belong to the current device's context (one context per GPU)
+  CUDA_TRY(cudaFuncSetAttribute(k_hands, cudaFuncAttributeMaxDynamicSharedMemorySize, HANDS_CAP2 * 16));
   int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)n + 1));
   if (!ovf) return GPDB_ERR_CUDA;
   int *ovf_count = ovf + n;
