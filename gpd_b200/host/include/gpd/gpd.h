@@ -57,11 +57,13 @@ class ConfigFile {
 class Cloud {
  public:
   Cloud() {}
-  // ASCII / binary .pcd with fields x y z [normal_x normal_y normal_z]; view_points 3 x k column-major
+  // .pcd / .ply with fields x y z [normal_x normal_y normal_z | nx ny nz]; view_points 3 x k column-major
   Cloud(const std::string &filename, const std::vector<double> &view_points);
   Cloud(const std::vector<float> &xyz, const std::vector<double> &normals, const std::vector<int> &camera_source,
         const std::vector<double> &view_points);
-  bool loadPointCloudFromFile(const std::string &filename);
+  bool loadPointCloudFromFile(const std::string &filename);  // .pcd (ascii | binary | binary_compressed) or .ply
+  bool loadPcd(const std::string &filename);
+  bool loadPly(const std::string &filename);
   void setNormalsFromFile(const std::string &filename);  // CSV, one normal per row or 3 x N (cloud.cpp:607-641)
   void setNormals(const std::vector<double> &normals) { normals_ = normals; touch(); }
   void setSampleIndices(const std::vector<int> &idx) { sample_indices_ = idx; }

@@ -90,12 +90,153 @@ Cloud::Cloud(const std::vector<float> &xyz, const std::vector<double> &normals, 
   touch();
 }
 
-// .pcd reader: header fields FIELDS/SIZE/TYPE/COUNT/POINTS/DATA (ascii | binary); NaN points are dropped
-// (Cloud::removeNans). Replaces pcl::io::loadPCDFile in cloud.cpp:643-660.
+// File readers (replace pcl::io::loadPCDFile / loadPLYFile in cloud.cpp:643-660); NaN points are dropped (Cloud::removeNans).
+// LZF decompression (Marc Lehmann's liblzf format, used by PCD "DATA binary_compressed"): control byte < 32 = literal run
+// of ctrl + 1 bytes; otherwise a back reference of length (ctrl >> 5) + 2 (7 = extended by the next byte) at distance
+// ((ctrl & 31) << 8 | next) + 1.
+static bool lzf_decompress(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len) {
+  size_t ip = 0, op = 0;
+  while (ip < in_len) {
+    unsigned ctrl = in[ip++];
+    if (ctrl < 32) {
+      size_t n = ctrl + 1;
+      if (ip + n > in_len || op + n > out_len) return false;
+      std::memcpy(out + op, in + ip, n);
+      ip += n;
+      op += n;
+    } else {
+      size_t len = ctrl >> 5;
+      if (len == 7) {
+        if (ip >= in_len) return false;
+        len += in[ip++];
+      }
+      if (ip >= in_len) return false;
+      size_t dist = ((size_t)(ctrl & 31) << 8) + in[ip++] + 1;
+      len += 2;
+      if (dist > op || op + len > out_len) return false;
+      for (size_t k = 0; k < len; k++, op++) out[op] = out[op - dist];  // may overlap: byte by byte
+    }
+  }
+  return op == out_len;
+}
+
+static double read_scalar(const char *src, const std::string &type, int size) {
+  if (type == "F" && size == 4) { float v; std::memcpy(&v, src, 4); return v; }
+  if (type == "F" && size == 8) { double v; std::memcpy(&v, src, 8); return v; }
+  if (size == 4) { int32_t v; std::memcpy(&v, src, 4); return type == "U" ? (double)(uint32_t)v : (double)v; }
+  if (size == 2) { int16_t v; std::memcpy(&v, src, 2); return type == "U" ? (double)(uint16_t)v : (double)v; }
+  return type == "I" ? (double)(signed char)src[0] : (double)(unsigned char)src[0];
+}
+
+// Cloud::loadPointCloudFromFile (cloud.cpp:643-660): .pcd (pcl::io::loadPCDFile) or .ply (pcl::io::loadPLYFile) by extension
 bool Cloud::loadPointCloudFromFile(const std::string &filename) {
+  const std::string extension = filename.size() >= 3 ? filename.substr(filename.size() - 3) : "";
+  if (extension == "ply") return loadPly(filename);
+  return loadPcd(filename);
+}
+
+// .ply reader: "format ascii 1.0" or "binary_little_endian 1.0", element vertex with properties x y z [nx ny nz] (any
+// scalar types; other properties and elements after the vertices are ignored; list properties inside the vertex element
+// are not supported). NaN points are dropped.
+bool Cloud::loadPly(const std::string &filename) {
   std::ifstream f(filename.c_str(), std::ios::binary);
   if (!f) {
-    std::cout << "Couldn't read .pcd file: " << filename << "\n";
+    std::cout << "Couldn't read PLY file: " << filename << "\n";
+    return false;
+  }
+  std::string line, format;
+  struct Prop { std::string name, type; int size; };
+  std::vector<Prop> props;
+  size_t nvert = 0;
+  bool in_vertex = false, vertex_first = true, seen_element = false;
+  auto type_size = [](const std::string &t) {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+  };
+  if (!std::getline(f, line) || line.substr(0, 3) != "ply") {
+    std::cout << "Not a PLY file: " << filename << "\n";
+    return false;
+  }
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::istringstream ss(line);
+    std::string tag;
+    ss >> tag;
+    if (tag == "format") ss >> format;
+    else if (tag == "element") {
+      std::string name;
+      size_t n;
+      ss >> name >> n;
+      in_vertex = name == "vertex";
+      if (in_vertex) { nvert = n; vertex_first = !seen_element; }
+      seen_element = true;
+    } else if (tag == "property" && in_vertex) {
+      std::string t, name;
+      ss >> t;
+      if (t == "list") { std::cout << "PLY: list property inside the vertex element is not supported\n"; return false; }
+      ss >> name;
+      props.push_back({name, t, type_size(t)});
+      if (props.back().size == 0) { std::cout << "PLY: unknown property type " << t << "\n"; return false; }
+    } else if (tag == "end_header") break;
+  }
+  auto idx_of = [&](const char *a, const char *b) { for (size_t i = 0; i < props.size(); i++) if (props[i].name == a || props[i].name == b) return (int)i; return -1; };
+  const int ix = idx_of("x", "x"), iy = idx_of("y", "y"), iz = idx_of("z", "z");
+  const int inx = idx_of("nx", "normal_x"), iny = idx_of("ny", "normal_y"), inz = idx_of("nz", "normal_z");
+  if (ix < 0 || iy < 0 || iz < 0 || !vertex_first) {
+    std::cout << "PLY: need a leading vertex element with x y z: " << filename << "\n";
+    return false;
+  }
+  points_.clear();
+  normals_.clear();
+  std::vector<double> row(props.size());
+  auto push = [&]() {
+    if (!std::isfinite(row[ix]) || !std::isfinite(row[iy]) || !std::isfinite(row[iz])) return;
+    points_.push_back((float)row[ix]); points_.push_back((float)row[iy]); points_.push_back((float)row[iz]);
+    if (inx >= 0 && iny >= 0 && inz >= 0) {
+      normals_.push_back((double)(float)row[inx]); normals_.push_back((double)(float)row[iny]); normals_.push_back((double)(float)row[inz]);
+    }
+  };
+  if (format == "ascii") {
+    for (size_t v = 0; v < nvert && std::getline(f, line); v++) {
+      std::istringstream ss(line);
+      bool ok = true;
+      for (size_t i = 0; i < props.size() && ok; i++) {
+        std::string tok;
+        if (!(ss >> tok)) ok = false;
+        else row[i] = (tok == "nan" || tok == "NaN") ? NAN : std::atof(tok.c_str());
+      }
+      if (ok) push();
+    }
+  } else if (format == "binary_little_endian") {
+    size_t stride = 0;
+    std::vector<size_t> off(props.size());
+    for (size_t i = 0; i < props.size(); i++) { off[i] = stride; stride += (size_t)props[i].size; }
+    std::vector<char> buf(stride);
+    for (size_t v = 0; v < nvert && f.read(buf.data(), stride); v++) {
+      for (size_t i = 0; i < props.size(); i++) {
+        const std::string &t = props[i].type;
+        const bool is_f = t[0] == 'f' || t[0] == 'd';
+        const bool is_u = t[0] == 'u';
+        row[i] = read_scalar(buf.data() + off[i], is_f ? "F" : (is_u ? "U" : "I"), props[i].size);
+      }
+      push();
+    }
+  } else {
+    std::cout << "Unsupported PLY format '" << format << "' (ascii and binary_little_endian are supported)\n";
+    return false;
+  }
+  printf("Loaded point cloud with %zu points\n", size());
+  return true;
+}
+
+// .pcd reader: header fields FIELDS/SIZE/TYPE/COUNT/POINTS/DATA (ascii | binary | binary_compressed)
+bool Cloud::loadPcd(const std::string &filename) {
+  std::ifstream f(filename.c_str(), std::ios::binary);
+  if (!f) {
+    std::cout << "Couldn't read PCD file: " << filename << "\n";
     return false;
   }
   std::vector<std::string> fields, types;
@@ -156,18 +297,31 @@ bool Cloud::loadPointCloudFromFile(const std::string &filename) {
     for (size_t i = 0; i < fields.size(); i++) { off[i] = stride; stride += (size_t)sizes[i] * counts[i]; }
     std::vector<char> buf(stride);
     for (size_t p = 0; p < npoints && f.read(buf.data(), stride); p++) {
-      for (size_t i = 0; i < fields.size(); i++) {
-        const char *src = buf.data() + off[i];
-        if (types[i] == "F" && sizes[i] == 4) { float v; std::memcpy(&v, src, 4); row[i] = v; }
-        else if (types[i] == "F" && sizes[i] == 8) { double v; std::memcpy(&v, src, 8); row[i] = v; }
-        else if (sizes[i] == 4) { int32_t v; std::memcpy(&v, src, 4); row[i] = v; }
-        else if (sizes[i] == 2) { int16_t v; std::memcpy(&v, src, 2); row[i] = v; }
-        else { row[i] = (double)(unsigned char)src[0]; }
-      }
+      for (size_t i = 0; i < fields.size(); i++) row[i] = read_scalar(buf.data() + off[i], types[i], sizes[i]);
+      push();
+    }
+  } else if (data_kind == "binary_compressed") {
+    // uint32 compressed size, uint32 uncompressed size, LZF stream; the payload is stored field by field (SoA):
+    // all values of field 0, then all of field 1, ... (pcl/io/pcd_io.cpp)
+    uint32_t csize = 0, usize = 0;
+    f.read(reinterpret_cast<char *>(&csize), 4);
+    f.read(reinterpret_cast<char *>(&usize), 4);
+    size_t stride = 0;
+    std::vector<size_t> foff(fields.size());
+    for (size_t i = 0; i < fields.size(); i++) { foff[i] = stride * npoints; stride += (size_t)sizes[i] * counts[i]; }
+    std::vector<unsigned char> comp(csize), raw(usize);
+    if (!f.read(reinterpret_cast<char *>(comp.data()), csize) || (size_t)usize != stride * npoints ||
+        !lzf_decompress(comp.data(), csize, raw.data(), usize)) {
+      std::cout << "Bad binary_compressed payload in: " << filename << "\n";
+      return false;
+    }
+    for (size_t p = 0; p < npoints; p++) {
+      for (size_t i = 0; i < fields.size(); i++)
+        row[i] = read_scalar(reinterpret_cast<const char *>(raw.data()) + foff[i] + p * (size_t)sizes[i] * counts[i], types[i], sizes[i]);
       push();
     }
   } else {
-    std::cout << "Unsupported .pcd DATA kind '" << data_kind << "' (ascii and binary are supported)\n";
+    std::cout << "Unsupported .pcd DATA kind '" << data_kind << "' (ascii, binary and binary_compressed are supported)\n";
     return false;
   }
   printf("Loaded point cloud with %zu points\n", size());

@@ -279,3 +279,79 @@ def test_shipped_cfg_files_parse_like_the_reference(cli):
     assert d["weights_file"].endswith("two_views_12_channels_curv_axis.bin")
     d = dump("all_axes_vino_12channels.cfg")
     assert (d["image_num_channels"], d["num_hand_axes"], d["hand_axes0"]) == (12, 3, 0)
+
+
+def _lzf_compress(data):
+    """Minimal LZF encoder for the test (greedy, 3-byte hash table): literals + back references, format of liblzf."""
+    out, lit, i, n, table = bytearray(), bytearray(), 0, len(data), {}
+
+    def flush():
+        nonlocal lit
+        while lit:
+            chunk, lit = lit[:32], lit[32:]
+            out.append(len(chunk) - 1)
+            out.extend(chunk)
+    while i < n:
+        key = bytes(data[i:i + 3])
+        ref = table.get(key) if len(key) == 3 else None
+        table[key] = i
+        if ref is not None and 0 < i - ref <= 8192:
+            ln = 3
+            while i + ln < n and ln < 264 and data[ref + ln] == data[i + ln]:
+                ln += 1
+            flush()
+            dist, l2 = i - ref - 1, ln - 2
+            if l2 < 7:
+                out.append((l2 << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8))
+                out.append(l2 - 7)
+            out.append(dist & 255)
+            i += ln
+        else:
+            lit.append(data[i])
+            i += 1
+    flush()
+    return bytes(out)
+
+
+def test_ply_and_compressed_pcd_readers(cli, tmp_path):
+    """Cloud::loadPointCloudFromFile reads .pcd and .ply (cloud.cpp:643-660): PLY ascii / binary_little_endian and PCD
+    binary_compressed (LZF, field-major payload) give the same cloud as the plain binary PCD."""
+    rng = np.random.default_rng(2)
+    xyz = np.round(rng.uniform(-1, 1, (300, 3)), 2).astype(np.float32)  # repeated byte patterns: back references occur
+    xyz[7] = [np.nan, 0, 0]
+    nrm = rng.standard_normal((300, 3)).astype(np.float32)
+    (tmp_path / "main.cfg").write_text("weights_file = /x/\n")
+
+    def dump(path):
+        out = subprocess.check_output([cli, "--dump-config", str(tmp_path / "main.cfg"), str(path)]).decode()
+        d = json.loads(out[out.index("{"):out.rindex("}") + 1])
+        return d["cloud_points"], d["cloud_has_normals"], d.get("first_point")
+    write_pcd(tmp_path / "plain.pcd", xyz, nrm, binary=True)
+    ref = dump(tmp_path / "plain.pcd")
+    assert ref[0] == 299 and ref[1] == 1
+    # PCD binary_compressed
+    soa = np.concatenate([np.hstack([xyz, nrm])[:, k] for k in range(6)]).astype(np.float32).tobytes()
+    comp = _lzf_compress(soa)
+    assert len(comp) < len(soa)
+    hdr = ("# .PCD v.7\nVERSION .7\nFIELDS x y z normal_x normal_y normal_z\nSIZE 4 4 4 4 4 4\nTYPE F F F F F F\nCOUNT 1 1 1 1 1 1\n"
+           "WIDTH 300\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 300\nDATA binary_compressed\n")
+    open(tmp_path / "lzf.pcd", "wb").write(hdr.encode() + struct.pack("<II", len(comp), len(soa)) + comp)
+    assert dump(tmp_path / "lzf.pcd") == ref
+    # PLY
+    ply_hdr = lambda fmt: (f"ply\nformat {fmt} 1.0\ncomment test\nelement vertex 300\nproperty float x\nproperty float y\nproperty float z\n"
+                           "property float nx\nproperty float ny\nproperty float nz\nproperty uchar red\nelement face 0\n"
+                           "property list uchar int vertex_indices\nend_header\n")
+    with open(tmp_path / "a.ply", "w") as f:
+        f.write(ply_hdr("ascii"))
+        for p, q in zip(xyz, nrm):
+            f.write(" ".join(repr(float(v)) for v in list(p) + list(q)) + " 7\n")
+    with open(tmp_path / "b.ply", "wb") as f:
+        f.write(ply_hdr("binary_little_endian").encode())
+        for p, q in zip(xyz, nrm):
+            f.write(struct.pack("<6fB", *p, *q, 7))
+    assert dump(tmp_path / "a.ply") == ref and dump(tmp_path / "b.ply") == ref
+    # corrupt compressed payload is rejected, not mis-read
+    open(tmp_path / "bad.pcd", "wb").write(hdr.encode() + struct.pack("<II", len(comp), len(soa)) + comp[:-5] + b"\xff" * 5)
+    assert dump(tmp_path / "bad.pcd")[0] == 0
