@@ -44,6 +44,41 @@ def gather_scores(local_scores, n, poses_per_sample, rank, world, dist=None, dev
     return full.reshape(n, P)
 
 
+def select_global(local_candidates, num_selected, n, rank, world, dist=None, device=None):
+    """Global selectGrasps (grasp_detector.cpp:405-420) over sharded samples: every rank contributes its local
+    `num_selected` best pose records (gpdb_detect_select on its slice), ONE all-gather of fixed-stride record slots
+    (num_selected x sizeof(gpdb_pose) bytes per rank; 17.6 KB for the default 100), then every rank merges them: descending
+    score, ties in (rank, local order) = global candidate order, exactly like the single-GPU call. `sample_slot` is rebased
+    from the slice to the full sample array. local_candidates: numpy structured array (abi.POSE_DTYPE), already sorted by
+    descending score. Returns the global top records (numpy structured array), identical on all ranks."""
+    import torch
+
+    from . import abi
+
+    k = int(num_selected)
+    lo, _ = slice_bounds(n, rank, world)
+    loc = np.array(local_candidates[:k], dtype=abi.POSE_DTYPE, copy=True)
+    loc["sample_slot"] += lo
+    if world == 1:
+        return loc
+    rec = abi.POSE_DTYPE.itemsize
+    slot = np.zeros(k * rec + 8, np.uint8)
+    slot[:8] = np.frombuffer(np.int64(len(loc)).tobytes(), np.uint8)
+    slot[8:8 + len(loc) * rec] = np.frombuffer(loc.tobytes(), np.uint8)
+    t = torch.from_numpy(slot).to(device) if device is not None else torch.from_numpy(slot)
+    out = torch.empty(world * slot.size, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    buf = out.cpu().numpy()
+    parts = []
+    for r in range(world):
+        chunk = buf[r * slot.size:(r + 1) * slot.size]
+        cnt = int(np.frombuffer(chunk[:8].tobytes(), np.int64)[0])
+        parts.append(np.frombuffer(chunk[8:8 + cnt * rec].tobytes(), dtype=abi.POSE_DTYPE))
+    allc = np.concatenate(parts) if parts else loc[:0]
+    order = np.argsort(-allc["score"].astype(np.float64), kind="stable")[:k]
+    return allc[order].copy()
+
+
 def broadcast_cloud(cloud, rank, dist, device=None):
     """Broadcast the cloud arrays from rank 0 (ncclBroadcast over NVLink on GPUs)."""
     import torch

@@ -42,9 +42,14 @@ def _worker(rank, world, port, q):
     oc = oracle.OracleCloud(cloud["xyz"], cloud["normals"], cloud["cam_source"], cloud["view_points"])
     local = oc.detect(p, w, sidx[lo:hi], nthreads=2)
     full = sharding.gather_scores(local["pose_scores"].reshape(-1), n, 8, rank, world, dist)
+    # global top-k: local top-k per rank (what gpdb_detect_select returns), one all-gather of record slots, merge
+    k = 5
+    lc = local["candidates"]
+    lc = lc[np.argsort(-lc["score"].astype(np.float64), kind="stable")[:k]]
+    top = sharding.select_global(lc, k, n, rank, world, dist)
     if rank == 0:
         ref = oc.detect(p, w, sidx, nthreads=2)
-        q.put((full.numpy(), ref["pose_scores"]))
+        q.put((full.numpy(), ref["pose_scores"], top, ref["candidates"]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,7 +66,7 @@ def test_two_rank_gloo_allgather_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for pr in procs:
         pr.start()
-    full, ref = q.get(timeout=240)
+    full, ref, top, ref_cand = q.get(timeout=240)
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
@@ -69,6 +74,12 @@ def test_two_rank_gloo_allgather_matches_single_rank():
     assert np.array_equal(np.isnan(full), np.isnan(ref))
     m = ~np.isnan(ref)
     assert m.any() and np.array_equal(full[m], ref[m])
+    # sharded selectGrasps == single-rank selectGrasps (same records, same order, sample slots rebased)
+    want = ref_cand[np.argsort(-ref_cand["score"].astype(np.float64), kind="stable")[:5]]
+    assert len(top) == len(want) == 5
+    for f in top.dtype.names:
+        if f != "pad_":
+            assert np.array_equal(top[f], want[f]), f
 
 
 def test_reference_arm_prints_one_contract_line():
