@@ -453,7 +453,7 @@ static gpdb_ctx *make_ctx(const gpdb_params &p) {
 }
 static int upload_cloud(gpdb_ctx *ctx, const util::Cloud &cloud) {
   if (cloud.getNormals().size() != 3 * cloud.size()) {
-    printf("ERROR: the cloud has no surface normals (normal estimation is outside the accelerated path)\n");
+    printf("ERROR: the cloud has no surface normals: call GraspDetector::preprocessPointCloud first (gpdb_preprocess)\n");
     return GPDB_ERR_INVALID;
   }
   return gpdb_set_cloud(ctx, cloud.getPoints().data(), cloud.getNormals().data(),
