@@ -17,6 +17,7 @@
 #define GPD_B200_HOST_GPD_H_
 
 #include <array>
+#include <iostream>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -38,9 +39,11 @@ class ConfigFile {
   template <typename ValueType>
   ValueType getValueOfKey(const std::string &key, ValueType const &defaultValue) const {
     if (!keyExists(key)) return defaultValue;
+    // string_to_T (config_file.h:132-142): a value that does not parse is reported and yields the zero that a failed
+    // stream extraction leaves behind, NOT the default (pinned against the reference's parser, oracle/_ref)
     std::istringstream istr(contents.find(key)->second);
-    ValueType v;
-    if (!(istr >> v)) return defaultValue;
+    ValueType v{};
+    if (!(istr >> v)) std::cout << "CFG: Not a valid value received for key " << key << "!\n";
     return v;
   }
   std::string getValueOfKeyAsString(const std::string &key, const std::string &defaultValue) const;
@@ -292,6 +295,12 @@ int freeMemoryGrasps(struct Grasp *in);  // unlike the reference (`delete[] in` 
 void gpdQuaternionFromMatrix(const double *m, double *q);
 // Clustering::findClusters over plain pose records (testing aid): out has room for n records; returns the cluster count
 int gpdFindClusters(const gpdb_pose *hands, int n, int min_inliers, int remove_inliers, gpdb_pose *out);
+// util::ConfigFile of the shim over plain C types (testing aid: pinned against the reference's own parser, oracle/_ref)
+int gpdConfigGet(const char *file, const char *key, const char *def, char *out, int out_len);
+double gpdConfigGetDouble(const char *file, const char *key, double def);
+int gpdConfigGetInt(const char *file, const char *key, int def);
+int gpdConfigGetBool(const char *file, const char *key, int def);
+int gpdConfigGetDoubles(const char *file, const char *key, const char *def, double *out, int cap);
 }
 
 #endif  // GPD_B200_HOST_GPD_H_

@@ -16,6 +16,10 @@ namespace util {
 
 ConfigFile::ConfigFile(const std::string &fName) : fName(fName) {}
 
+// Follows the reference's parser statement by statement, corner cases included (config_file.cpp:6-101; pinned against
+// the reference's own object code, oracle/_ref): only '#' starts a comment; a line counts as blank only if it consists of
+// SPACES; a line without '=' or with nothing after it is reported but STILL stored (key = first token, value = the
+// rest of the line resp. ""); the first occurrence of a key wins; '\r' is not stripped.
 bool ConfigFile::ExtractKeys() {
   std::ifstream file(fName.c_str());
   if (!file) {
@@ -27,26 +31,27 @@ bool ConfigFile::ExtractKeys() {
   while (std::getline(file, line)) {
     lineNo++;
     if (line.empty()) continue;
-    if (line.find('#') != line.npos) line.erase(line.find('#'));          // removeComment
-    if (line.find_first_not_of(" \t\r") == line.npos) continue;            // onlyWhitespace
-    size_t sep = line.find('=');
-    if (sep == line.npos) {
-      std::cout << "CFG: Couldn't find separator on line: " << lineNo << "\n";
-      continue;
+    if (line.find('#') != line.npos) line.erase(line.find('#'));   // removeComment
+    if (line.find_first_not_of(' ') == line.npos) continue;        // onlyWhitespace
+    if (line.find('=') == line.npos) std::cout << "CFG: Couldn't find separator on line: " << lineNo << "\n";
+    {  // validLine: only reported
+      std::string t = line;
+      t.erase(0, t.find_first_not_of("\t "));
+      bool valid = false;
+      if (!(t.size() > 0 && t[0] == '='))
+        for (size_t i = t.find('=') + 1; i < t.length(); i++)
+          if (t[i] != ' ') { valid = true; break; }
+      if (!valid) std::cout << "CFG: Bad format for line: " << lineNo << "\n";
     }
+    // extractContents
     std::string temp = line;
     temp.erase(0, temp.find_first_not_of("\t "));
-    sep = temp.find('=');
-    std::string key = temp.substr(0, sep);
-    if (key.find_first_of("\t ") != key.npos) key.erase(key.find_first_of("\t "));
-    std::string value = temp.substr(sep + 1);
+    const size_t sepPos = temp.find('=');
+    std::string key = temp.substr(0, sepPos);
+    if (key.find('\t') != temp.npos || key.find(' ') != temp.npos) key.erase(key.find_first_of("\t "));
+    std::string value = temp.substr(sepPos + 1);  // sepPos == npos: the whole line (npos + 1 wraps to 0), as upstream
     value.erase(0, value.find_first_not_of("\t "));
-    size_t last = value.find_last_not_of("\t \r");
-    value.erase(last == value.npos ? 0 : last + 1);
-    if (key.empty() || value.empty()) {
-      std::cout << "CFG: Bad format for line: " << lineNo << "\n";
-      continue;
-    }
+    value.erase(value.find_last_not_of("\t ") + 1);
     if (!keyExists(key)) contents.insert(std::make_pair(key, value));
     else std::cout << "CFG: Can only have unique key names!\n";
   }
@@ -61,16 +66,24 @@ std::string ConfigFile::getValueOfKeyAsString(const std::string &key, const std:
 }
 
 std::vector<double> ConfigFile::getValueOfKeyAsStdVectorDouble(const std::string &key, const std::string &defaultValue) const {
-  std::stringstream ss(getValueOfKeyAsString(key, defaultValue));
+  std::stringstream ss(getValueOfKeyAsString(key, defaultValue));  // stringToDouble (config_file.cpp:139-152)
   std::vector<double> v;
   double x;
-  while (ss >> x) v.push_back(x);
+  while (ss >> x) {
+    v.push_back(x);
+    if (ss.peek() == ' ') ss.ignore();
+  }
   return v;
 }
 
 std::vector<int> ConfigFile::getValueOfKeyAsStdVectorInt(const std::string &key, const std::string &defaultValue) const {
+  std::stringstream ss(getValueOfKeyAsString(key, defaultValue));  // stringToInt reads doubles and truncates (:154-167)
   std::vector<int> v;
-  for (double x : getValueOfKeyAsStdVectorDouble(key, defaultValue)) v.push_back((int)x);
+  double x;
+  while (ss >> x) {
+    v.push_back((int)x);
+    if (ss.peek() == ' ') ss.ignore();
+  }
   return v;
 }
 
@@ -926,6 +939,35 @@ void gpdQuaternionFromMatrix(const double *m, double *q) {
     q[j] = (M(j, i) + M(i, j)) * t;
     q[k] = (M(k, i) + M(i, k)) * t;
   }
+}
+
+int gpdConfigGet(const char *file, const char *key, const char *def, char *out, int out_len) {
+  gpd::util::ConfigFile cfg(file);
+  const bool ok = cfg.ExtractKeys();
+  std::snprintf(out, (size_t)out_len, "%s", cfg.getValueOfKeyAsString(key, def).c_str());
+  return ok ? 1 : 0;
+}
+double gpdConfigGetDouble(const char *file, const char *key, double def) {
+  gpd::util::ConfigFile cfg(file);
+  cfg.ExtractKeys();
+  return cfg.getValueOfKey<double>(key, def);
+}
+int gpdConfigGetInt(const char *file, const char *key, int def) {
+  gpd::util::ConfigFile cfg(file);
+  cfg.ExtractKeys();
+  return cfg.getValueOfKey<int>(key, def);
+}
+int gpdConfigGetBool(const char *file, const char *key, int def) {
+  gpd::util::ConfigFile cfg(file);
+  cfg.ExtractKeys();
+  return cfg.getValueOfKey<bool>(key, def != 0) ? 1 : 0;
+}
+int gpdConfigGetDoubles(const char *file, const char *key, const char *def, double *out, int cap) {
+  gpd::util::ConfigFile cfg(file);
+  cfg.ExtractKeys();
+  std::vector<double> v = cfg.getValueOfKeyAsStdVectorDouble(key, def);
+  for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+  return (int)v.size();
 }
 
 int gpdFindClusters(const gpdb_pose *hands, int n, int min_inliers, int remove_inliers, gpdb_pose *out) {

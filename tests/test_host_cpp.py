@@ -355,3 +355,58 @@ def test_ply_and_compressed_pcd_readers(cli, tmp_path):
     # corrupt compressed payload is rejected, not mis-read
     open(tmp_path / "bad.pcd", "wb").write(hdr.encode() + struct.pack("<II", len(comp), len(soa)) + comp[:-5] + b"\xff" * 5)
     assert dump(tmp_path / "bad.pcd")[0] == 0
+
+
+REF_CFG_SO = os.path.join(ROOT, "oracle", "_ref", "libgpd_ref_config.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG_SO) and not os.path.isdir("/root/reference/src/gpd/util"),
+                    reason="oracle/_ref (the reference's own cfg parser) is built only where /root/reference exists")
+def test_cfg_parser_against_the_references_own_parser(cli, tmp_path):
+    """The shim's util::ConfigFile against the REFERENCE's util::ConfigFile, compiled from /root/reference into
+    oracle/_ref/libgpd_ref_config.so (the one source file of the reference that builds without PCL / Eigen / OpenCV):
+    identical values for every key and getter on a cfg with the format's corner cases and on the shipped cfg files."""
+    import ctypes as C
+    if not os.path.exists(REF_CFG_SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref", "-s"], env={**os.environ, "CXX": "g++"})
+    R, H = C.CDLL(REF_CFG_SO), C.CDLL(os.path.join(HOST, "libgpd_host.so"))
+    for L, pre in ((R, "gpdref_config_get"), (H, "gpdConfigGet")):
+        getattr(L, pre).argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        for suf, rt, dt in (("_double" if L is R else "Double", C.c_double, C.c_double), ("_int" if L is R else "Int", C.c_int, C.c_int),
+                            ("_bool" if L is R else "Bool", C.c_int, C.c_int)):
+            f = getattr(L, pre + suf)
+            f.argtypes, f.restype = [C.c_char_p, C.c_char_p, dt], rt
+        f = getattr(L, pre + ("_doubles" if L is R else "Doubles"))
+        f.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int]
+
+    def both(path, key):
+        out = []
+        for L, pre, n in ((R, "gpdref_config_get", ("_double", "_int", "_bool", "_doubles")), (H, "gpdConfigGet", ("Double", "Int", "Bool", "Doubles"))):
+            buf = C.create_string_buffer(512)
+            found = getattr(L, pre)(path.encode(), key.encode(), b"<default>", buf, 512)
+            vec = (C.c_double * 16)()
+            nv = getattr(L, pre + n[3])(path.encode(), key.encode(), b"1.5 2.5", vec, 16)
+            out.append((found, buf.value, getattr(L, pre + n[0])(path.encode(), key.encode(), -7.25),
+                        getattr(L, pre + n[1])(path.encode(), key.encode(), -7), getattr(L, pre + n[2])(path.encode(), key.encode(), 1),
+                        nv, list(vec[:min(nv, 16)])))
+        return out
+    tricky = tmp_path / "tricky.cfg"
+    tricky.write_text("# comment line\n\n   \nalpha = 1.5\nbeta=2\n\tgamma\t=\t3.25   # trailing comment\n  delta   =  a b  c  \nalpha = 99\n"
+                      "vec = 0.1 -2 3e-3 4\nflag0 = 0\nflag1 = 1\nempty_after_hash = #nothing\nint_as_float = 7.9\nweights_file = ../x/y/\n"
+                      "spaced key = 5\n")
+    keys = ["alpha", "beta", "gamma", "delta", "vec", "flag0", "flag1", "empty_after_hash", "int_as_float", "weights_file", "spaced",
+            "spaced key", "missing"]
+    for k in keys:
+        r, h = both(str(tricky), k)
+        assert r == h, (k, r, h)
+    if os.path.isdir("/root/reference/cfg"):
+        for name in ("eigen_params.cfg", "caffe_params.cfg", "vino_params_12channels.cfg", "hand_geometry.cfg", "image_geometry_15channels.cfg",
+                     "ros_eigen_params.cfg"):
+            path = "/root/reference/cfg/" + name
+            for k in ("hand_geometry_filename", "image_geometry_filename", "weights_file", "model_file", "workspace", "workspace_grasps",
+                      "num_samples", "num_threads", "voxelize", "voxel_size", "hand_axes", "finger_width", "hand_outer_diameter",
+                      "volume_width", "image_num_channels", "camera_position", "min_inliers", "num_selected", "direction", "thresh_rad"):
+                r, h = both(path, k)
+                assert r == h, (name, k, r, h)
+    r, h = both(str(tmp_path / "does_not_exist.cfg"), "alpha")
+    assert r == h and r[0] == 0
