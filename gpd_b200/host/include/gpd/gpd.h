@@ -301,6 +301,8 @@ double gpdConfigGetDouble(const char *file, const char *key, double def);
 int gpdConfigGetInt(const char *file, const char *key, int def);
 int gpdConfigGetBool(const char *file, const char *key, int def);
 int gpdConfigGetDoubles(const char *file, const char *key, const char *def, double *out, int cap);
+void gpdHandGeometry(const char *file, double out[5]);                  // candidate::HandGeometry(filepath)
+void gpdImageGeometry(const char *file, double out[3], int out2[2]);   // descriptor::ImageGeometry(filepath)
 }
 
 #endif  // GPD_B200_HOST_GPD_H_

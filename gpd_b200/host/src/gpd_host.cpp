@@ -970,6 +970,15 @@ int gpdConfigGetDoubles(const char *file, const char *key, const char *def, doub
   return (int)v.size();
 }
 
+void gpdHandGeometry(const char *file, double out[5]) {
+  gpd::candidate::HandGeometry g{std::string(file)};
+  out[0] = g.finger_width_; out[1] = g.outer_diameter_; out[2] = g.depth_; out[3] = g.height_; out[4] = g.init_bite_;
+}
+void gpdImageGeometry(const char *file, double out[3], int out2[2]) {
+  gpd::descriptor::ImageGeometry g{std::string(file)};
+  out[0] = g.outer_diameter_; out[1] = g.depth_; out[2] = g.height_; out2[0] = g.size_; out2[1] = g.num_channels_;
+}
+
 int gpdFindClusters(const gpdb_pose *hands, int n, int min_inliers, int remove_inliers, gpdb_pose *out) {
   std::vector<std::unique_ptr<gpd::candidate::Hand>> list;
   for (int i = 0; i < n; i++) list.push_back(std::make_unique<gpd::candidate::Hand>(hands[i]));

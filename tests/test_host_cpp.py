@@ -410,3 +410,17 @@ def test_cfg_parser_against_the_references_own_parser(cli, tmp_path):
                 assert r == h, (name, k, r, h)
     r, h = both(str(tmp_path / "does_not_exist.cfg"), "alpha")
     assert r == h and r[0] == 0
+    # candidate::HandGeometry(filepath) / descriptor::ImageGeometry(filepath): the reference's object code vs the shim's
+    files = [str(tricky), str(tmp_path / "does_not_exist.cfg")]
+    if os.path.isdir("/root/reference/cfg"):
+        files += ["/root/reference/cfg/" + n for n in ("hand_geometry.cfg", "ur5_hand_geometry.cfg", "image_geometry_15channels.cfg",
+                                                       "image_geometry_12channels.cfg", "image_geometry_3channels.cfg",
+                                                       "image_geometry_1channels.cfg", "eigen_params.cfg")]
+    for path in files:
+        vals = []
+        for L, hg, ig in ((R, "gpdref_hand_geometry", "gpdref_image_geometry"), (H, "gpdHandGeometry", "gpdImageGeometry")):
+            a, b, c2 = (C.c_double * 5)(), (C.c_double * 3)(), (C.c_int * 2)()
+            getattr(L, hg)(path.encode(), a)
+            getattr(L, ig)(path.encode(), b, c2)
+            vals.append((list(a), list(b), list(c2)))
+        assert vals[0] == vals[1], (path, vals)
