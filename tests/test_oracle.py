@@ -186,3 +186,35 @@ def test_config1_krylon_500_samples_3ch_cpu_plumbing():
     assert (np.diff(top) <= 0).all()
     r2 = oc.detect(p, oracle.WeightPack(w), sidx, nthreads=1)
     assert np.array_equal(r2["pose_flags"], r["pose_flags"]) and np.array_equal(r2["candidates"]["score"], r["candidates"]["score"])
+
+
+def test_rotation_set_restatements_against_scipy_and_numpy():
+    """Eigen::AngleAxisd::toRotationMatrix and VectorXd::LinSpaced restated in the oracle (hand_set.cpp:52-53,68-69,
+    hand_search.cpp:151-155) against scipy's Rotation and numpy.linspace; the derived radii against the reference's
+    formulas (hand_search.cpp:13-17, image_generator.cpp:43-46). The half-turn about y carries the +-1.22e-16
+    off-diagonals of sin(pi) that Eigen produces."""
+    import ctypes as C
+    from scipy.spatial.transform import Rotation
+    L = oracle.lib()
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        axis = rng.standard_normal(3)
+        axis /= np.linalg.norm(axis)
+        ang = rng.uniform(-np.pi, np.pi)
+        R = np.zeros(9)
+        L.gpdo_angle_axis(C.c_double(ang), axis.ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p))
+        assert np.allclose(R.reshape(3, 3).T, Rotation.from_rotvec(ang * axis).as_matrix(), atol=1e-15)  # column-major
+    p = abi.default_params(15)
+    out = np.zeros(4 + p.num_orientations + 9)
+    L.gpdo_derived(C.byref(p), out.ctypes.data_as(C.c_void_p))
+    assert out[0] == 8 and out[1] == 0.11 and out[2] == 0.10 and out[3] == 0.10
+    angles = out[4:12]
+    assert np.allclose(angles, np.linspace(-np.pi / 2, np.pi / 2, 9)[:8], atol=2e-16) and angles[0] == -np.pi / 2
+    rb = out[12:21].reshape(3, 3).T
+    assert np.allclose(rb, np.diag([-1.0, 1.0, -1.0]), atol=2e-16) and abs(rb[0, 2]) == abs(rb[2, 0]) == np.sin(np.pi)
+    p2 = abi.default_params(15, num_orientations=5, hand_outer_diameter=0.2, finger_width=0.02, hand_depth=0.3, volume_width=0.05,
+                            volume_depth=0.07)
+    out2 = np.zeros(4 + 5 + 9)
+    L.gpdo_derived(C.byref(p2), out2.ctypes.data_as(C.c_void_p))
+    assert out2[0] == 5 and out2[1] == 0.3 and out2[2] == 0.07
+    assert np.allclose(out2[4:9], np.linspace(-np.pi / 2, np.pi / 2, 6)[:5], atol=2e-16)
