@@ -189,3 +189,33 @@ def test_hand_search_oracle_matches_the_numpy_restatement(scene, over):
     # numpy's 3x3 products may differ from the oracle's fixed summation order in the last bit: a strict inequality on a
     # boundary can flip in principle; none is tolerated here unless it actually occurs
     assert mism == 0 and n_valid >= 20, (mism, n_valid)
+
+
+def test_local_frames_against_numpy_eigh():
+    """LocalFrame::findAverageNormalAxis (local_frame.cpp:14-41) against numpy.linalg.eigh on the same r = nn_radius
+    balls: the normal (largest eigenvalue, flipped to agree with the summed normals) must match, the curvature axis
+    (smallest eigenvalue) up to the sign that only Eigen's iterative solver fixes (restated in the oracle),
+    and binormal = curvature x normal."""
+    c = scenes.synthetic_table_scene(7, n_points=60000)
+    oc = oracle.OracleCloud(c["xyz"], c["normals"], c["cam_source"], c["view_points"])
+    p = abi.default_params(15)
+    sidx = scenes.sample_indices(3, 60000, 200)
+    frames, valid = oc.frames(p, sidx)
+    checked = 0
+    for i, si in enumerate(sidx):
+        idx, _ = oc.radius_search(c["xyz"][si], p.nn_radius)
+        assert bool(valid[i]) == (len(idx) > 0)
+        if not valid[i]:
+            continue
+        Nn = c["normals"][idx]
+        w, v = np.linalg.eigh(Nn.T @ Nn)
+        if (w[1] - w[0]) < 1e-6 * w[2] or (w[2] - w[1]) < 1e-6 * w[2]:
+            continue  # (near-)degenerate spectrum: the eigenvectors are not unique
+        normal = v[:, 2] if v[:, 2] @ Nn.sum(0) >= 0 else -v[:, 2]
+        f = frames[i].reshape(3, 3)                      # rows: normal | binormal | curvature axis (column-major 3x3)
+        assert np.allclose(f[0], normal, atol=1e-9)
+        s = np.sign(f[2] @ v[:, 0])
+        assert np.allclose(f[2], s * v[:, 0], atol=1e-9)
+        assert np.allclose(f[1], np.cross(f[2], f[0]), atol=1e-12)
+        checked += 1
+    assert checked >= 150
