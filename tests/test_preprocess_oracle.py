@@ -114,3 +114,78 @@ def test_literal_std_set_emulation_quantifies_the_upstream_quirk(golden_dir):
     src2, missed2 = oracle.voxelize_literal(rs)
     ex2 = oracle.preprocess(rs, None, np.zeros((1, 3)), pp, normals=zeros)
     assert missed2 == 0 and np.array_equal(src2, ex2["src"])
+
+
+def test_normals_against_a_float32_numpy_restatement(golden_dir):
+    """Second restatement of pcl::NormalEstimation (PCL 1.9.1: computeMeanAndCovarianceMatrix float32 single pass in the
+    kd-tree's (dist, index) order, solvePlaneParameters / pcl::eigen33 closed form, flipNormalTowardsViewpoint) with numpy
+    float32 scalars, written separately from the C++ oracle: the float32 sums must agree bit for bit (same order, no
+    FMA), the normals to ~1e-6 (numpy's float32 atan2 / cos / sin vs glibc's)."""
+    f32 = np.float32
+    g = np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))
+    xyz, ref = g["xyz"], g["normals"]
+    oc = oracle.OracleCloud(xyz, np.zeros((len(xyz), 3)), None, np.zeros((1, 3)))
+
+    def roots2(b, c):
+        d = f32(float(f32(b * b)) - 4.0 * float(c))
+        d = f32(0.0) if d < 0 else d
+        sd = f32(np.sqrt(d))
+        return [f32(0.0), f32(0.5) * (b - sd), f32(0.5) * (b + sd)]
+
+    def roots(m):
+        c0 = (m[0][0] * m[1][1] * m[2][2] + f32(2) * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2]
+              - m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1])
+        c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] - m[1][2] * m[1][2]
+        c2 = m[0][0] + m[1][1] + m[2][2]
+        if abs(c0) < np.finfo(f32).eps:
+            return roots2(c2, c1)
+        inv3, sqrt3 = f32(1.0 / 3.0), f32(np.sqrt(f32(3.0)))
+        c2o3 = c2 * inv3
+        a3 = (c1 - c2 * c2o3) * inv3
+        a3 = f32(0) if a3 > 0 else a3
+        hb = f32(0.5) * (c0 + c2o3 * (f32(2) * c2o3 * c2o3 - c1))
+        q = hb * hb + a3 * a3 * a3
+        q = f32(0) if q > 0 else q
+        rho = f32(np.sqrt(-a3))
+        theta = f32(np.arctan2(f32(np.sqrt(-q)), hb)) * inv3
+        ct, st = f32(np.cos(theta)), f32(np.sin(theta))
+        r = [c2o3 + f32(2) * rho * ct, c2o3 - rho * (ct + sqrt3 * st), c2o3 - rho * (ct - sqrt3 * st)]
+        if r[0] >= r[1]:
+            r[0], r[1] = r[1], r[0]
+        if r[1] >= r[2]:
+            r[1], r[2] = r[2], r[1]
+            if r[0] >= r[1]:
+                r[0], r[1] = r[1], r[0]
+        return roots2(c2, c1) if r[0] <= 0 else r
+
+    checked, worst = 0, 0.0
+    for i in range(0, len(xyz), 37):
+        idx, _ = oc.radius_search(xyz[i], 0.03)
+        acc = [f32(0)] * 9
+        for j in idx:                                        # sorted (dist, index) order
+            x, y, z = xyz[j]
+            for k, v in enumerate((x * x, x * y, x * z, y * y, y * z, z * z, x, y, z)):
+                acc[k] = f32(acc[k] + v)
+        acc = [a / f32(len(idx)) for a in acc]
+        cov = [[acc[0] - acc[6] * acc[6], acc[1] - acc[6] * acc[7], acc[2] - acc[6] * acc[8]],
+               [None, acc[3] - acc[7] * acc[7], acc[4] - acc[7] * acc[8]], [None, None, acc[5] - acc[8] * acc[8]]]
+        cov[1][0], cov[2][0], cov[2][1] = cov[0][1], cov[0][2], cov[1][2]
+        scale = max(abs(v) for r in cov for v in r)
+        sm = [[v / scale for v in r] for r in cov]
+        ev = roots(sm)
+        for d in range(3):
+            sm[d][d] = sm[d][d] - ev[0]
+        cr = lambda a, b: [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+        vs = [cr(sm[0], sm[1]), cr(sm[0], sm[2]), cr(sm[1], sm[2])]
+        ln = [v[0] * v[0] + v[1] * v[1] + v[2] * v[2] for v in vs]
+        b = 0 if (ln[0] >= ln[1] and ln[0] >= ln[2]) else (1 if (ln[1] >= ln[0] and ln[1] >= ln[2]) else 2)
+        n = np.array([c / f32(np.sqrt(ln[b])) for c in vs[b]], f32)
+        vpv = f32(0) - xyz[i]                                # view point (0,0,0) - point, float32
+        if vpv[0] * n[0] + vpv[1] * n[1] + vpv[2] * n[2] < 0:
+            n = -n
+        nd = n.astype(np.float64)
+        if nd @ xyz[i].astype(np.float64) >= 0:              # reverseNormals: must point towards the camera at the origin
+            nd = -nd
+        worst = max(worst, float(np.abs(nd - ref[i]).max()))
+        checked += 1
+    assert checked >= 60 and worst <= 2e-6, (checked, worst)
