@@ -112,6 +112,7 @@ class Result(C.Structure):
         ("ms_classify", C.c_double),
         ("kernel_launches", C.c_int64),
         ("n_total_candidates", C.c_int32),
+        ("owner_", C.c_void_p),
     ]
 
 

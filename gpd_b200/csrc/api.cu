@@ -1,6 +1,7 @@
 // api.cu — the C-ABI of libgpd_b200.so (include/gpd_b200.h): context, cloud upload, the chunked
 // detect pipeline and the stage-level entry points. Host-side logic only; kernels live in
 // geometry.cu / lenet_simt.cu / lenet_tc.cu. There is no CPU fallback anywhere in this library.
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -291,6 +292,7 @@ int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out) {
   int rc = fill_dev_params(ctx);
   if (rc != GPDB_OK) {
     strncpy(g_create_err, ctx->err, sizeof(g_create_err) - 1);
+    delete ctx->st;
     delete ctx;
     return rc;
   }
@@ -307,6 +309,7 @@ int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out) {
          cudaMemset(ctx->d_err, 0, sizeof(int) * GPDB_NERR) == cudaSuccess;
   }
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  ok = ok && gpdb_pipe_create(ctx) == GPDB_OK;
   if (!ok) {
     gpdb_set_error(nullptr, GPDB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     gpdb_destroy(ctx);
@@ -320,6 +323,8 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  gpdb_comm_destroy(ctx);
+  gpdb_pipe_destroy(ctx);
   cudaFree(ctx->dp);
   cudaFree(ctx->d_err);
   cudaFree(ctx->d_prof);
@@ -329,6 +334,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   cudaFree(ctx->d_nrm);
   cudaFree(ctx->d_cam);
   cudaFree(ctx->d_src);
+  cudaFree(ctx->d_samples);
   cudaFree(ctx->d_sel);
   cudaFree(ctx->d_cell_start);
   float *w[8] = {ctx->w.c1w, ctx->w.c1b, ctx->w.c2w, ctx->w.c2b, ctx->w.i1w, ctx->w.i1b, ctx->w.i2w, ctx->w.i2b};
@@ -410,6 +416,33 @@ int gpdb_cloud_reserve(gpdb_ctx *ctx, size_t n) {
   return GPDB_OK;
 }
 
+// The device arrays d_xyz / d_nrm / d_cam hold N points (uploaded by gpdb_set_cloud or received by ncclBroadcast): make
+// them the context's cloud and build the neighbour grid (bounds by a device reduction).
+int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points) {
+  ctx->cloud_set = false;
+  ctx->has_src = false;
+  ctx->hp.K = K;
+  for (int k = 0; k < K; k++)
+    for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];
+  ctx->N = N;
+  ctx->K = K;
+  ctx->cloud.pts4 = ctx->d_pts4;
+  ctx->cloud.xyz = ctx->d_xyz;
+  ctx->cloud.nrm = ctx->d_nrm;
+  ctx->cloud.cam = ctx->d_cam;
+  ctx->cloud.samples = nullptr;  // a new cloud drops the sample positions
+  ctx->cloud.n_points = N;
+  ctx->n_samples = 0;
+  float lo[3], hi[3];
+  int *d_bounds = (int *)gpdb_scratch(ctx, 4, sizeof(double) * 6 + sizeof(int) * 8);
+  if (!d_bounds) return GPDB_ERR_CUDA;
+  int rc = pre_bounds(ctx, ctx->d_xyz, N, d_bounds, lo, hi);
+  if (rc == GPDB_OK) rc = geo_build_grid(ctx, lo, hi, N);
+  if (rc != GPDB_OK) return rc;
+  ctx->cloud_set = true;
+  return GPDB_OK;
+}
+
 extern "C" {
 
 int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const int32_t *cam_source, int32_t N,
@@ -440,25 +473,13 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const
   CUDA_TRY(cudaMemcpyAsync(ctx->d_nrm, normals, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(ctx->d_cam, cam.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->hp.K = K;
-  for (int k = 0; k < K; k++)
-    for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];
-  ctx->N = N;
-  ctx->K = K;
-  ctx->cloud.pts4 = ctx->d_pts4;
-  ctx->cloud.xyz = ctx->d_xyz;
-  ctx->cloud.nrm = ctx->d_nrm;
-  ctx->cloud.cam = ctx->d_cam;
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = 0; i < N; i++)
-    for (int a = 0; a < 3; a++) {
-      lo[a] = fminf(lo[a], xyz[3 * (size_t)i + a]);
-      hi[a] = fmaxf(hi[a], xyz[3 * (size_t)i + a]);
-    }
-  int rc = geo_build_grid(ctx, lo, hi, N);
-  if (rc != GPDB_OK) return rc;
-  ctx->cloud_set = true;
-  return GPDB_OK;
+    for (int a = 0; a < 3; a++)
+      if (!std::isfinite(xyz[3 * (size_t)i + a])) {
+        gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_set_cloud: point %d has a non-finite coordinate (run removeNans / gpdb_preprocess first)", i);
+        return GPDB_ERR_INVALID;
+      }
+  return gpdb_install_device_cloud(ctx, N, K, view_points);
 }
 
 void gpdb_preprocess_params_default(gpdb_preprocess_params *p) {
@@ -530,6 +551,9 @@ int gpdb_preprocess(gpdb_ctx *ctx, const float *xyz, const double *normals, cons
   ctx->cloud.xyz = ctx->d_xyz;
   ctx->cloud.nrm = ctx->d_nrm;
   ctx->cloud.cam = ctx->d_cam;
+  ctx->cloud.samples = nullptr;  // a new cloud drops the sample positions
+  ctx->cloud.n_points = N;
+  ctx->n_samples = 0;
   float lo[3], hi[3];
   int *d_bounds = (int *)gpdb_scratch(ctx, 4, sizeof(double) * 6 + sizeof(int) * 8);
   if (!d_bounds) { drop_events(); return GPDB_ERR_CUDA; }
@@ -552,6 +576,28 @@ int gpdb_preprocess(gpdb_ctx *ctx, const float *xyz, const double *normals, cons
   drop_events();
   ctx->cloud_set = true;
   return N;
+}
+
+int gpdb_set_samples(gpdb_ctx *ctx, const double *samples, int32_t n) {
+  if (!ctx || n < 0 || (n > 0 && !samples)) return GPDB_ERR_INVALID;
+  if (!ctx->cloud_set) {
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "no point cloud: call gpdb_set_cloud / gpdb_preprocess first");
+    return GPDB_ERR_STATE;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_samples);
+  ctx->d_samples = nullptr;
+  ctx->n_samples = 0;
+  ctx->cloud.samples = nullptr;
+  if (n > 0) {
+    CUDA_TRY(cudaMalloc(&ctx->d_samples, sizeof(double) * 3 * (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_samples, samples, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->cloud.samples = ctx->d_samples;
+    ctx->n_samples = n;
+  }
+  return ctx->N;  // the first sample index that addresses samples[0]
 }
 
 int gpdb_get_cloud(gpdb_ctx *ctx, float *xyz_out, double *normals_out, int32_t *cam_source_out) {
@@ -597,9 +643,98 @@ int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]) {
 
 // ---- pipeline ------------------------------------------------------------------------------------
 
-namespace {
+// Page-locked host memory of one gpdb_result. The device writes the result arrays straight into it (no pageable
+// bounce, no second copy), chunk by chunk on the copy stream while the next chunk computes; gpdb_free_result hands it
+// back to the context for the next call. Reference-counted: a result may outlive its context.
+struct HostArena {
+  std::atomic<int> refs{1};        // the owning context + an outstanding result
+  std::atomic<bool> in_use{false};
+  void *buf[3] = {nullptr, nullptr, nullptr};  // 0: per-sample / per-pose arrays, 1: candidate records, 2: images
+  size_t cap[3] = {0, 0, 0};
+};
+static void arena_unref(HostArena *a) {
+  if (a->refs.fetch_sub(1) == 1) {
+    for (void *b : a->buf)
+      if (b) cudaFreeHost(b);
+    delete a;
+  }
+}
+// grows buffer `which` to at least `bytes`, keeping the first `keep` bytes (the caller has drained the copies into it)
+static bool arena_reserve(HostArena *a, int which, size_t bytes, size_t keep) {
+  if (a->cap[which] >= bytes) return true;
+  const size_t want = bytes + bytes / 2 + 4096;
+  void *nb = nullptr;
+  if (cudaHostAlloc(&nb, want, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a->buf[which]) {
+    if (keep) memcpy(nb, a->buf[which], keep);
+    cudaFreeHost(a->buf[which]);
+  }
+  a->buf[which] = nb;
+  a->cap[which] = want;
+  return true;
+}
 
-int check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) {
+struct PipeState {
+  cudaStream_t copy = nullptr;  // D2H of finished chunks + the per-chunk candidate count, concurrent with compute
+  cudaEvent_t ev_compact[2], ev_count[2], ev_scored[2], ev_copied[2], ev_frames;
+  int *h_count = nullptr;       // pinned [2]
+  std::vector<HostArena *> arenas;
+  bool ok = false;
+};
+int gpdb_pipe_create(gpdb_ctx *ctx) {
+  PipeState *ps = new PipeState();
+  ctx->pipe = ps;
+  bool ok = cudaStreamCreateWithFlags(&ps->copy, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaHostAlloc((void **)&ps->h_count, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+  cudaEvent_t *evs[9] = {&ps->ev_compact[0], &ps->ev_compact[1], &ps->ev_count[0], &ps->ev_count[1], &ps->ev_scored[0],
+                         &ps->ev_scored[1], &ps->ev_copied[0], &ps->ev_copied[1], &ps->ev_frames};
+  for (cudaEvent_t *e : evs) {
+    *e = nullptr;
+    ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  }
+  ps->ok = ok;
+  return ok ? GPDB_OK : GPDB_ERR_CUDA;
+}
+void gpdb_pipe_destroy(gpdb_ctx *ctx) {
+  PipeState *ps = ctx->pipe;
+  if (!ps) return;
+  if (ps->copy) {
+    cudaStreamSynchronize(ps->copy);
+    cudaStreamDestroy(ps->copy);
+  }
+  cudaEvent_t evs[9] = {ps->ev_compact[0], ps->ev_compact[1], ps->ev_count[0], ps->ev_count[1], ps->ev_scored[0],
+                        ps->ev_scored[1], ps->ev_copied[0], ps->ev_copied[1], ps->ev_frames};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  if (ps->h_count) cudaFreeHost(ps->h_count);
+  for (HostArena *a : ps->arenas) arena_unref(a);
+  delete ps;
+  ctx->pipe = nullptr;
+}
+static HostArena *arena_acquire(gpdb_ctx *ctx) {
+  PipeState &ps = *ctx->pipe;
+  for (HostArena *a : ps.arenas) {
+    bool expect = false;
+    if (a->in_use.compare_exchange_strong(expect, true)) {
+      a->refs.fetch_add(1);
+      return a;
+    }
+  }
+  if (ps.arenas.size() >= 8) {  // results that were never freed: do not pin host memory without bound
+    gpdb_set_error(ctx, GPDB_ERR_STATE, "8 results of this context are outstanding: release them with gpdb_free_result");
+    return nullptr;
+  }
+  HostArena *a = new HostArena();
+  a->in_use = true;
+  a->refs = 2;
+  ps.arenas.push_back(a);
+  return a;
+}
+
+int gpdb_check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) {
   if (!ctx) return GPDB_ERR_INVALID;
   if (need_cloud && !ctx->cloud_set) {
     gpdb_set_error(ctx, GPDB_ERR_STATE, "no point cloud: call gpdb_set_cloud first");
@@ -612,6 +747,8 @@ int check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   return GPDB_OK;
 }
+
+namespace {
 
 int check_device_errors(gpdb_ctx *ctx) {
   int e[GPDB_NERR];
@@ -628,164 +765,257 @@ int check_device_errors(gpdb_ctx *ctx) {
   return GPDB_OK;
 }
 
-// The chunked device pipeline behind gpdb_detect / gpdb_hand_search / gpdb_detect_resident.
+}  // namespace
+
+// The chunked device pipeline behind gpdb_detect / gpdb_hand_search / gpdb_detect_resident / gpdb_detect_sharded.
 //   resident == false: sample_idx is a HOST array, every result is copied back to the host (out)
 //   resident == true : sample_idx, flags_ext, scores_ext are DEVICE arrays; nothing but the per-chunk
 //                      candidate count crosses PCIe (out receives counts and timings only)
 // select_k >= 0 (gpdb_detect_select): the classified candidates of all chunks stay on the device, the select_k best are
 // sorted out there and only they are copied back; no per-sample / per-pose array is returned.
-int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
-                 bool resident, uint8_t *flags_ext, float *scores_ext, int select_k = -1) {
+//
+// Stream schedule (H = hand search + compaction of a chunk, I/L/S = images, LeNet, score scatter):
+//   compute: F  H0  H1  I0 L0 S0  H2  I1 L1 S1  ...      copy:  frames | n0 | n1 | cand0 flags0 scores0 | n2 | cand1 ...
+// The candidate count of chunk i is read back on the copy stream while H(i+1) runs, so the device never waits for the
+// host; every chunk is ONE k_images / LeNet launch sized to its candidate count (no tail launches), and the results of
+// chunk i go to the pinned arena while chunk i+1 computes.
+int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
+                      bool resident, uint8_t *flags_ext, float *scores_ext, int select_k, int slot_base) {
   const bool selecting = select_k >= 0;
   memset(out, 0, sizeof(*out));
+  PipeState &ps = *ctx->pipe;
   const int P = ctx->hp.P, S = ctx->hp.S, C = ctx->hp.C;
   const size_t isz = (size_t)S * S * C;
   out->n_samples = n;
   out->poses_per_sample = P;
   if (!resident)
     for (int i = 0; i < n; i++)
-      if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N) {
-        gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d at position %d outside the cloud (N = %d)", sample_idx[i],
-                       i, ctx->N);
+      if (sample_idx[i] < 0 || sample_idx[i] >= ctx->N + ctx->n_samples) {
+        gpdb_set_error(ctx, GPDB_ERR_INVALID, "sample index %d at position %d outside the cloud (N = %d, + %d sample positions)",
+                       sample_idx[i], i, ctx->N, ctx->n_samples);
         return GPDB_ERR_INVALID;
       }
   const int64_t launches0 = ctx->launches;
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int chunk = ctx->prm.chunk_samples > 0 ? ctx->prm.chunk_samples : 16384;
-  const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
+  const int batch_cap = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 32768;  // images per k_images / LeNet launch
   const bool keep = with_images_and_scores && ctx->prm.keep_images && !resident && !selecting;
+  const bool to_host = !resident && !selecting;  // per-sample / per-pose arrays + all candidate records go to the host
   const size_t nP = (size_t)n * P;
+  const int cmax = std::min(chunk, std::max(n, 1));
   int *d_sidx = resident ? const_cast<int *>(sample_idx) : (int *)gpdb_scratch(ctx, 7, sizeof(int) * (size_t)n);
   double *d_frames = (double *)gpdb_scratch(ctx, 8, sizeof(double) * 9 * (size_t)n);
   uint8_t *d_valid = (uint8_t *)gpdb_scratch(ctx, 9, (size_t)n);
   uint8_t *d_flags = resident ? flags_ext : (uint8_t *)gpdb_scratch(ctx, 10, nP);
   float *d_pscores = resident ? scores_ext : (float *)gpdb_scratch(ctx, 11, sizeof(float) * nP);
-  const int cmax = std::min(chunk, std::max(n, 1));
   gpdb_pose *d_poses = (gpdb_pose *)gpdb_scratch(ctx, 12, sizeof(gpdb_pose) * (size_t)cmax * P);
-  gpdb_pose *d_cand = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)cmax * P);
+  gpdb_pose *d_cand2 = (gpdb_pose *)gpdb_scratch(ctx, 13, 2 * sizeof(gpdb_pose) * (size_t)cmax * P);  // double-buffered
   int *d_count = (int *)gpdb_scratch(ctx, 14, 64);
-  if (!d_sidx || !d_frames || !d_valid || !d_flags || !d_pscores || !d_poses || !d_cand || !d_count) return GPDB_ERR_CUDA;
+  if (!d_sidx || !d_frames || !d_valid || !d_flags || !d_pscores || !d_poses || !d_cand2 || !d_count) return GPDB_ERR_CUDA;
+  gpdb_pose *d_cand[2] = {d_cand2, d_cand2 + (size_t)cmax * P};
+
+  HostArena *ar = nullptr;
+  int rc = GPDB_OK;
+  // every exit after this point goes through finish(): drains both streams, clears the device error counters, collects
+  // the stage timers and releases the arena on failure, so that a failed call leaves no state behind
+  auto finish = [&](int code) -> int {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ps.copy);
+    if (code >= 0) {
+      int e = check_device_errors(ctx);
+      if (e != GPDB_OK) code = e;
+    } else {
+      cudaMemsetAsync(ctx->d_err, 0, sizeof(int) * GPDB_NERR, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    st_collect(ctx, ms);
+    for (int i = 0; i < 8; i++) ctx->last_ms[i] = ms[i];
+    if (code < 0) {
+      if (ar) {
+        ar->in_use = false;
+        arena_unref(ar);
+      }
+      memset(out, 0, sizeof(*out));
+    }
+    return code;
+  };
+#define PIPE_TRY(expr)                                \
+  do {                                                \
+    if ((rc = (expr)) != GPDB_OK) return finish(rc);  \
+  } while (0)
+#define PIPE_CUDA(expr)                                                                                           \
+  do {                                                                                                            \
+    cudaError_t e__ = (expr);                                                                                     \
+    if (e__ != cudaSuccess) {                                                                                     \
+      gpdb_set_error(ctx, GPDB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+      return finish(GPDB_ERR_CUDA);                                                                               \
+    }                                                                                                             \
+  } while (0)
+
+  // host-side layout of the fixed-size arrays inside arena buffer 0
+  const size_t off_valid = 0, off_frames = ((size_t)n + 63) / 64 * 64, off_flags = off_frames + sizeof(double) * 9 * (size_t)n,
+               off_scores = (off_flags + nP + 63) / 64 * 64, fixed_bytes = off_scores + sizeof(float) * nP + 64;
+  if (!resident) {
+    ar = arena_acquire(ctx);
+    if (!ar) return GPDB_ERR_STATE;
+    const size_t guess = std::max((size_t)1024, nP / 8);  // grown on demand
+    if (!arena_reserve(ar, 0, to_host ? fixed_bytes : 64, 0) ||
+        !arena_reserve(ar, 1, sizeof(gpdb_pose) * (selecting ? (size_t)std::max(select_k, 1) : guess), 0)) {
+      gpdb_set_error(ctx, GPDB_ERR_CUDA, "cudaHostAlloc of the result arena failed");
+      return finish(GPDB_ERR_CUDA);
+    }
+  }
+  uint8_t *h_fixed = ar ? (uint8_t *)ar->buf[0] : nullptr;
+
   ctx->st->spans.clear();
   ctx->st->used = 0;
   cudaEvent_t t_all = gpdb_st_begin(ctx);
   if (n > 0) {
     if (!resident)
-      CUDA_TRY(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(d_pscores, 0xFF, sizeof(float) * nP, ctx->stream));  // 0xFFFFFFFF = NaN
+      PIPE_CUDA(cudaMemcpyAsync(d_sidx, sample_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    PIPE_CUDA(cudaMemsetAsync(d_pscores, 0xFF, sizeof(float) * nP, ctx->stream));  // 0xFFFFFFFF = NaN
   }
-  int rc;
   cudaEvent_t t0 = gpdb_st_begin(ctx);
-  if ((rc = geo_frames(ctx, d_sidx, n, d_frames, d_valid)) != GPDB_OK) return rc;
+  PIPE_TRY(geo_frames(ctx, d_sidx, n, d_frames, d_valid));
   gpdb_st_end(ctx, 0, t0);
-  std::vector<gpdb_pose> cands;
-  std::vector<uint8_t> images;
+  if (to_host && n > 0) {
+    PIPE_CUDA(cudaEventRecord(ps.ev_frames, ctx->stream));
+    PIPE_CUDA(cudaStreamWaitEvent(ps.copy, ps.ev_frames, 0));
+    PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ps.copy));
+    PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ps.copy));
+  }
+  const int nchunks = (n + chunk - 1) / chunk;
   int total_nc = 0;
-  for (int c0 = 0; c0 < n; c0 += chunk) {
-    const int nn = std::min(chunk, n - c0);
+  size_t img_host = 0;  // bytes of images already placed in arena buffer 2
+  bool cand_busy[2] = {false, false};  // a D2H copy out of d_cand[b] has been issued (ev_copied[b] marks its end)
+  auto launch_hands = [&](int ci) -> int {
+    const int c0 = ci * chunk, nn = std::min(chunk, n - c0), b = ci & 1;
+    if (cand_busy[b]) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ps.ev_copied[b], 0));  // chunk ci-2 has left d_cand[b]
     cudaEvent_t t1 = gpdb_st_begin(ctx);
-    if ((rc = geo_hands(ctx, d_sidx + c0, nn, c0, d_frames + 9 * (size_t)c0, d_valid + c0, d_poses,
-                        d_flags + (size_t)c0 * P)) != GPDB_OK)
-      return rc;
-    if ((rc = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand, d_count)) != GPDB_OK) return rc;
+    int r = geo_hands(ctx, d_sidx + c0, nn, c0 + slot_base, d_frames + 9 * (size_t)c0, d_valid + c0, d_poses,
+                      d_flags + (size_t)c0 * P);
+    if (r != GPDB_OK) return r;
+    if ((r = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand[b], d_count + b)) != GPDB_OK) return r;
     gpdb_st_end(ctx, 1, t1);
-    int nc = 0;
-    CUDA_TRY(cudaMemcpyAsync(&nc, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventRecord(ps.ev_compact[b], ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ps.copy, ps.ev_compact[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(ps.h_count + b, d_count + b, sizeof(int), cudaMemcpyDeviceToHost, ps.copy));
+    CUDA_TRY(cudaEventRecord(ps.ev_count[b], ps.copy));
+    return GPDB_OK;
+  };
+  if (nchunks > 0) PIPE_TRY(launch_hands(0));
+  for (int ci = 0; ci < nchunks; ci++) {
+    const int c0 = ci * chunk, nn = std::min(chunk, n - c0), b = ci & 1;
+    if (ci + 1 < nchunks) PIPE_TRY(launch_hands(ci + 1));  // queued BEHIND which the host now waits for chunk ci's count
+    PIPE_CUDA(cudaEventSynchronize(ps.ev_count[b]));
+    const int nc = ps.h_count[b];
     total_nc += nc;
+    uint8_t *d_img = nullptr;
     if (with_images_and_scores && nc > 0) {
       float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)nc);
-      if (!d_scores) return GPDB_ERR_CUDA;
-      const int ib = keep ? nc : std::min(nc, batch);
-      uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)ib);
-      if (!d_img) return GPDB_ERR_CUDA;
-      for (int b0 = 0; b0 < nc; b0 += batch) {
-        const int bn = std::min(batch, nc - b0);
+      const int ib = keep ? nc : std::min(nc, batch_cap);
+      d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)ib);
+      if (!d_scores || !d_img) return finish(GPDB_ERR_CUDA);
+      if (keep && ci > 0) PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ps.ev_copied[b ^ 1], 0));  // d_img is being read
+      for (int b0 = 0; b0 < nc; b0 += batch_cap) {
+        const int bn = std::min(batch_cap, nc - b0);
         uint8_t *dst = keep ? d_img + isz * (size_t)b0 : d_img;
         cudaEvent_t t2 = gpdb_st_begin(ctx);
-        if ((rc = geo_images(ctx, d_cand + b0, bn, dst)) != GPDB_OK) return rc;
+        PIPE_TRY(geo_images(ctx, d_cand[b] + b0, bn, dst));
         gpdb_st_end(ctx, 2, t2);
         cudaEvent_t t3 = gpdb_st_begin(ctx);
-        if ((rc = lenet_forward(ctx, dst, bn, d_scores + b0, nullptr)) != GPDB_OK) return rc;
+        PIPE_TRY(lenet_forward(ctx, dst, bn, d_scores + b0, nullptr));
         gpdb_st_end(ctx, 3, t3);
       }
-      if ((rc = geo_scatter_scores(ctx, d_cand, d_scores, nc, c0, P, d_pscores + (size_t)c0 * P, d_cand)) != GPDB_OK)
-        return rc;
+      PIPE_TRY(geo_scatter_scores(ctx, d_cand[b], d_scores, nc, c0 + slot_base, P, d_pscores + (size_t)c0 * P, d_cand[b]));
       if (keep) {
-        size_t off = images.size();
-        images.resize(off + isz * (size_t)nc);
-        CUDA_TRY(cudaMemcpyAsync(images.data() + off, d_img, isz * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+        PIPE_CUDA(cudaStreamSynchronize(ps.copy));  // growing moves the buffer: earlier image copies must have landed
+        if (!arena_reserve(ar, 2, img_host + isz * (size_t)nc, img_host)) {
+          gpdb_set_error(ctx, GPDB_ERR_CUDA, "cudaHostAlloc of %zu B for the images failed", img_host + isz * (size_t)nc);
+          return finish(GPDB_ERR_CUDA);
+        }
       }
     }
     if (nc > 0 && selecting) {  // keep the chunk's scored candidates on the device
       if ((size_t)total_nc > ctx->sel_cap) {
         const size_t cap = std::max((size_t)total_nc * 2, (size_t)65536);
         gpdb_pose *grown = nullptr;
-        CUDA_TRY(cudaMalloc(&grown, sizeof(gpdb_pose) * cap));
+        PIPE_CUDA(cudaMalloc(&grown, sizeof(gpdb_pose) * cap));
         if (ctx->d_sel && total_nc > nc)
-          CUDA_TRY(cudaMemcpyAsync(grown, ctx->d_sel, sizeof(gpdb_pose) * (size_t)(total_nc - nc), cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+          cudaMemcpyAsync(grown, ctx->d_sel, sizeof(gpdb_pose) * (size_t)(total_nc - nc), cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->d_sel);
         ctx->d_sel = grown;
         ctx->sel_cap = cap;
       }
-      CUDA_TRY(cudaMemcpyAsync(ctx->d_sel + (total_nc - nc), d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToDevice, ctx->stream));
-    } else if (nc > 0 && !resident) {
-      size_t off = cands.size();
-      cands.resize(off + nc);
-      CUDA_TRY(cudaMemcpyAsync(cands.data() + off, d_cand, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToHost,
-                               ctx->stream));
-      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      PIPE_CUDA(cudaMemcpyAsync(ctx->d_sel + (total_nc - nc), d_cand[b], sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (to_host) {  // this chunk's results leave for the pinned arena while the next chunk computes
+      if (sizeof(gpdb_pose) * (size_t)total_nc > ar->cap[1]) {
+        PIPE_CUDA(cudaStreamSynchronize(ps.copy));
+        if (!arena_reserve(ar, 1, sizeof(gpdb_pose) * (size_t)total_nc, sizeof(gpdb_pose) * (size_t)(total_nc - nc))) {
+          gpdb_set_error(ctx, GPDB_ERR_CUDA, "cudaHostAlloc of the candidate arena failed");
+          return finish(GPDB_ERR_CUDA);
+        }
+      }
+      PIPE_CUDA(cudaEventRecord(ps.ev_scored[b], ctx->stream));
+      PIPE_CUDA(cudaStreamWaitEvent(ps.copy, ps.ev_scored[b], 0));
+      if (nc > 0)
+        PIPE_CUDA(cudaMemcpyAsync((gpdb_pose *)ar->buf[1] + (total_nc - nc), d_cand[b], sizeof(gpdb_pose) * (size_t)nc,
+                                  cudaMemcpyDeviceToHost, ps.copy));
+      PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_flags + (size_t)c0 * P, d_flags + (size_t)c0 * P, (size_t)nn * P,
+                                cudaMemcpyDeviceToHost, ps.copy));
+      PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_scores + sizeof(float) * (size_t)c0 * P, d_pscores + (size_t)c0 * P,
+                                sizeof(float) * (size_t)nn * P, cudaMemcpyDeviceToHost, ps.copy));
+      if (keep && d_img) {
+        PIPE_CUDA(cudaMemcpyAsync((uint8_t *)ar->buf[2] + img_host, d_img, isz * (size_t)nc,
+                                  cudaMemcpyDeviceToHost, ps.copy));
+        img_host += isz * (size_t)nc;
+      }
+      PIPE_CUDA(cudaEventRecord(ps.ev_copied[b], ps.copy));
+      cand_busy[b] = true;
     }
   }
   int n_sel = 0;
   if (selecting) {
     n_sel = std::min(select_k, total_nc);
     if (n_sel > 0) {
-      gpdb_pose *d_top = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)std::max(n_sel, cmax * P));
-      if (!d_top) return GPDB_ERR_CUDA;
-      if ((rc = geo_select(ctx, ctx->d_sel, total_nc, n_sel, d_top)) != GPDB_OK) return rc;
-      cands.resize(n_sel);
-      CUDA_TRY(cudaMemcpyAsync(cands.data(), d_top, sizeof(gpdb_pose) * (size_t)n_sel, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-  }
-  if (!resident && !selecting) {
-    out->frame_valid = (uint8_t *)malloc((size_t)n + 1);
-    out->frames = (double *)malloc(sizeof(double) * 9 * (size_t)n + 8);
-    out->pose_flags = (uint8_t *)malloc(nP + 1);
-    out->pose_scores = (float *)malloc(sizeof(float) * nP + 4);
-    if (n > 0) {
-      CUDA_TRY(cudaMemcpyAsync(out->frame_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(cudaMemcpyAsync(out->frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(cudaMemcpyAsync(out->pose_flags, d_flags, nP, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(cudaMemcpyAsync(out->pose_scores, d_pscores, sizeof(float) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+      gpdb_pose *d_top = (gpdb_pose *)gpdb_scratch(ctx, 12, sizeof(gpdb_pose) * (size_t)std::max(n_sel, cmax * P));
+      if (!d_top) return finish(GPDB_ERR_CUDA);
+      PIPE_TRY(geo_select(ctx, ctx->d_sel, total_nc, n_sel, d_top));
+      PIPE_CUDA(cudaMemcpyAsync(ar->buf[1], d_top, sizeof(gpdb_pose) * (size_t)n_sel, cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
   gpdb_st_end(ctx, 4, t_all);
-  rc = check_device_errors(ctx);
-  st_collect(ctx, ms);
-  if (rc != GPDB_OK) {
-    gpdb_free_result(out);
-    return rc;
-  }
+  rc = finish(total_nc);
+  if (rc < 0) return rc;
+#undef PIPE_TRY
+#undef PIPE_CUDA
   out->n_candidates = selecting ? n_sel : total_nc;
   out->n_total_candidates = total_nc;
-  if (!resident) {
-    out->candidates = (gpdb_pose *)malloc(sizeof(gpdb_pose) * cands.size() + 8);
-    if (!cands.empty()) memcpy(out->candidates, cands.data(), sizeof(gpdb_pose) * cands.size());
-    if (keep) {
-      out->images = (uint8_t *)malloc(images.size() + 8);
-      if (!images.empty()) memcpy(out->images, images.data(), images.size());
+  if (ar) {
+    out->owner_ = ar;
+    out->candidates = (gpdb_pose *)ar->buf[1];
+    if (to_host) {
+      out->frame_valid = h_fixed + off_valid;
+      out->frames = (double *)(h_fixed + off_frames);
+      out->pose_flags = h_fixed + off_flags;
+      out->pose_scores = (float *)(h_fixed + off_scores);
+      if (keep) out->images = (uint8_t *)ar->buf[2];
     }
   }
   out->ms_candidates = ms[0] + ms[1];
   out->ms_images = ms[2];
   out->ms_classify = ms[3];
   out->kernel_launches = ctx->launches - launches0;
-  for (int i = 0; i < 8; i++) ctx->last_ms[i] = ms[i];
   return out->n_candidates;
 }
 
-}  // namespace
+static int run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
+                        bool resident, uint8_t *flags_ext, float *scores_ext, int select_k = -1) {
+  return gpdb_run_pipeline(ctx, sample_idx, n, out, with_images_and_scores, resident, flags_ext, scores_ext, select_k, 0);
+}
+static int check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights) { return gpdb_check_state(ctx, need_cloud, need_weights); }
 
 extern "C" {
 
@@ -916,12 +1146,23 @@ int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n, float *sc
 
 void gpdb_free_result(gpdb_result *r) {
   if (!r) return;
-  free(r->frame_valid);
-  free(r->frames);
-  free(r->pose_flags);
-  free(r->pose_scores);
-  free(r->candidates);
-  free(r->images);
+  if (r->owner_) {  // the arrays live in a pinned arena of the context that produced them: hand it back
+    HostArena *a = (HostArena *)r->owner_;
+    // gpdb_detect_sharded replaces the per-pose arrays by gathered ones that live outside the arena
+    const uint8_t *b0 = (const uint8_t *)a->buf[0];
+    auto outside = [&](const void *p) { return p && !((const uint8_t *)p >= b0 && (const uint8_t *)p < b0 + a->cap[0]); };
+    if (outside(r->pose_flags)) free(r->pose_flags);
+    if (outside(r->pose_scores)) free(r->pose_scores);
+    a->in_use = false;
+    arena_unref(a);
+  } else {
+    free(r->frame_valid);
+    free(r->frames);
+    free(r->pose_flags);
+    free(r->pose_scores);
+    free(r->candidates);
+    free(r->images);
+  }
   memset(r, 0, sizeof(*r));
 }
 

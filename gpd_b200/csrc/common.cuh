@@ -70,6 +70,9 @@ struct DevCloud {
   const double *nrm;
   const uint8_t *cam;
   const int *cell_start;
+  // Cloud::setSamples (gpdb_set_samples): float64 positions addressed by sample indices >= n_points
+  const double *samples;
+  int n_points;
 };
 
 // device error counters: [0] LRF capacity, [1] hand-search capacity (final tier), [2] image box list,
@@ -100,6 +103,8 @@ struct LenetTc {  // tensor-core (tcgen05) weight blobs, lenet_tc.cu
 };
 
 struct StageTimes;  // api.cu
+struct PipeState;   // api.cu: copy stream, events and the pinned result arenas of the chunk pipeline
+struct CommState;   // comm.cu: NCCL communicator (multi-GPU sharding)
 
 struct gpdb_ctx {
   gpdb_params prm;
@@ -109,6 +114,8 @@ struct gpdb_ctx {
   cudaStream_t stream;
   bool own_stream;
   StageTimes *st;
+  PipeState *pipe;
+  CommState *comm;
   int sm_count;
   char err[512];
   // cloud
@@ -136,6 +143,8 @@ struct gpdb_ctx {
   double pre_ms[6];   // gpdb_preprocess stage timings
   gpdb_pose *d_sel;   // gpdb_detect_select: all classified candidates of a call (grown on demand)
   size_t sel_cap;
+  double *d_samples;  // gpdb_set_samples positions (3 x n_samples), or nullptr
+  int n_samples;
   int *d_src;         // raw index of each processed point (valid after gpdb_preprocess: has_src)
   bool has_src;
   cudaEvent_t ev[8];
@@ -147,6 +156,16 @@ void gpdb_set_error(gpdb_ctx *ctx, int code, const char *fmt, ...);
 cudaEvent_t gpdb_st_begin(gpdb_ctx *ctx);
 void gpdb_st_end(gpdb_ctx *ctx, int stage, cudaEvent_t begin);
 void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes);  // returns nullptr on failure (error set)
+
+// api.cu
+int gpdb_pipe_create(gpdb_ctx *ctx);
+void gpdb_pipe_destroy(gpdb_ctx *ctx);
+int gpdb_check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights);
+// the chunked device pipeline (see api.cu); slot_base is added to every sample_slot (rank offset of a sharded call)
+int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
+                      bool resident, uint8_t *flags_ext, float *scores_ext, int select_k, int slot_base);
+// installs the cloud whose device arrays d_xyz / d_nrm / d_cam already hold N points (grid bounds by device reduction)
+int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points);
 
 // geometry.cu
 // builds the neighbour grid over ctx->d_xyz (N points) whose per-axis bounds are lo / hi

@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
     i = ovf[i];
   }
   const int si = sidx[i];
-  float q[3] = {cl.xyz[3 * (size_t)si], cl.xyz[3 * (size_t)si + 1], cl.xyz[3 * (size_t)si + 2]};
+  double sp[3];
+  sample_position(cl, si, sp);
+  float q[3] = {(float)sp[0], (float)sp[1], (float)sp[2]};
   SegRange sr = seg_range(P, q, P.rf_lrf);
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)warp * cap;
   unsigned long long *sorted = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)(LRF_WARPS + warp) * cap;
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(NT_HANDS, 4) k_hands(const DevParams *Pp, DevC
       S.nb0_key = ~0ull;
     }
     if (tid < 9) S.frame[tid] = frames[9 * (size_t)i + tid];
-    if (tid < 3) S.sample[tid] = (double)cl.xyz[3 * (size_t)si + tid];
+    if (tid == 0) sample_position(cl, si, S.sample);
     __syncthreads();
     if (tid == 0) mat3_mul(S.frame, P.rotb, S.T);
     const bool fv = fvalid[i] != 0;
@@ -1021,31 +1023,37 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
     }                                                                   \
   } while (0)
 
-__global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
-                                                   uint8_t *images, const double *qtab, int *err, int img_off,
-                                                   unsigned long long *prof) {
+// Residency (round 2): TWO uint64 tiles + a box list of `box_cap` entries and no staged image (the channels are written
+// straight to global memory; partial sectors merge in L2) = 57.6 KB + 36 B x box_cap: 94 KB at box_cap = 1024, so that TWO
+// CTAs share an SM (__launch_bounds__(512, 2): 64 registers). tier 0 runs every image with the small list; images whose
+// box holds more points are appended to `ovf` and re-run by tier 1 (persistent CTAs, box_cap = BOX_CAP, one CTA per SM).
+__global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
+                                                      uint8_t *images, const double *qtab, int *err, int img_off,
+                                                      unsigned long long *prof, int box_cap, int *ovf, int *ovf_count,
+                                                      int tier) {
   long long t_phase = 0;
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ ImgSmem sm;
   const int S = P.S, C = P.C, SS = S * S;
+  const int BC = box_cap;
   unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn);
   unsigned long long *tileB = tileA + SS;
-  unsigned long long *tileC = tileB + SS;
-  unsigned char *lbase = reinterpret_cast<unsigned char *>(tileC + SS);
+  unsigned char *lbase = reinterpret_cast<unsigned char *>(tileB + SS);
   unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(lbase);
-  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BOX_CAP);   // [3][CAP]
-  unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
-  float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
+  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BC);        // [3][CAP]
+  unsigned *bcell = bq + 3 * BC;                                  // packed 3 x 8 bit
+  float *bnrm = reinterpret_cast<float *>(bcell + BC);            // [3][CAP]
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
-  float *nrmT = reinterpret_cast<float *>(tileB);                 // float[3*SS] over tileB..tileC
-  float *depF = nrmT + 3 * SS;                                    // float[SS]
-  uint8_t *simg = dyn + img_off;                                  // uint8[SS*C] HWC staging of the output image
+  float *nrmT = reinterpret_cast<float *>(tileA);                 // float[3*SS] over tileA and half of tileB ...
+  float *depF = nrmT + 3 * SS;                                    // ... float[SS]: the other half of tileB
   const int tid = threadIdx.x, lane = tid & 31;
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
+  const int work_n = tier == 0 ? nc : *ovf_count;
 
-  for (int b = blockIdx.x; b < nc; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < work_n; wi += gridDim.x) {
+    const int b = tier == 0 ? wi : ovf[wi];
     __syncthreads();
     {
       const int *src = reinterpret_cast<const int *>(cand + b);
@@ -1061,7 +1069,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
     PHASE(1);   // image start
     const gpdb_pose &h = sm.h;
     uint8_t *gout = images + (size_t)b * SS * C;
-    uint8_t *gimg = simg;  // channels are written to the shared-memory staging image, flushed once at the end
+    uint8_t *gimg = gout;  // channels are written straight to global memory (byte stores; sectors merge in L2)
     const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
     SegRange sr = seg_range(P, q, P.rf_img);
@@ -1097,11 +1105,11 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
         base = __shfl_sync(0xffffffffu, base, leader);
         int pos = base + __popc(mk & ((1u << lane) - 1));
-        if (inb && pos < BOX_CAP) {
+        if (inb && pos < BC) {
           bkeys[pos] = key;
           bq[pos] = __float_as_uint(p.x);  // raw coordinates, replaced by the fixed-point unit coordinates below
-          bq[BOX_CAP + pos] = __float_as_uint(p.y);
-          bq[2 * BOX_CAP + pos] = __float_as_uint(p.z);
+          bq[BC + pos] = __float_as_uint(p.y);
+          bq[2 * BC + pos] = __float_as_uint(p.z);
         }
       }
     });
@@ -1134,18 +1142,22 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       sm.center[0] = a0 / nn;
       sm.center[1] = a1 / nn;
       sm.center[2] = a2 / nn;
-      if (sm.box_n > BOX_CAP) {
-        atomicAdd(err + 2, 1);
-        sm.box_n = BOX_CAP;
+      if (sm.box_n > BC) {
+        if (tier == 0) ovf[atomicAdd(ovf_count, 1)] = b;  // re-run with the large list
+        else {
+          atomicAdd(err + 2, 1);
+          sm.box_n = BC;
+        }
       }
     }
     __syncthreads();
     PHASE(2);  // scan 1 + reductions done
+    if (sm.box_n > BC) continue;  // tier 0 overflow (uniform: box_n is shared); tier 1 clamped it above
     const int bn = sm.box_n;
     // dense pass over the box points: hand-frame coordinates -> unit cube, cell indices, |R^T n| (all lanes busy)
     for (int k = tid; k < bn; k += NT_IMG) {
-      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP + k]),
-                   pz = (double)__uint_as_float(bq[2 * BOX_CAP + k]);
+      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BC + k]),
+                   pz = (double)__uint_as_float(bq[2 * BC + k]);
       double x, y, z, u0, u1, u2;
       int c0, c1, c2;
       to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], x, y, z);
@@ -1153,15 +1165,15 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
       unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
       bq[k] = unit_q32(u0);
-      bq[BOX_CAP + k] = unit_q32(u1);
-      bq[2 * BOX_CAP + k] = unit_q32(u2);
+      bq[BC + k] = unit_q32(u1);
+      bq[2 * BC + k] = unit_q32(u2);
       bcell[k] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
       const double *nn = cl.nrm + 3 * (size_t)(unsigned)(bkeys[k] & 0xffffffffull);
       double n0, n1, n2;
       to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
       bnrm[k] = (float)fabs(n0);
-      bnrm[BOX_CAP + k] = (float)fabs(n1);
-      bnrm[2 * BOX_CAP + k] = (float)fabs(n2);
+      bnrm[BC + k] = (float)fabs(n1);
+      bnrm[2 * BC + k] = (float)fabs(n2);
     }
     __syncthreads();
 
@@ -1178,7 +1190,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
         int pix = (S - 1 - v) * S + hcol;
         atomicMax(tileA + pix, bkeys[k]);
-        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
+        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BC + k]);
       }
       __syncthreads();
       unsigned long long dreg[(MAXPIX + NT_IMG - 1) / NT_IMG];
@@ -1186,6 +1198,15 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
         int pix = tid + t * NT_IMG;
         dreg[t] = pix < SS ? tileB[pix] : 0ull;
+      }
+      // winner of each cell = the box point whose key is the cell's maximum; decided HERE, while the key tile is
+      // intact, and remembered as one bit per owned box point (k = tid + j NT_IMG): the float images below overwrite
+      // both tiles
+      unsigned wmask = 0;
+      for (int k = tid, j = 0; k < bn; k += NT_IMG, j++) {
+        unsigned cc = bcell[k];
+        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
+        if (tileA[(S - 1 - v) * S + hcol] == bkeys[k]) wmask |= 1u << j;
       }
       __syncthreads();
 #pragma unroll
@@ -1207,14 +1228,14 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         }
       }
       __syncthreads();
-      for (int k = tid; k < bn; k += NT_IMG) {
+      for (int k = tid, j = 0; k < bn; k += NT_IMG, j++) {
         unsigned cc = bcell[k];
         int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
         int pix = (S - 1 - v) * S + hcol;
-        if (tileA[pix] == bkeys[k]) {
+        if ((wmask >> j) & 1) {
           nrmT[pix * 3] = bnrm[k];
-          nrmT[pix * 3 + 1] = bnrm[BOX_CAP + k];
-          nrmT[pix * 3 + 2] = bnrm[2 * BOX_CAP + k];
+          nrmT[pix * 3 + 1] = bnrm[BC + k];
+          nrmT[pix * 3 + 2] = bnrm[2 * BC + k];
         }
       }
       __syncthreads();
@@ -1285,7 +1306,7 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
       // region; (2) the (point, draw) pairs are spread evenly over all threads — draw t of a point comes from
       // the closed-form LCG skip-ahead seed_t = A^(t+1) seed_0 + C_(t+1) (mod 2^32).
       float4 *wl = reinterpret_cast<float4 *>(tileA);
-      const int WL_CAP = (3 * SS * 8) / 20;
+      const int WL_CAP = (2 * SS * 8) / 20;  // work list over the two tiles
       unsigned *wrange = reinterpret_cast<unsigned *>(wl + WL_CAP);
       // image box in the hand frame, widened by voxel truncation (<= 0.003 sqrt 3) + jitter (<= gmax 0.0009 sqrt 3)
       const double wm = 0.0105;
@@ -1413,14 +1434,13 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
           bitmap[wd] = acc;
         }
       }
-      for (int k = tid; k < 3 * SS; k += NT_IMG) tileA[k] = 0ull;
-      __syncthreads();
       // compact the set bits into a list (behind bitmap 0, in the dead box-list region) so that the per-voxel work
       // is spread evenly: shadow voxels are spatially clustered, a thread-per-word loop would be badly unbalanced
       const int nbits = 64 * d1 * d2;
       unsigned *blist = bitmap + bm_words;
-      const int BL_CAP = (img_off - 3 * SS * 8) / 4 - bm_words;
-      auto eval_voxel = [&](unsigned packed) {  // b0 | b1 << 8 | b2 << 16
+      const int BL_CAP = (img_off - 2 * SS * 8) / 4 - bm_words;
+      // the sums of projections [pj_lo, pj_hi) go to tiles 0 .. pj_hi - pj_lo - 1
+      auto eval_voxel = [&](unsigned packed, int pj_lo, int pj_hi) {  // b0 | b1 << 8 | b2 << 16
         int b0 = packed & 255, b1 = (packed >> 8) & 255, b2 = packed >> 16;
         double x, y, z;
         if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) return;
@@ -1431,89 +1451,95 @@ __global__ void __launch_bounds__(NT_IMG) k_images(const DevParams *Pp, DevCloud
         unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u[2], cellv[2]);
 #pragma unroll
         for (int pj = 0; pj < 3; pj++) {
+          if (pj < pj_lo || pj >= pj_hi) continue;
           const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
           int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
-          atomicAdd(tileA + (size_t)pj * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
+          atomicAdd(tileA + (size_t)(pj - pj_lo) * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
         }
       };
-      if (tid == 0) sm.wl_n = 0;
-      __syncthreads();
-      for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
-        const int wd = wd0 + tid;
-        unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
-        int cntb = __popc(bits);
-        int incl = cntb;  // warp-aggregated reservation of list slots
+      // Two tiles hold the per-cell sums of two projections at a time: pass 0 = projections 0 and 1, pass 1 = projection 2
+      // (the voxel list is compacted once; it is re-walked, and voxels that did not fit the list re-evaluated in place)
+      int nset_all = 0;
+      for (int pass = 0; pass < 2; pass++) {
+        const int pj_lo = pass == 0 ? 0 : 2, pj_hi = pass == 0 ? 2 : 3;
+        for (int k = tid; k < 2 * SS; k += NT_IMG) tileA[k] = 0ull;
+        const bool recompact = pass == 0 || nset_all > BL_CAP;
+        if (recompact && tid == 0) sm.wl_n = 0;
+        __syncthreads();
+        if (recompact) {
+          for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
+            const int wd = wd0 + tid;
+            unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
+            int cntb = __popc(bits);
+            int incl = cntb;  // warp-aggregated reservation of list slots
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
-        if (lane == 31 && total) base = atomicAdd(&sm.wl_n, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + incl - cntb;
-        const int rowi = wd >> 1;  // (b2 * d1 + b1)
-        const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
-        while (bits) {
-          int bi = __ffs(bits) - 1;
-          bits &= bits - 1;
-          if (pos < BL_CAP) blist[pos] = hi | (unsigned)bi;
-          else eval_voxel(hi | (unsigned)bi);  // list full: evaluate in place
-          pos++;
-        }
-      }
-      __syncthreads();
-      const int nset = min(sm.wl_n, BL_CAP);
-      if (prof && tid == 0) {
-        atomicAdd(prof + 11, (unsigned long long)sm.wl_n);
-        atomicAdd(prof + 12, (unsigned long long)bn);
-        atomicAdd(prof + 13, (unsigned long long)sm.n_img);
-      }
-      for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i]);
-      __syncthreads();
-      PHASE(6);  // S2 bitmap pass done
-      // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
-      for (int pj = 0; pj < 3; pj++) {
-        unsigned long long *tile = tileA + (size_t)pj * SS;
-        float *srcF = reinterpret_cast<float *>(tile);
-        float avgr[(MAXPIX + NT_IMG - 1) / NT_IMG];
-        unsigned occ = 0;
-        float mn = FLT_MAX, mx = -FLT_MAX;
-#pragma unroll
-        for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-          int pix = tid + t * NT_IMG;
-          avgr[t] = 0.0f;
-          if (pix < SS) {
-            unsigned long long acc = tile[pix];
-            unsigned cntc = (unsigned)(acc >> 48);
-            if (cntc) {
-              double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
-              avgr[t] = (float)mean;
-              occ |= 1u << t;
-              mx = fmaxf(mx, avgr[t]);
+            for (int o = 1; o < 32; o <<= 1) {
+              int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
+            if (lane == 31 && total) base = atomicAdd(&sm.wl_n, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + incl - cntb;
+            const int rowi = wd >> 1;  // (b2 * d1 + b1)
+            const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
+            while (bits) {
+              int bi = __ffs(bits) - 1;
+              bits &= bits - 1;
+              if (pass == 0 && pos < BL_CAP) blist[pos] = hi | (unsigned)bi;
+              else eval_voxel(hi | (unsigned)bi, pj_lo, pj_hi);  // list full (pass 0) / list not reproducible (pass 1): in place
+              pos++;
             }
           }
+          __syncthreads();
+          nset_all = sm.wl_n;
         }
-        block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between reads and writes
-        const float maxf = (mx == -FLT_MAX) ? 0.0f : mx;
-#pragma unroll
-        for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-          int pix = tid + t * NT_IMG;
-          if (pix < SS) srcF[pix] = ((occ >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
+        const int nset = (pass == 1 && recompact) ? 0 : min(nset_all, BL_CAP);
+        if (pass == 0 && prof && tid == 0) {
+          atomicAdd(prof + 11, (unsigned long long)nset_all);
+          atomicAdd(prof + 12, (unsigned long long)bn);
+          atomicAdd(prof + 13, (unsigned long long)sm.n_img);
         }
+        for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i], pj_lo, pj_hi);
         __syncthreads();
-        postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
+        if (pass == 0) PHASE(6);  // S2 bitmap pass (first pass) done
+        // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
+        for (int pj = pj_lo; pj < pj_hi; pj++) {
+          unsigned long long *tile = tileA + (size_t)(pj - pj_lo) * SS;
+          float *srcF = reinterpret_cast<float *>(tile);
+          float avgr[(MAXPIX + NT_IMG - 1) / NT_IMG];
+          unsigned occ = 0;
+          float mn = FLT_MAX, mx = -FLT_MAX;
+#pragma unroll
+          for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+            int pix = tid + t * NT_IMG;
+            avgr[t] = 0.0f;
+            if (pix < SS) {
+              unsigned long long acc = tile[pix];
+              unsigned cntc = (unsigned)(acc >> 48);
+              if (cntc) {
+                double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+                avgr[t] = (float)mean;
+                occ |= 1u << t;
+                mx = fmaxf(mx, avgr[t]);
+              }
+            }
+          }
+          block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between reads and writes
+          const float maxf = (mx == -FLT_MAX) ? 0.0f : mx;
+#pragma unroll
+          for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
+            int pix = tid + t * NT_IMG;
+            if (pix < SS) srcF[pix] = ((occ >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
+          }
+          __syncthreads();
+          postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
+        }
       }
     }
-    // ---- flush the staged image with coalesced 16-byte stores
     __syncthreads();
     PHASE(7);  // shadow images done
-    {
-      const int nb = SS * C, nv = nb >> 4;
-      for (int v = tid; v < nv; v += NT_IMG) reinterpret_cast<uint4 *>(gout)[v] = reinterpret_cast<const uint4 *>(simg)[v];
-      for (int v = (nv << 4) + tid; v < nb; v += NT_IMG) gout[v] = simg[v];
-    }
-    PHASE(8);  // flush done
+    PHASE(8);  // (no flush: the channels were written straight to global memory)
   }
 }
 
@@ -1646,26 +1672,36 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
   return GPDB_OK;
 }
 
-static size_t images_smem_bytes(const DevParams &hp) {
-  size_t tiles = (size_t)3 * 8 * hp.S * hp.S;
-  size_t list = (size_t)BOX_CAP * (8 + 12 + 4 + 12);
+static size_t images_smem_bytes(const DevParams &hp, int box_cap) {
+  size_t tiles = (size_t)2 * 8 * hp.S * hp.S;
+  size_t list = (size_t)box_cap * (8 + 12 + 4 + 12);
   size_t bm = (size_t)hp.K * (2 * (size_t)hp.bm_dim * hp.bm_dim) * 4;
-  size_t work = tiles + std::max(list, hp.C == 15 ? bm : (size_t)0);
+  // shadow phase: the bitmaps alias the box list and the compacted voxel list follows bitmap 0: leave room for ~4 k voxels
+  size_t shadow = hp.C == 15 ? std::max(bm, (size_t)(2 * (size_t)hp.bm_dim * hp.bm_dim) * 4 + 4096 * 4) : (size_t)0;
+  size_t work = tiles + std::max(list, shadow);
   return (work + 15) / 16 * 16;
 }
 
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images) {
   if (nc <= 0) return GPDB_OK;
-  const size_t img_off = images_smem_bytes(ctx->hp);
-  size_t smem = img_off + ((size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C + 15) / 16 * 16;
-  if (smem > 219 * 1024) {
-    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem);
+  const int cap0 = 1024;  // tier 0: two CTAs per SM (a 3 mm cloud puts ~210, at most ~710 points into an image box)
+  const size_t smem0 = images_smem_bytes(ctx->hp, cap0), smem1 = images_smem_bytes(ctx->hp, BOX_CAP);
+  if (smem1 > 219 * 1024) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem1);
     return GPDB_ERR_INVALID;
   }
-  CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  int *ovf = (int *)gpdb_scratch(ctx, 6, sizeof(int) * ((size_t)nc + 1));
+  if (!ovf) return GPDB_ERR_CUDA;
+  int *ovf_count = ovf + nc;
+  CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
   int grid = std::min(nc, ctx->sm_count * 64);
-  k_images<<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
-                                                (int)img_off, ctx->d_prof);
+  k_images<<<grid, NT_IMG, smem0, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
+                                                 (int)smem0, ctx->d_prof, cap0, ovf, ovf_count, 0);
+  LAUNCH_CHECK();
+  // images whose box holds more than cap0 points (usually none): persistent CTAs over the overflow list, large list
+  k_images<<<ctx->sm_count, NT_IMG, smem1, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
+                                                          (int)smem1, ctx->d_prof, BOX_CAP, ovf, ovf_count, 1);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

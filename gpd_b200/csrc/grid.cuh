@@ -12,6 +12,21 @@ __device__ __forceinline__ int cell_of(const DevParams &P, float v, int a) {
   return min(max(c, 0), P.dim[a] - 1);
 }
 
+// position of a sample: a cloud point (index < n_points: Cloud::getSampleIndices) or an arbitrary float64 position
+// (index >= n_points: Cloud::setSamples / gpdb_set_samples)
+__device__ __forceinline__ void sample_position(const DevCloud &cl, int si, double out[3]) {
+  if (si < cl.n_points) {
+    out[0] = (double)cl.xyz[3 * (size_t)si];
+    out[1] = (double)cl.xyz[3 * (size_t)si + 1];
+    out[2] = (double)cl.xyz[3 * (size_t)si + 2];
+  } else {
+    const double *s = cl.samples + 3 * (size_t)(si - cl.n_points);
+    out[0] = s[0];
+    out[1] = s[1];
+    out[2] = s[2];
+  }
+}
+
 // FLANN L2_Simple<float> (float32, accumulated x,y,z in order)
 __device__ __forceinline__ float l2_simple(const float q[3], float x, float y, float z) {
   float dx = q[0] - x, dy = q[1] - y, dz = q[2] - z;

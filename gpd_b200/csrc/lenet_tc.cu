@@ -272,24 +272,38 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
   const uint32_t idesc_hi = umma::instr_desc(128, 128, umma::F16), idesc_lo = umma::instr_desc(128, 64, umma::F16);
   int gt = 0;  // running tile counter of this role
 
+  // The float32 activations of the NEXT half image are fetched into registers while the tensor cores work on the
+  // current one (the planes have no room for a second buffer: 155 KB of weights + 45 KB of planes + 22 KB of stage):
+  // the global-load latency of the conversion phase (HBM: a LeNet batch of P1 does not fit L2) is hidden behind the
+  // MMAs / epilogues; only the cvt + st.shared part stays between the barriers.
+  constexpr int C2_ITEMS = (448 * 3 + C2_NT - 1) / C2_NT;  // (pixel, plane) items per thread and half image
+  float4 pre[C2_ITEMS][2];
+  auto issue_loads = [&](int im2, int h2) {
+#pragma unroll
+    for (int j = 0; j < C2_ITEMS; j++) {
+      const int i = tid + j * C2_NT;
+      pre[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < 448 * 3 && im2 < n) {
+        const int lp = i / 3, p = i - lp * 3;
+        const float *src = p1 + (size_t)im2 * 784 * NF1 + (size_t)(12 * h2 * C2_W + lp) * NF1 + p * 8;
+        pre[j][0] = __ldg(reinterpret_cast<const float4 *>(src));
+        if (p < 2) pre[j][1] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+      }
+    }
+  };
+  issue_loads(blockIdx.x, 0);
+
   for (int im = blockIdx.x; im < n; im += gridDim.x) {
-    const float *g = p1 + (size_t)im * 784 * NF1;
     float *out = p2 + (size_t)im * 7200;
     for (int h = 0; h < 2; h++) {
-      // ---- float32 -> scaled fp16 hi/lo channel planes for input rows 12h .. 12h+15 (448 px)
-#pragma unroll 2
-      for (int i = tid; i < 448 * 3; i += C2_NT) {
-        int lp = i / 3, p = i - lp * 3;
-        const float *src = g + (size_t)(12 * h * C2_W + lp) * NF1 + p * 8;
-        float x[8];
-        float4 q0 = __ldg(reinterpret_cast<const float4 *>(src));
-        x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w;
-        if (p < 2) {
-          float4 q1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
-          x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
-        } else {
-          x[4] = x[5] = x[6] = x[7] = 0.0f;
-        }
+      // ---- float32 (prefetched) -> scaled fp16 hi/lo channel planes for input rows 12h .. 12h+15 (448 px)
+#pragma unroll
+      for (int j = 0; j < C2_ITEMS; j++) {
+        const int i = tid + j * C2_NT;
+        if (i >= 448 * 3) continue;
+        const int lp = i / 3, p = i - lp * 3;
+        const float x[8] = {pre[j][0].x, pre[j][0].y, pre[j][0].z, pre[j][0].w, pre[j][1].x, pre[j][1].y, pre[j][1].z, pre[j][1].w};
         __half hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -300,6 +314,9 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
         *reinterpret_cast<uint4 *>(sPl + (size_t)p * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(hi);
         *reinterpret_cast<uint4 *>(sPl + (size_t)(3 + p) * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(lo);
       }
+      // loads of the next half image (h = 1 of this image, or h = 0 of this CTA's next image) fly during the MMAs below
+      if (h == 0) issue_loads(im, 1);
+      else issue_loads(im + gridDim.x, 0);
       umma::fence_async_smem();
       __syncthreads();
       if (warp == 8) {

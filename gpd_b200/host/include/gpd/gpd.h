@@ -70,6 +70,10 @@ class Cloud {
   void setNormalsFromFile(const std::string &filename);  // CSV, one normal per row or 3 x N (cloud.cpp:607-641)
   void setNormals(const std::vector<double> &normals) { normals_ = normals; touch(); }
   void setSampleIndices(const std::vector<int> &idx) { sample_indices_ = idx; }
+  // Cloud::setSamples (cloud.cpp:662): arbitrary sample positions, 3 x n column-major float64; they take precedence over the
+  // sample indices in searchHands / detectGrasps (hand_search.cpp:33-47)
+  void setSamples(const std::vector<double> &samples) { samples_ = samples; }
+  const std::vector<double> &getSamples() const { return samples_; }
   // replaces cloud_processed_ / normals_ / camera_source_ (what Cloud::filterWorkspace / voxelizeCloud /
   // calculateNormals leave behind, cloud.cpp:207-348,458-535); sample indices are invalidated
   void setProcessed(std::vector<float> points, std::vector<double> normals, std::vector<int> camera_source);
@@ -90,6 +94,7 @@ class Cloud {
   std::vector<int> camera_source_;
   std::vector<double> view_points_;
   std::vector<int> sample_indices_;
+  std::vector<double> samples_;
   unsigned revision_{0};
   void touch();
 };

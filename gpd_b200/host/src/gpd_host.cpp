@@ -834,7 +834,17 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
     installed_cloud_ = &cloud;
     installed_revision_ = cloud.revision();
   }
-  const std::vector<int> &idx = cloud.getSampleIndices();
+  std::vector<int> idx = cloud.getSampleIndices();
+  if (!cloud.getSamples().empty()) {  // Cloud::setSamples positions take precedence (hand_search.cpp:33-47)
+    const int ns = (int)(cloud.getSamples().size() / 3);
+    const int first = gpdb_set_samples(ctx_, cloud.getSamples().data(), ns);
+    if (first < 0) {
+      printf("ERROR: %s\n", gpdb_last_error(ctx_));
+      return hands_out;
+    }
+    idx.resize(ns);
+    for (int i = 0; i < ns; i++) idx[i] = first + i;
+  }
   gpdb_result r;
   // steps 1-4 + selectGrasps in one call: the num_selected best hands are picked on the device and only they are
   // copied back (grasp_detector.cpp:222-283,405-420)

@@ -21,7 +21,9 @@ EXPORTS = [
     "gpdb_set_weights", "gpdb_set_cloud", "gpdb_detect", "gpdb_frames", "gpdb_hand_search", "gpdb_images",
     "gpdb_classify", "gpdb_free_result", "gpdb_last_timings", "gpdb_build_info", "gpdb_detect_resident",
     "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
-    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select", "gpdb_load_weights_file", "gpdb_read_weights_file",
+    "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select", "gpdb_load_weights_file", "gpdb_read_weights_file", "gpdb_set_samples",
+    "gpdb_comm_unique_id", "gpdb_comm_init", "gpdb_comm_destroy", "gpdb_shard_bounds", "gpdb_set_cloud_bcast",
+    "gpdb_detect_sharded", "gpdb_detect_sharded_resident", "gpdb_slot_bytes",
 ]
 
 
@@ -66,8 +68,19 @@ def lib():
     L.gpdb_preprocess_params_default.argtypes = [C.POINTER(abi.PreprocessParams)]
     L.gpdb_preprocess.argtypes = [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(abi.PreprocessParams)]
     L.gpdb_get_cloud.argtypes = [vp, vp, vp, vp]
+    L.gpdb_set_samples.argtypes = [vp, vp, C.c_int32]
     L.gpdb_get_cloud_source_index.argtypes = [vp, vp]
     L.gpdb_preprocess_timings.argtypes = [vp, vp]
+    L.gpdb_comm_unique_id.argtypes = [vp]
+    L.gpdb_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.gpdb_comm_destroy.argtypes = [vp]
+    L.gpdb_shard_bounds.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
+    L.gpdb_shard_bounds.restype = None
+    L.gpdb_set_cloud_bcast.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32]
+    L.gpdb_detect_sharded.argtypes = [vp, vp, C.c_int32, C.POINTER(abi.Result)]
+    L.gpdb_detect_sharded_resident.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(abi.Result)]
+    L.gpdb_slot_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.gpdb_slot_bytes.restype = C.c_int64
     _LIB = L
     return L
 
@@ -196,6 +209,50 @@ class Context:
             out["src"] = np.zeros(0, np.int32)
         return out
 
+    # ---- multi-GPU sharding inside the boundary (gpdb_comm_*) ----
+    def comm_init(self, unique_id, rank, nranks):
+        """ncclCommInitRank on this context's device; unique_id = 128 bytes from comm_unique_id() of one rank."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(lib().gpdb_comm_init(self.h, buf, int(rank), int(nranks)))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def set_cloud_bcast(self, root, xyz=None, normals=None, cam_source=None, view_points=None):
+        """gpdb_set_cloud on every rank from the root's host arrays (ncclBroadcast of the device copies)."""
+        if xyz is None:
+            return self._check(lib().gpdb_set_cloud_bcast(self.h, int(root), None, None, None, 0, None, 0))
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        vp = np.ascontiguousarray(view_points if view_points is not None else np.zeros((1, 3)), dtype=np.float64)
+        cam = None if cam_source is None else np.ascontiguousarray(cam_source, dtype=np.int32)
+        return self._check(lib().gpdb_set_cloud_bcast(self.h, int(root), _p(xyz), _p(normals), _p(cam), xyz.shape[0], _p(vp), vp.shape[0]))
+
+    def detect_sharded(self, sample_idx):
+        """gpdb_detect over sharded samples: gathered pose_flags / pose_scores of all ranks + this rank's pose records."""
+        sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        res = abi.Result()
+        self._check(lib().gpdb_detect_sharded(self.h, _p(sidx), len(sidx), C.byref(res)))
+        n, P, nc = res.n_samples, res.poses_per_sample, res.n_candidates
+        out = {"pose_flags": np.ctypeslib.as_array(res.pose_flags, (n, P)).copy(),
+               "pose_scores": np.ctypeslib.as_array(res.pose_scores, (n, P)).copy(),
+               "n_candidates": nc, "n_total_candidates": res.n_total_candidates,
+               "candidates": np.frombuffer(C.string_at(res.candidates, nc * C.sizeof(abi.Pose)), dtype=abi.POSE_DTYPE).copy()
+               if nc else np.zeros(0, dtype=abi.POSE_DTYPE)}
+        lib().gpdb_free_result(C.byref(res))
+        return out
+
+    def detect_sharded_raw(self, sidx_i32, res):
+        return self._check(lib().gpdb_detect_sharded(self.h, _p(sidx_i32), len(sidx_i32), C.byref(res)))
+
+    def detect_sharded_resident(self, d_sidx_local_ptr, n_local, slot_samples, d_gathered_ptr, stats):
+        return self._check(lib().gpdb_detect_sharded_resident(self.h, C.c_void_p(d_sidx_local_ptr), int(n_local), int(slot_samples),
+                                                              C.c_void_p(d_gathered_ptr), C.byref(stats)))
+
+    def set_samples(self, samples):
+        """Cloud::setSamples: arbitrary float64 positions [n, 3]; returns the sample indices that address them."""
+        sm = np.ascontiguousarray(samples, dtype=np.float64)
+        first = self._check(lib().gpdb_set_samples(self.h, _p(sm), len(sm)))
+        return np.arange(first, first + len(sm), dtype=np.int32)
+
     def get_cloud(self):
         n = self._check(lib().gpdb_get_cloud(self.h, None, None, None))
         xyz = np.zeros((n, 3), np.float32)
@@ -289,6 +346,26 @@ class Context:
         ms = np.zeros(8)
         lib().gpdb_last_timings(self.h, _p(ms))
         return ms
+
+
+def comm_unique_id():
+    """ncclGetUniqueId (128 bytes): call on one rank and distribute to the others."""
+    buf = C.create_string_buffer(128)
+    rc = lib().gpdb_comm_unique_id(buf)
+    if rc != 0:
+        raise GpdbError(rc, lib().gpdb_last_error(None).decode())
+    return buf.raw
+
+
+def shard_bounds(n, rank, nranks):
+    """(lo, hi, slot_samples) of gpdb_shard_bounds: the slice of `rank` and the fixed slot size of the all-gather."""
+    lo, hi, st = C.c_int32(), C.c_int32(), C.c_int32()
+    lib().gpdb_shard_bounds(int(n), int(rank), int(nranks), C.byref(lo), C.byref(hi), C.byref(st))
+    return lo.value, hi.value, st.value
+
+
+def slot_bytes(slot_samples, P):
+    return int(lib().gpdb_slot_bytes(int(slot_samples), int(P)))
 
 
 def free_result(res):

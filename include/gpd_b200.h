@@ -138,6 +138,7 @@ typedef struct gpdb_result {
   double ms_classify;       /*                "3. Classification"                            */
   int64_t kernel_launches;  /* CUDA kernels launched by this call                     */
   int32_t n_total_candidates; /* all poses with VALID and FILTERED set (= n_candidates except after gpdb_detect_select) */
+  void *owner_;             /* library-private: the pinned host arena the arrays above live in (gpdb_free_result) */
 } gpdb_result;
 
 typedef struct gpdb_ctx gpdb_ctx;
@@ -185,6 +186,15 @@ int gpdb_set_weights(gpdb_ctx *ctx, const float *conv1_w, const float *conv1_b,
 int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals,
                    const int32_t *cam_source, int32_t n_points, const double *view_points,
                    int32_t n_cams);
+
+/* Replaces: Cloud::setSamples (cloud.cpp:662; used by SequentialImportanceSampling, sequential_importance_sampling.cpp:
+ * 130-131,166-168): n arbitrary float64 sample positions (3 x n column-major) next to the installed cloud. Returns N, the
+ * first sample index that addresses them: gpdb_detect / gpdb_frames / gpdb_hand_search / gpdb_detect_select accept sample
+ * indices N .. N + n - 1 for these positions (indices < N keep addressing cloud points, Cloud::getSampleIndices). The
+ * local frame and the radius searches use the float32 image of the position, the hand-frame transforms the float64
+ * position, as the reference does; the shadow draws are seeded by the sample index as for cloud points. A new cloud
+ * (gpdb_set_cloud / gpdb_preprocess) drops the positions. */
+int gpdb_set_samples(gpdb_ctx *ctx, const double *samples_xyz, int32_t n_samples);
 
 /* Replaces: GraspDetector::detectGrasps steps 1-4 (grasp_detector.cpp:222-273) for the
  * samples cloud.getSampleIndices() (cloud.h:345). Returns n_candidates or a negative error. */
@@ -275,8 +285,39 @@ int gpdb_get_cloud_source_index(gpdb_ctx *ctx, int32_t *src_out);
  * ms[0] upload, ms[1] NaN/workspace filter, ms[2] voxelise, ms[3] grid build, ms[4] normals, ms[5] whole call. */
 int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]);
 
-/* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). */
+/* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). The arrays of a result live in page-locked host memory
+ * owned by the library (the device writes them directly, overlapped with compute); gpdb_free_result hands that memory
+ * back for the next call. A result may outlive its context. */
 void gpdb_free_result(gpdb_result *r);
+
+/* --- multi-GPU: one context per GPU, one process or thread per context ------------------------------
+ * The path shards by sample: every rank runs steps 1-4 on the contiguous slice [r*n/R, (r+1)*n/R) of the sample-index
+ * array over its own copy of the cloud (reference parallel loops: hand_search.cpp:168-182, image_generator.cpp:83-89,
+ * eigen_classifier.cpp:67-76); the only exchange is ONE ncclAllGather of fixed-stride {score f32, flags u8} slots.
+ * NCCL is loaded at run time (libnccl.so.2; the copy already in the process, e.g. PyTorch's, is reused). */
+#define GPDB_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, distribute the 128 bytes to the others by any means (MPI, torch.distributed, a pipe). */
+int gpdb_comm_unique_id(char id_out[GPDB_COMM_ID_BYTES]);
+/* ncclCommInitRank on the context's device and stream (collective: every rank calls it). nranks == 1 is allowed. */
+int gpdb_comm_init(gpdb_ctx *ctx, const char id[GPDB_COMM_ID_BYTES], int32_t rank, int32_t nranks);
+int gpdb_comm_destroy(gpdb_ctx *ctx);
+/* Slice of rank `rank` of `nranks` over n samples and the fixed slot size (largest slice) of the all-gather. */
+void gpdb_shard_bounds(int32_t n, int32_t rank, int32_t nranks, int32_t *lo, int32_t *hi, int32_t *slot_samples);
+/* gpdb_set_cloud on every rank from rank `root`'s host arrays (ncclBroadcast of the device copies over NVLink; the other
+ * ranks pass NULL arrays and any sizes). Every rank then builds its own neighbour grid. Returns N. */
+int gpdb_set_cloud_bcast(gpdb_ctx *ctx, int32_t root, const float *xyz, const double *normals, const int32_t *cam_source,
+                         int32_t n_points, const double *view_points, int32_t n_cams);
+/* gpdb_detect over sharded samples: every rank passes the SAME sample_idx[n]; on return out->pose_flags / out->pose_scores
+ * [n*P] hold the gathered results of ALL ranks (identical everywhere), out->candidates the pose records of this rank's
+ * slice (sample_slot = position in the full array), out->n_total_candidates the global count; frames / frame_valid
+ * are NULL. Returns this rank's candidate count. */
+int gpdb_detect_sharded(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n_samples, gpdb_result *out);
+/* Device-resident variant (measurement with inputs in HBM): d_sample_idx_local [n_local] = this rank's slice,
+ * d_gathered = nranks slots of gpdb_slot_bytes(slot_samples, P) bytes each: [scores f32 slot_samples*P][flags u8
+ * slot_samples*P, padded to 16 B]; this rank's results are written into slot `rank` and all-gathered in place. */
+int gpdb_detect_sharded_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx_local, int32_t n_local, int32_t slot_samples,
+                                 uint8_t *d_gathered, gpdb_result *stats);
+int64_t gpdb_slot_bytes(int32_t slot_samples, int32_t poses_per_sample);
 
 /* --- introspection ------------------------------------------------------------------------- */
 /* Device-side stage timings of the last gpdb_detect call, CUDA events on the context stream:

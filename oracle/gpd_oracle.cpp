@@ -75,6 +75,16 @@ struct Cloud {
   int dim[3] = {1, 1, 1};
   std::vector<int> cell_start;  // ncell + 1
   std::vector<int> order;       // point indices sorted by cell
+  // Cloud::setSamples (cloud.cpp:662): arbitrary sample positions (3 x n, float64). A sample index >= N addresses
+  // samples[index - N]; indices < N address the cloud points themselves (Cloud::getSampleIndices).
+  std::vector<double> samples;
+  void sample_position(int sample_index, double out[3]) const {
+    if (sample_index < N) {
+      for (int a = 0; a < 3; a++) out[a] = (double)xyz[3 * (size_t)sample_index + a];
+    } else {
+      for (int a = 0; a < 3; a++) out[a] = samples[3 * (size_t)(sample_index - N) + a];
+    }
+  }
 
   int cell_of(float v, int a) const {
     int c = (int)std::floor((v - lo[a]) / cell);
@@ -635,8 +645,11 @@ void fill_pose_header(gpdb_pose &h, const double *sample, const double *frame_ro
 // modifyCandidate/labelHypothesis (:235-261) + Hand::construct (hand.cpp:24-45).
 void eval_hand_set(const Cloud &c, const gpdb_params &pr, const Derived &dv, int sample_index, int slot,
                    const double *lframe9, gpdb_pose *poses, uint8_t *flags) {
-  float q[3] = {c.xyz[3 * (size_t)sample_index], c.xyz[3 * (size_t)sample_index + 1], c.xyz[3 * (size_t)sample_index + 2]};
-  double sample[3] = {(double)q[0], (double)q[1], (double)q[2]};
+  // the sample stays float64 for the hand-frame transform; the radius search is run at its float32 image
+  // (eigenVectorToPcl, hand_search.cpp:166-170)
+  double sample[3];
+  c.sample_position(sample_index, sample);
+  float q[3] = {(float)sample[0], (float)sample[1], (float)sample[2]};
   for (int j = 0; j < dv.P; j++) flags[j] = 0;
   std::vector<Nb> nn;
   radius_search(c, q, dv.nn_radius_hs, nn);
@@ -1445,6 +1458,10 @@ void *gpdo_cloud_create(const float *xyz, const double *normals, const int32_t *
   return c;
 }
 void gpdo_cloud_destroy(void *c) { delete (Cloud *)c; }
+// Cloud::setSamples: sample indices N .. N + n - 1 address these positions afterwards
+void gpdo_cloud_set_samples(void *c, const double *samples, int32_t n) {
+  ((Cloud *)c)->samples.assign(samples, samples + 3 * (size_t)n);
+}
 
 int gpdo_radius_search(void *cloud, const float *q, double radius, int32_t *idx_out, float *dist_out, int32_t cap) {
   std::vector<Nb> nn;
@@ -1478,7 +1495,9 @@ int gpdo_frames(void *cloud, const gpdb_params *pr, const int32_t *sidx, int32_t
     std::vector<Nb> nn;
 #pragma omp for schedule(dynamic, 16)
     for (int i = 0; i < n; i++) {
-      float q[3] = {c.xyz[3 * (size_t)sidx[i]], c.xyz[3 * (size_t)sidx[i] + 1], c.xyz[3 * (size_t)sidx[i] + 2]};
+      double sp[3];
+      c.sample_position(sidx[i], sp);
+      float q[3] = {(float)sp[0], (float)sp[1], (float)sp[2]};  // frame_estimator.cpp:70-73
       valid[i] = calc_frame(c, q, pr->nn_radius, frames + 9 * (size_t)i, nn) ? 1 : 0;
       if (!valid[i])
         for (int r = 0; r < 9; r++) frames[9 * (size_t)i + r] = 0.0;

@@ -39,6 +39,7 @@ def lib():
     L.gpdo_cloud_create.restype = vp
     L.gpdo_cloud_create.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32]
     L.gpdo_cloud_destroy.argtypes = [vp]
+    L.gpdo_cloud_set_samples.argtypes = [vp, vp, C.c_int32]
     L.gpdo_radius_search.argtypes = [vp, vp, C.c_double, vp, vp, C.c_int32]
     L.gpdo_eigen3.argtypes = [vp, vp, vp]
     L.gpdo_derived.argtypes = [C.POINTER(abi.Params), vp]
@@ -98,6 +99,12 @@ class OracleCloud:
         if getattr(self, "h", None):
             lib().gpdo_cloud_destroy(self.h)
             self.h = None
+
+    def set_samples(self, samples):
+        """Cloud::setSamples: arbitrary float64 sample positions [n, 3]; sample indices N .. N+n-1 address them."""
+        sm = np.ascontiguousarray(samples, dtype=np.float64)
+        lib().gpdo_cloud_set_samples(self.h, _p(sm), len(sm))
+        return np.arange(self.N, self.N + len(sm), dtype=np.int32)
 
     def radius_search(self, q, radius, cap=1 << 20):
         q = np.ascontiguousarray(q, dtype=np.float32)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import load_weights
-from gpd_b200 import lib, scenes
+from gpd_b200 import abi, lib, scenes
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -48,9 +48,7 @@ def assert_parity(ro, rg, ch):
 
 @pytest.mark.parametrize("ch,n", [(15, 160), (3, 96), (1, 40)])
 def test_krylon_matches_oracle(ch, n):
-    k = scenes.krylon_cloud()
-    if ch == 1:
-        pytest.skip("no 1-channel LeNet weights ship with the reference; images covered in test_images_entry_point")
+    k = scenes.krylon_cloud()  # ch == 1: random-init LeNet (conftest.load_weights), the reference ships none
     p, ctx, oc, w = make(k, ch, keep_images=1)
     sidx = scenes.sample_indices(2, len(k["xyz"]), n)
     assert_parity(oc.detect(p, w, sidx), ctx.detect(sidx), ch)
@@ -343,3 +341,75 @@ def test_detect_select_is_detect_plus_select_grasps():
     r = ctx.detect_select(sidx, 20)
     assert np.abs(r["candidates"]["score"] - ro["candidates"]["score"][oo]).max() <= 1e-4 * np.abs(ro["candidates"]["score"]).max()
     ctx.close()
+
+
+def test_sample_positions_match_oracle():
+    """gpdb_set_samples (Cloud::setSamples): arbitrary float64 sample positions addressed by indices >= N, against the
+    oracle; positions that coincide with cloud points reproduce the index-mode poses and flags."""
+    s = scenes.synthetic_table_scene(7, n_points=60000)
+    p, ctx, oc, w = make(s, 15, keep_images=1)
+    sidx = scenes.sample_indices(3, 60000, 300)
+    pos = s["xyz"][sidx].astype(np.float64) + np.random.default_rng(1).normal(0, 1e-3, (300, 3))
+    gi, oi = ctx.set_samples(pos), oc.set_samples(pos)
+    assert np.array_equal(gi, oi) and gi[0] == 60000
+    rg = ctx.detect(gi)
+    assert_parity(oc.detect(p, w, oi), rg, 15)
+    assert np.array_equal(rg["candidates"]["sample"], pos[rg["candidates"]["sample_slot"]])
+    # on-cloud positions == index mode; mixed indices in one call
+    gj = ctx.set_samples(s["xyz"][sidx].astype(np.float64))
+    a, b = ctx.detect(sidx), ctx.detect(gj)
+    assert np.array_equal(a["frames"], b["frames"]) and np.array_equal(a["pose_flags"], b["pose_flags"])
+    for f in ("sample", "frame", "position", "top", "bottom", "center", "width", "finger_idx"):
+        assert np.array_equal(a["candidates"][f], b["candidates"][f]), f
+    with pytest.raises(lib.GpdbError):
+        ctx.detect(np.array([60000 + 300], np.int32))  # beyond the sample positions
+    ctx.set_cloud(s["xyz"], s["normals"], s["cam_source"], s["view_points"])  # a new cloud drops the positions
+    with pytest.raises(lib.GpdbError):
+        ctx.detect(np.array([60000], np.int32))
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_sharded_entry_points_on_one_rank_equal_detect():
+    """The multi-GPU code path of the library (gpdb_comm_init -> ncclCommInitRank, gpdb_set_cloud_bcast -> ncclBroadcast,
+    gpdb_detect_sharded -> ncclAllGather) with a one-rank communicator: results bit-equal to gpdb_detect on the same samples.
+    (N > 1: tools/multi_gpu_check.py under torchrun, and bench.py's parity_check.)"""
+    s = scenes.krylon_cloud()
+    sidx = scenes.sample_indices(2, len(s["xyz"]), 300)
+    p, ctx, oc, w = make(s, 15)
+    ref = ctx.detect(sidx)
+    ctx.comm_init(lib.comm_unique_id(), 0, 1)
+    n = ctx.set_cloud_bcast(0, s["xyz"], s["normals"], s["cam_source"], s["view_points"])
+    assert n == len(s["xyz"])
+    sh = ctx.detect_sharded(sidx)
+    assert np.array_equal(sh["pose_flags"], ref["pose_flags"])
+    assert np.array_equal(sh["pose_scores"].view(np.uint32), ref["pose_scores"].view(np.uint32))
+    assert sh["n_candidates"] == ref["n_candidates"] == sh["n_total_candidates"]
+    assert sh["candidates"].tobytes() == ref["candidates"].tobytes()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_result_arena_is_reused_and_outlives_the_context():
+    """Results live in pinned host arenas of the context: freed results hand the arena back (same pointers on the next call),
+    two outstanding results get distinct arenas, and a result may be freed after gpdb_destroy."""
+    import ctypes as C
+    s = scenes.krylon_cloud()
+    sidx = np.ascontiguousarray(scenes.sample_indices(2, len(s["xyz"]), 200))
+    p, ctx, oc, w = make(s, 15, chunk_samples=64)
+    r1, r2 = abi.Result(), abi.Result()
+    n1 = ctx.detect_raw(sidx, r1)
+    a1 = C.cast(r1.candidates, C.c_void_p).value
+    snap = C.string_at(r1.candidates, n1 * C.sizeof(abi.Pose))
+    n2 = ctx.detect_raw(sidx, r2)  # r1 still outstanding -> another arena
+    a2 = C.cast(r2.candidates, C.c_void_p).value
+    assert n1 == n2 > 0 and a1 != a2
+    assert C.string_at(r1.candidates, n1 * C.sizeof(abi.Pose)) == snap == C.string_at(r2.candidates, n2 * C.sizeof(abi.Pose))
+    lib.free_result(r1)
+    assert not r1.candidates
+    n3 = ctx.detect_raw(sidx, r1)
+    assert n3 == n1 and C.cast(r1.candidates, C.c_void_p).value == a1  # the freed arena is reused
+    ctx.close()
+    assert C.string_at(r2.candidates, n2 * C.sizeof(abi.Pose)) == snap  # still readable after gpdb_destroy
+    lib.free_result(r1)
+    lib.free_result(r2)

@@ -218,3 +218,34 @@ def test_rotation_set_restatements_against_scipy_and_numpy():
     L.gpdo_derived(C.byref(p2), out2.ctypes.data_as(C.c_void_p))
     assert out2[0] == 5 and out2[1] == 0.3 and out2[2] == 0.07
     assert np.allclose(out2[4:9], np.linspace(-np.pi / 2, np.pi / 2, 6)[:5], atol=2e-16)
+
+
+def test_sample_positions_extend_the_sample_indices():
+    """Cloud::setSamples (cloud.cpp:662, used by the SIS outer loop): sample indices >= N address arbitrary float64
+    positions. Positions that coincide with cloud points reproduce the index results (everything but the sample index
+    and, for 15 channels, the index-seeded shadow draws); off-cloud positions keep their float64 value in the pose."""
+    k = scenes.krylon_cloud()
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpd_b200", "weights", "lenet_3ch.npz"))
+    w = oracle.WeightPack([z[n] for n in oracle.WeightPack.NAMES])
+    p = abi.default_params(3)
+    sidx = scenes.sample_indices(1, len(k["xyz"]), 40)
+    a = oc.detect(p, w, sidx)
+    pidx = oc.set_samples(k["xyz"][sidx].astype(np.float64))
+    assert pidx[0] == len(k["xyz"]) and len(pidx) == 40
+    b = oc.detect(p, w, pidx)
+    assert np.array_equal(a["frames"], b["frames"]) and np.array_equal(a["pose_flags"], b["pose_flags"])
+    assert np.array_equal(a["pose_scores"], b["pose_scores"], equal_nan=True) and a["n_candidates"] == b["n_candidates"] > 0
+    for f in a["candidates"].dtype.names:
+        if f not in ("sample_index", "pad_"):
+            assert np.array_equal(a["candidates"][f], b["candidates"][f]), f
+    assert np.array_equal(b["candidates"]["sample_index"], pidx[b["candidates"]["sample_slot"]])
+    # positions off the cloud: the pose keeps the float64 position, the search runs at its float32 image
+    off = k["xyz"][sidx].astype(np.float64) + np.random.default_rng(0).normal(0, 1e-3, (40, 3))
+    c = oc.detect(p, w, oc.set_samples(off))
+    assert c["frame_valid"].all() and c["n_candidates"] > 0
+    assert np.array_equal(c["candidates"]["sample"], off[c["candidates"]["sample_slot"]])
+    # mixed indices in one call
+    mix = np.concatenate([sidx[:5], oc.set_samples(off)[:5]]).astype(np.int32)
+    d = oc.detect(p, w, mix)
+    assert np.array_equal(d["pose_flags"][:5], a["pose_flags"][:5]) and np.array_equal(d["pose_flags"][5:], c["pose_flags"][:5])

@@ -102,3 +102,21 @@ def test_reference_arm_prints_one_contract_line():
     out2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                           capture_output=True, text=True, timeout=60, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert out2.returncode == 0 and out2.stdout.strip() == ""
+
+
+def test_c_abi_shard_bounds_match_the_python_plumbing():
+    """gpdb_shard_bounds / gpdb_slot_bytes (the slices gpdb_detect_sharded uses inside the library; pure host arithmetic, no
+    GPU needed) against sharding.slice_bounds / slot_stride, incl. n < nranks, n = 0 and n not divisible by nranks."""
+    from gpd_b200 import lib
+    for n in (0, 1, 5, 7, 100000, 100001, 1000000, 2 ** 31 - 1):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                lo, hi, st = lib.shard_bounds(n, r, world)
+                assert (lo, hi) == sharding.slice_bounds(n, r, world)
+                assert lo == covered and hi >= lo
+                covered = hi
+                if n < 2 ** 30:
+                    assert st == sharding.slot_stride(n, world)
+            assert covered == n
+    assert lib.slot_bytes(12501, 8) == 12501 * 8 * 4 + (12501 * 8 + 15) // 16 * 16
