@@ -67,7 +67,7 @@ class Pose(C.Structure):
         ("finger_idx", C.c_int16),
         ("half_antipodal", C.c_uint8),
         ("full_antipodal", C.c_uint8),
-        ("pad_", C.c_uint8 * 2),
+        ("pad_", C.c_uint8 * 6),
     ]
 
 
@@ -87,7 +87,7 @@ POSE_DTYPE = np.dtype(
         ("finger_idx", "<i2"),
         ("half_antipodal", "u1"),
         ("full_antipodal", "u1"),
-        ("pad_", "u1", (2,)),
+        ("pad_", "u1", (6,)),
     ],
     align=True,
 )

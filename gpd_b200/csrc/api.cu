@@ -342,7 +342,7 @@ void gpdb_destroy(gpdb_ctx *ctx) {
   cudaFree(ctx->tc.b1);
   cudaFree(ctx->tc.b2);
   cudaFree(ctx->tc.b3);
-  for (int i = 0; i < 16; i++) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < 24; i++) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -785,7 +785,8 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
   memset(out, 0, sizeof(*out));
   PipeState &ps = *ctx->pipe;
   const int P = ctx->hp.P, S = ctx->hp.S, C = ctx->hp.C;
-  const size_t isz = (size_t)S * S * C;
+  const size_t isz = (size_t)S * S * C;    // one image in the cv::Mat layout (what the caller receives)
+  const size_t psz = (size_t)S * S * 16;   // one image in the device layout (16-byte pixels, see k_images)
   out->n_samples = n;
   out->poses_per_sample = P;
   if (!resident)
@@ -910,21 +911,22 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
     PIPE_CUDA(cudaEventSynchronize(ps.ev_count[b]));
     const int nc = ps.h_count[b];
     total_nc += nc;
-    uint8_t *d_img = nullptr;
+    uint8_t *d_img = nullptr;  // keep_images: the chunk's images in the cv::Mat layout
     if (with_images_and_scores && nc > 0) {
       float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)nc);
-      const int ib = keep ? nc : std::min(nc, batch_cap);
-      d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)ib);
-      if (!d_scores || !d_img) return finish(GPDB_ERR_CUDA);
+      const int ib = std::min(nc, batch_cap);
+      uint8_t *d_p16 = (uint8_t *)gpdb_scratch(ctx, 0, psz * (size_t)ib);
+      if (keep) d_img = (uint8_t *)gpdb_scratch(ctx, 16, isz * (size_t)nc);
+      if (!d_scores || !d_p16 || (keep && !d_img)) return finish(GPDB_ERR_CUDA);
       if (keep && ci > 0) PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ps.ev_copied[b ^ 1], 0));  // d_img is being read
       for (int b0 = 0; b0 < nc; b0 += batch_cap) {
         const int bn = std::min(batch_cap, nc - b0);
-        uint8_t *dst = keep ? d_img + isz * (size_t)b0 : d_img;
         cudaEvent_t t2 = gpdb_st_begin(ctx);
-        PIPE_TRY(geo_images(ctx, d_cand[b] + b0, bn, dst));
+        PIPE_TRY(geo_images(ctx, d_cand[b] + b0, bn, d_p16));
+        if (keep) PIPE_TRY(geo_p16_to_hwc(ctx, d_p16, bn, d_img + isz * (size_t)b0));
         gpdb_st_end(ctx, 2, t2);
         cudaEvent_t t3 = gpdb_st_begin(ctx);
-        PIPE_TRY(lenet_forward(ctx, dst, bn, d_scores + b0, nullptr));
+        PIPE_TRY(lenet_forward(ctx, d_p16, bn, d_scores + b0, nullptr));
         gpdb_st_end(ctx, 3, t3);
       }
       PIPE_TRY(geo_scatter_scores(ctx, d_cand[b], d_scores, nc, c0 + slot_base, P, d_pscores + (size_t)c0 * P, d_cand[b]));
@@ -1102,15 +1104,17 @@ int gpdb_images(gpdb_ctx *ctx, const gpdb_pose *poses, int32_t n, uint8_t *image
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_images: bad arguments");
     return GPDB_ERR_INVALID;
   }
-  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C;
+  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C, psz = (size_t)ctx->hp.S * ctx->hp.S * 16;
   const int batch = 8192;
   for (int b0 = 0; b0 < n; b0 += batch) {
     const int bn = std::min(batch, n - b0);
     gpdb_pose *d_cand = (gpdb_pose *)gpdb_scratch(ctx, 13, sizeof(gpdb_pose) * (size_t)bn);
-    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)bn);
-    if (!d_cand || !d_img) return GPDB_ERR_CUDA;
+    uint8_t *d_p16 = (uint8_t *)gpdb_scratch(ctx, 0, psz * (size_t)bn);
+    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 16, isz * (size_t)bn);
+    if (!d_cand || !d_p16 || !d_img) return GPDB_ERR_CUDA;
     CUDA_TRY(cudaMemcpyAsync(d_cand, poses + b0, sizeof(gpdb_pose) * (size_t)bn, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = geo_images(ctx, d_cand, bn, d_img)) != GPDB_OK) return rc;
+    if ((rc = geo_images(ctx, d_cand, bn, d_p16)) != GPDB_OK) return rc;
+    if ((rc = geo_p16_to_hwc(ctx, d_p16, bn, d_img)) != GPDB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(images_out + isz * (size_t)b0, d_img, isz * (size_t)bn, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
@@ -1125,16 +1129,18 @@ int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n, float *sc
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_classify: bad arguments");
     return GPDB_ERR_INVALID;
   }
-  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C;
+  const size_t isz = (size_t)ctx->hp.S * ctx->hp.S * ctx->hp.C, psz = (size_t)ctx->hp.S * ctx->hp.S * 16;
   const int batch = ctx->prm.batch_size > 0 ? ctx->prm.batch_size : 8192;
   for (int b0 = 0; b0 < n; b0 += batch) {
     const int bn = std::min(batch, n - b0);
-    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 0, isz * (size_t)bn);
+    uint8_t *d_img = (uint8_t *)gpdb_scratch(ctx, 16, isz * (size_t)bn);
+    uint8_t *d_p16 = (uint8_t *)gpdb_scratch(ctx, 0, psz * (size_t)bn);
     float *d_scores = (float *)gpdb_scratch(ctx, 15, sizeof(float) * (size_t)bn * 3);
-    if (!d_img || !d_scores) return GPDB_ERR_CUDA;
+    if (!d_img || !d_p16 || !d_scores) return GPDB_ERR_CUDA;
     float *d_logits = d_scores + bn;
     CUDA_TRY(cudaMemcpyAsync(d_img, images_hwc + isz * (size_t)b0, isz * (size_t)bn, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = lenet_forward(ctx, d_img, bn, d_scores, d_logits)) != GPDB_OK) return rc;
+    if ((rc = geo_hwc_to_p16(ctx, d_img, bn, d_p16)) != GPDB_OK) return rc;  // cv::Mat bytes -> 16-byte pixels
+    if ((rc = lenet_forward(ctx, d_p16, bn, d_scores, d_logits)) != GPDB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(scores_out + b0, d_scores, sizeof(float) * (size_t)bn, cudaMemcpyDeviceToHost, ctx->stream));
     if (logits_out)
       CUDA_TRY(cudaMemcpyAsync(logits_out + 2 * (size_t)b0, d_logits, sizeof(float) * 2 * (size_t)bn,

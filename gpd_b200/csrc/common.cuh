@@ -134,8 +134,8 @@ struct gpdb_ctx {
   LenetWeights w;
   LenetTc tc;
   // scratch (grown on demand)
-  void *scratch[16];
-  size_t scratch_sz[16];
+  void *scratch[24];
+  size_t scratch_sz[24];
   int *d_err;
   unsigned long long *d_prof;  // optional phase counters (gpdb_debug_phase_cycles), nullptr = off
   int64_t launches;
@@ -176,7 +176,10 @@ int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *
 // compacts poses with VALID|FILTERED into d_cand (in (sample,pose) order); *d_count receives the count
 int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags, int n_poses, gpdb_pose *d_cand,
                 int *d_count);
-int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images);
+// grasp images in the P16 layout: S*S pixels of 16 bytes (channels 0..C-1, zero padded) per image = conv1's operand
+int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16);
+int geo_p16_to_hwc(gpdb_ctx *ctx, const uint8_t *d_p16, int n, uint8_t *d_hwc);  // -> cv::Mat layout (C bytes per pixel)
+int geo_hwc_to_p16(gpdb_ctx *ctx, const uint8_t *d_hwc, int n, uint8_t *d_p16);
 int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
                        float *d_pose_scores, gpdb_pose *d_cand_out);
 

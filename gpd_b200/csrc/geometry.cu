@@ -867,7 +867,23 @@ __global__ void k_gather_poses(const gpdb_pose *cand, const int *order, int k, g
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_images
+// k_images (round 2): one CTA per grasp image.
+//
+// Output stage. The reference post-processes every channel group as cv::dilate(3x3) -> cv::normalize(NORM_MINMAX over the
+// group's channels) -> convertTo(CV_8U, 255) (image_strategy.cpp:145-153,179-187,222-230). The affine map + rounding is
+// monotone non-decreasing, so it commutes with the max filter: the kernel quantises the OCCUPIED cells only (a few
+// hundred per projection) into uint8 planes in shared memory and dilates the bytes afterwards with packed 4-pixel SIMD
+// (__vmaxu4), while assembling the pixels. What the normalisation needs from the dilated float image is its max (= the
+// max over the occupied cells: dilation moves maxima, it does not change them) and its min, which is 0 whenever the
+// image has an all-empty 3x3 window (every value is >= 0 and the background is 0); the occupancy bitmap decides that
+// with a few word operations. Images without such a window (fully covered: very dense clouds) take a general path that
+// evaluates the min over the dilated float image explicitly (points_minmax_general / dilated_min), so the result is
+// the reference's for every input.
+//
+// Pixel layout written to HBM ("P16"): one 16-byte group per pixel = channels 0..C-1 in the reference's order, bytes
+// C..15 zero, pixels row-major — exactly the K-chunk the tcgen05 conv1 reads (lenet_tc.cu), so the classifier
+// bulk-copies an image straight into its operand plane; k_p16_to_hwc produces the cv::Mat layout for callers that
+// want the images themselves (gpdb_images, keep_images).
 // ------------------------------------------------------------------------------------------------
 struct ImgSmem {
   SegScan<NT_IMG> seg;
@@ -876,28 +892,20 @@ struct ImgSmem {
   double center[3];
   double sv[GPDB_MAX_CAMERAS][3];
   double svh[GPDB_MAX_CAMERAS][3];
+  unsigned long long occ[3][64];  // occupancy of the image rows (bit = column), per projection
   int cam_or;
   int n_img;
   int box_n;
   int wl_n;
+  int covered;                    // bit pj: projection pj has NO all-empty 3x3 window (general min path)
   int bm_org[3], bm_dims[3];
-  float fred[NT_IMG / 32][2];
-  float a, b;
-  float smax;
+  float fred[NT_IMG / 32][4];
 };
 
 __device__ __forceinline__ bool in_image_box(const DevParams &P, const gpdb_pose &h, double x, double y, double z) {
   const double half_od = P.vol_w / 2.0;
   return (x > h.bottom) && (x < h.bottom + P.vol_d) && (y > h.center - half_od) && (y < h.center + half_od) &&
          (z > -1.0 * P.vol_h) && (z < P.vol_h);
-}
-// transformPointsToUnitImage (image_strategy.cpp:72-90)
-__device__ __forceinline__ void unit_coords(const DevParams &P, const gpdb_pose &h, double x, double y, double z,
-                                            double &u0, double &u1, double &u2) {
-  const double half_od = P.vol_w / 2.0, double_height = 2.0 * P.vol_h;
-  u0 = (x - h.bottom) / P.vol_d;
-  u1 = (y - (h.center - half_od)) / P.vol_w;
-  u2 = (z + P.vol_h) / double_height;
 }
 // unit coordinate + cell of one axis without the two float64 divisions of the reference formulas
 // ((v - lo) / extent, floor(u / (1.0 / S))) in the common case: a reciprocal multiply gives u to ~2 ulp, and the cell is
@@ -914,105 +922,81 @@ __device__ __forceinline__ void unit_axis(double v, double lo, double extent, do
   }
   cell = min((int)fq, S - 1);
 }
-// findCellIndices (image_strategy.cpp:92-102)
-__device__ __forceinline__ int unit_cell(double u, int S) {
-  double cellsize = 1.0 / (double)S;
-  return min((int)floor(u / cellsize), S - 1);
-}
 __device__ __forceinline__ unsigned unit_q32(double u) {
   double t = u * 4294967296.0;
   t = fmin(fmax(t, 0.0), 4294967295.0);
   return (unsigned)t;
 }
 
-// block-wide min/max of floats
+// block-wide reduction of up to four floats with max (use negated values for min). Contains two barriers.
+template <int NT, int NV>
+__device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[4]) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int i = 0; i < NV; i++) red[threadIdx.x >> 5][i] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = red[0][i];
+  for (int w = 1; w < NT / 32; w++)
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = fmaxf(v[i], red[w][i]);
+}
+
+// cv::normalize(NORM_MINMAX, 0..1) + convertTo(CV_8U, 255) of one value, as OpenCV evaluates it: scale / shift in double,
+// cast to float, one fused multiply-add, round-half-even, saturate.
+struct Quant {
+  float a, b;
+  __device__ __forceinline__ Quant(float mn, float mx) {
+    const double smin = (double)mn, smax = (double)mx;
+    const double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
+    const double shift = 0.0 - smin * scale;
+    a = (float)scale;
+    b = (float)shift;
+  }
+  __device__ __forceinline__ unsigned operator()(float v) const {
+    const float t = fmaf(v, a, b);
+    const int q = __float2int_rn(t * 255.0f);
+    return (unsigned)min(max(q, 0), 255);
+  }
+};
+
+// true when the S x S occupancy (rows = 64-bit words) has NO all-empty 3x3 window; one warp, result on every lane
+__device__ __forceinline__ bool fully_covered(const unsigned long long *occ, int S) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long mask = S >= 64 ? ~0ull : ((1ull << S) - 1ull);
+  bool empty = false;
+  for (int r = lane; r < S; r += 32) {
+    unsigned long long o = occ[r];
+    if (r > 0) o |= occ[r - 1];
+    if (r + 1 < S) o |= occ[r + 1];
+    const unsigned long long d = (o | (o << 1) | (o >> 1)) & mask;
+    empty = empty || (d != mask);
+  }
+  return !__any_sync(0xffffffffu, empty);
+}
+
+// min over the 3x3-dilated (border ignored) image of channel plane F[SS] (float, row-major): general path only
 template <int NT>
-__device__ __forceinline__ void block_minmax(float &mn, float &mx, float (*red)[2]) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+__device__ __noinline__ float dilated_min(const float *F, int S) {
+  float mn = FLT_MAX;
+  for (int pix = threadIdx.x; pix < S * S; pix += NT) {
+    const int r = pix / S, c = pix - r * S;
+    float m = -FLT_MAX;
+    for (int dr = -1; dr <= 1; dr++)
+      for (int dc = -1; dc <= 1; dc++) {
+        const int rr = r + dr, cc = c + dc;
+        if (rr >= 0 && rr < S && cc >= 0 && cc < S) m = fmaxf(m, F[rr * S + cc]);
+      }
+    mn = fminf(mn, m);
   }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
-    red[threadIdx.x >> 5][0] = mn;
-    red[threadIdx.x >> 5][1] = mx;
-  }
-  __syncthreads();
-  mn = red[0][0];
-  mx = red[0][1];
-  for (int w = 1; w < NT / 32; w++) {
-    mn = fminf(mn, red[w][0]);
-    mx = fmaxf(mx, red[w][1]);
-  }
+  return mn;
 }
 
-// cv::dilate(3x3 rect, border ignored) -> cv::normalize(NORM_MINMAX over all channels) ->
-// convertTo(CV_8U, 255) of a CH-channel float image `src` (HWC, SxS), written into channels
-// [choff, choff+CH) of the C-channel HWC uint8 image (image_strategy.cpp:145-153,179-187,222-230).
-template <int CH>
-__device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int choff, ImgSmem &sm) {
-  // separable 3x3 max: one thread owns an 8-row strip of one column; the dilated values stay in registers
-  // between the min/max reduction and the quantisation (the image is read once).
-  const int strips = (S + 7) >> 3;
-  const bool active = (int)threadIdx.x < S * strips;
-  const int c = threadIdx.x % S, r0 = (threadIdx.x / S) << 3;
-  float m[8][CH];
-  float mn = FLT_MAX, mx = -FLT_MAX;
-  if (active) {
-    const int cl = max(c - 1, 0), cr = min(c + 1, S - 1);
-    float h0[CH], h1[CH], h2[CH];  // horizontal maxima of rows r-1, r, r+1 (sliding)
-    auto hrow = [&](int rr, float *h) {
-      if (rr < 0 || rr >= S) {
-#pragma unroll
-        for (int k = 0; k < CH; k++) h[k] = -FLT_MAX;
-      } else {
-        const float *p = src + (size_t)rr * S * CH;
-#pragma unroll
-        for (int k = 0; k < CH; k++) h[k] = fmaxf(fmaxf(p[cl * CH + k], p[c * CH + k]), p[cr * CH + k]);
-      }
-    };
-    hrow(r0 - 1, h0);
-    hrow(r0, h1);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      hrow(r0 + i + 1, h2);
-#pragma unroll
-      for (int k = 0; k < CH; k++) {
-        m[i][k] = fmaxf(fmaxf(h0[k], h1[k]), h2[k]);
-        if (r0 + i < S) {
-          mn = fminf(mn, m[i][k]);
-          mx = fmaxf(mx, m[i][k]);
-        }
-        h0[k] = h1[k];
-        h1[k] = h2[k];
-      }
-    }
-  }
-  block_minmax<NT_IMG>(mn, mx, sm.fred);
-  double smin = (double)mn, smax = (double)mx;
-  double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
-  double shift = 0.0 - smin * scale;
-  const float a = (float)scale, b = (float)shift;
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (r0 + i < S) {
-        uint8_t *o = gimg + (size_t)((r0 + i) * S + c) * C + choff;
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-          float v = fmaf(m[i][k], a, b);
-          int q = __float2int_rn(v * 255.0f);
-          o[k] = (uint8_t)min(max(q, 0), 255);  // shared-memory staging of the HWC image
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// dynamic smem layout (bytes): tiles 3 * 8*S*S | box list: keys 8*CAP, q 3*4*CAP, cells 4*CAP, nrm 3*4*CAP
-// (the shadow bitmaps alias the box list)
 // optional phase timing (development aid, gpdb_debug_phase_cycles): thread 0 accumulates clock64() deltas
 #define PHASE(i)                                                        \
   do {                                                                  \
@@ -1023,37 +1007,34 @@ __device__ void postprocess(const float *src, int S, uint8_t *gimg, int C, int c
     }                                                                   \
   } while (0)
 
-// Residency (round 2): TWO uint64 tiles + a box list of `box_cap` entries and no staged image (the channels are written
-// straight to global memory; partial sectors merge in L2) = 57.6 KB + 36 B x box_cap: 94 KB at box_cap = 1024, so that TWO
-// CTAs share an SM (__launch_bounds__(512, 2): 64 registers). tier 0 runs every image with the small list; images whose
-// box holds more points are appended to `ovf` and re-run by tier 1 (persistent CTAs, box_cap = BOX_CAP, one CTA per SM).
-__global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
-                                                      uint8_t *images, const double *qtab, int *err, int img_off,
-                                                      unsigned long long *prof, int box_cap, int *ovf, int *ovf_count,
-                                                      int tier) {
+// dynamic shared memory: planes C x S x RS bytes (RS = S rounded up to 4) | tiles 3 x 8 S S | box list 36 B x BOX_CAP
+// (the shadow bitmaps + voxel list alias the box list; the shadow work list aliases the tiles)
+template <int S_T>
+__global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
+                                                      uint8_t *p16, const double *qtab, int *err, int plane_bytes,
+                                                      int list_bytes, unsigned long long *prof) {
   long long t_phase = 0;
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ ImgSmem sm;
-  const int S = P.S, C = P.C, SS = S * S;
-  const int BC = box_cap;
-  unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn);
+  const int S = S_T > 0 ? S_T : P.S, C = P.C, SS = S * S;
+  const int RS = (S + 3) & ~3, RW = RS >> 2, PLB = S * RS;
+  uint8_t *planes = dyn;
+  unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn + plane_bytes);
   unsigned long long *tileB = tileA + SS;
-  unsigned char *lbase = reinterpret_cast<unsigned char *>(tileB + SS);
+  unsigned long long *tileC = tileB + SS;
+  unsigned char *lbase = reinterpret_cast<unsigned char *>(tileC + SS);
   unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(lbase);
-  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BC);        // [3][CAP]
-  unsigned *bcell = bq + 3 * BC;                                  // packed 3 x 8 bit
-  float *bnrm = reinterpret_cast<float *>(bcell + BC);            // [3][CAP]
+  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BOX_CAP);   // [3][CAP]
+  unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
+  float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
-  float *nrmT = reinterpret_cast<float *>(tileA);                 // float[3*SS] over tileA and half of tileB ...
-  float *depF = nrmT + 3 * SS;                                    // ... float[SS]: the other half of tileB
   const int tid = threadIdx.x, lane = tid & 31;
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
-  const int work_n = tier == 0 ? nc : *ovf_count;
+  const bool do_nrm = C != 1, do_dep = C == 1 || C >= 12;
 
-  for (int wi = blockIdx.x; wi < work_n; wi += gridDim.x) {
-    const int b = tier == 0 ? wi : ovf[wi];
+  for (int b = blockIdx.x; b < nc; b += gridDim.x) {
     __syncthreads();
     {
       const int *src = reinterpret_cast<const int *>(cand + b);
@@ -1064,12 +1045,12 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
       sm.cam_or = 0;
       sm.n_img = 0;
       sm.box_n = 0;
+      sm.covered = 0;
     }
+    for (int k = tid; k < plane_bytes >> 4; k += NT_IMG) reinterpret_cast<uint4 *>(planes)[k] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     PHASE(1);   // image start
     const gpdb_pose &h = sm.h;
-    uint8_t *gout = images + (size_t)b * SS * C;
-    uint8_t *gimg = gout;  // channels are written straight to global memory (byte stores; sectors merge in L2)
     const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
     SegRange sr = seg_range(P, q, P.rf_img);
@@ -1105,11 +1086,11 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
         if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
         base = __shfl_sync(0xffffffffu, base, leader);
         int pos = base + __popc(mk & ((1u << lane) - 1));
-        if (inb && pos < BC) {
+        if (inb && pos < BOX_CAP) {
           bkeys[pos] = key;
           bq[pos] = __float_as_uint(p.x);  // raw coordinates, replaced by the fixed-point unit coordinates below
-          bq[BC + pos] = __float_as_uint(p.y);
-          bq[2 * BC + pos] = __float_as_uint(p.z);
+          bq[BOX_CAP + pos] = __float_as_uint(p.y);
+          bq[2 * BOX_CAP + pos] = __float_as_uint(p.z);
         }
       }
     });
@@ -1142,22 +1123,18 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
       sm.center[0] = a0 / nn;
       sm.center[1] = a1 / nn;
       sm.center[2] = a2 / nn;
-      if (sm.box_n > BC) {
-        if (tier == 0) ovf[atomicAdd(ovf_count, 1)] = b;  // re-run with the large list
-        else {
-          atomicAdd(err + 2, 1);
-          sm.box_n = BC;
-        }
+      if (sm.box_n > BOX_CAP) {
+        atomicAdd(err + 2, 1);
+        sm.box_n = BOX_CAP;
       }
     }
     __syncthreads();
     PHASE(2);  // scan 1 + reductions done
-    if (sm.box_n > BC) continue;  // tier 0 overflow (uniform: box_n is shared); tier 1 clamped it above
     const int bn = sm.box_n;
     // dense pass over the box points: hand-frame coordinates -> unit cube, cell indices, |R^T n| (all lanes busy)
     for (int k = tid; k < bn; k += NT_IMG) {
-      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BC + k]),
-                   pz = (double)__uint_as_float(bq[2 * BC + k]);
+      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP + k]),
+                   pz = (double)__uint_as_float(bq[2 * BOX_CAP + k]);
       double x, y, z, u0, u1, u2;
       int c0, c1, c2;
       to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], x, y, z);
@@ -1165,15 +1142,15 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
       unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
       unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
       bq[k] = unit_q32(u0);
-      bq[BC + k] = unit_q32(u1);
-      bq[2 * BC + k] = unit_q32(u2);
+      bq[BOX_CAP + k] = unit_q32(u1);
+      bq[2 * BOX_CAP + k] = unit_q32(u2);
       bcell[k] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
       const double *nn = cl.nrm + 3 * (size_t)(unsigned)(bkeys[k] & 0xffffffffull);
       double n0, n1, n2;
       to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
       bnrm[k] = (float)fabs(n0);
-      bnrm[BC + k] = (float)fabs(n1);
-      bnrm[2 * BC + k] = (float)fabs(n2);
+      bnrm[BOX_CAP + k] = (float)fabs(n1);
+      bnrm[2 * BOX_CAP + k] = (float)fabs(n2);
     }
     __syncthreads();
 
@@ -1183,68 +1160,117 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
       // coordinate orders (x,y,z), (z,y,x), (z,x,y): rows cumulatively swapped {0<->2}, {1<->2}
       // (image_15_channels_strategy.cpp:57-64)
       const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
-      for (int k = tid; k < 2 * SS; k += NT_IMG) tileA[k] = 0ull;  // tileA + tileB
+      for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tileA + tileB
+      if (tid < 64) sm.occ[0][tid] = 0ull;
       __syncthreads();
       for (int k = tid; k < bn; k += NT_IMG) {
-        unsigned cc = bcell[k];
-        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
-        int pix = (S - 1 - v) * S + hcol;
+        const unsigned cc = bcell[k];
+        const int row = S - 1 - (int)((cc >> (8 * a0)) & 255), col = (cc >> (8 * a1)) & 255;
+        const int pix = row * S + col;
         atomicMax(tileA + pix, bkeys[k]);
-        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BC + k]);
+        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
+        atomicOr(&sm.occ[0][row], 1ull << col);
       }
       __syncthreads();
-      unsigned long long dreg[(MAXPIX + NT_IMG - 1) / NT_IMG];
-#pragma unroll
-      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-        int pix = tid + t * NT_IMG;
-        dreg[t] = pix < SS ? tileB[pix] : 0ull;
+      // the winner of a cell (its point with the largest key) carries the cell's values: |n| of that point, 1 - mean depth
+      auto cell_values = [&](int k, int &row, int &col, float &n0, float &n1, float &n2, float &dv) -> bool {
+        const unsigned cc = bcell[k];
+        row = S - 1 - (int)((cc >> (8 * a0)) & 255);
+        col = (cc >> (8 * a1)) & 255;
+        const int pix = row * S + col;
+        if (tileA[pix] != bkeys[k]) return false;
+        n0 = bnrm[k];
+        n1 = bnrm[BOX_CAP + k];
+        n2 = bnrm[2 * BOX_CAP + k];
+        const unsigned long long acc = tileB[pix];
+        const double mean = (double)(acc & 0xffffffffffffull) / ((double)(unsigned)(acc >> 48) * 4294967296.0);
+        const float avg = (float)mean;
+        dv = (float)(1.0 - (double)avg);
+        return true;
+      };
+      float mxv[2] = {0.0f, 0.0f};  // max of the normals group / of the depth channel (all values are >= 0)
+      for (int k = tid; k < bn; k += NT_IMG) {
+        int row, col;
+        float n0, n1, n2, dv;
+        if (cell_values(k, row, col, n0, n1, n2, dv)) {
+          mxv[0] = fmaxf(mxv[0], fmaxf(fmaxf(n0, n1), n2));
+          mxv[1] = fmaxf(mxv[1], dv);
+        }
       }
-      // winner of each cell = the box point whose key is the cell's maximum; decided HERE, while the key tile is
-      // intact, and remembered as one bit per owned box point (k = tid + j NT_IMG): the float images below overwrite
-      // both tiles
-      unsigned wmask = 0;
-      for (int k = tid, j = 0; k < bn; k += NT_IMG, j++) {
-        unsigned cc = bcell[k];
-        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
-        if (tileA[(S - 1 - v) * S + hcol] == bkeys[k]) wmask |= 1u << j;
+      if (tid < 32) {
+        const bool cov = fully_covered(sm.occ[0], S);
+        if (cov && tid == 0) sm.covered |= 1 << pj;
       }
-      __syncthreads();
+      block_max<NT_IMG, 2>(mxv, sm.fred);
+      float mnv[2] = {0.0f, 0.0f};  // min over the dilated image: 0 when an all-empty 3x3 window exists
+      if ((sm.covered >> pj) & 1) {
+        // general path (no empty window): materialise the four float channel images over the (now dead) tiles and take the
+        // min of their dilations. Winners keep their values in registers across the rewrite of the tiles.
+        constexpr int JMAX = (BOX_CAP + NT_IMG - 1) / NT_IMG;
+        float wv[JMAX][4];
+        int wpix[JMAX];
 #pragma unroll
-      for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-        int pix = tid + t * NT_IMG;
-        if (pix < SS) {
-          nrmT[pix * 3] = 0.0f;
-          nrmT[pix * 3 + 1] = 0.0f;
-          nrmT[pix * 3 + 2] = 0.0f;
-          unsigned long long acc = dreg[t];
-          unsigned cntc = (unsigned)(acc >> 48);
-          float val = 0.0f;
-          if (cntc) {
-            double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
-            float avg = (float)mean;
-            val = (float)(1.0 - (double)avg);
+        for (int j = 0; j < JMAX; j++) {
+          const int k = tid + j * NT_IMG;
+          wpix[j] = -1;
+          int row, col;
+          if (k < bn && cell_values(k, row, col, wv[j][0], wv[j][1], wv[j][2], wv[j][3])) wpix[j] = row * S + col;
+        }
+        __syncthreads();
+        float *F = reinterpret_cast<float *>(tileA);  // 4 x SS floats = tileA + tileB
+        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < JMAX; j++)
+          if (wpix[j] >= 0)
+#pragma unroll
+            for (int c = 0; c < 4; c++) F[c * SS + wpix[j]] = wv[j][c];
+        __syncthreads();
+        float neg[2];
+        neg[0] = -fminf(fminf(dilated_min<NT_IMG>(F, S), dilated_min<NT_IMG>(F + SS, S)), dilated_min<NT_IMG>(F + 2 * SS, S));
+        neg[1] = -dilated_min<NT_IMG>(F + 3 * SS, S);
+        block_max<NT_IMG, 2>(neg, sm.fred);
+        mnv[0] = -neg[0];
+        mnv[1] = -neg[1];
+        const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
+        const unsigned bg_n = qn(0.0f) * 0x01010101u, bg_d = qd(0.0f) * 0x01010101u;  // background = quantised 0
+        const int cb = (C == 1) ? 0 : pj * per;
+        for (int k = tid; k < (PLB >> 2); k += NT_IMG) {
+          if (do_nrm)
+#pragma unroll
+            for (int c = 0; c < 3; c++) reinterpret_cast<unsigned *>(planes + (size_t)(cb + c) * PLB)[k] = bg_n;
+          if (do_dep) reinterpret_cast<unsigned *>(planes + (size_t)(cb + (C == 1 ? 0 : 3)) * PLB)[k] = bg_d;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < JMAX; j++)
+          if (wpix[j] >= 0) {
+            const int row = wpix[j] / S, col = wpix[j] - row * S, o = row * RS + col;
+            if (do_nrm) {
+              planes[(size_t)(cb + 0) * PLB + o] = (uint8_t)qn(wv[j][0]);
+              planes[(size_t)(cb + 1) * PLB + o] = (uint8_t)qn(wv[j][1]);
+              planes[(size_t)(cb + 2) * PLB + o] = (uint8_t)qn(wv[j][2]);
+            }
+            if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(wv[j][3]);
           }
-          depF[pix] = val;
-        }
-      }
-      __syncthreads();
-      for (int k = tid, j = 0; k < bn; k += NT_IMG, j++) {
-        unsigned cc = bcell[k];
-        int v = (cc >> (8 * a0)) & 255, hcol = (cc >> (8 * a1)) & 255;
-        int pix = (S - 1 - v) * S + hcol;
-        if ((wmask >> j) & 1) {
-          nrmT[pix * 3] = bnrm[k];
-          nrmT[pix * 3 + 1] = bnrm[BC + k];
-          nrmT[pix * 3 + 2] = bnrm[2 * BC + k];
-        }
-      }
-      __syncthreads();
-      if (C == 1) {
-        postprocess<1>(depF, S, gimg, C, 0, sm);
       } else {
-        postprocess<3>(nrmT, S, gimg, C, pj * per, sm);
-        if (C >= 12) postprocess<1>(depF, S, gimg, C, pj * per + 3, sm);
+        const Quant qn(0.0f, mxv[0]), qd(0.0f, mxv[1]);
+        const int cb = (C == 1) ? 0 : pj * per;
+        for (int k = tid; k < bn; k += NT_IMG) {
+          int row, col;
+          float n0, n1, n2, dv;
+          if (cell_values(k, row, col, n0, n1, n2, dv)) {
+            const int o = row * RS + col;
+            if (do_nrm) {
+              planes[(size_t)(cb + 0) * PLB + o] = (uint8_t)qn(n0);
+              planes[(size_t)(cb + 1) * PLB + o] = (uint8_t)qn(n1);
+              planes[(size_t)(cb + 2) * PLB + o] = (uint8_t)qn(n2);
+            }
+            if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(dv);
+          }
+        }
       }
+      __syncthreads();
     }
 
     PHASE(3);  // points phase (3 projections) done
@@ -1287,6 +1313,7 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
         to_frame(h.frame, sm.sv[tid][0], sm.sv[tid][1], sm.sv[tid][2], sm.svh[tid][0], sm.svh[tid][1], sm.svh[tid][2]);
       }
       for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
+      if (tid < 3 * 64) sm.occ[tid >> 6][tid & 63] = 0ull;
       __syncthreads();
       PHASE(4);  // shadow setup done
       const int o0 = sm.bm_org[0], o1 = sm.bm_org[1], o2 = sm.bm_org[2];
@@ -1306,7 +1333,7 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
       // region; (2) the (point, draw) pairs are spread evenly over all threads — draw t of a point comes from
       // the closed-form LCG skip-ahead seed_t = A^(t+1) seed_0 + C_(t+1) (mod 2^32).
       float4 *wl = reinterpret_cast<float4 *>(tileA);
-      const int WL_CAP = (2 * SS * 8) / 20;  // work list over the two tiles
+      const int WL_CAP = (3 * SS * 8) / 20;
       unsigned *wrange = reinterpret_cast<unsigned *>(wl + WL_CAP);
       // image box in the hand frame, widened by voxel truncation (<= 0.003 sqrt 3) + jitter (<= gmax 0.0009 sqrt 3)
       const double wm = 0.0105;
@@ -1363,42 +1390,42 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
           if (!in) return;
           float d = l2_simple(q, p.x, p.y, p.z);
           if (!(d < P.r2_img)) return;
-            const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-            // conservative cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame)
-            // widened by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG
-            // value falls in [r0, r1] can produce a voxel point inside the box. float32 is enough here: its rounding
-            // (~1e-7 of coordinates < 0.2 m, 3e-7 of t) is covered by the extra 1e-5 of box margin and by the +-1 of
-            // slack on r0 / r1 (1 / 32767 = 3e-5); the draws themselves are evaluated in the reference's float64.
-            const float wx = p.x - fsx, wy = p.y - fsy, wz = p.z - fsz;
-            const float o3[3] = {fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz)), fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz)),
-                                 fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz))};
-            float tmin = 0.0f, tmax = 1.0f;
-            bool hit = true;
+          const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+          // conservative cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame)
+          // widened by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG
+          // value falls in [r0, r1] can produce a voxel point inside the box. float32 is enough here: its rounding
+          // (~1e-7 of coordinates < 0.2 m, 3e-7 of t) is covered by the extra 1e-5 of box margin and by the +-1 of
+          // slack on r0 / r1 (1 / 32767 = 3e-5); the draws themselves are evaluated in the reference's float64.
+          const float wx = p.x - fsx, wy = p.y - fsy, wz = p.z - fsz;
+          const float o3[3] = {fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz)), fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz)),
+                               fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz))};
+          float tmin = 0.0f, tmax = 1.0f;
+          bool hit = true;
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-              if (cull_par[a]) {  // segment (numerically) parallel to the slab: inside or outside for every u
-                hit = hit && o3[a] >= cull_lo[a] && o3[a] <= cull_hi[a];
-              } else {
-                const float t1 = (cull_lo[a] - o3[a]) * cull_inv[a], t2 = (cull_hi[a] - o3[a]) * cull_inv[a];
-                tmin = fmaxf(tmin, fminf(t1, t2));
-                tmax = fminf(tmax, fmaxf(t1, t2));
-              }
+          for (int a = 0; a < 3; a++) {
+            if (cull_par[a]) {  // segment (numerically) parallel to the slab: inside or outside for every u
+              hit = hit && o3[a] >= cull_lo[a] && o3[a] <= cull_hi[a];
+            } else {
+              const float t1 = (cull_lo[a] - o3[a]) * cull_inv[a], t2 = (cull_hi[a] - o3[a]) * cull_inv[a];
+              tmin = fmaxf(tmin, fminf(t1, t2));
+              tmax = fminf(tmax, fmaxf(t1, t2));
             }
-            if (!hit || tmin > tmax) return;
-            const int r0 = max((int)floorf(tmin * 32767.0f) - 1, 0), r1 = min((int)ceilf(tmax * 32767.0f) + 1, 32767);
-            unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
-            int pos = atomicAdd(&sm.wl_n, 1);
-            if (pos < WL_CAP) {
-              wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
-              wrange[pos] = (unsigned)r0 | ((unsigned)r1 << 16);
-            } else {  // work list full (very dense neighbourhood): cast this point's draws in place
-              unsigned seed = seed0;
-              for (int t = 0; t < P.nsp; t++) {
-                int r = (int)gpdb_fastrand(&seed);
-                if (r >= r0 && r <= r1) cast_draw(px, py, pz, seed, k, bm);
-              }
+          }
+          if (!hit || tmin > tmax) return;
+          const int r0 = max((int)floorf(tmin * 32767.0f) - 1, 0), r1 = min((int)ceilf(tmax * 32767.0f) + 1, 32767);
+          unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
+          int pos = atomicAdd(&sm.wl_n, 1);
+          if (pos < WL_CAP) {
+            wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
+            wrange[pos] = (unsigned)r0 | ((unsigned)r1 << 16);
+          } else {  // work list full (very dense neighbourhood): cast this point's draws in place
+            unsigned seed = seed0;
+            for (int t = 0; t < P.nsp; t++) {
+              int r = (int)gpdb_fastrand(&seed);
+              if (r >= r0 && r <= r1) cast_draw(px, py, pz, seed, k, bm);
             }
-                  });
+          }
+        });
         __syncthreads();
         const int nw = min(sm.wl_n, WL_CAP);
         if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
@@ -1434,13 +1461,14 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
           bitmap[wd] = acc;
         }
       }
+      for (int k = tid; k < (3 * SS) >> 1; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
       // compact the set bits into a list (behind bitmap 0, in the dead box-list region) so that the per-voxel work
       // is spread evenly: shadow voxels are spatially clustered, a thread-per-word loop would be badly unbalanced
       const int nbits = 64 * d1 * d2;
       unsigned *blist = bitmap + bm_words;
-      const int BL_CAP = (img_off - 2 * SS * 8) / 4 - bm_words;
-      // the sums of projections [pj_lo, pj_hi) go to tiles 0 .. pj_hi - pj_lo - 1
-      auto eval_voxel = [&](unsigned packed, int pj_lo, int pj_hi) {  // b0 | b1 << 8 | b2 << 16
+      const int BL_CAP = list_bytes / 4 - bm_words;
+      auto eval_voxel = [&](unsigned packed) {  // b0 | b1 << 8 | b2 << 16
         int b0 = packed & 255, b1 = (packed >> 8) & 255, b2 = packed >> 16;
         double x, y, z;
         if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) return;
@@ -1451,96 +1479,169 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images(const DevParams *Pp, DevCl
         unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u[2], cellv[2]);
 #pragma unroll
         for (int pj = 0; pj < 3; pj++) {
-          if (pj < pj_lo || pj >= pj_hi) continue;
           const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
-          int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
-          atomicAdd(tileA + (size_t)(pj - pj_lo) * SS + pix, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
+          const int row = S - 1 - cellv[a0], col = cellv[a1];
+          atomicAdd(tileA + (size_t)pj * SS + row * S + col, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
+          atomicOr(&sm.occ[pj][row], 1ull << col);
         }
       };
-      // Two tiles hold the per-cell sums of two projections at a time: pass 0 = projections 0 and 1, pass 1 = projection 2
-      // (the voxel list is compacted once; it is re-walked, and voxels that did not fit the list re-evaluated in place)
-      int nset_all = 0;
-      for (int pass = 0; pass < 2; pass++) {
-        const int pj_lo = pass == 0 ? 0 : 2, pj_hi = pass == 0 ? 2 : 3;
-        for (int k = tid; k < 2 * SS; k += NT_IMG) tileA[k] = 0ull;
-        const bool recompact = pass == 0 || nset_all > BL_CAP;
-        if (recompact && tid == 0) sm.wl_n = 0;
-        __syncthreads();
-        if (recompact) {
-          for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
-            const int wd = wd0 + tid;
-            unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
-            int cntb = __popc(bits);
-            int incl = cntb;  // warp-aggregated reservation of list slots
+      if (tid == 0) sm.wl_n = 0;
+      __syncthreads();
+      for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
+        const int wd = wd0 + tid;
+        unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
+        int cntb = __popc(bits);
+        int incl = cntb;  // warp-aggregated reservation of list slots
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              int v = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += v;
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
+        if (lane == 31 && total) base = atomicAdd(&sm.wl_n, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cntb;
+        const int rowi = wd >> 1;  // (b2 * d1 + b1)
+        const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
+        while (bits) {
+          int bi = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (pos < BL_CAP) blist[pos] = hi | (unsigned)bi;
+          else eval_voxel(hi | (unsigned)bi);  // list full: evaluate in place
+          pos++;
+        }
+      }
+      __syncthreads();
+      const int nset = min(sm.wl_n, BL_CAP);
+      if (prof && tid == 0) {
+        atomicAdd(prof + 11, (unsigned long long)sm.wl_n);
+        atomicAdd(prof + 12, (unsigned long long)bn);
+        atomicAdd(prof + 13, (unsigned long long)sm.n_img);
+      }
+      for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i]);
+      __syncthreads();
+      PHASE(6);  // S2 bitmap pass done
+      // createShadowImage (image_strategy.cpp:193-233): mean per cell, value = max over occupied - mean on occupied cells
+      if (tid < 32) {
+        int cov = 0;
+        for (int pj = 0; pj < 3; pj++)
+          if (fully_covered(sm.occ[pj], S)) cov |= 1 << pj;
+        if (tid == 0) sm.covered = cov;
+      }
+      constexpr int PIXT = (MAXPIX + NT_IMG - 1) / NT_IMG;
+      for (int pj = 0; pj < 3; pj++) {
+        const unsigned long long *tile = tileA + (size_t)pj * SS;
+        uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
+        float avgr[PIXT];
+        unsigned occm = 0;
+        float mm[2] = {-FLT_MAX, -FLT_MAX};  // max avg, -(min avg) over the occupied cells
+#pragma unroll
+        for (int t = 0; t < PIXT; t++) {
+          const int pix = tid + t * NT_IMG;
+          avgr[t] = 0.0f;
+          if (pix < SS) {
+            const unsigned long long acc = tile[pix];
+            const unsigned cntc = (unsigned)(acc >> 48);
+            if (cntc) {
+              const double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
+              avgr[t] = (float)mean;
+              occm |= 1u << t;
+              mm[0] = fmaxf(mm[0], avgr[t]);
+              mm[1] = fmaxf(mm[1], -avgr[t]);
             }
-            int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
-            if (lane == 31 && total) base = atomicAdd(&sm.wl_n, total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            int pos = base + incl - cntb;
-            const int rowi = wd >> 1;  // (b2 * d1 + b1)
-            const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
-            while (bits) {
-              int bi = __ffs(bits) - 1;
-              bits &= bits - 1;
-              if (pass == 0 && pos < BL_CAP) blist[pos] = hi | (unsigned)bi;
-              else eval_voxel(hi | (unsigned)bi, pj_lo, pj_hi);  // list full (pass 0) / list not reproducible (pass 1): in place
-              pos++;
-            }
+          }
+        }
+        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers also order the sm.covered write above)
+        const bool any = mm[0] != -FLT_MAX;
+        const float maxf = any ? mm[0] : 0.0f;
+        const float vmax = any ? maxf - (-mm[1]) : 0.0f;  // largest cell value = max avg - min avg
+        float vmin = 0.0f;
+        if ((sm.covered >> pj) & 1) {  // general path: min over the dilated float image
+          float *srcF = reinterpret_cast<float *>(tileA + (size_t)pj * SS);
+          __syncthreads();
+#pragma unroll
+          for (int t = 0; t < PIXT; t++) {
+            const int pix = tid + t * NT_IMG;
+            if (pix < SS) srcF[pix] = ((occm >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
           }
           __syncthreads();
-          nset_all = sm.wl_n;
+          float neg[1] = {-dilated_min<NT_IMG>(srcF, S)};
+          block_max<NT_IMG, 1>(neg, sm.fred);
+          vmin = -neg[0];
         }
-        const int nset = (pass == 1 && recompact) ? 0 : min(nset_all, BL_CAP);
-        if (pass == 0 && prof && tid == 0) {
-          atomicAdd(prof + 11, (unsigned long long)nset_all);
-          atomicAdd(prof + 12, (unsigned long long)bn);
-          atomicAdd(prof + 13, (unsigned long long)sm.n_img);
-        }
-        for (int i = tid; i < nset; i += NT_IMG) eval_voxel(blist[i], pj_lo, pj_hi);
-        __syncthreads();
-        if (pass == 0) PHASE(6);  // S2 bitmap pass (first pass) done
-        // createShadowImage (image_strategy.cpp:193-233): mean per cell, max over occupied - mean
-        for (int pj = pj_lo; pj < pj_hi; pj++) {
-          unsigned long long *tile = tileA + (size_t)(pj - pj_lo) * SS;
-          float *srcF = reinterpret_cast<float *>(tile);
-          float avgr[(MAXPIX + NT_IMG - 1) / NT_IMG];
-          unsigned occ = 0;
-          float mn = FLT_MAX, mx = -FLT_MAX;
+        const Quant qs(vmin, vmax);
+        const unsigned bg = qs(0.0f);
 #pragma unroll
-          for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-            int pix = tid + t * NT_IMG;
-            avgr[t] = 0.0f;
-            if (pix < SS) {
-              unsigned long long acc = tile[pix];
-              unsigned cntc = (unsigned)(acc >> 48);
-              if (cntc) {
-                double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
-                avgr[t] = (float)mean;
-                occ |= 1u << t;
-                mx = fmaxf(mx, avgr[t]);
-              }
-            }
+        for (int t = 0; t < PIXT; t++) {
+          const int pix = tid + t * NT_IMG;
+          if (pix < SS) {
+            const int row = pix / S, col = pix - row * S;
+            const bool oc = (occm >> t) & 1;
+            if (oc || bg) plane[row * RS + col] = (uint8_t)(oc ? qs(maxf - avgr[t]) : bg);
           }
-          block_minmax<NT_IMG>(mn, mx, sm.fred);  // contains the barrier between reads and writes
-          const float maxf = (mx == -FLT_MAX) ? 0.0f : mx;
-#pragma unroll
-          for (int t = 0; t < (MAXPIX + NT_IMG - 1) / NT_IMG; t++) {
-            int pix = tid + t * NT_IMG;
-            if (pix < SS) srcF[pix] = ((occ >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
-          }
-          __syncthreads();
-          postprocess<1>(srcF, S, gimg, C, pj * 5 + 4, sm);
         }
       }
     }
     __syncthreads();
     PHASE(7);  // shadow images done
-    PHASE(8);  // (no flush: the channels were written straight to global memory)
+    // ---- dilate (3x3 max, border ignored) the quantised planes four pixels at a time and assemble the 16-byte pixels
+    {
+      uint4 *gout = reinterpret_cast<uint4 *>(p16) + (size_t)b * SS;
+      for (int g = tid; g < S * RW; g += NT_IMG) {
+        const int row = g / RW, c4 = g - row * RW;
+        unsigned res[16];
+#pragma unroll
+        for (int ch = 0; ch < 16; ch++) {
+          res[ch] = 0u;
+          if (ch < C) {
+            const unsigned *W = reinterpret_cast<const unsigned *>(planes + (size_t)ch * PLB) + row * RW + c4;
+            const bool up = row > 0, dn = row + 1 < S, lf = c4 > 0, rt = c4 + 1 < RW;
+            unsigned vc = W[0], vl = lf ? W[-1] : 0u, vr = rt ? W[1] : 0u;
+            if (up) {
+              vc = __vmaxu4(vc, W[-RW]);
+              if (lf) vl = __vmaxu4(vl, W[-RW - 1]);
+              if (rt) vr = __vmaxu4(vr, W[-RW + 1]);
+            }
+            if (dn) {
+              vc = __vmaxu4(vc, W[RW]);
+              if (lf) vl = __vmaxu4(vl, W[RW - 1]);
+              if (rt) vr = __vmaxu4(vr, W[RW + 1]);
+            }
+            const unsigned L = __funnelshift_l(vl, vc, 8), R = __funnelshift_r(vc, vr, 8);
+            res[ch] = __vmaxu4(vc, __vmaxu4(L, R));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (c4 * 4 + i < S) {
+            const unsigned sel = (unsigned)i | ((unsigned)(4 + i) << 4);
+            uint4 o;
+            o.x = __byte_perm(__byte_perm(res[0], res[1], sel), __byte_perm(res[2], res[3], sel), 0x5410);
+            o.y = __byte_perm(__byte_perm(res[4], res[5], sel), __byte_perm(res[6], res[7], sel), 0x5410);
+            o.z = __byte_perm(__byte_perm(res[8], res[9], sel), __byte_perm(res[10], res[11], sel), 0x5410);
+            o.w = __byte_perm(__byte_perm(res[12], res[13], sel), __byte_perm(res[14], res[15], sel), 0x5410);
+            gout[row * S + c4 * 4 + i] = o;
+          }
+        }
+      }
+    }
+    PHASE(8);  // assembled image stored
   }
+}
+
+// P16 (16-byte pixels) <-> HWC (the cv::Mat layout, C bytes per pixel)
+__global__ void k_p16_to_hwc(const uint8_t *__restrict__ p16, size_t npix, int C, uint8_t *__restrict__ hwc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one output byte per thread
+  if (i >= npix * (size_t)C) return;
+  const size_t pix = i / C;
+  hwc[i] = p16[pix * 16 + (i - pix * C)];
+}
+__global__ void k_hwc_to_p16(const uint8_t *__restrict__ hwc, size_t npix, int C, uint8_t *__restrict__ p16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one pixel per thread
+  if (i >= npix) return;
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  for (int c = 0; c < C; c++) w[c >> 2] |= (unsigned)hwc[i * C + c] << (8 * (c & 3));
+  reinterpret_cast<uint4 *>(p16)[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 }  // namespace
@@ -1672,36 +1773,46 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
   return GPDB_OK;
 }
 
-static size_t images_smem_bytes(const DevParams &hp, int box_cap) {
-  size_t tiles = (size_t)2 * 8 * hp.S * hp.S;
-  size_t list = (size_t)box_cap * (8 + 12 + 4 + 12);
-  size_t bm = (size_t)hp.K * (2 * (size_t)hp.bm_dim * hp.bm_dim) * 4;
-  // shadow phase: the bitmaps alias the box list and the compacted voxel list follows bitmap 0: leave room for ~4 k voxels
-  size_t shadow = hp.C == 15 ? std::max(bm, (size_t)(2 * (size_t)hp.bm_dim * hp.bm_dim) * 4 + 4096 * 4) : (size_t)0;
-  size_t work = tiles + std::max(list, shadow);
-  return (work + 15) / 16 * 16;
-}
-
-int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_images) {
+// `d_p16`: nc images of S*S 16-byte pixels (see k_images)
+int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
   if (nc <= 0) return GPDB_OK;
-  const int cap0 = 1024;  // tier 0: two CTAs per SM (a 3 mm cloud puts ~210, at most ~710 points into an image box)
-  const size_t smem0 = images_smem_bytes(ctx->hp, cap0), smem1 = images_smem_bytes(ctx->hp, BOX_CAP);
-  if (smem1 > 219 * 1024) {
-    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem1);
+  const DevParams &hp = ctx->hp;
+  const int S = hp.S, RS = (S + 3) & ~3;
+  const size_t plane_bytes = ((size_t)hp.C * S * RS + 15) / 16 * 16;
+  const size_t tiles = (size_t)3 * 8 * S * S;
+  const size_t bm = (size_t)hp.K * (2 * (size_t)hp.bm_dim * hp.bm_dim) * 4;
+  // shadow phase: the bitmaps alias the box list and the compacted voxel list follows them: room for >= 4 k voxels
+  const size_t list_bytes = (std::max((size_t)BOX_CAP * 36, hp.C == 15 ? bm + 4096 * 4 : (size_t)0) + 15) / 16 * 16;
+  const size_t smem = plane_bytes + tiles + list_bytes;
+  if (smem > 219 * 1024) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem);
     return GPDB_ERR_INVALID;
   }
-  CUDA_TRY(cudaFuncSetAttribute(k_images, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  int *ovf = (int *)gpdb_scratch(ctx, 6, sizeof(int) * ((size_t)nc + 1));
-  if (!ovf) return GPDB_ERR_CUDA;
-  int *ovf_count = ovf + nc;
-  CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
-  int grid = std::min(nc, ctx->sm_count * 64);
-  k_images<<<grid, NT_IMG, smem0, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
-                                                 (int)smem0, ctx->d_prof, cap0, ovf, ovf_count, 0);
+  const int grid = std::min(nc, ctx->sm_count * 64);
+  if (S == 60) {
+    CUDA_TRY(cudaFuncSetAttribute(k_images<60>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_images<60><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                      (int)plane_bytes, (int)list_bytes, ctx->d_prof);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_images<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_images<0><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                     (int)plane_bytes, (int)list_bytes, ctx->d_prof);
+  }
   LAUNCH_CHECK();
-  // images whose box holds more than cap0 points (usually none): persistent CTAs over the overflow list, large list
-  k_images<<<ctx->sm_count, NT_IMG, smem1, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_images, ctx->d_qtab, ctx->d_err,
-                                                          (int)smem1, ctx->d_prof, BOX_CAP, ovf, ovf_count, 1);
+  return GPDB_OK;
+}
+
+int geo_p16_to_hwc(gpdb_ctx *ctx, const uint8_t *d_p16, int n, uint8_t *d_hwc) {
+  if (n <= 0) return GPDB_OK;
+  const size_t npix = (size_t)n * ctx->hp.S * ctx->hp.S, nb = npix * ctx->hp.C;
+  k_p16_to_hwc<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(d_p16, npix, ctx->hp.C, d_hwc);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+int geo_hwc_to_p16(gpdb_ctx *ctx, const uint8_t *d_hwc, int n, uint8_t *d_p16) {
+  if (n <= 0) return GPDB_OK;
+  const size_t npix = (size_t)n * ctx->hp.S * ctx->hp.S;
+  k_hwc_to_p16<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(d_hwc, npix, ctx->hp.C, d_p16);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

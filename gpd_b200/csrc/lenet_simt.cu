@@ -7,8 +7,9 @@
 //   conv2 (20->50, k5) + pool        : same shape of kernel, 100 KB of weights resident per CTA
 //   ip1 (7200->500) + ReLU           : tiled SGEMM over the batch
 //   ip2 (500->2), score = y1 - y0    : one warp per image
-// Input is the reference's cv::Mat layout (HWC uint8), raw 0..255 values, no scaling
-// (imageToArray, eigen_classifier.cpp:130-149).
+// Input: the images in the library's P16 layout (one 16-byte group per pixel: the cv::Mat HWC bytes of the pixel, zero
+// padded — written by k_images, or converted from the caller's cv::Mat data by gpdb_classify), raw 0..255 values, no
+// scaling (imageToArray, eigen_classifier.cpp:130-149).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -30,11 +31,11 @@ __global__ void __launch_bounds__(224) k_conv1_pool(const uint8_t *__restrict__ 
   for (int k = threadIdx.x; k < C * 25 * NF1; k += blockDim.x) sw[k] = w_t[k];
   for (int im = blockIdx.x; im < n; im += gridDim.x) {
     __syncthreads();
-    const uint8_t *g = images + (size_t)im * S * S * C;
-    // HWC -> CHW bytes
+    const uint8_t *g = images + (size_t)im * S * S * 16;
+    // P16 (16-byte pixels, channels 0..C-1) -> CHW bytes
     for (int k = threadIdx.x; k < S * S * C; k += blockDim.x) {
       int pix = k / C, c = k - pix * C;
-      simg[c * S * S + pix] = g[k];
+      simg[c * S * S + pix] = g[pix * 16 + c];
     }
     __syncthreads();
     const int items = 2 * Pp * Pp;

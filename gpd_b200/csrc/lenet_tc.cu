@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -39,7 +40,7 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// conv1: image 60x60xC uint8 (HWC) -> P1 [784 px][20] float32 (pixel-major), 2x2 max-pooled.
+// conv1: image 60x60 P16 (16-byte pixels: C uint8 channels, zero padded) -> P1 [784 px][20] float32 (pixel-major), 2x2 max-pooled.
 // Integer tensor-core path (tcgen05.mma kind::i8, int32 accumulators in TMEM): the uint8 image IS the A operand —
 // one pixel = one 16-byte K-chunk (C <= 16 channels, zero padded), so an instruction (K = 32) covers two filter taps.
 // Weights: w = s_o * W, W a 24-bit signed integer (s_o = max|w_o| / 8.3e6 per filter), W = 65536 d0 + 256 d1 + d2 with
@@ -47,13 +48,16 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 // dot products are EXACT integers; the epilogue recombines them in float32 (error ~1e-7 relative, like float32 itself).
 // tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
 // warps [0, 4 NG): NG epilogue groups (tile t -> group t % NG, TMEM buffer t % NG); warp 4 NG: MMA issuer;
-// warps 4 NG + 1 .. + 4: converters (raw HWC bytes of the NEXT image -> 16-byte pixels, double-buffered plane).
+// warp 4 NG + 1: producer — the images arrive from k_images already as 16-byte pixels (P16), so ONE bulk-async copy
+// (cp.async.bulk, mbarrier complete_tx) drops the next image straight into the free operand plane (double-buffered); no
+// thread ever touches the pixels.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
 constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: digit0 0..19 | digit1 20..39 | digit2 40..59 | 4 zero rows
 constexpr int C1_NCH = 25, C1_NMMA = 13;         // chunk c = kh*5 + kw (+1 zero-weight chunk)
 constexpr int C1_NG = 4;                         // epilogue groups = TMEM accumulator buffers
-constexpr int C1_MMA_WARP = 4 * C1_NG, C1_CONV_WARP0 = C1_MMA_WARP + 1, C1_NT = (C1_CONV_WARP0 + 4) * 32;
+constexpr int C1_MMA_WARP = 4 * C1_NG, C1_CONV_WARP0 = C1_MMA_WARP + 1, C1_NT = (C1_CONV_WARP0 + 1) * 32;
+constexpr int C1_IMG_BYTES = C1_W * C1_W * 16;  // one P16 image
 constexpr int C1_B_BYTES = 2 * C1_NMMA * C1_BCHUNK;
 
 // chunk c -> byte offset of row 0 inside the plane (monotonic in c)
@@ -64,18 +68,16 @@ __host__ __device__ constexpr uint32_t instr_desc_i8(int M, int N) {  // D = s32
   return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict__ images, int n, int C,
+__global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict__ images /* P16 */, int n,
                                                        const uint8_t *__restrict__ wblob, const float *__restrict__ bias,
                                                        int relu, float *__restrict__ p1) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[C1_NG], empty[C1_NG], pl_full[2], pl_empty[2], raw_full;
+  __shared__ uint64_t full[C1_NG], empty[C1_NG], pl_full[2], pl_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float sbias[NF1], sscale[NF1];
-  const int img_bytes = C1_W * C1_W * C;
   uint8_t *sB = smem;                                   // 26 chunks x 64 rows x 16 B (int8)
   uint8_t *sPl = sB + C1_B_BYTES;                       // 2 planes of 3616 px x 16 B (uint8)
   float *stage = reinterpret_cast<float *>(sPl + 2 * C1_PLANE);        // NG x [60][20]
-  uint8_t *sRaw = reinterpret_cast<uint8_t *>(stage + C1_NG * 60 * NF1);  // next image, raw HWC bytes
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
 
   for (int i = tid; i < C1_B_BYTES / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
@@ -90,60 +92,30 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
       umma::mbar_init(&empty[b], 4);  // one arrival per epilogue warp
     }
     for (int b = 0; b < 2; b++) {
-      umma::mbar_init(&pl_full[b], 4);   // one arrival per converter warp
+      umma::mbar_init(&pl_full[b], 1);   // the producer's expect_tx arrival + the bulk copy's bytes
       umma::mbar_init(&pl_empty[b], 1);  // tcgen05.commit after the image's last tile
     }
-    umma::mbar_init(&raw_full, 1);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(&tmem_base, 64 * C1_NG);
-  umma::fence_async_smem();
+  umma::fence_async_smem();  // the zero fill of the planes (generic proxy) before the bulk copies / MMAs (async proxy)
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
 
   if (warp >= C1_CONV_WARP0) {
-    // ===== converters: raw HWC stream -> one 16-byte group per pixel (channels C..15 zero) in plane (it & 1)
-    const int ct = tid - C1_CONV_WARP0 * 32;  // 0..127
-    if (ct == 0 && (int)blockIdx.x < n) {
-      umma::mbar_expect_tx(&raw_full, img_bytes);
-      umma::bulk_g2s(sRaw, images + (size_t)blockIdx.x * img_bytes, img_bytes, &raw_full);
-    }
-    uint32_t msk[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int nb = min(max(C - 4 * q, 0), 4);
-      msk[q] = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
-    }
-    int it = 0;
-    for (int im = blockIdx.x; im < n; im += gridDim.x, it++) {
-      const int buf = it & 1;
-      umma::mbar_wait(&pl_empty[buf], ((it >> 1) & 1) ^ 1);  // the MMAs of image it-2 have read this plane
-      umma::mbar_wait(&raw_full, it & 1);
-      uint8_t *pl = sPl + (size_t)buf * C1_PLANE;
-      for (int pix = ct; pix < C1_W * C1_W; pix += 128) {
-        // the C channel bytes of this pixel start at an arbitrary byte offset: fetch the aligned 32-bit words covering
-        // them and funnel-shift
-        const int off = pix * C;
-        const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(sRaw) + (off >> 2);
-        const int sh = (off & 3) * 8;
-        const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
-        uint4 o;
-        o.x = __funnelshift_r(w0, w1, sh) & msk[0];
-        o.y = __funnelshift_r(w1, w2, sh) & msk[1];
-        o.z = __funnelshift_r(w2, w3, sh) & msk[2];
-        o.w = __funnelshift_r(w3, w4, sh) & msk[3];
-        *reinterpret_cast<uint4 *>(pl + (size_t)pix * 16) = o;
+    // ===== producer: image `it` of this CTA -> plane (it & 1) as soon as the MMAs of image it-2 have released it
+    if (umma::elect_one()) {
+      int it = 0;
+      for (int im = blockIdx.x; im < n; im += gridDim.x, it++) {
+        const int buf = it & 1;
+        umma::mbar_wait(&pl_empty[buf], ((it >> 1) & 1) ^ 1);
+        umma::mbar_expect_tx(&pl_full[buf], C1_IMG_BYTES);
+        umma::bulk_g2s(sPl + (size_t)buf * C1_PLANE, images + (size_t)im * C1_IMG_BYTES, C1_IMG_BYTES, &pl_full[buf]);
       }
-      umma::fence_async_smem();
-      umma::named_bar_sync(1 + C1_NG, 128);  // all four converter warps are done with sRaw
-      if (ct == 0 && im + (int)gridDim.x < n) {
-        umma::mbar_expect_tx(&raw_full, img_bytes);
-        umma::bulk_g2s(sRaw, images + (size_t)(im + gridDim.x) * img_bytes, img_bytes, &raw_full);
-      }
-      if ((tid & 31) == 0) umma::mbar_arrive(&pl_full[buf]);
     }
+    __syncwarp();
   } else if (warp == C1_MMA_WARP) {
     // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt % NG), +64) as soon as that buffer has been
     // drained. The whole warp runs the (fully unrolled) loop so that every descriptor is a uniform-register
@@ -229,13 +201,20 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
 
 // ---------------------------------------------------------------------------------------------------------
 // conv2: P1 [784 px][20] f32 -> P2 [j = 12x12][50] f32 (k = c + 50 j, the ip1 input order), max-pooled.
-// The image is processed in two halves (input rows 12h .. 12h+15) of 3 tiles each; tile t = output rows
-// 12h + 4t .. +3 = GEMM rows m0 = 112 t .. +111 (of 128) in half-local pixel indices.
+// Tile T (6 per image) = output rows 4T .. 4T+3 = GEMM rows m = y*28 + x (112 of 128) over the EIGHT input rows
+// 4T .. 4T+7, held as six fp16 channel planes (hi p0..2, lo p0..2) of 232 pixels. The planes are DOUBLE-BUFFERED and
+// written by four dedicated converter warps (float32 -> scaled fp16 hi/lo), so that the conversion of tile T+1 — and
+// the global loads of tile T+2, prefetched into registers — overlap the MMAs of tile T; no CTA-wide barrier exists in
+// the steady state (round 1 converted half an image with the whole CTA between two __syncthreads: 7.6 ms against an
+// MMA floor of 4.2 ms per 50 k images). The 4 halo rows of a tile are converted twice (converters have the slack).
+//   warps 0-7: two epilogue groups (TMEM buffer = tile parity); warp 8: MMA issuer; warps 9-12: converters
+//   barriers: pl_full[2] (4 converter-warp arrivals) / pl_empty[2] (tcgen05.commit); full[2] / empty[2] for TMEM
 // ---------------------------------------------------------------------------------------------------------
-constexpr int C2_W = 28, C2_NPIX = 472, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
+constexpr int C2_W = 28, C2_NPIX = 232, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
 constexpr int C2_BCHUNK = 128 * 16;
+constexpr int C2_TILES = 6, C2_TILE_PIX = 8 * C2_W;  // 224 input pixels per tile
 
-constexpr int C2_NT = 288;  // two epilogue groups + MMA issuer warp 8
+constexpr int C2_MMA_WARP = 8, C2_CONV_WARP0 = 9, C2_NCONV = 4 * 32, C2_NT = (C2_CONV_WARP0 + 4) * 32;
 constexpr int IP_K = 7200, IP_KCH = IP_K / 8;  // ip1 reduction length, in 8-element chunks
 __host__ __device__ constexpr uint32_t c2_off(int c) {
   return (uint32_t)(((c >= C2_NCH ? C2_NCH - 1 : c) / 25) * C2_PLANE +
@@ -246,156 +225,167 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
                                                        const float *__restrict__ bias, float a_scale, float out_scale, int relu,
                                                        float *__restrict__ p2, __half *__restrict__ xc, float x_scale) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], empty[2];
+  __shared__ uint64_t full[2], empty[2], pl_full[2], pl_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float sbias[64];
   uint8_t *sB = smem;                                      // 76 chunks x 128 rows x 16 B
-  uint8_t *sPl = sB + (size_t)(2 * C2_NMMA) * C2_BCHUNK;   // 6 planes: hi p0..2, lo p0..2
-  float *stage = reinterpret_cast<float *>(sPl + 6 * C2_PLANE);  // 2 x [56][50]
+  uint8_t *sPl = sB + (size_t)(2 * C2_NMMA) * C2_BCHUNK;   // 2 buffers x 6 planes: hi p0..2, lo p0..2
+  float *stage = reinterpret_cast<float *>(sPl + 2 * 6 * C2_PLANE);  // 2 x [56][50]
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
   for (int i = tid; i < (2 * C2_NMMA) * C2_BCHUNK / 16; i += C2_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
-  for (int i = tid; i < 6 * C2_PLANE / 16; i += C2_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * 6 * C2_PLANE / 16; i += C2_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 64) sbias[tid] = tid < NF2 ? bias[tid] : 0.0f;
   if (tid == 0) {
     for (int b = 0; b < 2; b++) {
       umma::mbar_init(&full[b], 1);
       umma::mbar_init(&empty[b], 4);
+      umma::mbar_init(&pl_full[b], 4);
+      umma::mbar_init(&pl_empty[b], 1);
     }
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
+  umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tmem_base;
   const uint32_t idesc_hi = umma::instr_desc(128, 128, umma::F16), idesc_lo = umma::instr_desc(128, 64, umma::F16);
-  int gt = 0;  // running tile counter of this role
 
-  // The float32 activations of the NEXT half image are fetched into registers while the tensor cores work on the
-  // current one (the planes have no room for a second buffer: 155 KB of weights + 45 KB of planes + 22 KB of stage):
-  // the global-load latency of the conversion phase (HBM: a LeNet batch of P1 does not fit L2) is hidden behind the
-  // MMAs / epilogues; only the cvt + st.shared part stays between the barriers.
-  constexpr int C2_ITEMS = (448 * 3 + C2_NT - 1) / C2_NT;  // (pixel, plane) items per thread and half image
-  float4 pre[C2_ITEMS][2];
-  auto issue_loads = [&](int im2, int h2) {
+  if (warp >= C2_CONV_WARP0) {
+    // ===== converters: tile gt -> plane buffer gt & 1. (pixel, plane) items of a tile: 224 x 3, 6 per thread (last partial)
+    const int ct = tid - C2_CONV_WARP0 * 32;  // 0..127
+    constexpr int ITEMS = (C2_TILE_PIX * 3 + C2_NCONV - 1) / C2_NCONV;
+    float4 pre[ITEMS][2];
+    auto issue_loads = [&](int im2, int T2) {
 #pragma unroll
-    for (int j = 0; j < C2_ITEMS; j++) {
-      const int i = tid + j * C2_NT;
-      pre[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      pre[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < 448 * 3 && im2 < n) {
-        const int lp = i / 3, p = i - lp * 3;
-        const float *src = p1 + (size_t)im2 * 784 * NF1 + (size_t)(12 * h2 * C2_W + lp) * NF1 + p * 8;
-        pre[j][0] = __ldg(reinterpret_cast<const float4 *>(src));
-        if (p < 2) pre[j][1] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+      for (int j = 0; j < ITEMS; j++) {
+        const int i = ct + j * C2_NCONV;
+        pre[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pre[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < C2_TILE_PIX * 3 && im2 < n) {
+          const int lp = i / 3, p = i - lp * 3;
+          const float *src = p1 + (size_t)im2 * 784 * NF1 + (size_t)(4 * T2 * C2_W + lp) * NF1 + p * 8;
+          pre[j][0] = __ldg(reinterpret_cast<const float4 *>(src));
+          if (p < 2) pre[j][1] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+        }
+      }
+    };
+    issue_loads(blockIdx.x, 0);
+    int gt = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x) {
+      for (int T = 0; T < C2_TILES; T++, gt++) {
+        const int buf = gt & 1;
+        umma::mbar_wait(&pl_empty[buf], ((gt >> 1) & 1) ^ 1);  // the MMAs of tile gt-2 have read this buffer
+        uint8_t *pl = sPl + (size_t)buf * 6 * C2_PLANE;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+          const int i = ct + j * C2_NCONV;
+          if (i >= C2_TILE_PIX * 3) continue;
+          const int lp = i / 3, p = i - lp * 3;
+          const float x[8] = {pre[j][0].x, pre[j][0].y, pre[j][0].z, pre[j][0].w, pre[j][1].x, pre[j][1].y, pre[j][1].z, pre[j][1].w};
+          __half hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            float a = x[e] * a_scale;
+            hi[e] = __float2half_rn(a);
+            lo[e] = __float2half_rn(a - __half2float(hi[e]));
+          }
+          *reinterpret_cast<uint4 *>(pl + (size_t)p * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(hi);
+          *reinterpret_cast<uint4 *>(pl + (size_t)(3 + p) * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(lo);
+        }
+        // the loads of the NEXT tile fly while the tensor cores work on this one
+        if (T + 1 < C2_TILES) issue_loads(im, T + 1);
+        else issue_loads(im + gridDim.x, 0);
+        umma::fence_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0) umma::mbar_arrive(&pl_full[buf]);
       }
     }
-  };
-  issue_loads(blockIdx.x, 0);
-
-  for (int im = blockIdx.x; im < n; im += gridDim.x) {
-    float *out = p2 + (size_t)im * 7200;
-    for (int h = 0; h < 2; h++) {
-      // ---- float32 (prefetched) -> scaled fp16 hi/lo channel planes for input rows 12h .. 12h+15 (448 px)
+  } else if (warp == C2_MMA_WARP) {
+    const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
+    int gt = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x) {
+      for (int T = 0; T < C2_TILES; T++, gt++) {
+        const int b = gt & 1;
+        umma::mbar_wait(&pl_full[b], (gt >> 1) & 1);
+        umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
+        umma::fence_after_sync();
+        const uint32_t arow = sPl_u + (uint32_t)b * 6 * C2_PLANE;
+        const uint32_t dcol = tb + (uint32_t)b * 128;
+        if (umma::elect_one()) {
 #pragma unroll
-      for (int j = 0; j < C2_ITEMS; j++) {
-        const int i = tid + j * C2_NT;
-        if (i >= 448 * 3) continue;
-        const int lp = i / 3, p = i - lp * 3;
-        const float x[8] = {pre[j][0].x, pre[j][0].y, pre[j][0].z, pre[j][0].w, pre[j][1].x, pre[j][1].y, pre[j][1].z, pre[j][1].w};
-        __half hi[8], lo[8];
+          for (int i = 0; i < C2_NMMA; i++) {  // a_hi x [w_hi | w_lo]
+            const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
+            const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
+            umma::mma_f16(dcol, umma::desc_from(arow + a0, lbo, 128),
+                          umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_hi, i > 0);
+          }
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          float a = x[e] * a_scale;
-          hi[e] = __float2half_rn(a);
-          lo[e] = __float2half_rn(a - __half2float(hi[e]));
+          for (int i = 0; i < C2_NMMA; i++) {  // a_lo x w_hi
+            const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
+            const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
+            umma::mma_f16(dcol, umma::desc_from(arow + 3 * C2_PLANE + a0, lbo, 128),
+                          umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_lo, true);
+          }
+          umma::commit(&full[b]);      // accumulator of this tile complete
+          umma::commit(&pl_empty[b]);  // ... and its planes may be rewritten
         }
-        *reinterpret_cast<uint4 *>(sPl + (size_t)p * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(sPl + (size_t)(3 + p) * C2_PLANE + (size_t)lp * 16) = *reinterpret_cast<uint4 *>(lo);
+        __syncwarp();
       }
-      // loads of the next half image (h = 1 of this image, or h = 0 of this CTA's next image) fly during the MMAs below
-      if (h == 0) issue_loads(im, 1);
-      else issue_loads(im + gridDim.x, 0);
-      umma::fence_async_smem();
-      __syncthreads();
-      if (warp == 8) {
-        const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
-        for (int t = 0; t < 3; t++, gt++) {
-          const int b = gt & 1;
-          umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
-          umma::fence_after_sync();
-          const uint32_t arow = sPl_u + (uint32_t)(t * 112) * 16;
-          const uint32_t dcol = tb + (uint32_t)b * 128;
-          if (umma::elect_one()) {
+    }
+  } else {
+    const int grp = warp >> 2, r = tid & 127;
+    float *stg = stage + grp * (56 * NF2);
+    int gt = 0;
+    for (int im = blockIdx.x; im < n; im += gridDim.x) {
+      float *out = p2 + (size_t)im * 7200;
+      for (int T = 0; T < C2_TILES; T++, gt++) {
+        const int b = gt & 1;
+        if (b != grp) continue;
+        umma::mbar_wait(&full[b], (gt >> 1) & 1);
+        umma::fence_after_sync();
+        const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)((warp & 3) * 32) << 16);
+        const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
+        const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
+        umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
 #pragma unroll
-            for (int i = 0; i < C2_NMMA; i++) {  // a_hi x [w_hi | w_lo]
-              const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
-              const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
-              umma::mma_f16(dcol, umma::desc_from(arow + a0, lbo, 128),
-                            umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_hi, i > 0);
-            }
-#pragma unroll
-            for (int i = 0; i < C2_NMMA; i++) {  // a_lo x w_hi
-              const uint32_t a0 = c2_off(2 * i), a1 = c2_off(2 * i + 1);
-              const uint32_t lbo = (2 * i + 1 >= C2_NCH) ? 16u : (a1 - a0);
-              umma::mma_f16(dcol, umma::desc_from(arow + 3 * C2_PLANE + a0, lbo, 128),
-                            umma::desc_from(sB_u + (uint32_t)(2 * i) * C2_BCHUNK, C2_BCHUNK, 128), idesc_lo, true);
-            }
-            umma::commit(&full[b]);
+        for (int cb = 0; cb < 4; cb++) {
+          float a[16], bq[16];
+          umma::tmem_ld16(trow + cb * 16, a);
+          umma::tmem_ld16(trow + 64 + cb * 16, bq);
+          umma::tmem_ld_wait();
+          if (cb == 3) {
+            umma::fence_before_sync();
+            __syncwarp();
+            if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);
           }
-          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            float v = (a[j] + bq[j]) * out_scale;
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
+          }
         }
-      } else {
-        const int grp = warp >> 2, r = tid & 127;
-        float *stg = stage + grp * (56 * NF2);
-        for (int t = 0; t < 3; t++, gt++) {
-          const int b = gt & 1;
-          if (b != grp) continue;
-          umma::mbar_wait(&full[b], (gt >> 1) & 1);
-          umma::fence_after_sync();
-          const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)((warp & 3) * 32) << 16);
-          const int rr = r >> 1;  // [dy 0..3][x/2 0..13]
-          const bool wr = (r & 1) == 0 && r < 112 && (rr % 14) < 12;
-          umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
-#pragma unroll
-          for (int cb = 0; cb < 4; cb++) {
-            float a[16], bq[16];
-            umma::tmem_ld16(trow + cb * 16, a);
-            umma::tmem_ld16(trow + 64 + cb * 16, bq);
-            umma::tmem_ld_wait();
-            if (cb == 3) {
-              umma::fence_before_sync();
-              __syncwarp();
-              if ((tid & 31) == 0) umma::mbar_arrive(&empty[b]);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              float v = (a[j] + bq[j]) * out_scale;
-              v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-              if (wr && cb * 16 + j < NF2) stg[rr * NF2 + cb * 16 + j] = v;
-            }
-          }
-          umma::named_bar_sync(1 + grp, 128);
-          for (int i = r; i < 2 * 12 * NF2; i += 128) {
-            int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
-            float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
-            if (relu) m = fmaxf(m, 0.0f);
-            int j = (6 * h + 2 * t + q) * 12 + px;
-            if (p2) out[(size_t)j * NF2 + ch] = m;
-            if (xc) {  // ip1's A operand: [tile im/128][hi|lo][k/8][row im%128][k%8] fp16, scaled by 2^-8
-              const int k = ch + NF2 * j;
-              const float a = m * x_scale;
-              const __half hi = __float2half_rn(a);
-              const __half lo = __float2half_rn(a - __half2float(hi));
-              const size_t base = ((size_t)(im >> 7) * 2 * IP_KCH + (size_t)(k >> 3)) * 128 * 8 + (size_t)(im & 127) * 8 + (k & 7);
-              xc[base] = hi;
-              xc[base + (size_t)IP_KCH * 128 * 8] = lo;
-            }
+        umma::named_bar_sync(1 + grp, 128);
+        for (int i = r; i < 2 * 12 * NF2; i += 128) {
+          int ch = i % NF2, px = (i / NF2) % 12, q = i / (NF2 * 12);
+          float m = fmaxf(stg[((2 * q) * 14 + px) * NF2 + ch], stg[((2 * q + 1) * 14 + px) * NF2 + ch]) + sbias[ch];
+          if (relu) m = fmaxf(m, 0.0f);
+          int j = (2 * T + q) * 12 + px;
+          if (p2) out[(size_t)j * NF2 + ch] = m;
+          if (xc) {  // ip1's A operand: [tile im/128][hi|lo][k/8][row im%128][k%8] fp16, scaled by 2^-8
+            const int k = ch + NF2 * j;
+            const float a = m * x_scale;
+            const __half hi = __float2half_rn(a);
+            const __half lo = __float2half_rn(a - __half2float(hi));
+            const size_t base = ((size_t)(im >> 7) * 2 * IP_KCH + (size_t)(k >> 3)) * 128 * 8 + (size_t)(im & 127) * 8 + (k & 7);
+            xc[base] = hi;
+            xc[base + (size_t)IP_KCH * 128 * 8] = lo;
           }
         }
       }
-      __syncthreads();  // planes are rewritten by the next half; every tile of this half has completed
     }
   }
   umma::fence_before_sync();
@@ -556,7 +546,28 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   float mx = 0.0f;
   for (size_t i = 0; i < (size_t)NF2 * NF1 * 25; i++) mx = std::fmax(mx, std::fabs(w[2][i]));
   t.w2_scale = pow2_scale(mx, 16.0f);
-  t.a2_scale = 1.0f / 16.0f;
+  // Activation scales of the fp16 hi/lo split. The hi term must stay below the fp16 maximum (65504) for ANY input image:
+  // bound the activations from the weights (pool1 <= max_o sum_i |w1[o,i]| * 255 + |b1[o]|, propagated through conv2 for
+  // pool2) and shrink the default power-of-two scales (tuned on the reference's three weight sets) when another model's
+  // weights need it, so that scores can never silently become inf / NaN.
+  double a1_bound = 0.0;
+  for (int o = 0; o < NF1; o++) {
+    double sabs = 0.0;
+    for (size_t i = 0; i < (size_t)C * 25; i++) sabs += std::fabs((double)w[0][(size_t)o * C * 25 + i]);
+    a1_bound = std::max(a1_bound, sabs * 255.0 + std::fabs((double)w[1][o]));
+  }
+  double a2_bound = 0.0;
+  for (int o = 0; o < NF2; o++) {
+    double sabs = 0.0;
+    for (size_t i = 0; i < (size_t)NF1 * 25; i++) sabs += std::fabs((double)w[2][(size_t)o * NF1 * 25 + i]);
+    a2_bound = std::max(a2_bound, sabs * a1_bound + std::fabs((double)w[3][o]));
+  }
+  auto safe_scale = [](double bound, float preferred) {
+    float sc = preferred;
+    while ((double)sc * bound > 60000.0) sc *= 0.5f;
+    return sc;
+  };
+  t.a2_scale = safe_scale(a1_bound, 1.0f / 16.0f);
   std::vector<__half> b2((size_t)(2 * C2_NMMA) * 128 * 8, __float2half(0.0f));
   for (int c = 0; c < C2_NCH; c++) {
     int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
@@ -575,7 +586,7 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   mx = 0.0f;
   for (size_t i = 0; i < (size_t)NH * IP_K; i++) mx = std::fmax(mx, std::fabs(w[4][i]));
   t.w3_scale = pow2_scale(mx, 16.0f);
-  t.x3_scale = 1.0f / 256.0f;
+  t.x3_scale = safe_scale(a2_bound, 1.0f / 256.0f);
   std::vector<__half> b3((size_t)4 * IP_NKB * IP_KB_CH * 256 * 8, __float2half(0.0f));
   for (int ob = 0; ob < 4; ob++)
     for (int kc = 0; kc < IP_KCH; kc++) {
@@ -613,15 +624,15 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
 // conv1 + pool, conv2 + pool and ip1 + ReLU on tcgen05; p1 [n][784][20] f32, xc = fp16 hi/lo ip1 operand, h3 [n][500]
 int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, __half *xc, float *h3) {
   const LenetTc &t = ctx->tc;
-  const int C = ctx->prm.image_num_channels, relu = ctx->prm.relu_after_conv;
-  size_t sm1 = (size_t)C1_B_BYTES + 2 * (size_t)C1_PLANE + C1_NG * 60 * NF1 * sizeof(float) + (size_t)60 * 60 * C + 32;
-  size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
+  const int relu = ctx->prm.relu_after_conv;
+  size_t sm1 = (size_t)C1_B_BYTES + 2 * (size_t)C1_PLANE + C1_NG * 60 * NF1 * sizeof(float) + 32;
+  size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 2 * 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
   size_t sm3 = (size_t)IP_STAGES * IP_STAGE_BYTES;
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   CUDA_TRY(cudaFuncSetAttribute(k_ip1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
-  k_conv1_i8<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, C, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
+  k_conv1_i8<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 5, e1);
   cudaEvent_t e2 = gpdb_st_begin(ctx);

@@ -249,6 +249,18 @@ class GraspDetector {
   void preprocessPointCloud(util::Cloud &cloud);
   const gpdb_preprocess_params &getPreprocessParams() const { return pre_params_; }
   std::vector<std::unique_ptr<candidate::Hand>> selectGrasps(std::vector<std::unique_ptr<candidate::Hand>> &hands) const;
+  // GraspDetector::generateGraspCandidates + filterGraspsWorkspace / filterGraspsDirection (grasp_detector.cpp:330-398,
+  // 422-456, 458-470): positions (3 x m, column-major) of the samples of `cloud` (its setSamples positions, else its sample
+  // indices) at which at least one hand survives — what SequentialImportanceSampling keeps of a hand-set list between rounds
+  std::vector<double> candidateSamplePositions(const util::Cloud &cloud);
+  // GraspDetector::pruneGraspCandidates (grasp_detector.cpp:530-552) for hand sets given by their sample positions: images
+  // + classifier on the device, hands with score > min_score, in (sample, pose) order
+  std::vector<std::unique_ptr<candidate::Hand>> classifyAtPositions(const util::Cloud &cloud, const std::vector<double> &positions,
+                                                                    double min_score);
+  // multi-GPU detectGrasps (the reference's OpenMP loop over samples, sharded over GPUs instead of CPU threads): one thread
+  // and one context per device, cloud broadcast + sample slices + one all-gather inside libgpd_b200 (gpdb_comm_init,
+  // gpdb_set_cloud_bcast, gpdb_detect_sharded); returns the num_selected best hands over all devices, sorted by score
+  std::vector<std::unique_ptr<candidate::Hand>> detectGraspsMultiGpu(const util::Cloud &cloud, int num_gpus);
   const gpdb_params &getParams() const { return params_; }
   const candidate::HandSearch::Parameters &getHandSearchParameters() const { return hand_search_params_; }
   int getNumSamples() const { return num_samples_; }
@@ -265,6 +277,35 @@ class GraspDetector {
   bool cluster_grasps_{false};
   int min_inliers_{1};
   bool has_classifier_{false};
+  std::string model_file_, weights_file_;
+  bool ensureCloud(const util::Cloud &cloud);
+};
+
+// SequentialImportanceSampling (include/gpd/sequential_importance_sampling.h, src/gpd/sequential_importance_sampling.cpp:
+// 10-185): the cross-entropy outer loop over the same path — hand search at num_init_samples cloud points, then
+// num_iterations rounds of num_samples_per_iteration ARBITRARY positions (Cloud::setSamples -> gpdb_set_samples): Gaussians
+// around the samples of the hand sets found so far (sum- or max-of-Gaussians) mixed with prob_rand_samples uniform draws
+// inside the workspace; every round runs the hand search + filters on the device; at the end all surviving hand sets are
+// classified (pruneGraspCandidates) and clustered. The reference draws from rand() / std::random_device; here the
+// generator is seeded (setSeed) so that a run can be reproduced and checked.
+class SequentialImportanceSampling {
+ public:
+  explicit SequentialImportanceSampling(const std::string &config_filename);
+  std::vector<std::unique_ptr<candidate::Hand>> detectGrasps(util::Cloud &cloud);
+  void setSeed(unsigned seed) { seed_ = seed; }
+  // 3 x m positions of every sample that was evaluated / that carried a hand set, over all rounds (for the parity tests)
+  const std::vector<double> &evaluatedPositions() const { return evaluated_; }
+  const std::vector<double> &handSetPositions() const { return kept_; }
+  GraspDetector &detector() { return *grasp_detector_; }
+
+ private:
+  int num_init_samples_{50}, num_iterations_{5}, num_samples_{50}, sampling_method_{0};
+  double prob_rand_samples_{0.3}, radius_{0.02}, min_score_{0};
+  std::vector<double> workspace_;
+  std::unique_ptr<GraspDetector> grasp_detector_;
+  std::unique_ptr<Clustering> clustering_;
+  unsigned seed_{1};
+  std::vector<double> evaluated_, kept_;
 };
 
 // fills gpdb_params from the reference's cfg keys (grasp_detector.cpp:22-185); returns false if the file is missing

@@ -3,7 +3,12 @@
 // estimation: GraspDetector::preprocessPointCloud -> gpdb_preprocess); normals given as PCD fields or as a
 // NORMALS_FILE are kept.
 // --dump-config prints the parsed parameters as JSON and exits (used by the CPU tests).
+// --sis [SEED]  runs the reference's other entry point over the same path, cem_detect_grasps
+//               (src/cem_detect_grasps.cpp:14-66 -> SequentialImportanceSampling::detectGrasps), and prints the evaluated
+//               sample positions (SIS_SAMPLE lines) so that a test can recompute the result independently.
+// --gpus N      shards the samples over N GPUs inside libgpd_b200 (GraspDetector::detectGraspsMultiGpu).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -22,10 +27,16 @@ static bool checkFileExists(const std::string &file_name) {
 }
 
 int main(int argc, char *argv[]) {
-  bool dump = false;
+  bool dump = false, sis = false;
+  unsigned sis_seed = 1;
+  int gpus = 1;
   std::vector<std::string> args;
   for (int i = 1; i < argc; i++) {
     if (std::strcmp(argv[i], "--dump-config") == 0) dump = true;
+    else if (std::strcmp(argv[i], "--sis") == 0) {
+      sis = true;
+      if (i + 1 < argc && argv[i + 1][0] >= '0' && argv[i + 1][0] <= '9') sis_seed = (unsigned)std::atoi(argv[++i]);
+    } else if (std::strcmp(argv[i], "--gpus") == 0 && i + 1 < argc) gpus = std::atoi(argv[++i]);
     else args.push_back(argv[i]);
   }
   if (args.size() < (dump ? 1u : 2u)) {
@@ -83,6 +94,19 @@ int main(int argc, char *argv[]) {
     cloud.setNormalsFromFile(args[2]);
     std::cout << "Loaded surface normals from file: " << args[2] << "\n";
   }
+  if (sis) {  // cem_detect_grasps.cpp:52-64
+    SequentialImportanceSampling sampler(config_filename);
+    sampler.setSeed(sis_seed);
+    sampler.detector().preprocessPointCloud(cloud);
+    std::vector<std::unique_ptr<candidate::Hand>> grasps = sampler.detectGrasps(cloud);
+    const std::vector<double> &kept = sampler.handSetPositions();
+    for (size_t i = 0; i + 2 < kept.size(); i += 3) printf("SIS_SAMPLE %.17g %.17g %.17g\n", kept[i], kept[i + 1], kept[i + 2]);
+    for (size_t i = 0; i < grasps.size(); i++)
+      printf("SIS_GRASP %.9g %.17g %.17g %.17g\n", grasps[i]->getScore(), grasps[i]->getPosition()[0], grasps[i]->getPosition()[1],
+             grasps[i]->getPosition()[2]);
+    printf("RESULT n_grasps=%zu evaluated=%zu hand_sets=%zu\n", grasps.size(), sampler.evaluatedPositions().size() / 3, kept.size() / 3);
+    return 0;
+  }
   GraspDetector detector(config_filename);
   detector.preprocessPointCloud(cloud);
   bool centered_at_origin = config_file.getValueOfKey<bool>("centered_at_origin", false);
@@ -92,7 +116,7 @@ int main(int argc, char *argv[]) {
     cloud.setNormals(n);
     printf("Reversing normal directions ...\n");
   }
-  std::vector<std::unique_ptr<candidate::Hand>> grasps = detector.detectGrasps(cloud);
+  std::vector<std::unique_ptr<candidate::Hand>> grasps = gpus > 1 ? detector.detectGraspsMultiGpu(cloud, gpus) : detector.detectGrasps(cloud);
   for (size_t i = 0; i < grasps.size() && i < 5; i++) {
     printf("--- grasp %zu ---\n", i);
     grasps[i]->print();

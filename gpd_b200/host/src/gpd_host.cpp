@@ -1,4 +1,7 @@
 // gpd_host.cpp — implementation of the C++ host shims (include/gpd/gpd.h) over the C-ABI of libgpd_b200.so.
+#include <random>
+#include <thread>
+
 #include "gpd/gpd.h"
 
 #include <algorithm>
@@ -745,6 +748,8 @@ GraspDetector::GraspDetector(const std::string &config_filename) {
     if (config_file.ExtractKeys()) model_file = config_file.getValueOfKeyAsString("model_file", "");  // grasp_detector.cpp:130
   }
   if (relu_after_conv_of(model_file, weights_file, params_.image_num_channels)) params_.relu_after_conv = 1;
+  model_file_ = model_file;
+  weights_file_ = weights_file;
   ctx_ = make_ctx(params_);
   if (ctx_ && !weights_file.empty()) {
     // .bin parameter directory (EigenClassifier), .caffemodel (Caffe backend) or OpenVINO IR (classifier.cpp:33-61)
@@ -816,6 +821,143 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::selectGrasps(
   return out;
 }
 
+bool GraspDetector::ensureCloud(const util::Cloud &cloud) {
+  if (installed_cloud_ == &cloud && installed_revision_ == cloud.revision()) return true;
+  if (upload_cloud(ctx_, cloud) != GPDB_OK) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return false;
+  }
+  installed_cloud_ = &cloud;
+  installed_revision_ = cloud.revision();
+  return true;
+}
+
+// sample indices of a cloud for the C-ABI: its setSamples positions (installed with gpdb_set_samples) take precedence over
+// its sample indices (hand_search.cpp:33-47)
+static bool sample_indices_of(gpdb_ctx *ctx, const util::Cloud &cloud, std::vector<int> &idx) {
+  idx = cloud.getSampleIndices();
+  if (!cloud.getSamples().empty()) {
+    const int ns = (int)(cloud.getSamples().size() / 3);
+    const int first = gpdb_set_samples(ctx, cloud.getSamples().data(), ns);
+    if (first < 0) {
+      printf("ERROR: %s\n", gpdb_last_error(ctx));
+      return false;
+    }
+    idx.resize(ns);
+    for (int i = 0; i < ns; i++) idx[i] = first + i;
+  }
+  return true;
+}
+
+std::vector<double> GraspDetector::candidateSamplePositions(const util::Cloud &cloud) {
+  std::vector<double> out;
+  if (!ctx_ || !ensureCloud(cloud)) return out;
+  std::vector<int> idx;
+  if (!sample_indices_of(ctx_, cloud, idx) || idx.empty()) return out;
+  gpdb_result r;
+  if (gpdb_hand_search(ctx_, idx.data(), (int)idx.size(), &r) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return out;
+  }
+  int last_slot = -1;
+  for (int i = 0; i < r.n_candidates; i++) {  // candidates are in (sample slot, pose slot) order
+    if (r.candidates[i].sample_slot == last_slot) continue;
+    last_slot = r.candidates[i].sample_slot;
+    for (int k = 0; k < 3; k++) out.push_back(r.candidates[i].sample[k]);
+  }
+  gpdb_free_result(&r);
+  return out;
+}
+
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::classifyAtPositions(const util::Cloud &cloud,
+                                                                                const std::vector<double> &positions,
+                                                                                double min_score) {
+  std::vector<std::unique_ptr<candidate::Hand>> out;
+  const int ns = (int)(positions.size() / 3);
+  if (!ctx_ || !has_classifier_ || ns == 0 || !ensureCloud(cloud)) return out;
+  const int first = gpdb_set_samples(ctx_, positions.data(), ns);
+  if (first < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return out;
+  }
+  std::vector<int> idx(ns);
+  for (int i = 0; i < ns; i++) idx[i] = first + i;
+  gpdb_result r;
+  if (gpdb_detect(ctx_, idx.data(), ns, &r) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return out;
+  }
+  for (int i = 0; i < r.n_candidates; i++)
+    if ((double)r.candidates[i].score > min_score) out.push_back(std::make_unique<candidate::Hand>(r.candidates[i]));
+  gpdb_free_result(&r);
+  return out;
+}
+
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGraspsMultiGpu(const util::Cloud &cloud, int num_gpus) {
+  std::vector<std::unique_ptr<candidate::Hand>> hands;
+  if (num_gpus <= 1) return detectGrasps(cloud);
+  if (cloud.size() == 0 || !has_classifier_ || cloud.getNormals().size() != 3 * cloud.size()) {
+    printf("ERROR: detectGraspsMultiGpu needs a processed cloud with normals and classifier weights\n");
+    return hands;
+  }
+  std::vector<int> idx = cloud.getSampleIndices();
+  if (idx.empty()) {
+    printf("ERROR: no sample indices\n");
+    return hands;
+  }
+  char uid[GPDB_COMM_ID_BYTES];
+  if (gpdb_comm_unique_id(uid) != GPDB_OK) {
+    printf("ERROR: %s\n", gpdb_last_error(nullptr));
+    return hands;
+  }
+  std::vector<std::vector<gpdb_pose>> per_rank(num_gpus);
+  std::vector<int> rc(num_gpus, 0), total(num_gpus, 0);
+  std::vector<std::thread> th;
+  for (int r = 0; r < num_gpus; r++)
+    th.emplace_back([&, r]() {
+      gpdb_params p = params_;
+      p.device = r;
+      gpdb_ctx *c = nullptr;
+      // every rank joins every collective even after a local failure would deadlock the others: fail before the first one
+      if (gpdb_create(&p, &c) != GPDB_OK ||
+          gpdb_load_weights_file(c, model_file_.empty() ? nullptr : model_file_.c_str(), weights_file_.c_str()) != GPDB_OK) {
+        printf("ERROR (GPU %d): %s\n", r, gpdb_last_error(c));
+        rc[r] = -1;
+      }
+      if (gpdb_comm_init(c, uid, r, num_gpus) != GPDB_OK) rc[r] = -1;
+      if (rc[r] == 0) {
+        int n = r == 0 ? gpdb_set_cloud_bcast(c, 0, cloud.getPoints().data(), cloud.getNormals().data(),
+                                              cloud.getCameraSource().empty() ? nullptr : cloud.getCameraSource().data(),
+                                              (int)cloud.size(), cloud.getViewPoints().data(), cloud.numCameras())
+                       : gpdb_set_cloud_bcast(c, 0, nullptr, nullptr, nullptr, 0, nullptr, 0);
+        gpdb_result res;
+        if (n < 0 || gpdb_detect_sharded(c, idx.data(), (int)idx.size(), &res) < 0) {
+          printf("ERROR (GPU %d): %s\n", r, gpdb_last_error(c));
+          rc[r] = -1;
+        } else {
+          // this rank's num_selected best (ties keep the (sample, pose) order): the global top-k is among them
+          std::vector<gpdb_pose> loc(res.candidates, res.candidates + res.n_candidates);
+          std::stable_sort(loc.begin(), loc.end(), [](const gpdb_pose &a, const gpdb_pose &b) { return a.score > b.score; });
+          if ((int)loc.size() > num_selected_) loc.resize(num_selected_);
+          per_rank[r] = std::move(loc);
+          total[r] = res.n_total_candidates;
+          gpdb_free_result(&res);
+        }
+      }
+      if (c) gpdb_destroy(c);
+    });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < num_gpus; r++)
+    if (rc[r] != 0) return hands;
+  std::vector<gpdb_pose> all;
+  for (auto &v : per_rank) all.insert(all.end(), v.begin(), v.end());  // rank order = sample order
+  std::stable_sort(all.begin(), all.end(), [](const gpdb_pose &a, const gpdb_pose &b) { return a.score > b.score; });
+  if ((int)all.size() > num_selected_) all.resize(num_selected_);
+  printf("Number of grasp candidates within workspace and gripper width: %d (on %d GPUs)\n", total[0], num_gpus);
+  for (auto &p : all) hands.push_back(std::make_unique<candidate::Hand>(p));
+  return hands;
+}
+
 std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const util::Cloud &cloud) {
   std::vector<std::unique_ptr<candidate::Hand>> hands_out;
   if (cloud.size() == 0) {
@@ -826,25 +968,9 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
     printf("ERROR: detector not initialised (%s)\n", ctx_ ? "no classifier weights" : gpdb_last_error(nullptr));
     return hands_out;
   }
-  if (!(installed_cloud_ == &cloud && installed_revision_ == cloud.revision())) {
-    if (upload_cloud(ctx_, cloud) != GPDB_OK) {
-      printf("ERROR: %s\n", gpdb_last_error(ctx_));
-      return hands_out;
-    }
-    installed_cloud_ = &cloud;
-    installed_revision_ = cloud.revision();
-  }
-  std::vector<int> idx = cloud.getSampleIndices();
-  if (!cloud.getSamples().empty()) {  // Cloud::setSamples positions take precedence (hand_search.cpp:33-47)
-    const int ns = (int)(cloud.getSamples().size() / 3);
-    const int first = gpdb_set_samples(ctx_, cloud.getSamples().data(), ns);
-    if (first < 0) {
-      printf("ERROR: %s\n", gpdb_last_error(ctx_));
-      return hands_out;
-    }
-    idx.resize(ns);
-    for (int i = 0; i < ns; i++) idx[i] = first + i;
-  }
+  if (!ensureCloud(cloud)) return hands_out;
+  std::vector<int> idx;
+  if (!sample_indices_of(ctx_, cloud, idx)) return hands_out;
   gpdb_result r;
   // steps 1-4 + selectGrasps in one call: the num_selected best hands are picked on the device and only they are
   // copied back (grasp_detector.cpp:222-283,405-420)
@@ -880,6 +1006,97 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
          " 3. Classification: %3.4fs\n==========\n",
          last_ms_candidates * 1e-3, last_ms_images * 1e-3, last_ms_classify * 1e-3);
   return hands;
+}
+
+// ---- SequentialImportanceSampling (sequential_importance_sampling.cpp) -------------------------------------------------
+SequentialImportanceSampling::SequentialImportanceSampling(const std::string &config_filename) {
+  util::ConfigFile config_file(config_filename);
+  config_file.ExtractKeys();
+  num_init_samples_ = config_file.getValueOfKey<int>("num_init_samples", 50);  // :19-31
+  num_iterations_ = config_file.getValueOfKey<int>("num_iterations", 5);
+  num_samples_ = config_file.getValueOfKey<int>("num_samples_per_iteration", 50);
+  prob_rand_samples_ = config_file.getValueOfKey<double>("prob_rand_samples", 0.3);
+  radius_ = config_file.getValueOfKey<double>("standard_deviation", 0.02);
+  sampling_method_ = config_file.getValueOfKey<int>("sampling_method", 0);
+  min_score_ = config_file.getValueOfKey<double>("min_score", 0);
+  workspace_ = config_file.getValueOfKeyAsStdVectorDouble("workspace", "-1 1 -1 1 -1 1");
+  if (workspace_.size() != 6) workspace_ = {-1, 1, -1, 1, -1, 1};
+  grasp_detector_ = std::make_unique<GraspDetector>(config_filename);
+  clustering_ = std::make_unique<Clustering>(config_file.getValueOfKey<int>("min_inliers", 1));
+}
+
+std::vector<std::unique_ptr<candidate::Hand>> SequentialImportanceSampling::detectGrasps(util::Cloud &cloud) {
+  std::vector<std::unique_ptr<candidate::Hand>> none;
+  evaluated_.clear();
+  kept_.clear();
+  if (cloud.size() == 0) {
+    printf("Error: Point cloud is empty!");
+    return none;
+  }
+  std::mt19937 gen(seed_);
+  auto uniform_index = [&](size_t n) { return (size_t)(gen() % (unsigned long)n); };  // rand() % n upstream
+  // 1. Find initial grasp hypotheses (:68-79)
+  cloud.setSamples({});
+  cloud.subsample(num_init_samples_);
+  for (int i : cloud.getSampleIndices())
+    for (int k = 0; k < 3; k++) evaluated_.push_back((double)cloud.getPoints()[3 * (size_t)i + k]);
+  kept_ = grasp_detector_->candidateSamplePositions(cloud);
+  printf("Initially detected grasp candidates: %zu\n", kept_.size() / 3);
+  if (kept_.empty()) return none;
+  const int num_rand_samples = (int)(prob_rand_samples_ * num_samples_);  // :100-101
+  const int num_gauss_samples = num_samples_ - num_rand_samples;
+  const double sigma = radius_;
+  const double term = 1.0 / std::sqrt(std::pow(2.0 * M_PI, 3.0) * std::pow(sigma, 3.0));
+  std::normal_distribution<double> distr{0.0, sigma};
+  const std::vector<int> init_indices = cloud.getSampleIndices();
+  // 2. Find grasp hypotheses using importance sampling (:109-160)
+  for (int it = 0; it < num_iterations_; it++) {
+    std::vector<double> samples(3 * (size_t)num_samples_, 0.0);
+    const size_t m = kept_.size() / 3;
+    int j = 0;
+    while (j < num_gauss_samples) {  // 2.1 samples close to existing affordances (:187-236)
+      const size_t idx = uniform_index(m);
+      double x[3];
+      for (int k = 0; k < 3; k++) x[k] = kept_[3 * idx + k] + distr(gen);
+      if (sampling_method_ == 1) {  // MAX_OF_GAUSSIANS: rejection sampling (:213-234)
+        auto dens = [&](size_t h) {
+          double d2 = 0;
+          for (int k = 0; k < 3; k++) d2 += (x[k] - kept_[3 * h + k]) * (x[k] - kept_[3 * h + k]);
+          return term * std::exp((-1.0 / (2.0 * sigma)) * d2);
+        };
+        double maxp = 0;
+        for (size_t h = 0; h < m; h++) maxp = std::max(maxp, dens(h));
+        if (!(dens(idx) >= maxp)) continue;
+      }
+      for (int k = 0; k < 3; k++) samples[3 * (size_t)j + k] = x[k];
+      j++;
+    }
+    int i = 0, guard = 0;
+    while (i < num_rand_samples && guard++ < 1000000) {  // 2.2 uniform samples inside the workspace (:239-270)
+      const int pi = init_indices.empty() ? (int)uniform_index(cloud.size()) : init_indices[uniform_index(init_indices.size())];
+      const double sx = cloud.getPoints()[3 * (size_t)pi], sy = cloud.getPoints()[3 * (size_t)pi + 1], sz = cloud.getPoints()[3 * (size_t)pi + 2];
+      if (sx >= workspace_[0] && sx <= workspace_[1] && sy >= workspace_[2] && sy <= workspace_[3] && sz >= workspace_[4] &&
+          sz <= workspace_[5]) {
+        samples[3 * (size_t)(num_gauss_samples + i)] = sx;
+        samples[3 * (size_t)(num_gauss_samples + i) + 1] = sy;
+        samples[3 * (size_t)(num_gauss_samples + i) + 2] = sz;
+        i++;
+      }
+    }
+    // 2.3 evaluate grasp hypotheses at <samples> (:129-144)
+    cloud.setSamples(samples);
+    evaluated_.insert(evaluated_.end(), samples.begin(), samples.end());
+    std::vector<double> fresh = grasp_detector_->candidateSamplePositions(cloud);
+    kept_.insert(kept_.end(), fresh.begin(), fresh.end());
+    printf("Added %zu grasp candidates in round %d. Total: %zu.\n", fresh.size() / 3, it, kept_.size() / 3);
+  }
+  cloud.setSamples({});
+  // 3. Classify the grasps (:168-170), 4. cluster them (:177-179)
+  std::vector<std::unique_ptr<candidate::Hand>> valid = grasp_detector_->classifyAtPositions(cloud, kept_, min_score_);
+  printf("Valid grasps: %zu\n", valid.size());
+  if (clustering_->getMinInliers() > 0) valid = clustering_->findClusters(valid);
+  printf("Final result: found %zu grasps.\n", valid.size());
+  return valid;
 }
 
 }  // namespace gpd

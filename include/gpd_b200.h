@@ -118,7 +118,7 @@ typedef struct gpdb_pose {
   int16_t finger_idx;   /* Hand::finger_placement_index_                           */
   uint8_t half_antipodal;
   uint8_t full_antipodal;
-  uint8_t pad_[2];
+  uint8_t pad_[6];    /* explicit tail padding (zero): sizeof(gpdb_pose) = 176 with no implicit bytes */
 } gpdb_pose;
 
 /* Result of gpdb_detect / gpdb_hand_search: callee-allocated, release with gpdb_free_result. */

@@ -44,6 +44,7 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+#include <random>
 #endif
 
 #include "../include/gpd_b200.h"
@@ -937,6 +938,69 @@ void calculate_shadow(const Cloud &c, const PointList &pl, const double *qtab, d
   }
 }
 
+// A9 in the reference's LITERAL semantics (hand_set.cpp:118-233,263-266), for the statistical check of the deterministic
+// variant: ONE sequential LCG stream shared by all points, cameras and hand sets (the static
+// HandSet::seed_, initial value 0, hand_set.cpp:14; here the caller's `lcg_state`, advanced in place — what a
+// single-threaded run of the reference does), draw i belongs to point i / num_shadow_points (:211-218), voxel set per
+// camera, intersection as in the reference, then one std::normal_distribution<double>(0, 1) draw per voxel from a
+// std::mt19937 (seeded from std::random_device upstream, :191-193; here from the caller's generator) added to x, y and z
+// alike, in the set's iteration order. Irreproducible upstream by construction; two seeds give the reference's own
+// noise floor.
+void calculate_shadow_literal(const Cloud &c, const PointList &pl, double shadow_length, uint32_t &lcg_state,
+                              std::mt19937 &gen, std::vector<double> &shadow) {
+  shadow.clear();
+  const double voxel = 0.003;
+  const int num_shadow_points = (int)std::floor(shadow_length / voxel);
+  const int K = c.K, n = pl.size();
+  std::vector<int> camera_set(K, 0);
+  double center[3] = {0, 0, 0};
+  for (int j = 0; j < n; j++) {
+    for (int k = 0; k < K; k++) camera_set[k] += c.cam[(size_t)pl.gidx[j] * K + k];
+    for (int r = 0; r < 3; r++) center[r] += pl.p[3 * (size_t)j + r];
+  }
+  for (int r = 0; r < 3; r++) center[r] /= (double)n;
+  std::vector<VoxelSet> shadows(K);
+  const double mult = 1.0 / voxel, mx = 1.0 / 32767.0;
+  for (int k = 0; k < K; k++) {
+    if (camera_set[k] < 1) continue;
+    double sv[3] = {center[0] - c.vp[3 * k], center[1] - c.vp[3 * k + 1], center[2] - c.vp[3 * k + 2]};
+    double nrm = std::sqrt((sv[0] * sv[0] + sv[1] * sv[1]) + sv[2] * sv[2]);
+    for (int r = 0; r < 3; r++) sv[r] = shadow_length * sv[r] / nrm;
+    const int nd = n * num_shadow_points;
+    for (int i = 0; i < nd; i++) {
+      const int j = i / num_shadow_points;
+      lcg_state = 214013u * lcg_state + 2531011u;  // HandSet::fastrand (two's-complement int upstream)
+      double u = (double)((lcg_state >> 16) & 0x7FFFu) * mx;
+      std::array<int, 3> v;
+      for (int r = 0; r < 3; r++) v[r] = (int)((pl.p[3 * (size_t)j + r] + u * sv[r]) * mult);
+      shadows[k].insert(v);
+    }
+  }
+  VoxelSet all;
+  if (K == 1) {
+    all = std::move(shadows[0]);
+  } else {
+    all = shadows[0];
+    for (int k = 1; k < K; k++) {
+      if (camera_set[k] < 1) continue;
+      VoxelSet nx;
+      const VoxelSet &a = all.size() <= shadows[k].size() ? all : shadows[k];
+      const VoxelSet &b = all.size() <= shadows[k].size() ? shadows[k] : all;
+      for (const auto &v : a)
+        if (b.find(v) != b.end()) nx.insert(v);
+      all = std::move(nx);
+    }
+  }
+  std::normal_distribution<double> distr{0.0, 1.0};
+  shadow.resize(3 * all.size());
+  size_t i = 0;
+  for (const auto &v : all) {
+    const double jit = 1.0 * distr(gen) * voxel * 0.3;
+    for (int r = 0; r < 3; r++) shadow[3 * i + r] = (double)v[r] * voxel + jit;
+    i++;
+  }
+}
+
 // ImageStrategy::findPointsInUnitImage + transformPointsToUnitImage (image_strategy.cpp:53-90)
 // applied to already hand-framed points `pf` [3 x n]; returns indices and unit coords.
 void to_unit_image(const gpdb_params &pr, const gpdb_pose &h, const std::vector<double> &pf, int n,
@@ -1566,6 +1630,38 @@ int gpdo_images(void *cloud, const gpdb_params *pr, const gpdb_pose *poses, int3
         calculate_shadow(c, nnp, qt, dv.shadow_length, h0.sample_index, shadow);
       for (int i = set_start[g]; i < set_start[g + 1]; i++) create_image(*pr, poses[i], nnp, shadow, images + isz * i, s);
     }
+  }
+  return 0;
+}
+
+// gpdo_images with the shadow of the reference's literal semantics (calculate_shadow_literal): hand sets processed
+// sequentially in order (one shared LCG stream starting at `lcg_seed`; one mt19937 seeded with mt_seed + set index per
+// shadowVoxelsToPoints call). Used only by the statistical test of the deterministic variant.
+int gpdo_images_literal_shadow(void *cloud, const gpdb_params *pr, const gpdb_pose *poses, int32_t n_poses, uint8_t *images,
+                               uint32_t lcg_seed, uint32_t mt_seed) {
+  const Cloud &c = *(Cloud *)cloud;
+  Derived dv = derive(*pr);
+  const size_t isz = (size_t)pr->image_size * pr->image_size * pr->image_num_channels;
+  std::vector<Nb> nn;
+  PointList nnp;
+  std::vector<double> shadow;
+  ImgScratch s;
+  uint32_t lcg = lcg_seed;
+  int set_no = 0;
+  for (int i0 = 0; i0 < n_poses;) {
+    int i1 = i0 + 1;
+    while (i1 < n_poses && poses[i1].sample_slot == poses[i0].sample_slot && poses[i1].sample_index == poses[i0].sample_index) i1++;
+    float q[3] = {(float)poses[i0].sample[0], (float)poses[i0].sample[1], (float)poses[i0].sample[2]};
+    radius_search(c, q, dv.img_radius, nn);
+    slice_cloud(c, nn, nnp);
+    shadow.clear();
+    if (pr->image_num_channels == 15 && !nn.empty()) {
+      std::mt19937 gen(mt_seed + (uint32_t)set_no);
+      calculate_shadow_literal(c, nnp, dv.shadow_length, lcg, gen, shadow);
+    }
+    for (int i = i0; i < i1; i++) create_image(*pr, poses[i], nnp, shadow, images + isz * i, s);
+    i0 = i1;
+    set_no++;
   }
   return 0;
 }

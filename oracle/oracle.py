@@ -141,6 +141,17 @@ class OracleCloud:
         lib().gpdo_images(self.h, C.byref(params), _p(poses), n, _p(out), nthreads or num_threads())
         return out
 
+    def images_literal_shadow(self, params, poses, lcg_seed, mt_seed):
+        """Grasp images with the occlusion channels in the reference's LITERAL semantics (sequential shared LCG stream +
+        mt19937 Gaussian jitter; hand_set.cpp:187-233,263-266) for the two given seeds — the statistical yardstick of the
+        deterministic variant."""
+        poses = np.ascontiguousarray(poses, dtype=abi.POSE_DTYPE)
+        n = len(poses)
+        S, Cc = params.image_size, params.image_num_channels
+        out = np.zeros((n, S, S, Cc), np.uint8)
+        lib().gpdo_images_literal_shadow(self.h, C.byref(params), _p(poses), n, _p(out), C.c_uint32(lcg_seed), C.c_uint32(mt_seed))
+        return out
+
     def detect(self, params, weights, sample_idx, nthreads=0):
         sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
         res = abi.Result()
