@@ -1150,6 +1150,33 @@ int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n, float *sc
   return n;
 }
 
+int gpdb_find_clusters(gpdb_ctx *ctx, const gpdb_pose *hands, int32_t n, int32_t min_inliers, gpdb_pose *clusters_out) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!hands || !clusters_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_find_clusters: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  gpdb_pose *d_in = (gpdb_pose *)gpdb_scratch(ctx, 17, sizeof(gpdb_pose) * (size_t)n * 3);
+  uint8_t *d_keep = (uint8_t *)gpdb_scratch(ctx, 18, (size_t)n);
+  int *d_count = (int *)gpdb_scratch(ctx, 14, 64);
+  if (!d_in || !d_keep || !d_count) return GPDB_ERR_CUDA;
+  gpdb_pose *d_dense = d_in + n, *d_out = d_dense + n;
+  CUDA_TRY(cudaMemcpyAsync(d_in, hands, sizeof(gpdb_pose) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if ((rc = geo_clusters(ctx, d_in, n, min_inliers, d_dense, d_keep)) != GPDB_OK) return rc;
+  if ((rc = geo_compact(ctx, d_dense, d_keep, n, d_out, d_count + 2)) != GPDB_OK) return rc;  // order of i kept
+  int nc = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nc, d_count + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (nc > 0) {
+    CUDA_TRY(cudaMemcpyAsync(clusters_out, d_out, sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return nc;
+}
+
 void gpdb_free_result(gpdb_result *r) {
   if (!r) return;
   if (r->owner_) {  // the arrays live in a pinned arena of the context that produced them: hand it back

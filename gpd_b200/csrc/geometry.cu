@@ -30,7 +30,10 @@
 namespace {
 
 constexpr int NT_HANDS = 256;
-constexpr int NT_IMG = 512;
+#ifndef GPDB_NT_IMG
+#define GPDB_NT_IMG 512
+#endif
+constexpr int NT_IMG = GPDB_NT_IMG;  // threads of k_images (one CTA per SM: 214 KB of shared memory)
 constexpr int LRF_WARPS = 4;
 constexpr int LRF_CAP = 1024;  // points of the r = nn_radius ball (dynamic shared memory: 2 x 8 B x LRF_CAP per warp)
 constexpr int BOX_CAP = 2048;  // points inside one image box
@@ -867,6 +870,75 @@ __global__ void k_gather_poses(const gpdb_pose *cand, const int *order, int k, g
 }
 
 // ------------------------------------------------------------------------------------------------
+// Clustering::findClusters (clustering.cpp:5-105, remove_inliers = false): hand i becomes a cluster when at least
+// min_inliers OTHER hands have an axis within 12 degrees, a position within 5 cm and an axis-orthogonal offset within
+// 5 mm; cluster position = mean inlier position, score = lower bound of the 99 % confidence interval of the inlier
+// scores (Welford update in index order, :62-70). One warp per hand: the lanes test 32 hands j at a time, lane 0 folds
+// the inliers of the ballot IN INDEX ORDER, so the float64 running mean / variance are the reference's sequential ones.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_clusters(const gpdb_pose *__restrict__ hands, int n, int min_inliers, double cos_thresh,
+                           gpdb_pose *__restrict__ out, uint8_t *__restrict__ keep) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double AXIS_ALIGN_DIST_THRESH = 0.005, MAX_DIST_THRESH = 0.05;
+  const double ai[3] = {hands[i].frame[6], hands[i].frame[7], hands[i].frame[8]};
+  const double pi[3] = {hands[i].position[0], hands[i].position[1], hands[i].position[2]};
+  double outer[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) outer[r][c] = ai[r] * ai[c];
+  int num_inliers = 0;
+  double pd[3] = {0.0, 0.0, 0.0}, mean = 0.0, sd = 0.0;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    bool inl = false;
+    if (j < n && j != i) {
+      const double aj[3] = {hands[j].frame[6], hands[j].frame[7], hands[j].frame[8]};
+      const double axis_aligned = ai[0] * aj[0] + ai[1] * aj[1] + ai[2] * aj[2];
+      const double d[3] = {pi[0] - hands[j].position[0], pi[1] - hands[j].position[1], pi[2] - hands[j].position[2]};
+      double proj[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        proj[r] = ((r == 0 ? 1.0 : 0.0) - outer[r][0]) * d[0] + ((r == 1 ? 1.0 : 0.0) - outer[r][1]) * d[1] +
+                  ((r == 2 ? 1.0 : 0.0) - outer[r][2]) * d[2];
+      inl = fabs(axis_aligned) > cos_thresh && sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) <= MAX_DIST_THRESH &&
+            sqrt(proj[0] * proj[0] + proj[1] * proj[1] + proj[2] * proj[2]) <= AXIS_ALIGN_DIST_THRESH;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, inl);
+    if (lane == 0)
+      while (m) {
+        const int jj = j0 + __ffs(m) - 1;
+        m &= m - 1;
+        num_inliers++;
+#pragma unroll
+        for (int r = 0; r < 3; r++) pd[r] += hands[jj].position[r];
+        const double old_mean = mean, sj = (double)hands[jj].score;
+        mean += (sj - mean) / (double)num_inliers;
+        sd += (sj - mean) * (sj - old_mean);
+      }
+  }
+  if (lane == 0) {
+    gpdb_pose o = hands[i];
+    uint8_t k = 0;
+    if (num_inliers >= min_inliers) {
+      const double dn = (double)num_inliers;
+#pragma unroll
+      for (int r = 0; r < 3; r++) pd[r] = pd[r] / dn - pi[r];
+      sd /= dn;
+      if (sd != 0) sd = sqrt(sd);
+      const double conf_lb = mean - 2.576 * sd / sqrt((double)num_inliers);
+#pragma unroll
+      for (int r = 0; r < 3; r++) o.position[r] = pi[r] + pd[r];
+      o.score = (float)conf_lb;
+      k = 3;  // VALID | FILTERED: geo_compact keeps it
+    }
+    out[i] = o;
+    keep[i] = k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_images (round 2): one CTA per grasp image.
 //
 // Output stage. The reference post-processes every channel group as cv::dilate(3x3) -> cv::normalize(NORM_MINMAX over the
@@ -892,12 +964,12 @@ struct ImgSmem {
   double center[3];
   double sv[GPDB_MAX_CAMERAS][3];
   double svh[GPDB_MAX_CAMERAS][3];
-  unsigned long long occ[3][64];  // occupancy of the image rows (bit = column), per projection
+  unsigned occf[MAXPIX / 32 + 2];  // occupancy of the image cells, flat (bit = pixel index), written by warp ballots
+  unsigned lcgA[GPDB_MAX_NSP], lcgC[GPDB_MAX_NSP];  // LCG skip-ahead tables (DevParams), staged once per CTA
   int cam_or;
   int n_img;
   int box_n;
   int wl_n;
-  int covered;                    // bit pj: projection pj has NO all-empty 3x3 window (general min path)
   int bm_org[3], bm_dims[3];
   float fred[NT_IMG / 32][4];
 };
@@ -965,19 +1037,32 @@ struct Quant {
   }
 };
 
-// true when the S x S occupancy (rows = 64-bit words) has NO all-empty 3x3 window; one warp, result on every lane
-__device__ __forceinline__ bool fully_covered(const unsigned long long *occ, int S) {
+// true when the S x S occupancy has NO all-empty 3x3 window. occf: flat bitmap (bit = row * S + col) followed by two
+// zero-readable words. Evaluated by every warp on its own (32 rows per pass, a few word operations per row): the result is
+// warp-uniform and identical in all warps, so no flag has to travel through shared memory.
+__device__ __forceinline__ bool fully_covered(const unsigned *occf, int S) {
   const int lane = threadIdx.x & 31;
   const unsigned long long mask = S >= 64 ? ~0ull : ((1ull << S) - 1ull);
+  auto row_bits = [&](int r) -> unsigned long long {
+    if (r < 0 || r >= S) return 0ull;
+    const int b = r * S, w = b >> 5, sh = b & 31;
+    unsigned long long x = ((unsigned long long)occf[w] | ((unsigned long long)occf[w + 1] << 32)) >> sh;
+    if (sh + S > 64) x |= (unsigned long long)occf[w + 2] << (64 - sh);
+    return x & mask;
+  };
   bool empty = false;
   for (int r = lane; r < S; r += 32) {
-    unsigned long long o = occ[r];
-    if (r > 0) o |= occ[r - 1];
-    if (r + 1 < S) o |= occ[r + 1];
+    const unsigned long long o = row_bits(r - 1) | row_bits(r) | row_bits(r + 1);
     const unsigned long long d = (o | (o << 1) | (o >> 1)) & mask;
     empty = empty || (d != mask);
   }
   return !__any_sync(0xffffffffu, empty);
+}
+// one bit per cell from a per-thread predicate over pix = tid + t * NT (warp-aligned): word (pix >> 5) of the flat bitmap
+template <int NT>
+__device__ __forceinline__ void occ_ballot(unsigned *occf, int t, bool occupied) {
+  const unsigned word = __ballot_sync(0xffffffffu, occupied);
+  if ((threadIdx.x & 31) == 0) occf[(threadIdx.x >> 5) + t * (NT / 32)] = word;
 }
 
 // min over the 3x3-dilated (border ignored) image of channel plane F[SS] (float, row-major): general path only
@@ -1033,6 +1118,12 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
   const bool do_nrm = C != 1, do_dep = C == 1 || C >= 12;
+  constexpr int PIXT = (MAXPIX + NT_IMG - 1) / NT_IMG;
+  for (int k = tid; k < GPDB_MAX_NSP; k += NT_IMG) {
+    sm.lcgA[k] = P.lcgA[k];
+    sm.lcgC[k] = P.lcgC[k];
+  }
+  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = 0u;
 
   for (int b = blockIdx.x; b < nc; b += gridDim.x) {
     __syncthreads();
@@ -1045,7 +1136,6 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       sm.cam_or = 0;
       sm.n_img = 0;
       sm.box_n = 0;
-      sm.covered = 0;
     }
     for (int k = tid; k < plane_bytes >> 4; k += NT_IMG) reinterpret_cast<uint4 *>(planes)[k] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -1161,7 +1251,6 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       // (image_15_channels_strategy.cpp:57-64)
       const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
       for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tileA + tileB
-      if (tid < 64) sm.occ[0][tid] = 0ull;
       __syncthreads();
       for (int k = tid; k < bn; k += NT_IMG) {
         const unsigned cc = bcell[k];
@@ -1169,9 +1258,13 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         const int pix = row * S + col;
         atomicMax(tileA + pix, bkeys[k]);
         atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
-        atomicOr(&sm.occ[0][row], 1ull << col);
       }
       __syncthreads();
+#pragma unroll
+      for (int t = 0; t < PIXT; t++) {  // occupancy bitmap of the projection (no atomics: one ballot per 32 cells)
+        const int pix = tid + t * NT_IMG;
+        if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, pix < SS && (tileB[pix] >> 48) != 0ull);
+      }
       // the winner of a cell (its point with the largest key) carries the cell's values: |n| of that point, 1 - mean depth
       auto cell_values = [&](int k, int &row, int &col, float &n0, float &n1, float &n2, float &dv) -> bool {
         const unsigned cc = bcell[k];
@@ -1197,13 +1290,9 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           mxv[1] = fmaxf(mxv[1], dv);
         }
       }
-      if (tid < 32) {
-        const bool cov = fully_covered(sm.occ[0], S);
-        if (cov && tid == 0) sm.covered |= 1 << pj;
-      }
-      block_max<NT_IMG, 2>(mxv, sm.fred);
+      block_max<NT_IMG, 2>(mxv, sm.fred);  // (its barriers publish the occupancy words)
       float mnv[2] = {0.0f, 0.0f};  // min over the dilated image: 0 when an all-empty 3x3 window exists
-      if ((sm.covered >> pj) & 1) {
+      if (fully_covered(sm.occf, S)) {
         // general path (no empty window): materialise the four float channel images over the (now dead) tiles and take the
         // min of their dilations. Winners keep their values in registers across the rewrite of the tiles.
         constexpr int JMAX = (BOX_CAP + NT_IMG - 1) / NT_IMG;
@@ -1313,7 +1402,6 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         to_frame(h.frame, sm.sv[tid][0], sm.sv[tid][1], sm.sv[tid][2], sm.svh[tid][0], sm.svh[tid][1], sm.svh[tid][2]);
       }
       for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
-      if (tid < 3 * 64) sm.occ[tid >> 6][tid & 63] = 0ull;
       __syncthreads();
       PHASE(4);  // shadow setup done
       const int o0 = sm.bm_org[0], o1 = sm.bm_org[1], o2 = sm.bm_org[2];
@@ -1437,7 +1525,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           // w / nsp by multiply-high: exact for w < 2^32 / nsp (w < WL_CAP * nsp < 2^20)
           int item = nsp > 1 ? (int)__umulhi((unsigned)w, nsp_magic) : w, t = w - item * nsp;
           float4 e = wl[item];
-          unsigned seed = P.lcgA[t] * __float_as_uint(e.w) + P.lcgC[t];
+          unsigned seed = sm.lcgA[t] * __float_as_uint(e.w) + sm.lcgC[t];
           unsigned rg = wrange[item];
           int r = (int)((seed >> 16) & 0x7FFFu);
           if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) return -1;
@@ -1482,7 +1570,6 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
           const int row = S - 1 - cellv[a0], col = cellv[a1];
           atomicAdd(tileA + (size_t)pj * SS + row * S + col, (1ull << 48) + (unsigned long long)unit_q32(u[a2]));
-          atomicOr(&sm.occ[pj][row], 1ull << col);
         }
       };
       if (tid == 0) sm.wl_n = 0;
@@ -1522,13 +1609,6 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       __syncthreads();
       PHASE(6);  // S2 bitmap pass done
       // createShadowImage (image_strategy.cpp:193-233): mean per cell, value = max over occupied - mean on occupied cells
-      if (tid < 32) {
-        int cov = 0;
-        for (int pj = 0; pj < 3; pj++)
-          if (fully_covered(sm.occ[pj], S)) cov |= 1 << pj;
-        if (tid == 0) sm.covered = cov;
-      }
-      constexpr int PIXT = (MAXPIX + NT_IMG - 1) / NT_IMG;
       for (int pj = 0; pj < 3; pj++) {
         const unsigned long long *tile = tileA + (size_t)pj * SS;
         uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
@@ -1539,6 +1619,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         for (int t = 0; t < PIXT; t++) {
           const int pix = tid + t * NT_IMG;
           avgr[t] = 0.0f;
+          bool oc = false;
           if (pix < SS) {
             const unsigned long long acc = tile[pix];
             const unsigned cntc = (unsigned)(acc >> 48);
@@ -1546,17 +1627,19 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
               const double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
               avgr[t] = (float)mean;
               occm |= 1u << t;
+              oc = true;
               mm[0] = fmaxf(mm[0], avgr[t]);
               mm[1] = fmaxf(mm[1], -avgr[t]);
             }
           }
+          if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, oc);
         }
-        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers also order the sm.covered write above)
+        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers publish the occupancy words)
         const bool any = mm[0] != -FLT_MAX;
         const float maxf = any ? mm[0] : 0.0f;
         const float vmax = any ? maxf - (-mm[1]) : 0.0f;  // largest cell value = max avg - min avg
         float vmin = 0.0f;
-        if ((sm.covered >> pj) & 1) {  // general path: min over the dilated float image
+        if (fully_covered(sm.occf, S)) {  // general path: min over the dilated float image
           float *srcF = reinterpret_cast<float *>(tileA + (size_t)pj * SS);
           __syncthreads();
 #pragma unroll
@@ -1589,26 +1672,27 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       uint4 *gout = reinterpret_cast<uint4 *>(p16) + (size_t)b * SS;
       for (int g = tid; g < S * RW; g += NT_IMG) {
         const int row = g / RW, c4 = g - row * RW;
+        // 3x3 max of 4 pixels x 1 channel per word. Bytes are split into their even / odd 16-bit lanes (E = [b0, b2],
+        // O = [b1, b3]) so that every max is ONE native VIMNMX3.U16x2 (the 8-bit SIMD max is emulated on sm_100): vertical
+        // max of the three rows first (centre word: E and O; left word: only O, whose high lane is pixel -1; right word:
+        // only E, whose low lane is pixel +4), then the horizontal neighbours by lane shifts.
         unsigned res[16];
+        const bool up = row > 0, dn = row + 1 < S, lf = c4 > 0, rt = c4 + 1 < RW;
 #pragma unroll
         for (int ch = 0; ch < 16; ch++) {
           res[ch] = 0u;
           if (ch < C) {
             const unsigned *W = reinterpret_cast<const unsigned *>(planes + (size_t)ch * PLB) + row * RW + c4;
-            const bool up = row > 0, dn = row + 1 < S, lf = c4 > 0, rt = c4 + 1 < RW;
-            unsigned vc = W[0], vl = lf ? W[-1] : 0u, vr = rt ? W[1] : 0u;
-            if (up) {
-              vc = __vmaxu4(vc, W[-RW]);
-              if (lf) vl = __vmaxu4(vl, W[-RW - 1]);
-              if (rt) vr = __vmaxu4(vr, W[-RW + 1]);
-            }
-            if (dn) {
-              vc = __vmaxu4(vc, W[RW]);
-              if (lf) vl = __vmaxu4(vl, W[RW - 1]);
-              if (rt) vr = __vmaxu4(vr, W[RW + 1]);
-            }
-            const unsigned L = __funnelshift_l(vl, vc, 8), R = __funnelshift_r(vc, vr, 8);
-            res[ch] = __vmaxu4(vc, __vmaxu4(L, R));
+            const unsigned m0 = W[0], u0 = up ? W[-RW] : 0u, d0 = dn ? W[RW] : 0u;
+            const unsigned ml = lf ? W[-1] : 0u, ul = (up && lf) ? W[-RW - 1] : 0u, dl = (dn && lf) ? W[RW - 1] : 0u;
+            const unsigned mr = rt ? W[1] : 0u, ur = (up && rt) ? W[-RW + 1] : 0u, dr = (dn && rt) ? W[RW + 1] : 0u;
+            const unsigned E = __vimax3_u16x2(__byte_perm(u0, 0u, 0x4240), __byte_perm(m0, 0u, 0x4240), __byte_perm(d0, 0u, 0x4240));
+            const unsigned O = __vimax3_u16x2(__byte_perm(u0, 0u, 0x4341), __byte_perm(m0, 0u, 0x4341), __byte_perm(d0, 0u, 0x4341));
+            const unsigned LO = __vimax3_u16x2(__byte_perm(ul, 0u, 0x4341), __byte_perm(ml, 0u, 0x4341), __byte_perm(dl, 0u, 0x4341));
+            const unsigned RE = __vimax3_u16x2(__byte_perm(ur, 0u, 0x4240), __byte_perm(mr, 0u, 0x4240), __byte_perm(dr, 0u, 0x4240));
+            const unsigned En = __vimax3_u16x2(E, O, __byte_perm(LO, O, 0x5432));   // [max(p-1,p0,p1), max(p1,p2,p3)]
+            const unsigned On = __vimax3_u16x2(O, E, __byte_perm(E, RE, 0x5432));   // [max(p0,p1,p2), max(p2,p3,p4)]
+            res[ch] = __byte_perm(En, On, 0x6240);
           }
         }
 #pragma unroll
@@ -1813,6 +1897,14 @@ int geo_hwc_to_p16(gpdb_ctx *ctx, const uint8_t *d_hwc, int n, uint8_t *d_p16) {
   if (n <= 0) return GPDB_OK;
   const size_t npix = (size_t)n * ctx->hp.S * ctx->hp.S;
   k_hwc_to_p16<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(d_hwc, npix, ctx->hp.C, d_p16);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+int geo_clusters(gpdb_ctx *ctx, const gpdb_pose *d_hands, int n, int min_inliers, gpdb_pose *d_dense, uint8_t *d_keep) {
+  if (n <= 0) return GPDB_OK;
+  const double cos_thresh = std::cos(12.0 * M_PI / 180.0);  // AXIS_ALIGN_ANGLE_THRESH (clustering.cpp:9)
+  k_clusters<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(d_hands, n, min_inliers, cos_thresh, d_dense, d_keep);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

@@ -213,7 +213,7 @@ static int read_weights(const char *model_file, const std::string &wf, int C, st
     *relu_layers = n_relu;
     std::vector<float> raw[8];
     for (int i = 0; i < 8; i++) {
-      if (blobs[i].second != sizes[i] * 4 || blobs[i].first + blobs[i].second > bin.size()) {
+      if (blobs[i].second != sizes[i] * 4 || blobs[i].first > bin.size() || blobs[i].second > bin.size() - blobs[i].first) {  // no wrap-around
         FAIL(GPDB_ERR_IO, "%s: blob %d has %zu bytes, expected %zu for %d channels", xml_path.c_str(), i, blobs[i].second, sizes[i] * 4, C);
       }
       raw[i].resize(sizes[i]);

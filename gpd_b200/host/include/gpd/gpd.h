@@ -226,7 +226,8 @@ class Classifier {
 // Clustering::findClusters (include/gpd/clustering.h:50-80, src/gpd/clustering.cpp:5-105): a grasp whose axis, position
 // and axis-orthogonal offset agree with at least min_inliers other grasps becomes a cluster: position = mean inlier
 // position, score = lower bound of the 99 % confidence interval of the inlier scores. O(n^2) over the SELECTED grasps
-// (n <= num_selected), host side.
+// (n <= num_selected). This class is the host-side restatement (also remove_inliers = true); GraspDetector and
+// SequentialImportanceSampling run the default remove_inliers = false form on the device (gpdb_find_clusters).
 class Clustering {
  public:
   explicit Clustering(int min_inliers) : min_inliers_(min_inliers) {}
@@ -257,6 +258,10 @@ class GraspDetector {
   // + classifier on the device, hands with score > min_score, in (sample, pose) order
   std::vector<std::unique_ptr<candidate::Hand>> classifyAtPositions(const util::Cloud &cloud, const std::vector<double> &positions,
                                                                     double min_score);
+  // Clustering::findClusters(hands, remove_inliers = false) on the device (gpdb_find_clusters); the host class Clustering
+  // below stays for remove_inliers = true and for callers without a detector
+  std::vector<std::unique_ptr<candidate::Hand>> findClustersOnDevice(const std::vector<std::unique_ptr<candidate::Hand>> &hands,
+                                                                     int min_inliers);
   // multi-GPU detectGrasps (the reference's OpenMP loop over samples, sharded over GPUs instead of CPU threads): one thread
   // and one context per device, cloud broadcast + sample slices + one all-gather inside libgpd_b200 (gpdb_comm_init,
   // gpdb_set_cloud_bcast, gpdb_detect_sharded); returns the num_selected best hands over all devices, sorted by score

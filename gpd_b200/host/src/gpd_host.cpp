@@ -1,4 +1,5 @@
 // gpd_host.cpp — implementation of the C++ host shims (include/gpd/gpd.h) over the C-ABI of libgpd_b200.so.
+#include <atomic>
 #include <random>
 #include <thread>
 
@@ -273,7 +274,11 @@ bool Cloud::loadPcd(const std::string &filename) {
     else if (tag == "DATA") { ss >> data_kind; break; }
   }
   if (counts.empty()) counts.assign(fields.size(), 1);
-  if (fields.empty() || sizes.size() != fields.size() || types.size() != fields.size()) {
+  bool header_ok = !fields.empty() && sizes.size() == fields.size() && types.size() == fields.size() && counts.size() == fields.size();
+  for (size_t i = 0; header_ok && i < fields.size(); i++)  // the readers below index buffers with these: trust nothing
+    header_ok = (sizes[i] == 1 || sizes[i] == 2 || sizes[i] == 4 || sizes[i] == 8) && counts[i] >= 1 && counts[i] <= 4096 &&
+                (types[i] == "F" || types[i] == "I" || types[i] == "U") && !(types[i] == "F" && sizes[i] < 4);
+  if (!header_ok) {
     std::cout << "Bad .pcd header: " << filename << "\n";
     return false;
   }
@@ -370,7 +375,7 @@ void Cloud::setNormalsFromFile(const std::string &filename) {
 }
 
 void Cloud::touch() {
-  static unsigned counter = 0;
+  static std::atomic<unsigned> counter{0};  // clouds may be built on several threads
   revision_ = ++counter;
 }
 
@@ -551,12 +556,16 @@ std::vector<std::unique_ptr<HandSet>> HandSearch::searchHands(const util::Cloud 
   for (int i = 0; i < r.n_samples; i++) {
     if (!r.frame_valid[i]) continue;  // frames without neighbours are dropped (frame_estimator.cpp:24-29)
     auto hs = std::make_unique<HandSet>();
+    if (idx[i] < (int)cloud_cam.size())  // evalHandSet always sets sample_ (hand_set.cpp:36), also for sets without a hand
+      for (int k = 0; k < 3; k++) hs->sample_[k] = (double)cloud_cam.getPoints()[3 * (size_t)idx[i] + k];
     for (int k = 0; k < 9; k++) hs->frame_[k] = r.frames[9 * (size_t)i + k];
     hs->hands_.resize(P);
     hs->is_valid_.assign(P, false);
     for (int j = 0; j < P; j++) {
       const uint8_t fl = r.pose_flags[(size_t)i * P + j];
-      hs->is_valid_[j] = (fl & GPDB_POSE_VALID) != 0;
+      // a hand is handed on only when it is valid AND survives the filters (its record exists): a VALID pose that a filter
+      // removed must not reach ImageGenerator::createImages with an empty Hand
+      hs->is_valid_[j] = (fl & 3) == 3;
       if ((fl & 3) == 3) {
         hs->hands_[j] = std::make_unique<Hand>(r.candidates[c]);
         for (int k = 0; k < 3; k++) hs->sample_[k] = r.candidates[c].sample[k];
@@ -849,6 +858,22 @@ static bool sample_indices_of(gpdb_ctx *ctx, const util::Cloud &cloud, std::vect
   return true;
 }
 
+// Clustering::findClusters (remove_inliers = false) on the device: gpdb_find_clusters
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::findClustersOnDevice(
+    const std::vector<std::unique_ptr<candidate::Hand>> &hands, int min_inliers) {
+  std::vector<std::unique_ptr<candidate::Hand>> out;
+  if (!ctx_ || hands.empty()) return out;
+  std::vector<gpdb_pose> in(hands.size()), res(hands.size());
+  for (size_t i = 0; i < hands.size(); i++) in[i] = hands[i]->raw();
+  const int n = gpdb_find_clusters(ctx_, in.data(), (int)in.size(), min_inliers, res.data());
+  if (n < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return out;
+  }
+  for (int i = 0; i < n; i++) out.push_back(std::make_unique<candidate::Hand>(res[i]));
+  return out;
+}
+
 std::vector<double> GraspDetector::candidateSamplePositions(const util::Cloud &cloud) {
   std::vector<double> out;
   if (!ctx_ || !ensureCloud(cloud)) return out;
@@ -989,7 +1014,7 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGrasps(const 
   last_ms_classify = r.ms_classify;
   gpdb_free_result(&r);
   if (cluster_grasps_) {  // 6. Cluster the grasps (grasp_detector.cpp:283-301)
-    std::vector<std::unique_ptr<candidate::Hand>> clusters = Clustering(min_inliers_).findClusters(hands);
+    std::vector<std::unique_ptr<candidate::Hand>> clusters = findClustersOnDevice(hands, min_inliers_);
     printf("Found %d clusters.\n", (int)clusters.size());
     if (clusters.size() <= 3) {
       printf("Not enough clusters found! Adding all grasps from previous step.");
@@ -1094,7 +1119,7 @@ std::vector<std::unique_ptr<candidate::Hand>> SequentialImportanceSampling::dete
   // 3. Classify the grasps (:168-170), 4. cluster them (:177-179)
   std::vector<std::unique_ptr<candidate::Hand>> valid = grasp_detector_->classifyAtPositions(cloud, kept_, min_score_);
   printf("Valid grasps: %zu\n", valid.size());
-  if (clustering_->getMinInliers() > 0) valid = clustering_->findClusters(valid);
+  if (clustering_->getMinInliers() > 0) valid = grasp_detector_->findClustersOnDevice(valid, clustering_->getMinInliers());
   printf("Final result: found %zu grasps.\n", valid.size());
   return valid;
 }

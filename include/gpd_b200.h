@@ -285,6 +285,14 @@ int gpdb_get_cloud_source_index(gpdb_ctx *ctx, int32_t *src_out);
  * ms[0] upload, ms[1] NaN/workspace filter, ms[2] voxelise, ms[3] grid build, ms[4] normals, ms[5] whole call. */
 int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]);
 
+/* Replaces: Clustering::findClusters(hand_list, remove_inliers = false) (clustering.cpp:5-105; GraspDetector::detectGrasps
+ * step 6, grasp_detector.cpp:283-301; SequentialImportanceSampling step 4) on the device: one warp per hand over the n
+ * hands (n <= num_selected in detectGrasps), inliers folded in index order so that the running mean / variance are the
+ * reference's. hands [n] are host records (score, position, frame read); clusters_out has room for n records and receives
+ * the clusters in the order of their seed hands (position = mean inlier position, score = lower 99 % confidence bound).
+ * Returns the number of clusters. */
+int gpdb_find_clusters(gpdb_ctx *ctx, const gpdb_pose *hands, int32_t n_hands, int32_t min_inliers, gpdb_pose *clusters_out);
+
 /* Replaces: freeMemoryGrasps (detect_grasps_python.cpp:598-601). The arrays of a result live in page-locked host memory
  * owned by the library (the device writes them directly, overlapped with compute); gpdb_free_result hands that memory
  * back for the next call. A result may outlive its context. */

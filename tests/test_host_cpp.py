@@ -496,3 +496,31 @@ def test_detect_grasps_cli_on_two_gpus_equals_one(cli, tmp_path):
     c1 = [l for l in one.splitlines() if "gripper width" in l][0].split(":")[1].split()[0]
     c2 = [l for l in two.splitlines() if "gripper width" in l][0].split(":")[1].split()[0]
     assert c1 == c2
+
+
+@pytest.mark.gpu
+def test_device_clustering_equals_the_host_restatement(cli):
+    """gpdb_find_clusters (one warp per hand, inliers folded in index order) against the shim's host Clustering::findClusters
+    (itself checked against a Python restatement above): bit-equal cluster records on real detections."""
+    import ctypes as C
+    from conftest import load_weights
+    from gpd_b200 import abi, lib
+    k = scenes.krylon_cloud()
+    w, _ = load_weights(15)
+    p = lib.default_params(channels=15)
+    ctx = lib.Context(p)
+    ctx.set_weights(w)
+    ctx.set_cloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    hands = ctx.detect_select(np.arange(0, len(k["xyz"]), 2, dtype=np.int32), 400)["candidates"]
+    assert len(hands) == 400
+    H = C.CDLL(os.path.join(HOST, "libgpd_host.so"))
+    H.gpdFindClusters.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    for min_inliers in (1, 3, 10):
+        ref = np.zeros(len(hands), dtype=abi.POSE_DTYPE)
+        n = H.gpdFindClusters(hands.ctypes.data, len(hands), min_inliers, 0, ref.ctypes.data)
+        dev = ctx.find_clusters(hands, min_inliers)
+        assert len(dev) == n and n > 0
+        for f in ("position", "score", "frame", "sample_index", "pose_slot", "full_antipodal"):
+            assert np.array_equal(dev[f], ref[:n][f]), (min_inliers, f)
+    assert len(ctx.find_clusters(hands[:1], 1)) == 0 and len(ctx.find_clusters(hands[:0], 1)) == 0
+    ctx.close()
