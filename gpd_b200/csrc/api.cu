@@ -418,10 +418,11 @@ int gpdb_cloud_reserve(gpdb_ctx *ctx, size_t n) {
 
 // The device arrays d_xyz / d_nrm / d_cam hold N points (uploaded by gpdb_set_cloud or received by ncclBroadcast): make
 // them the context's cloud and build the neighbour grid (bounds by a device reduction).
-int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points) {
+int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points, int all_seen) {
   ctx->cloud_set = false;
   ctx->has_src = false;
   ctx->hp.K = K;
+  ctx->hp.all_seen = all_seen;
   for (int k = 0; k < K; k++)
     for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];
   ctx->N = N;
@@ -479,7 +480,9 @@ int gpdb_set_cloud(gpdb_ctx *ctx, const float *xyz, const double *normals, const
         gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_set_cloud: point %d has a non-finite coordinate (run removeNans / gpdb_preprocess first)", i);
         return GPDB_ERR_INVALID;
       }
-  return gpdb_install_device_cloud(ctx, N, K, view_points);
+  bool all_seen = true;  // no per-point camera mask has to be read by the image kernel when every camera sees every point
+  for (int i = 0; i < N && all_seen; i++) all_seen = cam[i] == (uint8_t)((1u << K) - 1);
+  return gpdb_install_device_cloud(ctx, N, K, view_points, all_seen ? 1 : 0);
 }
 
 void gpdb_preprocess_params_default(gpdb_preprocess_params *p) {
@@ -541,6 +544,7 @@ int gpdb_preprocess(gpdb_ctx *ctx, const float *xyz, const double *normals, cons
   // ---- install as the context's cloud (the arrays were written in place)
   ctx->N = N;
   ctx->K = K;
+  ctx->hp.all_seen = cam_source ? 0 : 1;  // without a camera-source matrix every point counts as seen by every camera
   ctx->hp.K = K;
   for (int k = 0; k < K; k++)
     for (int r = 0; r < 3; r++) ctx->hp.vp[k][r] = view_points[3 * k + r];

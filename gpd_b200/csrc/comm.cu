@@ -174,6 +174,10 @@ int gpdb_set_cloud_bcast(gpdb_ctx *ctx, int32_t root, const float *xyz, const do
       for (size_t i = 0; i < 3 * (size_t)N && ok; i++) ok = std::isfinite(xyz[i]);
     hdr[0] = ok ? N : -1;
     hdr[1] = K;
+    bool all_seen = true;
+    if (ok && cam_source)
+      for (size_t i = 0; i < (size_t)N * K && all_seen; i++) all_seen = cam_source[i] > 0;
+    hdr[2] = all_seen ? 1 : 0;
     if (ok) memcpy(hdr + 4, view_points, sizeof(double) * 3 * (size_t)K);
   }
   double *d_hdr = (double *)gpdb_scratch(ctx, 4, sizeof(hdr));
@@ -210,7 +214,7 @@ int gpdb_set_cloud_bcast(gpdb_ctx *ctx, int32_t root, const float *xyz, const do
   NCCL_TRY(g_nccl.Broadcast(ctx->d_nrm, ctx->d_nrm, sizeof(double) * 3 * (size_t)N, ncclUint8, root, cs.comm, ctx->stream));
   NCCL_TRY(g_nccl.Broadcast(ctx->d_cam, ctx->d_cam, (size_t)N, ncclUint8, root, cs.comm, ctx->stream));
   NCCL_TRY(g_nccl.GroupEnd());
-  if ((rc = gpdb_install_device_cloud(ctx, N, K, hdr + 4)) != GPDB_OK) return rc;
+  if ((rc = gpdb_install_device_cloud(ctx, N, K, hdr + 4, (int)hdr[2])) != GPDB_OK) return rc;
   return N;
 }
 

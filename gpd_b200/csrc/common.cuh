@@ -59,6 +59,7 @@ struct DevParams {
   int dim[3];
   // cloud
   int N, K;
+  int all_seen;                // every point is seen by every camera (cam mask complete): the per-point masks need not be read
   double vp[GPDB_MAX_CAMERAS][3];
   // LeNet
   int relu_after_conv;
@@ -165,7 +166,7 @@ int gpdb_check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights);
 int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
                       bool resident, uint8_t *flags_ext, float *scores_ext, int select_k, int slot_base);
 // installs the cloud whose device arrays d_xyz / d_nrm / d_cam already hold N points (grid bounds by device reduction)
-int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points);
+int gpdb_install_device_cloud(gpdb_ctx *ctx, int N, int K, const double *view_points, int all_seen);
 
 // geometry.cu
 // builds the neighbour grid over ctx->d_xyz (N points) whose per-axis bounds are lo / hi

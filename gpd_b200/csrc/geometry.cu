@@ -89,7 +89,8 @@ __device__ __forceinline__ int seg_batch(const DevParams &P, const int *cell_sta
 // Ball scan with exact load balance: the row bounds are fetched once (one thread per row), prefix-summed across
 // the CTA, and every warp walks an equal share [T w / NW, T (w+1) / NW) of the flattened candidate range, row by row
 // (rows are contiguous segments of the cell-sorted point array -> coalesced float4 loads, no per-candidate search).
-// body(in_range, point) is called by all 32 lanes together. Contains __syncthreads: call from uniform control flow.
+// body(in_range, point, position in the cell-sorted array) is called by all 32 lanes together. Contains __syncthreads:
+// call from uniform control flow.
 template <int NT, class F>
 __device__ __forceinline__ void scan_balanced(const DevParams &P, const DevCloud &cl, const SegRange &sr, SegScan<NT> &seg,
                                               F &&body) {
@@ -109,9 +110,10 @@ __device__ __forceinline__ void scan_balanced(const DevParams &P, const DevCloud
     // software pipeline: the load of chunk i+1 is issued before chunk i is processed (the scan is latency bound:
     // ~10 short row segments per warp, each a dependent L2 round trip)
     int r = lo, c = c_begin;
-    auto fetch = [&](bool &have, bool &in, float4 &p) {
+    auto fetch = [&](bool &have, bool &in, float4 &p, int &where) {
       have = false;
       in = false;
+      where = 0;
       p = make_float4(0.f, 0.f, 0.f, 0.f);
       while (c < c_end) {
         const int pe = (r + 1 < nr) ? seg.prefix[r + 1] : total;
@@ -122,7 +124,8 @@ __device__ __forceinline__ void scan_balanced(const DevParams &P, const DevCloud
         }
         const int k = c + lane;
         in = k < seg_end;
-        if (in) p = __ldg(cl.pts4 + (seg.start[r] - seg.prefix[r]) + k);
+        where = (seg.start[r] - seg.prefix[r]) + k;
+        if (in) p = __ldg(cl.pts4 + where);
         c = min(c + 32, seg_end);
         have = true;
         return;
@@ -130,13 +133,15 @@ __device__ __forceinline__ void scan_balanced(const DevParams &P, const DevCloud
     };
     bool have0, in0, have1, in1;
     float4 p0, p1;
-    fetch(have0, in0, p0);
+    int w0, w1;
+    fetch(have0, in0, p0, w0);
     while (have0) {
-      fetch(have1, in1, p1);
-      body(in0, p0);
+      fetch(have1, in1, p1, w1);
+      body(in0, p0, w0);
       have0 = have1;
       in0 = in1;
       p0 = p1;
+      w0 = w1;
     }
   }
 }
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(NT_HANDS, 4) k_hands(const DevParams *Pp, DevC
     const double hz = P.hand_height * 1.001 + 1e-9;
     unsigned long long best = ~0ull;
     int nball = 0;
-    scan_balanced<NT_HANDS>(P, cl, sr, S.seg, [&](bool in, const float4 &p) {
+    scan_balanced<NT_HANDS>(P, cl, sr, S.seg, [&](bool in, const float4 &p, int) {
       bool keep = false;
       if (in) {
         float d = l2_simple(q, p.x, p.y, p.z);
@@ -970,8 +975,10 @@ struct ImgSmem {
   int n_img;
   int box_n;
   int wl_n;
+  int ball_n;                     // in-ball points recorded by scan 1 (positions in the cell-sorted array)
   int bm_org[3], bm_dims[3];
-  float fred[NT_IMG / 32][4];
+  unsigned occs[3][MAXPIX / 32 + 2];  // the same for the three shadow projections
+  float fred[NT_IMG / 32][8];
 };
 
 __device__ __forceinline__ bool in_image_box(const DevParams &P, const gpdb_pose &h, double x, double y, double z) {
@@ -1000,9 +1007,9 @@ __device__ __forceinline__ unsigned unit_q32(double u) {
   return (unsigned)t;
 }
 
-// block-wide reduction of up to four floats with max (use negated values for min). Contains two barriers.
+// block-wide reduction of up to eight floats with max (use negated values for min). Contains two barriers.
 template <int NT, int NV>
-__device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[4]) {
+__device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[8]) {
 #pragma unroll
   for (int o = 16; o; o >>= 1)
 #pragma unroll
@@ -1114,6 +1121,11 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
   unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
   float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
+  // scan 1 records WHERE the in-ball points are (position in the cell-sorted array, 4 B each) in tile C, which nothing
+  // else touches before the shadow phase: the shadow casting re-reads the neighbourhood as independent loads from that
+  // list (one L2 round trip) instead of walking the grid again (cell bounds -> prefix scan -> search -> points).
+  int *ball = reinterpret_cast<int *>(tileC);
+  const int BALL_CAP = 2 * SS;  // 8 S S bytes / 4
   const int tid = threadIdx.x, lane = tid & 31;
   const int nproj = (C >= 12) ? 3 : 1;
   const int per = (C == 15) ? 5 : 4;
@@ -1123,7 +1135,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
     sm.lcgA[k] = P.lcgA[k];
     sm.lcgC[k] = P.lcgC[k];
   }
-  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = 0u;
+  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = sm.occs[0][k] = sm.occs[1][k] = sm.occs[2][k] = 0u;
 
   for (int b = blockIdx.x; b < nc; b += gridDim.x) {
     __syncthreads();
@@ -1136,10 +1148,13 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       sm.cam_or = 0;
       sm.n_img = 0;
       sm.box_n = 0;
+      sm.ball_n = 0;
     }
     for (int k = tid; k < plane_bytes >> 4; k += NT_IMG) reinterpret_cast<uint4 *>(planes)[k] = make_uint4(0, 0, 0, 0);
+    for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tiles A, B: clean
     __syncthreads();
     PHASE(1);   // image start
+    const bool need_cam = (C == 15) && !P.all_seen;  // the camera set of the neighbourhood is only read by the shadow
     const gpdb_pose &h = sm.h;
     const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
     float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
@@ -1148,26 +1163,38 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
     //      and the list of points inside the image box (ImageStrategy::transformToUnitImage)
     double sx = 0, sy = 0, sz = 0;
     int cnt = 0, cam_or = 0;
-    scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p) {
+    scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p, int where) {
       // the scan only APPENDS the raw box points (few lanes qualify: doing the per-point work here would run it at
       // ~6 % lane utilisation); unit coordinates, cells and normals are computed densely after the scan
-      bool inb = false;
+      bool inb = false, inball = false;
       unsigned long long key = 0;
       if (in) {
         float d = l2_simple(q, p.x, p.y, p.z);
         if (d < P.r2_img) {
+          inball = true;
           const int idx = __float_as_int(p.w);
           sx += (double)p.x;
           sy += (double)p.y;
           sz += (double)p.z;
           cnt++;
-          cam_or |= cl.cam[idx];
+          if (need_cam) cam_or |= cl.cam[idx];
           double x, y, z;
           to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
           if (in_image_box(P, h, x, y, z)) {
             inb = true;
             key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
           }
+        }
+      }
+      if (C == 15) {  // remember where the neighbourhood lives (warp-aggregated append)
+        const unsigned mb = __ballot_sync(0xffffffffu, inball);
+        if (mb) {
+          const int leader = __ffs(mb) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&sm.ball_n, __popc(mb));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const int pos = base + __popc(mb & ((1u << lane) - 1));
+          if (inball && pos < BALL_CAP) ball[pos] = where;
         }
       }
       unsigned mk = __ballot_sync(0xffffffffu, inb);
@@ -1210,6 +1237,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         a2 += sm.red[w][2];
       }
       double nn = (double)sm.n_img;
+      if (!need_cam && sm.n_img > 0) sm.cam_or = (1 << P.K) - 1;  // every point is seen by every camera (set at upload)
       sm.center[0] = a0 / nn;
       sm.center[1] = a1 / nn;
       sm.center[2] = a2 / nn;
@@ -1250,21 +1278,16 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       // coordinate orders (x,y,z), (z,y,x), (z,x,y): rows cumulatively swapped {0<->2}, {1<->2}
       // (image_15_channels_strategy.cpp:57-64)
       const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
-      for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tileA + tileB
-      __syncthreads();
+      // tiles A and B are clean here (zeroed at image start; every projection wipes the cells it touched), occf likewise
       for (int k = tid; k < bn; k += NT_IMG) {
         const unsigned cc = bcell[k];
         const int row = S - 1 - (int)((cc >> (8 * a0)) & 255), col = (cc >> (8 * a1)) & 255;
         const int pix = row * S + col;
         atomicMax(tileA + pix, bkeys[k]);
         atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
+        atomicOr(&sm.occf[pix >> 5], 1u << (pix & 31));
       }
       __syncthreads();
-#pragma unroll
-      for (int t = 0; t < PIXT; t++) {  // occupancy bitmap of the projection (no atomics: one ballot per 32 cells)
-        const int pix = tid + t * NT_IMG;
-        if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, pix < SS && (tileB[pix] >> 48) != 0ull);
-      }
       // the winner of a cell (its point with the largest key) carries the cell's values: |n| of that point, 1 - mean depth
       auto cell_values = [&](int k, int &row, int &col, float &n0, float &n1, float &n2, float &dv) -> bool {
         const unsigned cc = bcell[k];
@@ -1276,7 +1299,9 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         n1 = bnrm[BOX_CAP + k];
         n2 = bnrm[2 * BOX_CAP + k];
         const unsigned long long acc = tileB[pix];
-        const double mean = (double)(acc & 0xffffffffffffull) / ((double)(unsigned)(acc >> 48) * 4294967296.0);
+        const unsigned cntc = (unsigned)(acc >> 48);
+        const double sum = (double)(acc & 0xffffffffffffull);
+        const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);  // exact scaling
         const float avg = (float)mean;
         dv = (float)(1.0 - (double)avg);
         return true;
@@ -1342,6 +1367,8 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
             }
             if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(wv[j][3]);
           }
+        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // float images -> clean
+        for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
       } else {
         const Quant qn(0.0f, mxv[0]), qd(0.0f, mxv[1]);
         const int cb = (C == 1) ? 0 : pj * per;
@@ -1357,6 +1384,14 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
             }
             if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(dv);
           }
+        }
+        __syncthreads();  // every winner has read its cell: wipe the touched cells for the next projection
+        for (int k = tid; k < bn; k += NT_IMG) {
+          const unsigned cc = bcell[k];
+          const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
+          tileA[pix] = 0ull;
+          tileB[pix] = 0ull;
+          sm.occf[pix >> 5] = 0u;
         }
       }
       __syncthreads();
@@ -1421,7 +1456,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       // region; (2) the (point, draw) pairs are spread evenly over all threads — draw t of a point comes from
       // the closed-form LCG skip-ahead seed_t = A^(t+1) seed_0 + C_(t+1) (mod 2^32).
       float4 *wl = reinterpret_cast<float4 *>(tileA);
-      const int WL_CAP = (3 * SS * 8) / 20;
+      const int WL_CAP = (2 * SS * 8) / 20;  // tiles A + B (tile C holds the ball list until the casting is done)
       unsigned *wrange = reinterpret_cast<unsigned *>(wl + WL_CAP);
       // image box in the hand frame, widened by voxel truncation (<= 0.003 sqrt 3) + jitter (<= gmax 0.0009 sqrt 3)
       const double wm = 0.0105;
@@ -1474,16 +1509,12 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         __syncthreads();
         if (tid == 0) sm.wl_n = 0;
         __syncthreads();
-        scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p) {
-          if (!in) return;
-          float d = l2_simple(q, p.x, p.y, p.z);
-          if (!(d < P.r2_img)) return;
-          const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-          // conservative cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame)
-          // widened by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG
-          // value falls in [r0, r1] can produce a voxel point inside the box. float32 is enough here: its rounding
-          // (~1e-7 of coordinates < 0.2 m, 3e-7 of t) is covered by the extra 1e-5 of box margin and by the +-1 of
-          // slack on r0 / r1 (1 / 32767 = 3e-5); the draws themselves are evaluated in the reference's float64.
+        // conservative cull: clip the shadow segment p + u sv, u in [0,1], against the image box (hand frame)
+        // widened by the largest displacement voxel truncation + jitter can add; only draws whose 15-bit LCG
+        // value falls in [r0, r1] can produce a voxel point inside the box. float32 is enough here: its rounding
+        // (~1e-7 of coordinates < 0.2 m, 3e-7 of t) is covered by the extra 1e-5 of box margin and by the +-1 of
+        // slack on r0 / r1 (1 / 32767 = 3e-5); the draws themselves are evaluated in the reference's float64.
+        auto cull = [&](const float4 &p, unsigned &rg) -> bool {
           const float wx = p.x - fsx, wy = p.y - fsy, wz = p.z - fsz;
           const float o3[3] = {fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz)), fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz)),
                                fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz))};
@@ -1499,21 +1530,54 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
               tmax = fminf(tmax, fmaxf(t1, t2));
             }
           }
-          if (!hit || tmin > tmax) return;
+          if (!hit || tmin > tmax) return false;
           const int r0 = max((int)floorf(tmin * 32767.0f) - 1, 0), r1 = min((int)ceilf(tmax * 32767.0f) + 1, 32767);
-          unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
-          int pos = atomicAdd(&sm.wl_n, 1);
+          rg = (unsigned)r0 | ((unsigned)r1 << 16);
+          return true;
+        };
+        // appends the point to the work list (one shared-memory atomic per warp); called by all 32 lanes together
+        auto append = [&](bool ok, const float4 &p, unsigned rg) {
+          const unsigned mk = __ballot_sync(0xffffffffu, ok);
+          if (!mk) return;
+          const int leader = __ffs(mk) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&sm.wl_n, __popc(mk));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (!ok) return;
+          const int pos = base + __popc(mk & ((1u << lane) - 1));
+          const unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
           if (pos < WL_CAP) {
             wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
-            wrange[pos] = (unsigned)r0 | ((unsigned)r1 << 16);
+            wrange[pos] = rg;
           } else {  // work list full (very dense neighbourhood): cast this point's draws in place
             unsigned seed = seed0;
+            const int r0 = (int)(rg & 0xFFFFu), r1 = (int)(rg >> 16);
             for (int t = 0; t < P.nsp; t++) {
               int r = (int)gpdb_fastrand(&seed);
-              if (r >= r0 && r <= r1) cast_draw(px, py, pz, seed, k, bm);
+              if (r >= r0 && r <= r1) cast_draw((double)p.x, (double)p.y, (double)p.z, seed, k, bm);
             }
           }
-        });
+        };
+        const int nball = sm.ball_n;
+        if (nball <= BALL_CAP) {  // the neighbourhood recorded by scan 1: independent loads, all lanes busy
+          for (int i0 = 0; i0 < nball; i0 += NT_IMG) {
+            const int i = i0 + tid;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned rg = 0;
+            bool ok = false;
+            if (i < nball) {
+              p = __ldg(cl.pts4 + ball[i]);
+              ok = cull(p, rg);
+            }
+            append(ok, p, rg);
+          }
+        } else {  // more in-ball points than the list holds: walk the grid again
+          scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p, int) {
+            unsigned rg = 0;
+            const bool ok = in && l2_simple(q, p.x, p.y, p.z) < P.r2_img && cull(p, rg);
+            append(ok, p, rg);
+          });
+        }
         __syncthreads();
         const int nw = min(sm.wl_n, WL_CAP);
         if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
@@ -1529,6 +1593,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           unsigned rg = wrange[item];
           int r = (int)((seed >> 16) & 0x7FFFu);
           if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) return -1;
+          if (prof) atomicAdd(prof + 10, 1ull);
           return draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
         };
         for (int w = tid; w < nw * nsp; w += 2 * NT_IMG) {
@@ -1609,43 +1674,50 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       __syncthreads();
       PHASE(6);  // S2 bitmap pass done
       // createShadowImage (image_strategy.cpp:193-233): mean per cell, value = max over occupied - mean on occupied cells
+      // pass 1 over the three sum tiles: per-cell means (kept in registers), their max / min, the occupancy bitmaps
+      float avgr[3][PIXT];
+      unsigned occm[3] = {0u, 0u, 0u};
+      float mm[6] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};  // per projection: max avg, -(min avg)
+#pragma unroll
       for (int pj = 0; pj < 3; pj++) {
         const unsigned long long *tile = tileA + (size_t)pj * SS;
-        uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
-        float avgr[PIXT];
-        unsigned occm = 0;
-        float mm[2] = {-FLT_MAX, -FLT_MAX};  // max avg, -(min avg) over the occupied cells
 #pragma unroll
         for (int t = 0; t < PIXT; t++) {
           const int pix = tid + t * NT_IMG;
-          avgr[t] = 0.0f;
+          avgr[pj][t] = 0.0f;
           bool oc = false;
           if (pix < SS) {
             const unsigned long long acc = tile[pix];
             const unsigned cntc = (unsigned)(acc >> 48);
             if (cntc) {
-              const double mean = (double)(acc & 0xffffffffffffull) / ((double)cntc * 4294967296.0);
-              avgr[t] = (float)mean;
-              occm |= 1u << t;
+              const double sum = (double)(acc & 0xffffffffffffull);
+              // one voxel in the cell: sum / 2^32 is an exact scaling, the same bits as the division
+              const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
+              avgr[pj][t] = (float)mean;
+              occm[pj] |= 1u << t;
               oc = true;
-              mm[0] = fmaxf(mm[0], avgr[t]);
-              mm[1] = fmaxf(mm[1], -avgr[t]);
+              mm[2 * pj] = fmaxf(mm[2 * pj], avgr[pj][t]);
+              mm[2 * pj + 1] = fmaxf(mm[2 * pj + 1], -avgr[pj][t]);
             }
           }
-          if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, oc);
+          if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occs[pj], t, oc);
         }
-        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers publish the occupancy words)
-        const bool any = mm[0] != -FLT_MAX;
-        const float maxf = any ? mm[0] : 0.0f;
-        const float vmax = any ? maxf - (-mm[1]) : 0.0f;  // largest cell value = max avg - min avg
+      }
+      block_max<NT_IMG, 6>(mm, sm.fred);  // one reduction for the three projections (its barriers publish the bitmaps)
+#pragma unroll
+      for (int pj = 0; pj < 3; pj++) {
+        uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
+        const bool any = mm[2 * pj] != -FLT_MAX;
+        const float maxf = any ? mm[2 * pj] : 0.0f;
+        const float vmax = any ? maxf - (-mm[2 * pj + 1]) : 0.0f;  // largest cell value = max avg - min avg
         float vmin = 0.0f;
-        if (fully_covered(sm.occf, S)) {  // general path: min over the dilated float image
+        if (fully_covered(sm.occs[pj], S)) {  // general path: min over the dilated float image
           float *srcF = reinterpret_cast<float *>(tileA + (size_t)pj * SS);
           __syncthreads();
 #pragma unroll
           for (int t = 0; t < PIXT; t++) {
             const int pix = tid + t * NT_IMG;
-            if (pix < SS) srcF[pix] = ((occm >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
+            if (pix < SS) srcF[pix] = ((occm[pj] >> t) & 1) ? (maxf - avgr[pj][t]) : 0.0f;
           }
           __syncthreads();
           float neg[1] = {-dilated_min<NT_IMG>(srcF, S)};
@@ -1659,8 +1731,8 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           const int pix = tid + t * NT_IMG;
           if (pix < SS) {
             const int row = pix / S, col = pix - row * S;
-            const bool oc = (occm >> t) & 1;
-            if (oc || bg) plane[row * RS + col] = (uint8_t)(oc ? qs(maxf - avgr[t]) : bg);
+            const bool oc = (occm[pj] >> t) & 1;
+            if (oc || bg) plane[row * RS + col] = (uint8_t)(oc ? qs(maxf - avgr[pj][t]) : bg);
           }
         }
       }
