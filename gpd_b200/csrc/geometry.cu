@@ -977,7 +977,6 @@ struct ImgSmem {
   int wl_n;
   int ball_n;                     // in-ball points recorded by scan 1 (positions in the cell-sorted array)
   int bm_org[3], bm_dims[3];
-  unsigned occs[3][MAXPIX / 32 + 2];  // the same for the three shadow projections
   float fred[NT_IMG / 32][8];
 };
 
@@ -1135,7 +1134,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
     sm.lcgA[k] = P.lcgA[k];
     sm.lcgC[k] = P.lcgC[k];
   }
-  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = sm.occs[0][k] = sm.occs[1][k] = sm.occs[2][k] = 0u;
+  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = 0u;
 
   for (int b = blockIdx.x; b < nc; b += gridDim.x) {
     __syncthreads();
@@ -1674,17 +1673,16 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       __syncthreads();
       PHASE(6);  // S2 bitmap pass done
       // createShadowImage (image_strategy.cpp:193-233): mean per cell, value = max over occupied - mean on occupied cells
-      // pass 1 over the three sum tiles: per-cell means (kept in registers), their max / min, the occupancy bitmaps
-      float avgr[3][PIXT];
-      unsigned occm[3] = {0u, 0u, 0u};
-      float mm[6] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};  // per projection: max avg, -(min avg)
-#pragma unroll
       for (int pj = 0; pj < 3; pj++) {
         const unsigned long long *tile = tileA + (size_t)pj * SS;
+        uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
+        float avgr[PIXT];
+        unsigned occm = 0;
+        float mm[2] = {-FLT_MAX, -FLT_MAX};  // max avg, -(min avg) over the occupied cells
 #pragma unroll
         for (int t = 0; t < PIXT; t++) {
           const int pix = tid + t * NT_IMG;
-          avgr[pj][t] = 0.0f;
+          avgr[t] = 0.0f;
           bool oc = false;
           if (pix < SS) {
             const unsigned long long acc = tile[pix];
@@ -1693,31 +1691,27 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
               const double sum = (double)(acc & 0xffffffffffffull);
               // one voxel in the cell: sum / 2^32 is an exact scaling, the same bits as the division
               const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
-              avgr[pj][t] = (float)mean;
-              occm[pj] |= 1u << t;
+              avgr[t] = (float)mean;
+              occm |= 1u << t;
               oc = true;
-              mm[2 * pj] = fmaxf(mm[2 * pj], avgr[pj][t]);
-              mm[2 * pj + 1] = fmaxf(mm[2 * pj + 1], -avgr[pj][t]);
+              mm[0] = fmaxf(mm[0], avgr[t]);
+              mm[1] = fmaxf(mm[1], -avgr[t]);
             }
           }
-          if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occs[pj], t, oc);
+          if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, oc);
         }
-      }
-      block_max<NT_IMG, 6>(mm, sm.fred);  // one reduction for the three projections (its barriers publish the bitmaps)
-#pragma unroll
-      for (int pj = 0; pj < 3; pj++) {
-        uint8_t *plane = planes + (size_t)(pj * 5 + 4) * PLB;
-        const bool any = mm[2 * pj] != -FLT_MAX;
-        const float maxf = any ? mm[2 * pj] : 0.0f;
-        const float vmax = any ? maxf - (-mm[2 * pj + 1]) : 0.0f;  // largest cell value = max avg - min avg
+        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers publish the occupancy words)
+        const bool any = mm[0] != -FLT_MAX;
+        const float maxf = any ? mm[0] : 0.0f;
+        const float vmax = any ? maxf - (-mm[1]) : 0.0f;  // largest cell value = max avg - min avg
         float vmin = 0.0f;
-        if (fully_covered(sm.occs[pj], S)) {  // general path: min over the dilated float image
+        if (fully_covered(sm.occf, S)) {  // general path: min over the dilated float image
           float *srcF = reinterpret_cast<float *>(tileA + (size_t)pj * SS);
           __syncthreads();
 #pragma unroll
           for (int t = 0; t < PIXT; t++) {
             const int pix = tid + t * NT_IMG;
-            if (pix < SS) srcF[pix] = ((occm[pj] >> t) & 1) ? (maxf - avgr[pj][t]) : 0.0f;
+            if (pix < SS) srcF[pix] = ((occm >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
           }
           __syncthreads();
           float neg[1] = {-dilated_min<NT_IMG>(srcF, S)};
@@ -1731,11 +1725,14 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           const int pix = tid + t * NT_IMG;
           if (pix < SS) {
             const int row = pix / S, col = pix - row * S;
-            const bool oc = (occm[pj] >> t) & 1;
-            if (oc || bg) plane[row * RS + col] = (uint8_t)(oc ? qs(maxf - avgr[pj][t]) : bg);
+            const bool oc = (occm >> t) & 1;
+            if (oc || bg) plane[row * RS + col] = (uint8_t)(oc ? qs(maxf - avgr[t]) : bg);
           }
         }
       }
+      // the points phase of the next image expects a clean occupancy bitmap
+      __syncthreads();
+      for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
     }
     __syncthreads();
     PHASE(7);  // shadow images done
