@@ -22,6 +22,7 @@
 // All float64 geometry is evaluated in the oracle's operation order; this file is compiled with
 // -fmad=false so that no multiply-add is contracted (strict '<' on doubles).
 #include <cfloat>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -976,6 +977,7 @@ struct ImgSmem {
   int box_n;
   int wl_n;
   int ball_n;                     // in-ball points recorded by scan 1 (positions in the cell-sorted array)
+  int dl_n;                       // shadow draws that passed the window test (draw list)
   int bm_org[3], bm_dims[3];
   float fred[NT_IMG / 32][8];
 };
@@ -1103,7 +1105,9 @@ __device__ __noinline__ float dilated_min(const float *F, int S) {
 template <int S_T>
 __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
                                                       uint8_t *p16, const double *qtab, int *err, int plane_bytes,
-                                                      int list_bytes, unsigned long long *prof) {
+                                                      int list_bytes, unsigned long long *prof, const int *work,
+                                                      const int *work_n) {
+  // work != nullptr: only the images work[0 .. *work_n) (the overflow list of k_images2)
   long long t_phase = 0;
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -1136,7 +1140,9 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
   }
   for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = 0u;
 
-  for (int b = blockIdx.x; b < nc; b += gridDim.x) {
+  const int n_work = work ? *work_n : nc;
+  for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int b = work ? work[wi] : wi;
     __syncthreads();
     {
       const int *src = reinterpret_cast<const int *>(cand + b);
@@ -1492,6 +1498,8 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         int bit = draw_bit(px, py, pz, seed, k);
         if (bit >= 0) atomicOr(bm + (bit >> 5), 1u << (bit & 31));
       };
+      const int nball = sm.ball_n;
+      bool ball_valid = nball <= BALL_CAP;
       for (int k = 0; k < K; k++) {
         if (!((cam_set >> k) & 1)) continue;  // camera_set(i) >= 1 (hand_set.cpp:141)
         unsigned *bm = bitmap + (size_t)k * bm_words;
@@ -1557,8 +1565,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
             }
           }
         };
-        const int nball = sm.ball_n;
-        if (nball <= BALL_CAP) {  // the neighbourhood recorded by scan 1: independent loads, all lanes busy
+        if (ball_valid) {  // the neighbourhood recorded by scan 1: independent loads, all lanes busy
           for (int i0 = 0; i0 < nball; i0 += NT_IMG) {
             const int i = i0 + tid;
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1582,21 +1589,60 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
         const int nsp = P.nsp;
         const unsigned nsp_magic = nsp > 1 ? (unsigned)((0x100000000ull + (unsigned)nsp - 1) / (unsigned)nsp) : 0u;  // ceil(2^32 / nsp)
-        // two independent (point, draw) pairs per iteration: the float64 chains of the two draws interleave
-        auto work_bit = [&](int w) -> int {
-          if (w >= nw * nsp) return -1;
-          // w / nsp by multiply-high: exact for w < 2^32 / nsp (w < WL_CAP * nsp < 2^20)
-          int item = nsp > 1 ? (int)__umulhi((unsigned)w, nsp_magic) : w, t = w - item * nsp;
-          float4 e = wl[item];
-          unsigned seed = sm.lcgA[t] * __float_as_uint(e.w) + sm.lcgC[t];
-          unsigned rg = wrange[item];
-          int r = (int)((seed >> 16) & 0x7FFFu);
-          if (r < (int)(rg & 0xFFFFu) || r > (int)(rg >> 16)) return -1;
-          if (prof) atomicAdd(prof + 10, 1ull);
+        // Draws in two dense steps. (1) the cheap part of every (point, draw) pair — LCG skip-ahead + the window test of
+        // the slab cull, which ~60 % of the draws fail — with the survivors compacted into a list in tile C (the ball list is
+        // dead once the work list exists); (2) the float64 voxel arithmetic of the survivors only, all lanes busy (doing
+        // it in place kept the 70-instruction body running at ~40 % lane utilisation).
+        unsigned *dlist = reinterpret_cast<unsigned *>(tileC);  // item << 7 | t
+        const int DL_CAP = 2 * SS;
+        __syncthreads();  // the ball list has been consumed
+        ball_valid = false;  // ... and is overwritten by the draw list: a further camera walks the grid again
+        if (tid == 0) sm.dl_n = 0;
+        __syncthreads();
+        const int nd = nw * nsp;
+        for (int w0 = 0; w0 < nd; w0 += NT_IMG) {
+          const int w = w0 + tid;
+          bool pass = false;
+          unsigned code = 0, seed = 0;
+          if (w < nd) {
+            // w / nsp by multiply-high: exact for w < 2^32 / nsp (w < WL_CAP * nsp < 2^20)
+            const int item = nsp > 1 ? (int)__umulhi((unsigned)w, nsp_magic) : w, t = w - item * nsp;
+            seed = sm.lcgA[t] * __float_as_uint(wl[item].w) + sm.lcgC[t];
+            const unsigned rg = wrange[item];
+            const int r = (int)((seed >> 16) & 0x7FFFu);
+            pass = r >= (int)(rg & 0xFFFFu) && r <= (int)(rg >> 16);
+            code = ((unsigned)item << 7) | (unsigned)t;
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, pass);
+          if (mk) {
+            const int leader = __ffs(mk) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sm.dl_n, __popc(mk));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+              const int pos = base + __popc(mk & ((1u << lane) - 1));
+              if (pos < DL_CAP) dlist[pos] = code;
+              else {  // list full: evaluate in place
+                const float4 e = wl[code >> 7];
+                const int bit = draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
+                if (bit >= 0) atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        const int ndl = min(sm.dl_n, DL_CAP);
+        if (prof && tid == 0) atomicAdd(prof + 10, (unsigned long long)sm.dl_n);
+        auto list_bit = [&](int i) -> int {
+          if (i >= ndl) return -1;
+          const unsigned code = dlist[i];
+          const float4 e = wl[code >> 7];
+          const int t = (int)(code & 127u);
+          const unsigned seed = sm.lcgA[t] * __float_as_uint(e.w) + sm.lcgC[t];
           return draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
         };
-        for (int w = tid; w < nw * nsp; w += 2 * NT_IMG) {
-          const int bit_a = work_bit(w), bit_b = work_bit(w + NT_IMG);
+        for (int i = tid; i < ndl; i += 2 * NT_IMG) {  // two independent float64 chains per thread
+          const int bit_a = list_bit(i), bit_b = list_bit(i + NT_IMG);
           if (bit_a >= 0) atomicOr(bm + (bit_a >> 5), 1u << (bit_a & 31));
           if (bit_b >= 0) atomicOr(bm + (bit_b >> 5), 1u << (bit_b & 31));
         }
@@ -1782,6 +1828,682 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_images2: the fast path of the image stage — the same algorithm as k_images in 103 KB of shared memory and 64
+// registers, so that TWO 512-thread CTAs share an SM (k_images needs 214 KB: one CTA per SM, 16 warps, issue slots idle
+// behind barriers and dependent-issue stalls). What makes the footprint fit:
+//   * the box list holds 1024 points (24 B each: key, unit coordinates, cells; the normal of a WINNER is re-read from the
+//     cloud); images with more box points are appended to `ovf` and redone by k_images (2048 points, one CTA per SM);
+//   * two 64-bit tiles instead of three: the shadow sums of projections 0 and 1 are taken first, the per-voxel result for
+//     projection 2 (cell + fixed-point coordinate) is stashed next to the voxel code and summed in a second, cheap pass;
+//   * the quantised POINT channels are scattered straight into the image's own (still unused) 57.6 KB of HBM / L2 as twelve
+//     byte planes and read back into the dead tiles before the dilation; only the three shadow planes stay in shared memory.
+// Requires image_size 60 and at most two cameras (otherwise k_images does all the work). Results are bit-identical to
+// k_images (tests/test_gpu_parity.py::test_image_kernels_agree).
+// ------------------------------------------------------------------------------------------------
+constexpr int BOX_CAP2 = 1024;
+struct Img2Smem {
+  SegScan<NT_IMG> seg;
+  gpdb_pose h;
+  double red[NT_IMG / 32][4];
+  double center[3];
+  double sv[2][3];
+  double svh[2][3];
+  unsigned occf[MAXPIX / 32 + 2];
+  unsigned lcgA[GPDB_MAX_NSP], lcgC[GPDB_MAX_NSP];
+  int cam_or, n_img, box_n, wl_n, dl_n, st_n;
+  int bm_org[3], bm_dims[3];
+  float fred[NT_IMG / 32][8];
+};
+
+__global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
+                                                       uint8_t *p16, const double *qtab, int *ovf, int *ovf_count,
+                                                       unsigned long long *prof) {
+  long long t_phase = 0;
+  const DevParams &P = *Pp;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ Img2Smem sm;
+  constexpr int S = 60, SS = S * S, RW = S / 4, PLB = SS;  // 15 words per row, 3600-byte planes
+  constexpr int PIXT = (SS + NT_IMG - 1) / NT_IMG;
+  constexpr int JW = BOX_CAP2 / NT_IMG;  // box points per thread
+  const int C = P.C;
+  unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn);
+  unsigned long long *tileB = tileA + SS;
+  uint8_t *splanes = reinterpret_cast<uint8_t *>(tileB + SS);       // 3 shadow planes
+  unsigned char *lbase = splanes + 3 * PLB;
+  constexpr int LIST_BYTES = BOX_CAP2 * 36;                         // 24 B per box point + room for the shadow phase
+  unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(lbase);
+  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BOX_CAP2);    // [3][CAP]
+  unsigned *bcell = bq + 3 * BOX_CAP2;                              // packed 3 x 8 bit
+  unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);           // shadow phase: aliases the (dead) box list
+  uint8_t *tplanes = reinterpret_cast<uint8_t *>(tileA);            // final stage: the 12 point planes over the dead tiles
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nproj = (C >= 12) ? 3 : 1;
+  const bool do_nrm = C != 1, do_dep = C == 1 || C >= 12;
+  const int npp = (C == 15 || C == 12) ? 12 : C;  // point planes (C = 1: the depth plane is plane 0)
+  for (int k = tid; k < GPDB_MAX_NSP; k += NT_IMG) {
+    sm.lcgA[k] = P.lcgA[k];
+    sm.lcgC[k] = P.lcgC[k];
+  }
+  for (int k = tid; k < MAXPIX / 32 + 2; k += NT_IMG) sm.occf[k] = 0u;
+
+  for (int b = blockIdx.x; b < nc; b += gridDim.x) {
+    __syncthreads();
+    {
+      const int *src = reinterpret_cast<const int *>(cand + b);
+      int *dst = reinterpret_cast<int *>(&sm.h);
+      for (int k = tid; k < (int)(sizeof(gpdb_pose) / 4); k += NT_IMG) dst[k] = src[k];
+    }
+    if (tid == 0) {
+      sm.cam_or = 0;
+      sm.n_img = 0;
+      sm.box_n = 0;
+    }
+    uint8_t *gimg = p16 + (size_t)b * SS * 16;  // the image's own memory: first the point planes, finally the pixels
+    for (int k = tid; k < (npp * PLB) >> 4; k += NT_IMG) reinterpret_cast<uint4 *>(gimg)[k] = make_uint4(0, 0, 0, 0);
+    for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tiles A, B
+    for (int k = tid; k < (3 * PLB) >> 4; k += NT_IMG) reinterpret_cast<uint4 *>(splanes)[k] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    PHASE(1);
+    const gpdb_pose &h = sm.h;
+    const bool need_cam = (C == 15) && !P.all_seen;
+    const double inv_d = 1.0 / P.vol_d, inv_w = 1.0 / P.vol_w, inv_h = 1.0 / (2.0 * P.vol_h);
+    float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
+    SegRange sr = seg_range(P, q, P.rf_img);
+    // ---- ball scan 1: neighbourhood centre, camera set, raw box points
+    double sx = 0, sy = 0, sz = 0;
+    int cnt = 0, cam_or = 0;
+    scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p, int) {
+      bool inb = false;
+      unsigned long long key = 0;
+      if (in) {
+        float d = l2_simple(q, p.x, p.y, p.z);
+        if (d < P.r2_img) {
+          const int idx = __float_as_int(p.w);
+          sx += (double)p.x;
+          sy += (double)p.y;
+          sz += (double)p.z;
+          cnt++;
+          if (need_cam) cam_or |= cl.cam[idx];
+          double x, y, z;
+          to_frame(h.frame, (double)p.x - h.sample[0], (double)p.y - h.sample[1], (double)p.z - h.sample[2], x, y, z);
+          if (in_image_box(P, h, x, y, z)) {
+            inb = true;
+            key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+          }
+        }
+      }
+      unsigned mk = __ballot_sync(0xffffffffu, inb);
+      if (mk) {
+        int leader = __ffs(mk) - 1, base = 0;
+        if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        int pos = base + __popc(mk & ((1u << lane) - 1));
+        if (inb && pos < BOX_CAP2) {
+          bkeys[pos] = key;
+          bq[pos] = __float_as_uint(p.x);
+          bq[BOX_CAP2 + pos] = __float_as_uint(p.y);
+          bq[2 * BOX_CAP2 + pos] = __float_as_uint(p.z);
+        }
+      }
+    });
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    cnt = warp_sum(cnt);
+    cam_or = __reduce_or_sync(0xffffffffu, (unsigned)cam_or);
+    __syncthreads();
+    if (lane == 0) {
+      sm.red[tid >> 5][0] = sx;
+      sm.red[tid >> 5][1] = sy;
+      sm.red[tid >> 5][2] = sz;
+      atomicAdd(&sm.n_img, cnt);
+      atomicOr(&sm.cam_or, cam_or);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a0 = 0, a1 = 0, a2 = 0;
+      for (int w = 0; w < NT_IMG / 32; w++) {
+        a0 += sm.red[w][0];
+        a1 += sm.red[w][1];
+        a2 += sm.red[w][2];
+      }
+      double nn = (double)sm.n_img;
+      if (!need_cam && sm.n_img > 0) sm.cam_or = (1 << P.K) - 1;
+      sm.center[0] = a0 / nn;
+      sm.center[1] = a1 / nn;
+      sm.center[2] = a2 / nn;
+      if (sm.box_n > BOX_CAP2) ovf[atomicAdd(ovf_count, 1)] = b;  // redone by k_images (larger list)
+    }
+    __syncthreads();
+    PHASE(2);
+    if (sm.box_n > BOX_CAP2) continue;  // uniform
+    const int bn = sm.box_n;
+    for (int k = tid; k < bn; k += NT_IMG) {
+      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP2 + k]),
+                   pz = (double)__uint_as_float(bq[2 * BOX_CAP2 + k]);
+      double x, y, z, u0, u1, u2;
+      int c0, c1, c2;
+      to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], x, y, z);
+      unit_axis(x, h.bottom, P.vol_d, inv_d, S, u0, c0);
+      unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
+      unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
+      bq[k] = unit_q32(u0);
+      bq[BOX_CAP2 + k] = unit_q32(u1);
+      bq[2 * BOX_CAP2 + k] = unit_q32(u2);
+      bcell[k] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
+    }
+    __syncthreads();
+
+    // ---- points phase
+    for (int pj = 0; pj < nproj; pj++) {
+      const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
+      for (int k = tid; k < bn; k += NT_IMG) {
+        const unsigned cc = bcell[k];
+        const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
+        atomicMax(tileA + pix, bkeys[k]);
+        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP2 + k]);
+        atomicOr(&sm.occf[pix >> 5], 1u << (pix & 31));
+      }
+      __syncthreads();
+      // winners (largest key of their cell) carry the cell's values; each thread owns <= JW box points
+      float wv[JW][4];
+      int wpix[JW];
+      float mxv[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < JW; j++) {
+        const int k = tid + j * NT_IMG;
+        wpix[j] = -1;
+        if (k < bn) {
+          const unsigned cc = bcell[k];
+          const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
+          const unsigned long long key = bkeys[k];
+          if (tileA[pix] == key) {
+            wpix[j] = pix;
+            const double *nn = cl.nrm + 3 * (size_t)(unsigned)(key & 0xffffffffull);
+            double n0, n1, n2;
+            to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
+            wv[j][0] = (float)fabs(n0);
+            wv[j][1] = (float)fabs(n1);
+            wv[j][2] = (float)fabs(n2);
+            const unsigned long long acc = tileB[pix];
+            const unsigned cntc = (unsigned)(acc >> 48);
+            const double sum = (double)(acc & 0xffffffffffffull);
+            const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
+            const float avg = (float)mean;
+            wv[j][3] = (float)(1.0 - (double)avg);
+            mxv[0] = fmaxf(mxv[0], fmaxf(fmaxf(wv[j][0], wv[j][1]), wv[j][2]));
+            mxv[1] = fmaxf(mxv[1], wv[j][3]);
+          }
+        }
+      }
+      block_max<NT_IMG, 2>(mxv, sm.fred);
+      float mnv[2] = {0.0f, 0.0f};
+      const int cb = (C == 1) ? 0 : pj * 4;  // first point plane of the projection
+      const bool covered = fully_covered(sm.occf, S);
+      if (covered) {  // general path: no all-empty 3x3 window -> min over the dilated float images
+        float *F = reinterpret_cast<float *>(tileA);  // 4 x SS floats = tiles A + B (every winner holds its values)
+        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < JW; j++)
+          if (wpix[j] >= 0)
+#pragma unroll
+            for (int c = 0; c < 4; c++) F[c * SS + wpix[j]] = wv[j][c];
+        __syncthreads();
+        float neg[2];
+        neg[0] = -fminf(fminf(dilated_min<NT_IMG>(F, S), dilated_min<NT_IMG>(F + SS, S)), dilated_min<NT_IMG>(F + 2 * SS, S));
+        neg[1] = -dilated_min<NT_IMG>(F + 3 * SS, S);
+        block_max<NT_IMG, 2>(neg, sm.fred);
+        mnv[0] = -neg[0];
+        mnv[1] = -neg[1];
+        const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
+        const unsigned bg_n = qn(0.0f) * 0x01010101u, bg_d = qd(0.0f) * 0x01010101u;  // background = quantised 0
+        for (int k = tid; k < (PLB >> 2); k += NT_IMG) {
+          if (do_nrm)
+#pragma unroll
+            for (int c = 0; c < 3; c++) reinterpret_cast<unsigned *>(gimg + (size_t)(cb + c) * PLB)[k] = bg_n;
+          if (do_dep) reinterpret_cast<unsigned *>(gimg + (size_t)(cb + (C == 1 ? 0 : 3)) * PLB)[k] = bg_d;
+        }
+        __syncthreads();  // the background is in place before the winners overwrite their cells
+      }
+      {
+        const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
+#pragma unroll
+        for (int j = 0; j < JW; j++)
+          if (wpix[j] >= 0) {
+            if (do_nrm) {
+              gimg[(size_t)(cb + 0) * PLB + wpix[j]] = (uint8_t)qn(wv[j][0]);
+              gimg[(size_t)(cb + 1) * PLB + wpix[j]] = (uint8_t)qn(wv[j][1]);
+              gimg[(size_t)(cb + 2) * PLB + wpix[j]] = (uint8_t)qn(wv[j][2]);
+            }
+            if (do_dep) gimg[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + wpix[j]] = (uint8_t)qd(wv[j][3]);
+          }
+      }
+      // clean tiles / occupancy for the next projection
+      if (covered) {
+        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
+      } else {
+        __syncthreads();  // every winner has read its cell
+        for (int k = tid; k < bn; k += NT_IMG) {
+          const unsigned cc = bcell[k];
+          const int pix = (S - 1 - (int)((cc >> (8 * a0)) & 255)) * S + (int)((cc >> (8 * a1)) & 255);
+          tileA[pix] = 0ull;
+          tileB[pix] = 0ull;
+          sm.occf[pix >> 5] = 0u;
+        }
+      }
+      __syncthreads();
+    }
+    PHASE(3);
+
+    // ---- shadow phase (15 channels)
+    if (C == 15) {
+      const int K = P.K;
+      const int bmd = P.bm_dim;
+      const int bm_words = 2 * bmd * bmd;
+      const double gmax = qtab[GPDB_QTAB_SIZE - 1];
+      const double voxel = GPDB_SHADOW_VOXEL;
+      if (tid == 0) {
+        const double jmax = gmax * voxel * 0.3 + 1e-9;
+        const double half_od = P.vol_w / 2.0;
+        double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int cr = 0; cr < 8; cr++) {
+          double cx = (cr & 1) ? h.bottom + P.vol_d : h.bottom;
+          double cy = (cr & 2) ? h.center + half_od : h.center - half_od;
+          double cz = (cr & 4) ? P.vol_h : -P.vol_h;
+          for (int r = 0; r < 3; r++) {
+            double wv2 = h.frame[r] * cx + h.frame[3 + r] * cy + h.frame[6 + r] * cz + h.sample[r];
+            mn[r] = fmin(mn[r], wv2);
+            mx[r] = fmax(mx[r], wv2);
+          }
+        }
+        for (int r = 0; r < 3; r++) {
+          int lo = (int)floor((mn[r] - jmax) * P.vox_mult) - 1;
+          int hi = (int)floor((mx[r] + jmax) * P.vox_mult) + 1;
+          sm.bm_org[r] = lo;
+          sm.bm_dims[r] = min(hi - lo + 1, bmd);
+        }
+      }
+      if (tid < K) {
+        double s0 = sm.center[0] - P.vp[tid][0], s1 = sm.center[1] - P.vp[tid][1], s2 = sm.center[2] - P.vp[tid][2];
+        double nn = sqrt((s0 * s0 + s1 * s1) + s2 * s2);
+        sm.sv[tid][0] = P.shadow_length * s0 / nn;
+        sm.sv[tid][1] = P.shadow_length * s1 / nn;
+        sm.sv[tid][2] = P.shadow_length * s2 / nn;
+        to_frame(h.frame, sm.sv[tid][0], sm.sv[tid][1], sm.sv[tid][2], sm.svh[tid][0], sm.svh[tid][1], sm.svh[tid][2]);
+      }
+      for (int k = tid; k < bm_words * K; k += NT_IMG) bitmap[k] = 0u;
+      __syncthreads();
+      PHASE(4);
+      const int o0 = sm.bm_org[0], o1 = sm.bm_org[1], o2 = sm.bm_org[2];
+      const int d0 = sm.bm_dims[0], d1 = sm.bm_dims[1], d2 = sm.bm_dims[2];
+      const double mxu = 1.0 / 32767.0;
+      auto voxel_point_in_box = [&](int v0, int v1, int v2, double &x, double &y, double &z) -> bool {
+        double g = qtab[gpdb_voxel_hash(v0, v1, v2) & (GPDB_QTAB_SIZE - 1)];
+        double jit = 1.0 * g * voxel * 0.3;
+        double w0 = (double)v0 * voxel + jit, w1 = (double)v1 * voxel + jit, w2 = (double)v2 * voxel + jit;
+        to_frame(h.frame, w0 - h.sample[0], w1 - h.sample[1], w2 - h.sample[2], x, y, z);
+        return in_image_box(P, h, x, y, z);
+      };
+      const int cam_set = sm.cam_or;
+      float4 *wl = reinterpret_cast<float4 *>(tileA);       // work list over tile A ...
+      constexpr int WL_CAP = (SS * 8) / 20;
+      unsigned *wrange = reinterpret_cast<unsigned *>(wl + WL_CAP);
+      unsigned *dlist = reinterpret_cast<unsigned *>(tileB);  // ... draw list over tile B
+      constexpr int DL_CAP = 2 * SS;
+      const double wm = 0.0105;
+      const double bx_lo[3] = {h.bottom - wm, h.center - P.vol_w / 2.0 - wm, -P.vol_h - wm};
+      const double bx_hi[3] = {h.bottom + P.vol_d + wm, h.center + P.vol_w / 2.0 + wm, P.vol_h + wm};
+      float fR[9];
+#pragma unroll
+      for (int e = 0; e < 9; e++) fR[e] = (float)h.frame[e];
+      const float fsx = (float)h.sample[0], fsy = (float)h.sample[1], fsz = (float)h.sample[2];
+      const float jm = (float)(gmax * voxel * 0.3 * 1.7320508075688772 + 2e-5);
+      const float fbx_lo[3] = {(float)h.bottom - jm, (float)(h.center - P.vol_w / 2.0) - jm, (float)(-P.vol_h) - jm};
+      const float fbx_hi[3] = {(float)(h.bottom + P.vol_d) + jm, (float)(h.center + P.vol_w / 2.0) + jm, (float)P.vol_h + jm};
+      auto draw_bit = [&](double px, double py, double pz, unsigned seed, int k) -> int {
+        const double s0 = sm.sv[k][0], s1 = sm.sv[k][1], s2 = sm.sv[k][2];
+        double u = (double)((seed >> 16) & 0x7FFFu) * mxu;
+        int v0 = (int)((px + u * s0) * P.vox_mult);
+        int v1 = (int)((py + u * s1) * P.vox_mult);
+        int v2 = (int)((pz + u * s2) * P.vox_mult);
+        int b0 = v0 - o0, b1 = v1 - o1, b2 = v2 - o2;
+        if ((unsigned)b0 >= (unsigned)d0 || (unsigned)b1 >= (unsigned)d1 || (unsigned)b2 >= (unsigned)d2) return -1;
+        const float wx = fmaf((float)v0, 0.003f, -fsx), wy = fmaf((float)v1, 0.003f, -fsy), wz = fmaf((float)v2, 0.003f, -fsz);
+        const float hx = fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz));
+        const float hy = fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz));
+        const float hz = fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz));
+        if (hx < fbx_lo[0] || hx > fbx_hi[0] || hy < fbx_lo[1] || hy > fbx_hi[1] || hz < fbx_lo[2] || hz > fbx_hi[2]) return -1;
+        return ((b2 * d1 + b1) << 6) + b0;
+      };
+      for (int k = 0; k < K; k++) {
+        if (!((cam_set >> k) & 1)) continue;
+        unsigned *bm = bitmap + (size_t)k * bm_words;
+        float cull_lo[3], cull_hi[3], cull_inv[3];
+        bool cull_par[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const float dv = (float)sm.svh[k][a];
+          cull_par[a] = fabsf(dv) < 1e-6f;
+          cull_inv[a] = cull_par[a] ? 0.0f : 1.0f / dv;
+          cull_lo[a] = (float)bx_lo[a] - 1e-5f;
+          cull_hi[a] = (float)bx_hi[a] + 1e-5f;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          sm.wl_n = 0;
+          sm.dl_n = 0;
+        }
+        __syncthreads();
+        auto cull = [&](const float4 &p, unsigned &rg) -> bool {
+          const float wx = p.x - fsx, wy = p.y - fsy, wz = p.z - fsz;
+          const float o3[3] = {fmaf(fR[0], wx, fmaf(fR[1], wy, fR[2] * wz)), fmaf(fR[3], wx, fmaf(fR[4], wy, fR[5] * wz)),
+                               fmaf(fR[6], wx, fmaf(fR[7], wy, fR[8] * wz))};
+          float tmin = 0.0f, tmax = 1.0f;
+          bool hit = true;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            if (cull_par[a]) {
+              hit = hit && o3[a] >= cull_lo[a] && o3[a] <= cull_hi[a];
+            } else {
+              const float t1 = (cull_lo[a] - o3[a]) * cull_inv[a], t2 = (cull_hi[a] - o3[a]) * cull_inv[a];
+              tmin = fmaxf(tmin, fminf(t1, t2));
+              tmax = fminf(tmax, fmaxf(t1, t2));
+            }
+          }
+          if (!hit || tmin > tmax) return false;
+          const int r0 = max((int)floorf(tmin * 32767.0f) - 1, 0), r1 = min((int)ceilf(tmax * 32767.0f) + 1, 32767);
+          rg = (unsigned)r0 | ((unsigned)r1 << 16);
+          return true;
+        };
+        scan_balanced<NT_IMG>(P, cl, sr, sm.seg, [&](bool in, const float4 &p, int) {
+          unsigned rg = 0;
+          const bool ok = in && l2_simple(q, p.x, p.y, p.z) < P.r2_img && cull(p, rg);
+          const unsigned mk = __ballot_sync(0xffffffffu, ok);
+          if (!mk) return;
+          const int leader = __ffs(mk) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&sm.wl_n, __popc(mk));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (!ok) return;
+          const int pos = base + __popc(mk & ((1u << lane) - 1));
+          const unsigned seed0 = gpdb_shadow_seed((unsigned)h.sample_index, (unsigned)__float_as_int(p.w), (unsigned)k);
+          if (pos < WL_CAP) {
+            wl[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(seed0));
+            wrange[pos] = rg;
+          } else {  // work list full: cast this point's draws in place
+            unsigned seed = seed0;
+            const int r0 = (int)(rg & 0xFFFFu), r1 = (int)(rg >> 16);
+            for (int t = 0; t < P.nsp; t++) {
+              int r = (int)gpdb_fastrand(&seed);
+              if (r >= r0 && r <= r1) {
+                int bit = draw_bit((double)p.x, (double)p.y, (double)p.z, seed, k);
+                if (bit >= 0) atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+              }
+            }
+          }
+        });
+        __syncthreads();
+        const int nw = min(sm.wl_n, WL_CAP);
+        if (prof && tid == 0) atomicAdd(prof + 9, (unsigned long long)nw);
+        const int nsp = P.nsp;
+        const unsigned nsp_magic = nsp > 1 ? (unsigned)((0x100000000ull + (unsigned)nsp - 1) / (unsigned)nsp) : 0u;
+        const int nd = nw * nsp;
+        for (int w0 = 0; w0 < nd; w0 += NT_IMG) {  // window test of every draw, survivors compacted
+          const int w = w0 + tid;
+          bool pass = false;
+          unsigned code = 0, seed = 0;
+          if (w < nd) {
+            const int item = nsp > 1 ? (int)__umulhi((unsigned)w, nsp_magic) : w, t = w - item * nsp;
+            seed = sm.lcgA[t] * __float_as_uint(wl[item].w) + sm.lcgC[t];
+            const unsigned rg = wrange[item];
+            const int r = (int)((seed >> 16) & 0x7FFFu);
+            pass = r >= (int)(rg & 0xFFFFu) && r <= (int)(rg >> 16);
+            code = ((unsigned)item << 7) | (unsigned)t;
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, pass);
+          if (mk) {
+            const int leader = __ffs(mk) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sm.dl_n, __popc(mk));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+              const int pos = base + __popc(mk & ((1u << lane) - 1));
+              if (pos < DL_CAP) dlist[pos] = code;
+              else {
+                const float4 e = wl[code >> 7];
+                const int bit = draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
+                if (bit >= 0) atomicOr(bm + (bit >> 5), 1u << (bit & 31));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        const int ndl = min(sm.dl_n, DL_CAP);
+        if (prof && tid == 0) atomicAdd(prof + 10, (unsigned long long)sm.dl_n);
+        auto list_bit = [&](int i) -> int {
+          if (i >= ndl) return -1;
+          const unsigned code = dlist[i];
+          const float4 e = wl[code >> 7];
+          const int t = (int)(code & 127u);
+          const unsigned seed = sm.lcgA[t] * __float_as_uint(e.w) + sm.lcgC[t];
+          return draw_bit((double)e.x, (double)e.y, (double)e.z, seed, k);
+        };
+        for (int i = tid; i < ndl; i += 2 * NT_IMG) {
+          const int bit_a = list_bit(i), bit_b = list_bit(i + NT_IMG);
+          if (bit_a >= 0) atomicOr(bm + (bit_a >> 5), 1u << (bit_a & 31));
+          if (bit_b >= 0) atomicOr(bm + (bit_b >> 5), 1u << (bit_b & 31));
+        }
+      }
+      __syncthreads();
+      PHASE(5);
+      if (K > 1) {  // intersection, starting from camera 0's set even when it is empty (hand_set.cpp:153-176)
+        for (int wd = tid; wd < bm_words; wd += NT_IMG) {
+          unsigned acc = bitmap[wd];
+          for (int k = 1; k < K; k++)
+            if ((cam_set >> k) & 1) acc &= bitmap[(size_t)k * bm_words + wd];
+          bitmap[wd] = acc;
+        }
+      }
+      for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tiles A, B
+      if (tid == 0) sm.st_n = 0;
+      __syncthreads();
+      // voxel list (8 B per voxel behind the bitmaps): .x = voxel code, later the stash for projection 2
+      const int nbits = 64 * d1 * d2;
+      uint2 *stash = reinterpret_cast<uint2 *>(bitmap + (((size_t)bm_words * (K > 1 ? K : 1) + 1) & ~(size_t)1));
+      const int ST_CAP = (LIST_BYTES - (int)((reinterpret_cast<unsigned char *>(stash)) - lbase)) / 8;
+      // one voxel: exact box test, then the sums of projections [pj_lo, pj_hi) (tile pj - pj_lo); returns the stash entry of
+      // projection 2 (cell | 1 << 31, fixed-point coordinate), zero when the voxel point lies outside the box
+      auto eval_voxel = [&](unsigned packed, int pj_lo, int pj_hi) -> uint2 {
+        int b0 = packed & 255, b1 = (packed >> 8) & 255, b2 = packed >> 16;
+        double x, y, z;
+        if (!voxel_point_in_box(b0 + o0, b1 + o1, b2 + o2, x, y, z)) return make_uint2(0u, 0u);
+        double u[3];
+        int cellv[3];
+        unit_axis(x, h.bottom, P.vol_d, inv_d, S, u[0], cellv[0]);
+        unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u[1], cellv[1]);
+        unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u[2], cellv[2]);
+        uint2 st = make_uint2(0u, 0u);
+#pragma unroll
+        for (int pj = 0; pj < 3; pj++) {
+          const int a0 = (pj == 0) ? 0 : 2, a1 = (pj == 2) ? 0 : 1, a2 = (pj == 0) ? 2 : (pj == 1 ? 0 : 1);
+          const int pix = (S - 1 - cellv[a0]) * S + cellv[a1];
+          const unsigned qv = unit_q32(u[a2]);
+          if (pj >= pj_lo && pj < pj_hi) atomicAdd(tileA + (size_t)(pj - pj_lo) * SS + pix, (1ull << 48) + (unsigned long long)qv);
+          if (pj == 2) st = make_uint2((unsigned)pix | 0x80000000u, qv);
+        }
+        return st;
+      };
+      for (int wd0 = 0; wd0 * 32 < nbits; wd0 += NT_IMG) {
+        const int wd = wd0 + tid;
+        unsigned bits = (wd * 32 < nbits) ? bitmap[wd] : 0u;
+        int cntb = __popc(bits);
+        int incl = cntb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
+        if (lane == 31 && total) base = atomicAdd(&sm.st_n, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cntb;
+        const int rowi = wd >> 1;
+        const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
+        while (bits) {
+          int bi = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (pos < ST_CAP) stash[pos].x = hi | (unsigned)bi;
+          else eval_voxel(hi | (unsigned)bi, 0, 2);  // list full: projections 0 and 1 in place (2: second walk below)
+          pos++;
+        }
+      }
+      __syncthreads();
+      const int nset_all = sm.st_n, nset = min(nset_all, ST_CAP);
+      if (prof && tid == 0) {
+        atomicAdd(prof + 11, (unsigned long long)nset_all);
+        atomicAdd(prof + 12, (unsigned long long)bn);
+        atomicAdd(prof + 13, (unsigned long long)sm.n_img);
+      }
+      for (int i = tid; i < nset; i += NT_IMG) stash[i] = eval_voxel(stash[i].x, 0, 2);
+      __syncthreads();
+      PHASE(6);
+      // createShadowImage (image_strategy.cpp:193-233) for one sum tile -> shadow plane pj
+      auto shadow_channel = [&](int pj, unsigned long long *tile) {
+        uint8_t *plane = splanes + (size_t)pj * PLB;
+        float avgr[PIXT];
+        unsigned occm = 0;
+        float mm[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int t = 0; t < PIXT; t++) {
+          const int pix = tid + t * NT_IMG;
+          avgr[t] = 0.0f;
+          bool oc = false;
+          if (pix < SS) {
+            const unsigned long long acc = tile[pix];
+            const unsigned cntc = (unsigned)(acc >> 48);
+            if (cntc) {
+              const double sum = (double)(acc & 0xffffffffffffull);
+              const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
+              avgr[t] = (float)mean;
+              occm |= 1u << t;
+              oc = true;
+              mm[0] = fmaxf(mm[0], avgr[t]);
+              mm[1] = fmaxf(mm[1], -avgr[t]);
+            }
+          }
+          occ_ballot<NT_IMG>(sm.occf, t, oc);
+        }
+        block_max<NT_IMG, 2>(mm, sm.fred);
+        const bool any = mm[0] != -FLT_MAX;
+        const float maxf = any ? mm[0] : 0.0f;
+        const float vmax = any ? maxf - (-mm[1]) : 0.0f;
+        float vmin = 0.0f;
+        if (fully_covered(sm.occf, S)) {
+          float *srcF = reinterpret_cast<float *>(tile);
+          __syncthreads();
+#pragma unroll
+          for (int t = 0; t < PIXT; t++) {
+            const int pix = tid + t * NT_IMG;
+            if (pix < SS) srcF[pix] = ((occm >> t) & 1) ? (maxf - avgr[t]) : 0.0f;
+          }
+          __syncthreads();
+          float neg[1] = {-dilated_min<NT_IMG>(srcF, S)};
+          block_max<NT_IMG, 1>(neg, sm.fred);
+          vmin = -neg[0];
+        }
+        const Quant qs(vmin, vmax);
+        const unsigned bg = qs(0.0f);
+#pragma unroll
+        for (int t = 0; t < PIXT; t++) {
+          const int pix = tid + t * NT_IMG;
+          if (pix < SS) {
+            const bool oc = (occm >> t) & 1;
+            if (oc || bg) plane[pix] = (uint8_t)(oc ? qs(maxf - avgr[t]) : bg);
+          }
+        }
+      };
+      shadow_channel(0, tileA);
+      shadow_channel(1, tileB);
+      __syncthreads();
+      for (int k = tid; k < SS / 2; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // tile A
+      __syncthreads();
+      // projection 2: from the stash, or — when the voxel list overflowed — by a second walk over the whole bitmap
+      if (nset_all <= ST_CAP) {
+        for (int i = tid; i < nset; i += NT_IMG) {
+          const uint2 st = stash[i];
+          if (st.x & 0x80000000u) atomicAdd(tileA + (st.x & 0x7fffffffu), (1ull << 48) + (unsigned long long)st.y);
+        }
+      } else {
+        for (int wd = tid; wd * 32 < nbits; wd += NT_IMG) {
+          unsigned bits = bitmap[wd];
+          const int rowi = wd >> 1;
+          const unsigned hi = ((unsigned)(rowi % d1) << 8) | ((unsigned)(rowi / d1) << 16) | ((unsigned)(wd & 1) << 5);
+          while (bits) {
+            int bi = __ffs(bits) - 1;
+            bits &= bits - 1;
+            eval_voxel(hi | (unsigned)bi, 2, 3);
+          }
+        }
+      }
+      __syncthreads();
+      shadow_channel(2, tileA);
+      __syncthreads();
+      for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
+    }
+    __syncthreads();
+    PHASE(7);
+    // ---- the point planes come back from the image's memory into the dead tiles, then dilation + pixel assembly
+    for (int k = tid; k < (npp * PLB) >> 4; k += NT_IMG)
+      reinterpret_cast<uint4 *>(tplanes)[k] = __ldcg(reinterpret_cast<const uint4 *>(gimg) + k);  // written by this CTA: L2, not L1
+    __syncthreads();
+    {
+      uint4 *gout = reinterpret_cast<uint4 *>(gimg);
+      for (int g = tid; g < S * RW; g += NT_IMG) {
+        const int row = g / RW, c4 = g - row * RW;
+        unsigned res[16];
+        const bool up = row > 0, dn = row + 1 < S, lf = c4 > 0, rt = c4 + 1 < RW;
+#pragma unroll
+        for (int ch = 0; ch < 16; ch++) {
+          res[ch] = 0u;
+          if (ch < C) {
+            // reference channel ch -> its plane: point channels in the tile region, shadow channels in splanes
+            const uint8_t *pl = (C == 15) ? ((ch % 5 == 4) ? splanes + (size_t)(ch / 5) * PLB : tplanes + (size_t)(4 * (ch / 5) + ch % 5) * PLB)
+                                          : tplanes + (size_t)ch * PLB;
+            const unsigned *W = reinterpret_cast<const unsigned *>(pl) + row * RW + c4;
+            const unsigned m0 = W[0], u0 = up ? W[-RW] : 0u, d0w = dn ? W[RW] : 0u;
+            const unsigned ml = lf ? W[-1] : 0u, ul = (up && lf) ? W[-RW - 1] : 0u, dl = (dn && lf) ? W[RW - 1] : 0u;
+            const unsigned mr = rt ? W[1] : 0u, ur = (up && rt) ? W[-RW + 1] : 0u, dr = (dn && rt) ? W[RW + 1] : 0u;
+            const unsigned E = __vimax3_u16x2(__byte_perm(u0, 0u, 0x4240), __byte_perm(m0, 0u, 0x4240), __byte_perm(d0w, 0u, 0x4240));
+            const unsigned O = __vimax3_u16x2(__byte_perm(u0, 0u, 0x4341), __byte_perm(m0, 0u, 0x4341), __byte_perm(d0w, 0u, 0x4341));
+            const unsigned LO = __vimax3_u16x2(__byte_perm(ul, 0u, 0x4341), __byte_perm(ml, 0u, 0x4341), __byte_perm(dl, 0u, 0x4341));
+            const unsigned RE = __vimax3_u16x2(__byte_perm(ur, 0u, 0x4240), __byte_perm(mr, 0u, 0x4240), __byte_perm(dr, 0u, 0x4240));
+            const unsigned En = __vimax3_u16x2(E, O, __byte_perm(LO, O, 0x5432));
+            const unsigned On = __vimax3_u16x2(O, E, __byte_perm(E, RE, 0x5432));
+            res[ch] = __byte_perm(En, On, 0x6240);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const unsigned sel = (unsigned)i | ((unsigned)(4 + i) << 4);
+          uint4 o;
+          o.x = __byte_perm(__byte_perm(res[0], res[1], sel), __byte_perm(res[2], res[3], sel), 0x5410);
+          o.y = __byte_perm(__byte_perm(res[4], res[5], sel), __byte_perm(res[6], res[7], sel), 0x5410);
+          o.z = __byte_perm(__byte_perm(res[8], res[9], sel), __byte_perm(res[10], res[11], sel), 0x5410);
+          o.w = __byte_perm(__byte_perm(res[12], res[13], sel), __byte_perm(res[14], res[15], sel), 0x5410);
+          gout[row * S + c4 * 4 + i] = o;
+        }
+      }
+    }
+    PHASE(8);
+  }
+}
+
 // P16 (16-byte pixels) <-> HWC (the cv::Mat layout, C bytes per pixel)
 __global__ void k_p16_to_hwc(const uint8_t *__restrict__ p16, size_t npix, int C, uint8_t *__restrict__ hwc) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one output byte per thread
@@ -1926,7 +2648,9 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
   return GPDB_OK;
 }
 
-// `d_p16`: nc images of S*S 16-byte pixels (see k_images)
+// `d_p16`: nc images of S*S 16-byte pixels (see k_images). Fast path: k_images2 (two CTAs per SM) over every image, then
+// k_images over the images whose box list overflowed; k_images alone when the geometry is outside the fast path's limits
+// (image_size != 60, more than two cameras) or when GPD_B200_IMAGES_KERNEL=1 forces it (tests compare the two kernels).
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
   if (nc <= 0) return GPDB_OK;
   const DevParams &hp = ctx->hp;
@@ -1941,15 +2665,31 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
     gpdb_set_error(ctx, GPDB_ERR_INVALID, "image geometry needs %zu B of shared memory per CTA (max 224256)", smem);
     return GPDB_ERR_INVALID;
   }
-  const int grid = std::min(nc, ctx->sm_count * 64);
+  const char *force = getenv("GPD_B200_IMAGES_KERNEL");
+  const bool fast = S == 60 && (hp.C != 15 || (hp.K <= 2 && bm + 2048 <= (size_t)BOX_CAP2 * 36)) && !(force && force[0] == '1');
+  const int *d_work = nullptr, *d_work_n = nullptr;
+  if (fast) {
+    int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)nc + 1));
+    if (!ovf) return GPDB_ERR_CUDA;
+    int *ovf_count = ovf + nc;
+    CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
+    const size_t smem2 = (size_t)2 * 8 * S * S + (size_t)3 * S * S + (size_t)BOX_CAP2 * 36;
+    CUDA_TRY(cudaFuncSetAttribute(k_images2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_images2<<<std::min(nc, ctx->sm_count * 64), NT_IMG, smem2, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ovf,
+                                                                               ovf_count, ctx->d_prof);
+    LAUNCH_CHECK();
+    d_work = ovf;
+    d_work_n = ovf_count;
+  }
+  const int grid = fast ? ctx->sm_count : std::min(nc, ctx->sm_count * 64);
   if (S == 60) {
     CUDA_TRY(cudaFuncSetAttribute(k_images<60>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_images<60><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
-                                                      (int)plane_bytes, (int)list_bytes, ctx->d_prof);
+                                                      (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(k_images<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_images<0><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
-                                                     (int)plane_bytes, (int)list_bytes, ctx->d_prof);
+                                                     (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n);
   }
   LAUNCH_CHECK();
   return GPDB_OK;

@@ -413,3 +413,21 @@ def test_result_arena_is_reused_and_outlives_the_context():
     assert C.string_at(r2.candidates, n2 * C.sizeof(abi.Pose)) == snap  # still readable after gpdb_destroy
     lib.free_result(r1)
     lib.free_result(r2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch,two_cams", [(15, False), (15, True), (12, True), (3, False), (1, False)])
+def test_image_kernels_agree(ch, two_cams, monkeypatch):
+    """The two image kernels — k_images2 (fast path: two CTAs per SM, 1024-point box list, two-pass shadow sums, point
+    planes parked in the image's own memory) and k_images (general tier, also the overflow tier of the fast path) — must
+    produce bit-identical images; both are compared with the oracle elsewhere."""
+    s = scenes.synthetic_table_scene(5 if two_cams else 7, n_points=60000, two_cameras=two_cams)
+    p, ctx, oc, w = make(s, ch)
+    poses = ctx.hand_search(scenes.sample_indices(3, 60000, 1500))["candidates"]
+    assert len(poses) > 300
+    monkeypatch.setenv("GPD_B200_IMAGES_KERNEL", "1")
+    general = ctx.images(poses)
+    monkeypatch.delenv("GPD_B200_IMAGES_KERNEL")
+    fast = ctx.images(poses)
+    assert np.array_equal(general, fast)
+    ctx.close()
