@@ -653,8 +653,8 @@ int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]) {
 struct HostArena {
   std::atomic<int> refs{1};        // the owning context + an outstanding result
   std::atomic<bool> in_use{false};
-  void *buf[3] = {nullptr, nullptr, nullptr};  // 0: per-sample / per-pose arrays, 1: candidate records, 2: images
-  size_t cap[3] = {0, 0, 0};
+  void *buf[4] = {nullptr, nullptr, nullptr, nullptr};  // 0: per-sample / per-pose arrays, 1: candidate records, 2: images,
+  size_t cap[4] = {0, 0, 0, 0};                         // 3: extra (gathered per-pose arrays of gpdb_detect_sharded)
 };
 static void arena_unref(HostArena *a) {
   if (a->refs.fetch_sub(1) == 1) {
@@ -718,6 +718,13 @@ void gpdb_pipe_destroy(gpdb_ctx *ctx) {
   delete ps;
   ctx->pipe = nullptr;
 }
+// pinned memory that lives and dies with a result (gpdb_detect_sharded: the gathered per-pose arrays of all ranks)
+void *gpdb_result_extra(gpdb_result *r, size_t bytes) {
+  if (!r || !r->owner_) return nullptr;
+  HostArena *a = (HostArena *)r->owner_;
+  return arena_reserve(a, 3, bytes, 0) ? a->buf[3] : nullptr;
+}
+
 static HostArena *arena_acquire(gpdb_ctx *ctx) {
   PipeState &ps = *ctx->pipe;
   for (HostArena *a : ps.arenas) {
@@ -1185,11 +1192,6 @@ void gpdb_free_result(gpdb_result *r) {
   if (!r) return;
   if (r->owner_) {  // the arrays live in a pinned arena of the context that produced them: hand it back
     HostArena *a = (HostArena *)r->owner_;
-    // gpdb_detect_sharded replaces the per-pose arrays by gathered ones that live outside the arena
-    const uint8_t *b0 = (const uint8_t *)a->buf[0];
-    auto outside = [&](const void *p) { return p && !((const uint8_t *)p >= b0 && (const uint8_t *)p < b0 + a->cap[0]); };
-    if (outside(r->pose_flags)) free(r->pose_flags);
-    if (outside(r->pose_scores)) free(r->pose_scores);
     a->in_use = false;
     arena_unref(a);
   } else {

@@ -63,6 +63,7 @@ const char *load_nccl() {  // returns nullptr on success, else the reason
 struct CommState {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  int32_t count = 0;  // this rank's candidate count of the last sharded call (staged into its slot)
 };
 
 #define NCCL_TRY(expr)                                                                                              \
@@ -150,9 +151,10 @@ void gpdb_shard_bounds(int32_t n, int32_t rank, int32_t nranks, int32_t *lo, int
   }
 }
 
+// slot = [scores f32 np][flags u8 np, padded to 16 B][int32 candidate count of the rank, 12 B pad]
 int64_t gpdb_slot_bytes(int32_t slot_samples, int32_t P) {
   const int64_t np = (int64_t)slot_samples * P;
-  return np * 4 + (np + 15) / 16 * 16;
+  return np * 4 + (np + 15) / 16 * 16 + 16;
 }
 
 int gpdb_set_cloud_bcast(gpdb_ctx *ctx, int32_t root, const float *xyz, const double *normals, const int32_t *cam_source,
@@ -240,6 +242,8 @@ int gpdb_detect_sharded_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx_loca
   }
   int nc = gpdb_run_pipeline(ctx, d_sample_idx_local, n_local, stats, true, true, d_flags, d_scores, -1, 0);
   if (nc < 0) return nc;
+  cs.count = nc;
+  CUDA_TRY(cudaMemcpyAsync(mine + slot - 16, &cs.count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   NCCL_TRY(g_nccl.AllGather(mine, d_gathered, slot, ncclUint8, cs.comm, ctx->stream));  // in place
   ctx->launches++;
   stats->kernel_launches++;
@@ -276,38 +280,43 @@ int gpdb_detect_sharded(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpd
     cu(cudaMemcpyAsync(mine, ctx->scratch[11], sizeof(float) * np_l, cudaMemcpyDeviceToDevice, ctx->stream));
     cu(cudaMemcpyAsync(mine + sizeof(float) * np_s, ctx->scratch[10], np_l, cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  cs.count = nc;
+  cu(cudaMemcpyAsync(mine + slot - 16, &cs.count, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   if (err == GPDB_OK && g_nccl.AllGather(mine, d_gath, slot, ncclUint8, cs.comm, ctx->stream) != ncclSuccess) {
     gpdb_set_error(ctx, GPDB_ERR_CUDA, "ncclAllGather failed");
     err = GPDB_ERR_CUDA;
   }
   ctx->launches++;
-  // global arrays [n*P] on the host (plain malloc: the arena holds the slice-sized arrays)
-  float *h_scores = (float *)malloc(sizeof(float) * (size_t)n * P + 4);
-  uint8_t *h_flags = (uint8_t *)malloc((size_t)n * P + 1);
-  std::vector<int32_t> counts((size_t)cs.nranks, 0);
+  // the gathered arrays [n*P] of all ranks go to pinned memory owned by the result (freed with it), the per-rank
+  // candidate counts ride in the slot tails
+  const size_t nP = (size_t)n * P, off_flags = (sizeof(float) * nP + 63) / 64 * 64, off_counts = (off_flags + nP + 63) / 64 * 64;
+  uint8_t *h = (uint8_t *)gpdb_result_extra(out, off_counts + 16 * (size_t)cs.nranks + 64);
+  if (!h && err == GPDB_OK) {
+    gpdb_set_error(ctx, GPDB_ERR_CUDA, "cudaHostAlloc of the gathered result arrays failed");
+    err = GPDB_ERR_CUDA;
+  }
   for (int r = 0; r < cs.nranks && err == GPDB_OK; r++) {
     int32_t a, b;
     gpdb_shard_bounds(n, r, cs.nranks, &a, &b, nullptr);
     const uint8_t *src = d_gath + slot * (size_t)r;
     if (b > a) {
-      cu(cudaMemcpyAsync(h_scores + (size_t)a * P, src, sizeof(float) * (size_t)(b - a) * P, cudaMemcpyDeviceToHost, ctx->stream));
-      cu(cudaMemcpyAsync(h_flags + (size_t)a * P, src + sizeof(float) * np_s, (size_t)(b - a) * P, cudaMemcpyDeviceToHost, ctx->stream));
+      cu(cudaMemcpyAsync(h + sizeof(float) * (size_t)a * P, src, sizeof(float) * (size_t)(b - a) * P, cudaMemcpyDeviceToHost, ctx->stream));
+      cu(cudaMemcpyAsync(h + off_flags + (size_t)a * P, src + sizeof(float) * np_s, (size_t)(b - a) * P, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    cu(cudaMemcpyAsync(h + off_counts + 16 * (size_t)r, src + slot - 16, 16, cudaMemcpyDeviceToHost, ctx->stream));
   }
   cu(cudaStreamSynchronize(ctx->stream));
   if (err != GPDB_OK) {
-    free(h_scores);
-    free(h_flags);
     gpdb_free_result(out);
     return err;
   }
   int total = 0;
-  for (size_t i = 0; i < (size_t)n * P; i++) total += (h_flags[i] & 3) == 3;
+  for (int r = 0; r < cs.nranks; r++) total += *reinterpret_cast<const int32_t *>(h + off_counts + 16 * (size_t)r);
   // the slice-sized per-pose arrays of the arena are replaced by the gathered ones; frames stay per-slice -> not returned
   out->frame_valid = nullptr;
   out->frames = nullptr;
-  out->pose_flags = h_flags;
-  out->pose_scores = h_scores;
+  out->pose_scores = reinterpret_cast<float *>(h);
+  out->pose_flags = h + off_flags;
   out->n_samples = n;
   out->n_total_candidates = total;
   out->kernel_launches++;

@@ -162,6 +162,7 @@ void *gpdb_scratch(gpdb_ctx *ctx, int slot, size_t bytes);  // returns nullptr o
 int gpdb_pipe_create(gpdb_ctx *ctx);
 void gpdb_pipe_destroy(gpdb_ctx *ctx);
 int gpdb_check_state(gpdb_ctx *ctx, bool need_cloud, bool need_weights);
+void *gpdb_result_extra(gpdb_result *r, size_t bytes);  // pinned host memory owned by the result (freed with it)
 // the chunked device pipeline (see api.cu); slot_base is added to every sample_slot (rank offset of a sharded call)
 int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_result *out, bool with_images_and_scores,
                       bool resident, uint8_t *flags_ext, float *scores_ext, int select_k, int slot_base);

@@ -995,7 +995,8 @@ __device__ __forceinline__ void unit_axis(double v, double lo, double extent, do
   u = (v - lo) * inv_extent;
   double q = u * (double)S;
   double fq = floor(q);
-  if (q - fq < 1e-9 || fq + 1.0 - q < 1e-9) {
+  const double fr = q - fq;  // in [0, 1): exact (Sterbenz) for q >= 1
+  if (fr < 1e-9 || fr > 1.0 - 1e-9) {
     u = (v - lo) / extent;
     double cellsize = 1.0 / (double)S;
     fq = floor(u / cellsize);
@@ -1008,9 +1009,13 @@ __device__ __forceinline__ unsigned unit_q32(double u) {
   return (unsigned)t;
 }
 
-// block-wide reduction of up to eight floats with max (use negated values for min). Contains two barriers.
+__device__ __forceinline__ bool fully_covered(const unsigned *occf, int S);
+// block-wide reduction of up to eight floats with max (use negated values for min). Contains two barriers. With `occf`
+// non-null, warp 0 also evaluates fully_covered(occf) between the barriers (the occupancy words were written before the
+// call) and every thread receives the verdict in *covered — one evaluation per CTA, no extra barrier.
 template <int NT, int NV>
-__device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[8]) {
+__device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[8], const unsigned *occf = nullptr, int S = 0,
+                                          bool *covered = nullptr) {
 #pragma unroll
   for (int o = 16; o; o >>= 1)
 #pragma unroll
@@ -1019,12 +1024,17 @@ __device__ __forceinline__ void block_max(float (&v)[NV], float (*red)[8]) {
   if ((threadIdx.x & 31) == 0)
 #pragma unroll
     for (int i = 0; i < NV; i++) red[threadIdx.x >> 5][i] = v[i];
+  if (occf && threadIdx.x < 32) {
+    const bool c = fully_covered(occf, S);
+    if (threadIdx.x == 0) red[0][7] = c ? 1.0f : 0.0f;  // slot 7 is never used by a reduction (NV <= 6)
+  }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; i++) v[i] = red[0][i];
   for (int w = 1; w < NT / 32; w++)
 #pragma unroll
     for (int i = 0; i < NV; i++) v[i] = fmaxf(v[i], red[w][i]);
+  if (covered) *covered = red[0][7] != 0.0f;
 }
 
 // cv::normalize(NORM_MINMAX, 0..1) + convertTo(CV_8U, 255) of one value, as OpenCV evaluates it: scale / shift in double,
@@ -1046,8 +1056,7 @@ struct Quant {
 };
 
 // true when the S x S occupancy has NO all-empty 3x3 window. occf: flat bitmap (bit = row * S + col) followed by two
-// zero-readable words. Evaluated by every warp on its own (32 rows per pass, a few word operations per row): the result is
-// warp-uniform and identical in all warps, so no flag has to travel through shared memory.
+// zero-readable words. One warp (32 rows per pass, a few word operations per row); block_max distributes the verdict.
 __device__ __forceinline__ bool fully_covered(const unsigned *occf, int S) {
   const int lane = threadIdx.x & 31;
   const unsigned long long mask = S >= 64 ? ~0ull : ((1ull << S) - 1ull);
@@ -1320,9 +1329,10 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           mxv[1] = fmaxf(mxv[1], dv);
         }
       }
-      block_max<NT_IMG, 2>(mxv, sm.fred);  // (its barriers publish the occupancy words)
+      bool covered_pj;
+      block_max<NT_IMG, 2>(mxv, sm.fred, sm.occf, S, &covered_pj);  // (its barriers publish the occupancy words)
       float mnv[2] = {0.0f, 0.0f};  // min over the dilated image: 0 when an all-empty 3x3 window exists
-      if (fully_covered(sm.occf, S)) {
+      if (covered_pj) {
         // general path (no empty window): materialise the four float channel images over the (now dead) tiles and take the
         // min of their dilations. Winners keep their values in registers across the rewrite of the tiles.
         constexpr int JMAX = (BOX_CAP + NT_IMG - 1) / NT_IMG;
@@ -1746,12 +1756,13 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
           }
           if (t * NT_IMG < SS) occ_ballot<NT_IMG>(sm.occf, t, oc);
         }
-        block_max<NT_IMG, 2>(mm, sm.fred);  // (its barriers publish the occupancy words)
+        bool covered_pj;
+        block_max<NT_IMG, 2>(mm, sm.fred, sm.occf, S, &covered_pj);  // (its barriers publish the occupancy words)
         const bool any = mm[0] != -FLT_MAX;
         const float maxf = any ? mm[0] : 0.0f;
         const float vmax = any ? maxf - (-mm[1]) : 0.0f;  // largest cell value = max avg - min avg
         float vmin = 0.0f;
-        if (fully_covered(sm.occf, S)) {  // general path: min over the dilated float image
+        if (covered_pj) {  // general path: min over the dilated float image
           float *srcF = reinterpret_cast<float *>(tileA + (size_t)pj * SS);
           __syncthreads();
 #pragma unroll
@@ -2040,10 +2051,10 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
           }
         }
       }
-      block_max<NT_IMG, 2>(mxv, sm.fred);
+      bool covered;
+      block_max<NT_IMG, 2>(mxv, sm.fred, sm.occf, S, &covered);
       float mnv[2] = {0.0f, 0.0f};
       const int cb = (C == 1) ? 0 : pj * 4;  // first point plane of the projection
-      const bool covered = fully_covered(sm.occf, S);
       if (covered) {  // general path: no all-empty 3x3 window -> min over the dilated float images
         float *F = reinterpret_cast<float *>(tileA);  // 4 x SS floats = tiles A + B (every winner holds its values)
         for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
@@ -2399,12 +2410,13 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
           }
           occ_ballot<NT_IMG>(sm.occf, t, oc);
         }
-        block_max<NT_IMG, 2>(mm, sm.fred);
+        bool covered_pj;
+        block_max<NT_IMG, 2>(mm, sm.fred, sm.occf, S, &covered_pj);
         const bool any = mm[0] != -FLT_MAX;
         const float maxf = any ? mm[0] : 0.0f;
         const float vmax = any ? maxf - (-mm[1]) : 0.0f;
         float vmin = 0.0f;
-        if (fully_covered(sm.occf, S)) {
+        if (covered_pj) {
           float *srcF = reinterpret_cast<float *>(tile);
           __syncthreads();
 #pragma unroll

@@ -119,4 +119,4 @@ def test_c_abi_shard_bounds_match_the_python_plumbing():
                 if n < 2 ** 30:
                     assert st == sharding.slot_stride(n, world)
             assert covered == n
-    assert lib.slot_bytes(12501, 8) == 12501 * 8 * 4 + (12501 * 8 + 15) // 16 * 16
+    assert lib.slot_bytes(12501, 8) == 12501 * 8 * 4 + (12501 * 8 + 15) // 16 * 16 + 16
