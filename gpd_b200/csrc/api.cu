@@ -770,7 +770,7 @@ int check_device_errors(gpdb_ctx *ctx) {
     gpdb_set_error(ctx, GPDB_ERR_CAPACITY,
                    "neighbourhood exceeded an on-chip tile (frame ball: %d samples, hand-search ball: %d samples, "
                    "image box: %d images): the cloud is denser than the supported %d / %d / %d points",
-                   e[0], e[1], e[2], 1024, 12800, 2048);
+                   e[0], e[1], e[2], 1024, 131072, 32768);
     return GPDB_ERR_CAPACITY;
   }
   return GPDB_OK;
@@ -1158,6 +1158,25 @@ int gpdb_classify(gpdb_ctx *ctx, const uint8_t *images_hwc, int32_t n, float *sc
                                cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
+  return n;
+}
+
+int gpdb_reevaluate(gpdb_ctx *ctx, gpdb_pose *hands, int32_t n, int32_t *labels_out) {
+  int rc = check_state(ctx, true, false);
+  if (rc != GPDB_OK) return rc;
+  if (n < 0 || (n > 0 && (!hands || !labels_out))) {
+    gpdb_set_error(ctx, GPDB_ERR_INVALID, "gpdb_reevaluate: bad arguments");
+    return GPDB_ERR_INVALID;
+  }
+  if (n == 0) return 0;
+  gpdb_pose *d_h = (gpdb_pose *)gpdb_scratch(ctx, 17, sizeof(gpdb_pose) * (size_t)n);
+  int *d_l = (int *)gpdb_scratch(ctx, 18, sizeof(int) * (size_t)n);
+  if (!d_h || !d_l) return GPDB_ERR_CUDA;
+  CUDA_TRY(cudaMemcpyAsync(d_h, hands, sizeof(gpdb_pose) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = geo_reeval(ctx, d_h, n, d_l)) != GPDB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(hands, d_h, sizeof(gpdb_pose) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(labels_out, d_l, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return n;
 }
 

@@ -185,6 +185,8 @@ int geo_hwc_to_p16(gpdb_ctx *ctx, const uint8_t *d_hwc, int n, uint8_t *d_p16);
 int geo_scatter_scores(gpdb_ctx *ctx, const gpdb_pose *d_cand, const float *d_scores, int nc, int slot0, int P,
                        float *d_pose_scores, gpdb_pose *d_cand_out);
 
+// HandSearch::reevaluateHypotheses: labels + half / full flags of the given hands against the installed cloud
+int geo_reeval(gpdb_ctx *ctx, gpdb_pose *d_hands, int n, int *d_labels);
 // Clustering::findClusters (remove_inliers = false): dense per-hand cluster records + keep flags (3 = cluster), for geo_compact
 int geo_clusters(gpdb_ctx *ctx, const gpdb_pose *d_hands, int n, int min_inliers, gpdb_pose *d_dense, uint8_t *d_keep);
 // the k highest-scoring of the n candidate records (scores filled), descending, stable -> d_out[k]

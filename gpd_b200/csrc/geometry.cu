@@ -465,22 +465,25 @@ struct HandsSmem {
 };
 
 // one CTA per sample; dynamic smem: float4 list[cap]
+// tiers: in_list == nullptr: every sample, else the samples in_list[0 .. *in_count) (the overflow of the previous tier);
+// samples whose slab does not fit `cap` go to out_list (next tier) or, in the last tier (out_list == nullptr), are an error.
+// glist != nullptr: the staged neighbourhood lives in a per-CTA slice of global memory (last tier, any density up to cap).
 __global__ void __launch_bounds__(NT_HANDS, 4) k_hands(const DevParams *Pp, DevCloud cl, const int *sidx, int n, int slot0,
                                                     const double *frames, const uint8_t *fvalid, gpdb_pose *poses,
-                                                    uint8_t *flags, int cap, int *ovf_list, int *ovf_count,
-                                                    int list_mode, int *err) {
+                                                    uint8_t *flags, int cap, const int *in_list, const int *in_count,
+                                                    int *out_list, int *out_count, float4 *glist, int *err) {
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
-  float4 *list = reinterpret_cast<float4 *>(dyn);
+  float4 *list = glist ? glist + (size_t)blockIdx.x * cap : reinterpret_cast<float4 *>(dyn);
   __shared__ HandsSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int work_n = list_mode ? *ovf_count : n;
+  const int work_n = in_list ? *in_count : n;
   if (tid < 2 * P.nfp) {
     S.fs[tid] = P.fs[tid];
     S.fsw[tid] = P.fsw[tid];
   }
   for (int w = blockIdx.x; w < work_n; w += gridDim.x) {
-    const int i = list_mode ? ovf_list[w] : w;
+    const int i = in_list ? in_list[w] : w;
     const int si = sidx[i];
     __syncthreads();
     if (tid == 0) {
@@ -553,17 +556,17 @@ __global__ void __launch_bounds__(NT_HANDS, 4) k_hands(const DevParams *Pp, DevC
     __syncthreads();
     const int m = S.count;
     if (m > cap) {
-      // does not fit this tier: defer to the large-tile pass (or report)
+      // does not fit this tier: defer to the next one (or report)
       if (tid == 0) {
-        if (ovf_list && !list_mode) {
-          int k = atomicAdd(ovf_count, 1);
-          ovf_list[k] = i;
-          atomicAdd(err + 3, 1);
+        if (out_list) {
+          int k = atomicAdd(out_count, 1);
+          out_list[k] = i;
+          if (!in_list) atomicAdd(err + 3, 1);
         } else {
           atomicAdd(err + 1, 1);
         }
       }
-      if (!(ovf_list && !list_mode)) {
+      if (!out_list) {
         for (int p = tid; p < P.P; p += NT_HANDS) flags[(size_t)i * P.P + p] = 0;
       }
       continue;
@@ -876,6 +879,185 @@ __global__ void k_gather_poses(const gpdb_pose *cand, const int *order, int k, g
 }
 
 // ------------------------------------------------------------------------------------------------
+// HandSearch::reevaluateHypotheses (hand_search.cpp:66-134,190-228): the given hands are re-labelled against the installed
+// cloud (GraspDetector::evalGroundTruth: a ground-truth mesh cloud). One WARP per hand; the r = nn_radius_hs ball is
+// walked four times straight from the grid (L2-resident cloud) — finger test of the hand's own slot at its own depth,
+// closing region, the two Antipodal passes — with the same order-free reductions and neighbour-0 padding weights as
+// k_hands. A labelling path, not a throughput path: no shared-memory staging.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void warp_scan_ball(const DevParams &P, const DevCloud &cl, const SegRange &sr, const float q[3], float r2,
+                                               F &&body) {  // body(point) for every in-ball point, lanes in lockstep
+  const int lane = threadIdx.x & 31;
+  for (int j0 = 0; j0 < sr.nrows; j0 += 32) {
+    const int myrow = j0 + lane;
+    int st = 0, len = 0;
+    if (myrow < sr.nrows) seg_row(P, cl.cell_start, sr, myrow, st, len);
+    unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+    while (nonempty) {
+      const int j = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const int rs = __shfl_sync(0xffffffffu, st, j), rl = __shfl_sync(0xffffffffu, len, j);
+      for (int k0 = 0; k0 < rl; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < rl) {
+          const float4 p = __ldg(cl.pts4 + rs + k);
+          if (l2_simple(q, p.x, p.y, p.z) < r2) body(p);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_reeval(const DevParams *Pp, DevCloud cl, gpdb_pose *hands, int n, int *labels) {
+  const DevParams &P = *Pp;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  gpdb_pose &h = hands[i];
+  double R[9], smp[3];
+#pragma unroll
+  for (int r = 0; r < 9; r++) R[r] = h.frame[r];
+#pragma unroll
+  for (int r = 0; r < 3; r++) smp[r] = h.sample[r];
+  const int idx = h.finger_idx;
+  const double top = h.top, bottom = top - P.hand_depth, hh = P.hand_height;  // evaluateFingers(points, hand.getTop(), idx)
+  const float q[3] = {(float)smp[0], (float)smp[1], (float)smp[2]};            // eigenVectorToPcl (:136-142)
+  const SegRange sr = seg_range(P, q, P.rf_hs);
+  int label = 0;
+  bool half = false, full = false;
+  if (idx >= 0 && idx < P.nfp) {
+    const double s0 = P.fs[idx], s0w = P.fsw[idx], s1 = P.fs[P.nfp + idx], s1w = P.fsw[P.nfp + idx];
+    // pass 1: neighbour 0, crop count, back-of-hand collision, the two finger gaps
+    int nball = 0, k = 0;
+    unsigned long long best = ~0ull;
+    unsigned anyA = 0, anyB = 0, blocked = 0;
+    auto finger_test = [&](double x, double y) {
+      if (x < top) {
+        anyA = 1;
+        if (x < bottom) anyB = 1;
+        if ((y > s0 && y < s0w) || (y > s1 && y < s1w)) blocked = 1;
+      }
+    };
+    warp_scan_ball(P, cl, sr, q, P.r2_hs, [&](const float4 &p) {
+      nball++;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(l2_simple(q, p.x, p.y, p.z)) << 32) | (unsigned)__float_as_int(p.w);
+      best = key < best ? key : best;
+      double x, y, z;
+      to_frame(R, (double)p.x - smp[0], (double)p.y - smp[1], (double)p.z - smp[2], x, y, z);
+      if (z > -1.0 * hh && z < hh) {
+        k++;
+        finger_test(x, y);
+      }
+    });
+    nball = warp_sum(nball);
+    k = warp_sum(k);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      best = ob < best ? ob : best;
+    }
+    const int npad = nball - k;  // cropByHandHeight pads with copies of neighbour 0 (point_list.cpp:44-55)
+    const int nb0 = (int)(unsigned)(best & 0xffffffffull);
+    double x0 = 0, y0 = 0, z0 = 0;
+    if (nball > 0)
+      to_frame(R, (double)cl.xyz[3 * (size_t)nb0] - smp[0], (double)cl.xyz[3 * (size_t)nb0 + 1] - smp[1],
+               (double)cl.xyz[3 * (size_t)nb0 + 2] - smp[2], x0, y0, z0);
+    if (npad > 0 && lane == 0) finger_test(x0, y0);
+    anyA = __reduce_or_sync(0xffffffffu, anyA);
+    anyB = __reduce_or_sync(0xffffffffu, anyB);
+    blocked = __reduce_or_sync(0xffffffffu, blocked);
+    if (nball > 0 && anyA && !anyB && !blocked) {
+      // pass 2: computePointsInClosingRegion (finger_hand.cpp:141-171)
+      const double left = s0w, right = s1;
+      int cnt = 0;
+      double mny = DBL_MAX, mxy = -DBL_MAX;
+      auto in_region = [&](double x, double y) { return x > bottom && x < top && y > left && y < right; };
+      warp_scan_ball(P, cl, sr, q, P.r2_hs, [&](const float4 &p) {
+        double x, y, z;
+        to_frame(R, (double)p.x - smp[0], (double)p.y - smp[1], (double)p.z - smp[2], x, y, z);
+        if (z > -1.0 * hh && z < hh && in_region(x, y)) {
+          cnt++;
+          mny = fmin(mny, y);
+          mxy = fmax(mxy, y);
+        }
+      });
+      const bool nb_in = npad > 0 && in_region(x0, y0);
+      cnt = warp_sum(cnt) + (nb_in ? npad : 0);
+      mny = warp_min(mny);
+      mxy = warp_max(mxy);
+      if (nb_in) {
+        mny = fmin(mny, y0);
+        mxy = fmax(mxy, y0);
+      }
+      if (cnt > 0) {
+        // passes 3 and 4: Antipodal::evaluateGrasp (antipodal.cpp:10-96), as in k_hands
+        const double min_x = mny + 0.003, max_x = mxy - 0.003;
+        int cl_ = 0, cr_ = 0;
+        double lmaxx = -DBL_MAX, lminx = DBL_MAX, lmaxz = -DBL_MAX, lminz = DBL_MAX;
+        double rmaxx = -DBL_MAX, rminx = DBL_MAX, rmaxz = -DBL_MAX, rminz = DBL_MAX;
+        auto dots = [&](int pidx, double &ldot, double &rdot) {
+          const double *nn = cl.nrm + 3 * (size_t)pidx;
+          double n0, n1, n2;
+          to_frame(R, nn[0], nn[1], nn[2], n0, n1, n2);
+          ldot = (0.0 * n0 + -1.0 * n1) + 0.0 * n2;
+          rdot = (0.0 * n0 + 1.0 * n1) + 0.0 * n2;
+        };
+        auto visitD = [&](double x, double y, double z, int pidx, int wgt) {
+          double ldot, rdot;
+          dots(pidx, ldot, rdot);
+          if (ldot > P.cosf && y < min_x) {
+            cl_ += wgt;
+            lmaxx = fmax(lmaxx, x); lminx = fmin(lminx, x); lmaxz = fmax(lmaxz, z); lminz = fmin(lminz, z);
+          }
+          if (rdot > P.cosf && y > max_x) {
+            cr_ += wgt;
+            rmaxx = fmax(rmaxx, x); rminx = fmin(rminx, x); rmaxz = fmax(rmaxz, z); rminz = fmin(rminz, z);
+          }
+        };
+        warp_scan_ball(P, cl, sr, q, P.r2_hs, [&](const float4 &p) {
+          double x, y, z;
+          to_frame(R, (double)p.x - smp[0], (double)p.y - smp[1], (double)p.z - smp[2], x, y, z);
+          if (z > -1.0 * hh && z < hh && in_region(x, y)) visitD(x, y, z, __float_as_int(p.w), 1);
+        });
+        if (nb_in && lane == 0) visitD(x0, y0, z0, nb0, npad);
+        cl_ = warp_sum(cl_);
+        cr_ = warp_sum(cr_);
+        half = cl_ > 0 || cr_ > 0;
+        if (cl_ > 0 && cr_ > 0) {
+          lmaxx = warp_max(lmaxx); lminx = warp_min(lminx); lmaxz = warp_max(lmaxz); lminz = warp_min(lminz);
+          rmaxx = warp_max(rmaxx); rminx = warp_min(rminx); rmaxz = warp_max(rmaxz); rminz = warp_min(rminz);
+          const double top_y = fmin(lmaxx, rmaxx), bot_y = fmax(lminx, rminx);
+          const double top_z = fmin(lmaxz, rmaxz), bot_z = fmax(lminz, rminz);
+          int nl = 0, nr = 0;
+          auto visitE = [&](double x, double y, double z, int pidx, int wgt) {
+            double ldot, rdot;
+            dots(pidx, ldot, rdot);
+            const bool inw = x >= bot_y && x <= top_y && z >= bot_z && z <= top_z;
+            if (ldot > P.cosf && y < min_x && inw) nl += wgt;
+            if (rdot > P.cosf && y > max_x && inw) nr += wgt;
+          };
+          warp_scan_ball(P, cl, sr, q, P.r2_hs, [&](const float4 &p) {
+            double x, y, z;
+            to_frame(R, (double)p.x - smp[0], (double)p.y - smp[1], (double)p.z - smp[2], x, y, z);
+            if (z > -1.0 * hh && z < hh && in_region(x, y)) visitE(x, y, z, __float_as_int(p.w), 1);
+          });
+          if (nb_in && lane == 0) visitE(x0, y0, z0, nb0, npad);
+          nl = warp_sum(nl);
+          nr = warp_sum(nr);
+          full = nl >= P.min_viable && nr >= P.min_viable;
+        }
+        if (full) label = 1;
+      }
+    }
+  }
+  if (lane == 0) {
+    h.half_antipodal = half ? 1 : 0;
+    h.full_antipodal = full ? 1 : 0;
+    labels[i] = label;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Clustering::findClusters (clustering.cpp:5-105, remove_inliers = false): hand i becomes a cluster when at least
 // min_inliers OTHER hands have an axis within 12 degrees, a position within 5 cm and an axis-orthogonal offset within
 // 5 mm; cluster position = mean inlier position, score = lower bound of the 99 % confidence interval of the inlier
@@ -1111,12 +1293,17 @@ __device__ __noinline__ float dilated_min(const float *F, int S) {
 
 // dynamic shared memory: planes C x S x RS bytes (RS = S rounded up to 4) | tiles 3 x 8 S S | box list 36 B x BOX_CAP
 // (the shadow bitmaps + voxel list alias the box list; the shadow work list aliases the tiles)
-template <int S_T>
+// GL = true is the last tier: the box list (and the float images of the general min path) live in a per-CTA slice of global
+// memory (`gl_base`, `gl_cap` points: L2-resident scratch) instead of shared memory, for clouds so dense that an image box
+// holds more than BOX_CAP points (the reference has no limit; image_generator.cpp:54-64).
+template <int S_T, bool GL>
 __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCloud cl, const gpdb_pose *cand, int nc,
                                                       uint8_t *p16, const double *qtab, int *err, int plane_bytes,
                                                       int list_bytes, unsigned long long *prof, const int *work,
-                                                      const int *work_n) {
-  // work != nullptr: only the images work[0 .. *work_n) (the overflow list of k_images2)
+                                                      const int *work_n, unsigned char *gl_base, int gl_cap, int *ovf2,
+                                                      int *ovf2_count) {
+  // work != nullptr: only the images work[0 .. *work_n) (the overflow list of the previous tier); ovf2 != nullptr: images
+  // whose box list overflows THIS tier are appended there (and redone by the next one) instead of being an error
   long long t_phase = 0;
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -1128,10 +1315,14 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
   unsigned long long *tileB = tileA + SS;
   unsigned long long *tileC = tileB + SS;
   unsigned char *lbase = reinterpret_cast<unsigned char *>(tileC + SS);
-  unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(lbase);
-  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BOX_CAP);   // [3][CAP]
-  unsigned *bcell = bq + 3 * BOX_CAP;                             // packed 3 x 8 bit
-  float *bnrm = reinterpret_cast<float *>(bcell + BOX_CAP);       // [3][CAP]
+  const int BC = GL ? gl_cap : BOX_CAP;
+  const int SS_ = (S_T > 0 ? S_T : P.S) * (S_T > 0 ? S_T : P.S);
+  unsigned char *list_mem = GL ? gl_base + (size_t)blockIdx.x * ((size_t)gl_cap * 36 + (size_t)16 * SS_) : lbase;
+  unsigned long long *bkeys = reinterpret_cast<unsigned long long *>(list_mem);
+  unsigned *bq = reinterpret_cast<unsigned *>(bkeys + BC);        // [3][CAP]
+  unsigned *bcell = bq + 3 * BC;                                  // packed 3 x 8 bit
+  float *bnrm = reinterpret_cast<float *>(bcell + BC);            // [3][CAP]
+  float *gF = reinterpret_cast<float *>(bnrm + 3 * BC);           // GL: 4 float images of the general min path
   unsigned *bitmap = reinterpret_cast<unsigned *>(lbase);         // aliases the list (shadow phase)
   // scan 1 records WHERE the in-ball points are (position in the cell-sorted array, 4 B each) in tile C, which nothing
   // else touches before the shadow phase: the shadow casting re-reads the neighbourhood as independent loads from that
@@ -1217,11 +1408,11 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         if (lane == leader) base = atomicAdd(&sm.box_n, __popc(mk));
         base = __shfl_sync(0xffffffffu, base, leader);
         int pos = base + __popc(mk & ((1u << lane) - 1));
-        if (inb && pos < BOX_CAP) {
+        if (inb && pos < BC) {
           bkeys[pos] = key;
           bq[pos] = __float_as_uint(p.x);  // raw coordinates, replaced by the fixed-point unit coordinates below
-          bq[BOX_CAP + pos] = __float_as_uint(p.y);
-          bq[2 * BOX_CAP + pos] = __float_as_uint(p.z);
+          bq[BC + pos] = __float_as_uint(p.y);
+          bq[2 * BC + pos] = __float_as_uint(p.z);
         }
       }
     });
@@ -1255,18 +1446,22 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       sm.center[0] = a0 / nn;
       sm.center[1] = a1 / nn;
       sm.center[2] = a2 / nn;
-      if (sm.box_n > BOX_CAP) {
-        atomicAdd(err + 2, 1);
-        sm.box_n = BOX_CAP;
+      if (sm.box_n > BC) {
+        if (ovf2) ovf2[atomicAdd(ovf2_count, 1)] = b;  // redone by the next tier (larger list)
+        else {
+          atomicAdd(err + 2, 1);
+          sm.box_n = BC;
+        }
       }
     }
     __syncthreads();
     PHASE(2);  // scan 1 + reductions done
+    if (sm.box_n > BC) continue;  // handed to the next tier (uniform; without a next tier box_n was clamped)
     const int bn = sm.box_n;
     // dense pass over the box points: hand-frame coordinates -> unit cube, cell indices, |R^T n| (all lanes busy)
     for (int k = tid; k < bn; k += NT_IMG) {
-      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP + k]),
-                   pz = (double)__uint_as_float(bq[2 * BOX_CAP + k]);
+      const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BC + k]),
+                   pz = (double)__uint_as_float(bq[2 * BC + k]);
       double x, y, z, u0, u1, u2;
       int c0, c1, c2;
       to_frame(h.frame, px - h.sample[0], py - h.sample[1], pz - h.sample[2], x, y, z);
@@ -1274,15 +1469,15 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       unit_axis(y, h.center - P.vol_w / 2.0, P.vol_w, inv_w, S, u1, c1);
       unit_axis(z, -P.vol_h, 2.0 * P.vol_h, inv_h, S, u2, c2);
       bq[k] = unit_q32(u0);
-      bq[BOX_CAP + k] = unit_q32(u1);
-      bq[2 * BOX_CAP + k] = unit_q32(u2);
+      bq[BC + k] = unit_q32(u1);
+      bq[2 * BC + k] = unit_q32(u2);
       bcell[k] = (unsigned)c0 | ((unsigned)c1 << 8) | ((unsigned)c2 << 16);
       const double *nn = cl.nrm + 3 * (size_t)(unsigned)(bkeys[k] & 0xffffffffull);
       double n0, n1, n2;
       to_frame(h.frame, nn[0], nn[1], nn[2], n0, n1, n2);
       bnrm[k] = (float)fabs(n0);
-      bnrm[BOX_CAP + k] = (float)fabs(n1);
-      bnrm[2 * BOX_CAP + k] = (float)fabs(n2);
+      bnrm[BC + k] = (float)fabs(n1);
+      bnrm[2 * BC + k] = (float)fabs(n2);
     }
     __syncthreads();
 
@@ -1298,7 +1493,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         const int row = S - 1 - (int)((cc >> (8 * a0)) & 255), col = (cc >> (8 * a1)) & 255;
         const int pix = row * S + col;
         atomicMax(tileA + pix, bkeys[k]);
-        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BOX_CAP + k]);
+        atomicAdd(tileB + pix, (1ull << 48) + (unsigned long long)bq[a2 * BC + k]);
         atomicOr(&sm.occf[pix >> 5], 1u << (pix & 31));
       }
       __syncthreads();
@@ -1310,8 +1505,8 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         const int pix = row * S + col;
         if (tileA[pix] != bkeys[k]) return false;
         n0 = bnrm[k];
-        n1 = bnrm[BOX_CAP + k];
-        n2 = bnrm[2 * BOX_CAP + k];
+        n1 = bnrm[BC + k];
+        n2 = bnrm[2 * BC + k];
         const unsigned long long acc = tileB[pix];
         const unsigned cntc = (unsigned)(acc >> 48);
         const double sum = (double)(acc & 0xffffffffffffull);
@@ -1333,57 +1528,105 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
       block_max<NT_IMG, 2>(mxv, sm.fred, sm.occf, S, &covered_pj);  // (its barriers publish the occupancy words)
       float mnv[2] = {0.0f, 0.0f};  // min over the dilated image: 0 when an all-empty 3x3 window exists
       if (covered_pj) {
-        // general path (no empty window): materialise the four float channel images over the (now dead) tiles and take the
-        // min of their dilations. Winners keep their values in registers across the rewrite of the tiles.
-        constexpr int JMAX = (BOX_CAP + NT_IMG - 1) / NT_IMG;
-        float wv[JMAX][4];
-        int wpix[JMAX];
+        if constexpr (GL) {
+          // general path, global-list tier: the float images live in the CTA's global slice, the tiles stay intact and the
+          // winners are simply re-derived (cell_values) — no per-thread value cache sized by the list capacity
+          float *F = gF;
+          for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
+          __syncthreads();
+          for (int k = tid; k < bn; k += NT_IMG) {
+            int row, col;
+            float v[4];
+            if (cell_values(k, row, col, v[0], v[1], v[2], v[3]))
 #pragma unroll
-        for (int j = 0; j < JMAX; j++) {
-          const int k = tid + j * NT_IMG;
-          wpix[j] = -1;
-          int row, col;
-          if (k < bn && cell_values(k, row, col, wv[j][0], wv[j][1], wv[j][2], wv[j][3])) wpix[j] = row * S + col;
-        }
-        __syncthreads();
-        float *F = reinterpret_cast<float *>(tileA);  // 4 x SS floats = tileA + tileB
-        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < JMAX; j++)
-          if (wpix[j] >= 0)
-#pragma unroll
-            for (int c = 0; c < 4; c++) F[c * SS + wpix[j]] = wv[j][c];
-        __syncthreads();
-        float neg[2];
-        neg[0] = -fminf(fminf(dilated_min<NT_IMG>(F, S), dilated_min<NT_IMG>(F + SS, S)), dilated_min<NT_IMG>(F + 2 * SS, S));
-        neg[1] = -dilated_min<NT_IMG>(F + 3 * SS, S);
-        block_max<NT_IMG, 2>(neg, sm.fred);
-        mnv[0] = -neg[0];
-        mnv[1] = -neg[1];
-        const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
-        const unsigned bg_n = qn(0.0f) * 0x01010101u, bg_d = qd(0.0f) * 0x01010101u;  // background = quantised 0
-        const int cb = (C == 1) ? 0 : pj * per;
-        for (int k = tid; k < (PLB >> 2); k += NT_IMG) {
-          if (do_nrm)
-#pragma unroll
-            for (int c = 0; c < 3; c++) reinterpret_cast<unsigned *>(planes + (size_t)(cb + c) * PLB)[k] = bg_n;
-          if (do_dep) reinterpret_cast<unsigned *>(planes + (size_t)(cb + (C == 1 ? 0 : 3)) * PLB)[k] = bg_d;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < JMAX; j++)
-          if (wpix[j] >= 0) {
-            const int row = wpix[j] / S, col = wpix[j] - row * S, o = row * RS + col;
-            if (do_nrm) {
-              planes[(size_t)(cb + 0) * PLB + o] = (uint8_t)qn(wv[j][0]);
-              planes[(size_t)(cb + 1) * PLB + o] = (uint8_t)qn(wv[j][1]);
-              planes[(size_t)(cb + 2) * PLB + o] = (uint8_t)qn(wv[j][2]);
-            }
-            if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(wv[j][3]);
+              for (int c = 0; c < 4; c++) F[c * SS + row * S + col] = v[c];
           }
-        for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // float images -> clean
-        for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
+          __syncthreads();
+          float neg[2];
+          neg[0] = -fminf(fminf(dilated_min<NT_IMG>(F, S), dilated_min<NT_IMG>(F + SS, S)), dilated_min<NT_IMG>(F + 2 * SS, S));
+          neg[1] = -dilated_min<NT_IMG>(F + 3 * SS, S);
+          block_max<NT_IMG, 2>(neg, sm.fred);
+          mnv[0] = -neg[0];
+          mnv[1] = -neg[1];
+          const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
+          const unsigned bg_n = qn(0.0f) * 0x01010101u, bg_d = qd(0.0f) * 0x01010101u;
+          const int cb = (C == 1) ? 0 : pj * per;
+          for (int k = tid; k < (PLB >> 2); k += NT_IMG) {
+            if (do_nrm)
+#pragma unroll
+              for (int c = 0; c < 3; c++) reinterpret_cast<unsigned *>(planes + (size_t)(cb + c) * PLB)[k] = bg_n;
+            if (do_dep) reinterpret_cast<unsigned *>(planes + (size_t)(cb + (C == 1 ? 0 : 3)) * PLB)[k] = bg_d;
+          }
+          __syncthreads();
+          for (int k = tid; k < bn; k += NT_IMG) {
+            int row, col;
+            float n0, n1, n2, dv;
+            if (cell_values(k, row, col, n0, n1, n2, dv)) {
+              const int o = row * RS + col;
+              if (do_nrm) {
+                planes[(size_t)(cb + 0) * PLB + o] = (uint8_t)qn(n0);
+                planes[(size_t)(cb + 1) * PLB + o] = (uint8_t)qn(n1);
+                planes[(size_t)(cb + 2) * PLB + o] = (uint8_t)qn(n2);
+              }
+              if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(dv);
+            }
+          }
+          __syncthreads();
+          for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);
+          for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
+        } else {
+        // general path (no empty window): materialise the four float channel images over the (now dead) tiles and take the
+          // min of their dilations. Winners keep their values in registers across the rewrite of the tiles.
+          constexpr int JMAX = (BOX_CAP + NT_IMG - 1) / NT_IMG;
+          float wv[JMAX][4];
+          int wpix[JMAX];
+  #pragma unroll
+          for (int j = 0; j < JMAX; j++) {
+            const int k = tid + j * NT_IMG;
+            wpix[j] = -1;
+            int row, col;
+            if (k < bn && cell_values(k, row, col, wv[j][0], wv[j][1], wv[j][2], wv[j][3])) wpix[j] = row * S + col;
+          }
+          __syncthreads();
+          float *F = reinterpret_cast<float *>(tileA);  // 4 x SS floats = tileA + tileB
+          for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(F)[k] = make_uint4(0, 0, 0, 0);
+          __syncthreads();
+  #pragma unroll
+          for (int j = 0; j < JMAX; j++)
+            if (wpix[j] >= 0)
+  #pragma unroll
+              for (int c = 0; c < 4; c++) F[c * SS + wpix[j]] = wv[j][c];
+          __syncthreads();
+          float neg[2];
+          neg[0] = -fminf(fminf(dilated_min<NT_IMG>(F, S), dilated_min<NT_IMG>(F + SS, S)), dilated_min<NT_IMG>(F + 2 * SS, S));
+          neg[1] = -dilated_min<NT_IMG>(F + 3 * SS, S);
+          block_max<NT_IMG, 2>(neg, sm.fred);
+          mnv[0] = -neg[0];
+          mnv[1] = -neg[1];
+          const Quant qn(mnv[0], mxv[0]), qd(mnv[1], mxv[1]);
+          const unsigned bg_n = qn(0.0f) * 0x01010101u, bg_d = qd(0.0f) * 0x01010101u;  // background = quantised 0
+          const int cb = (C == 1) ? 0 : pj * per;
+          for (int k = tid; k < (PLB >> 2); k += NT_IMG) {
+            if (do_nrm)
+  #pragma unroll
+              for (int c = 0; c < 3; c++) reinterpret_cast<unsigned *>(planes + (size_t)(cb + c) * PLB)[k] = bg_n;
+            if (do_dep) reinterpret_cast<unsigned *>(planes + (size_t)(cb + (C == 1 ? 0 : 3)) * PLB)[k] = bg_d;
+          }
+          __syncthreads();
+  #pragma unroll
+          for (int j = 0; j < JMAX; j++)
+            if (wpix[j] >= 0) {
+              const int row = wpix[j] / S, col = wpix[j] - row * S, o = row * RS + col;
+              if (do_nrm) {
+                planes[(size_t)(cb + 0) * PLB + o] = (uint8_t)qn(wv[j][0]);
+                planes[(size_t)(cb + 1) * PLB + o] = (uint8_t)qn(wv[j][1]);
+                planes[(size_t)(cb + 2) * PLB + o] = (uint8_t)qn(wv[j][2]);
+              }
+              if (do_dep) planes[(size_t)(cb + (C == 1 ? 0 : 3)) * PLB + o] = (uint8_t)qd(wv[j][3]);
+            }
+          for (int k = tid; k < SS; k += NT_IMG) reinterpret_cast<uint4 *>(tileA)[k] = make_uint4(0, 0, 0, 0);  // float images -> clean
+          for (int k = tid; k < MAXPIX / 32; k += NT_IMG) sm.occf[k] = 0u;
+        }
       } else {
         const Quant qn(0.0f, mxv[0]), qd(0.0f, mxv[1]);
         const int cb = (C == 1) ? 0 : pj * per;
@@ -2616,23 +2859,30 @@ int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_
 }
 
 static const int HANDS_CAP1 = 2176, HANDS_CAP2 = 12800;  // tier 1: 4 CTAs per SM (34 KB + 20 KB static each, <= 64 registers)
+static const int HANDS_CAP3 = 131072;                    // last tier: neighbourhood staged in global memory (2 MB per CTA)
 
 int geo_hands(gpdb_ctx *ctx, const int *d_sidx, int n, int slot0, const double *d_frames, const uint8_t *d_valid,
               gpdb_pose *d_poses, uint8_t *d_flags) {
   if (n <= 0) return GPDB_OK;
   // per call, not once per process: function attributes belong to the current device's context (one context per GPU)
   CUDA_TRY(cudaFuncSetAttribute(k_hands, cudaFuncAttributeMaxDynamicSharedMemorySize, HANDS_CAP2 * 16));
-  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)n + 1));
-  if (!ovf) return GPDB_ERR_CUDA;
-  int *ovf_count = ovf + n;
+  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * 2 * ((size_t)n + 1));
+  float4 *glist = (float4 *)gpdb_scratch(ctx, 21, sizeof(float4) * (size_t)HANDS_CAP3 * ctx->sm_count);
+  if (!ovf || !glist) return GPDB_ERR_CUDA;
+  int *ovf_count = ovf + n, *ovf2 = ovf + n + 1, *ovf2_count = ovf2 + n;
   CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ovf2_count, 0, sizeof(int), ctx->stream));
   k_hands<<<n, NT_HANDS, HANDS_CAP1 * 16, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, slot0, d_frames, d_valid, d_poses,
-                                                         d_flags, HANDS_CAP1, ovf, ovf_count, 0, ctx->d_err);
+                                                         d_flags, HANDS_CAP1, nullptr, nullptr, ovf, ovf_count, nullptr, ctx->d_err);
   LAUNCH_CHECK();
-  // large-tile pass over the samples whose neighbourhood did not fit tier 1 (persistent CTAs)
+  // large-tile pass over the samples whose neighbourhood did not fit tier 1 (persistent CTAs) ...
   k_hands<<<ctx->sm_count, NT_HANDS, HANDS_CAP2 * 16, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, slot0, d_frames,
                                                                      d_valid, d_poses, d_flags, HANDS_CAP2, ovf, ovf_count,
-                                                                     1, ctx->d_err);
+                                                                     ovf2, ovf2_count, nullptr, ctx->d_err);
+  LAUNCH_CHECK();
+  // ... and the last tier over what did not fit that either: neighbourhood in global memory (usually an empty list)
+  k_hands<<<ctx->sm_count, NT_HANDS, 16, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, slot0, d_frames, d_valid, d_poses,
+                                                        d_flags, HANDS_CAP3, ovf2, ovf2_count, nullptr, nullptr, glist, ctx->d_err);
   LAUNCH_CHECK();
   return GPDB_OK;
 }
@@ -2661,8 +2911,10 @@ int geo_compact(gpdb_ctx *ctx, const gpdb_pose *d_poses, const uint8_t *d_flags,
 }
 
 // `d_p16`: nc images of S*S 16-byte pixels (see k_images). Fast path: k_images2 (two CTAs per SM) over every image, then
-// k_images over the images whose box list overflowed; k_images alone when the geometry is outside the fast path's limits
-// (image_size != 60, more than two cameras) or when GPD_B200_IMAGES_KERNEL=1 forces it (tests compare the two kernels).
+// k_images over the images whose box list (1 024 points) overflowed, then its global-list instance over the images whose box
+// holds more than 2 048 points (up to 32 768; the overflow lists are usually empty: those launches return at once);
+// k_images alone when the geometry is outside the fast path's limits (image_size != 60, more than two cameras) or when
+// GPD_B200_IMAGES_KERNEL=1 forces it (tests compare the kernels).
 int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
   if (nc <= 0) return GPDB_OK;
   const DevParams &hp = ctx->hp;
@@ -2693,15 +2945,37 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
     d_work = ovf;
     d_work_n = ovf_count;
   }
+  // general tier (2 048-point box list in shared memory): everything, or the overflow list of the fast path; its own
+  // overflow goes to a second list ...
+  int *ovf2 = (int *)gpdb_scratch(ctx, 20, sizeof(int) * ((size_t)nc + 1));
+  const int gl_cap = 32768;
+  const size_t gl_slice = (size_t)gl_cap * 36 + (size_t)16 * S * S;
+  unsigned char *gl = (unsigned char *)gpdb_scratch(ctx, 19, gl_slice * (size_t)ctx->sm_count);
+  if (!ovf2 || !gl) return GPDB_ERR_CUDA;
+  int *ovf2_count = ovf2 + nc;
+  CUDA_TRY(cudaMemsetAsync(ovf2_count, 0, sizeof(int), ctx->stream));
   const int grid = fast ? ctx->sm_count : std::min(nc, ctx->sm_count * 64);
   if (S == 60) {
-    CUDA_TRY(cudaFuncSetAttribute(k_images<60>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_images<60><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
-                                                      (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n);
+    CUDA_TRY(cudaFuncSetAttribute(k_images<60, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_images<60, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_images<60, false><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                             (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n,
+                                                             nullptr, 0, ovf2, ovf2_count);
+    LAUNCH_CHECK();
+    // ... which the last tier redoes with the box list in global memory (32 768 points; beyond: GPDB_ERR_CAPACITY)
+    k_images<60, true><<<ctx->sm_count, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                                     (int)plane_bytes, (int)list_bytes, ctx->d_prof, ovf2, ovf2_count,
+                                                                     gl, gl_cap, nullptr, nullptr);
   } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_images<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_images<0><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
-                                                     (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n);
+    CUDA_TRY(cudaFuncSetAttribute(k_images<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_images<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_images<0, false><<<grid, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                            (int)plane_bytes, (int)list_bytes, ctx->d_prof, d_work, d_work_n,
+                                                            nullptr, 0, ovf2, ovf2_count);
+    LAUNCH_CHECK();
+    k_images<0, true><<<ctx->sm_count, NT_IMG, smem, ctx->stream>>>(ctx->dp, ctx->cloud, d_cand, nc, d_p16, ctx->d_qtab, ctx->d_err,
+                                                                    (int)plane_bytes, (int)list_bytes, ctx->d_prof, ovf2, ovf2_count,
+                                                                    gl, gl_cap, nullptr, nullptr);
   }
   LAUNCH_CHECK();
   return GPDB_OK;
@@ -2718,6 +2992,13 @@ int geo_hwc_to_p16(gpdb_ctx *ctx, const uint8_t *d_hwc, int n, uint8_t *d_p16) {
   if (n <= 0) return GPDB_OK;
   const size_t npix = (size_t)n * ctx->hp.S * ctx->hp.S;
   k_hwc_to_p16<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(d_hwc, npix, ctx->hp.C, d_p16);
+  LAUNCH_CHECK();
+  return GPDB_OK;
+}
+
+int geo_reeval(gpdb_ctx *ctx, gpdb_pose *d_hands, int n, int *d_labels) {
+  if (n <= 0) return GPDB_OK;
+  k_reeval<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->dp, ctx->cloud, d_hands, n, d_labels);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

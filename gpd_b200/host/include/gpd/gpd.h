@@ -124,6 +124,7 @@ class Hand {
   void setScore(double s) { p_.score = (float)s; }
   void setPosition(const std::array<double, 3> &p) { for (int i = 0; i < 3; i++) p_.position[i] = p[i]; }
   void setFullAntipodal(bool b) { p_.full_antipodal = b ? 1 : 0; }
+  void setHalfAntipodal(bool b) { p_.half_antipodal = b ? 1 : 0; }
   bool isFullAntipodal() const { return p_.full_antipodal != 0; }
   bool isHalfAntipodal() const { return p_.half_antipodal != 0; }
   double getTop() const { return p_.top; }
@@ -258,6 +259,9 @@ class GraspDetector {
   // + classifier on the device, hands with score > min_score, in (sample, pose) order
   std::vector<std::unique_ptr<candidate::Hand>> classifyAtPositions(const util::Cloud &cloud, const std::vector<double> &positions,
                                                                     double min_score);
+  // GraspDetector::evalGroundTruth (grasp_detector.cpp:523-527) -> HandSearch::reevaluateHypotheses: re-labels the hands
+  // against `cloud_gt` (e.g. a ground-truth mesh cloud) on the device; returns 1 per full-antipodal hand, updates the flags
+  std::vector<int> evalGroundTruth(const util::Cloud &cloud_gt, std::vector<std::unique_ptr<candidate::Hand>> &hands);
   // Clustering::findClusters(hands, remove_inliers = false) on the device (gpdb_find_clusters); the host class Clustering
   // below stays for remove_inliers = true and for callers without a detector
   std::vector<std::unique_ptr<candidate::Hand>> findClustersOnDevice(const std::vector<std::unique_ptr<candidate::Hand>> &hands,

@@ -858,6 +858,22 @@ static bool sample_indices_of(gpdb_ctx *ctx, const util::Cloud &cloud, std::vect
   return true;
 }
 
+std::vector<int> GraspDetector::evalGroundTruth(const util::Cloud &cloud_gt, std::vector<std::unique_ptr<candidate::Hand>> &hands) {
+  std::vector<int> labels(hands.size(), 0);
+  if (!ctx_ || hands.empty() || !ensureCloud(cloud_gt)) return labels;
+  std::vector<gpdb_pose> rec(hands.size());
+  for (size_t i = 0; i < hands.size(); i++) rec[i] = hands[i]->raw();
+  if (gpdb_reevaluate(ctx_, rec.data(), (int)rec.size(), labels.data()) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return std::vector<int>(hands.size(), 0);
+  }
+  for (size_t i = 0; i < hands.size(); i++) {
+    hands[i]->setHalfAntipodal(rec[i].half_antipodal != 0);
+    hands[i]->setFullAntipodal(rec[i].full_antipodal != 0);
+  }
+  return labels;
+}
+
 // Clustering::findClusters (remove_inliers = false) on the device: gpdb_find_clusters
 std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::findClustersOnDevice(
     const std::vector<std::unique_ptr<candidate::Hand>> &hands, int min_inliers) {

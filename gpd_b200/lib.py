@@ -23,7 +23,7 @@ EXPORTS = [
     "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
     "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select", "gpdb_load_weights_file", "gpdb_read_weights_file", "gpdb_set_samples",
     "gpdb_comm_unique_id", "gpdb_comm_init", "gpdb_comm_destroy", "gpdb_shard_bounds", "gpdb_set_cloud_bcast",
-    "gpdb_detect_sharded", "gpdb_detect_sharded_resident", "gpdb_slot_bytes", "gpdb_find_clusters",
+    "gpdb_detect_sharded", "gpdb_detect_sharded_resident", "gpdb_slot_bytes", "gpdb_find_clusters", "gpdb_reevaluate",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
     L.gpdb_slot_bytes.argtypes = [C.c_int32, C.c_int32]
     L.gpdb_slot_bytes.restype = C.c_int64
     L.gpdb_find_clusters.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
+    L.gpdb_reevaluate.argtypes = [vp, vp, C.c_int32, vp]
     _LIB = L
     return L
 
@@ -247,6 +248,13 @@ class Context:
     def detect_sharded_resident(self, d_sidx_local_ptr, n_local, slot_samples, d_gathered_ptr, stats):
         return self._check(lib().gpdb_detect_sharded_resident(self.h, C.c_void_p(d_sidx_local_ptr), int(n_local), int(slot_samples),
                                                               C.c_void_p(d_gathered_ptr), C.byref(stats)))
+
+    def reevaluate(self, hands):
+        """HandSearch::reevaluateHypotheses against the installed cloud: (labels int32, re-labelled records)."""
+        hands = np.array(hands, dtype=abi.POSE_DTYPE, copy=True)
+        labels = np.zeros(len(hands), np.int32)
+        self._check(lib().gpdb_reevaluate(self.h, _p(hands), len(hands), _p(labels)))
+        return labels, hands
 
     def find_clusters(self, hands, min_inliers):
         """Clustering::findClusters (remove_inliers = false) on the device; hands / result: abi.POSE_DTYPE records."""

@@ -285,6 +285,13 @@ int gpdb_get_cloud_source_index(gpdb_ctx *ctx, int32_t *src_out);
  * ms[0] upload, ms[1] NaN/workspace filter, ms[2] voxelise, ms[3] grid build, ms[4] normals, ms[5] whole call. */
 int gpdb_preprocess_timings(const gpdb_ctx *ctx, double ms_out[6]);
 
+/* Replaces: HandSearch::reevaluateHypotheses (hand_search.cpp:66-134; GraspDetector::evalGroundTruth,
+ * grasp_detector.cpp:523-527): the given hands (sample, frame, top, finger_idx are read) are re-labelled against the cloud
+ * installed in the context — radius search around the hand's sample, its own frame, evaluateFingers at its own depth and
+ * finger placement, closing region, Antipodal::evaluateGrasp. labels_out[i] = 1 for a full antipodal grasp, else 0; the
+ * half_antipodal / full_antipodal fields of the records are updated in place. Returns n. */
+int gpdb_reevaluate(gpdb_ctx *ctx, gpdb_pose *hands, int32_t n_hands, int32_t *labels_out);
+
 /* Replaces: Clustering::findClusters(hand_list, remove_inliers = false) (clustering.cpp:5-105; GraspDetector::detectGrasps
  * step 6, grasp_detector.cpp:283-301; SequentialImportanceSampling step 4) on the device: one warp per hand over the n
  * hands (n <= num_selected in detectGrasps), inliers folded in index order so that the running mean / variance are the

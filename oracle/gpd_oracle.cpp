@@ -1666,6 +1666,47 @@ int gpdo_images_literal_shadow(void *cloud, const gpdb_params *pr, const gpdb_po
   return 0;
 }
 
+// HandSearch::reevaluateHypotheses (hand_search.cpp:66-134) + reevaluateHypothesis (:190-209) + labelHypothesis (:211-228):
+// the given hands are re-labelled against THIS cloud (the ground-truth mesh cloud of the data-generation path,
+// GraspDetector::evalGroundTruth, grasp_detector.cpp:523-527): radius search r = nn_radius_hs around the hand's sample
+// (eigenVectorToPcl: float32 image of the position), hand-frame transform with the hand's own frame, height crop (padding
+// quirk), evaluateFingers(points, hand.top, hand.finger_idx) + evaluateHand(idx), closing region, Antipodal::evaluateGrasp.
+// labels[i] = 1 for a full grasp, else 0; half / full flags are written back into the records.
+int gpdo_reevaluate(void *cloud, const gpdb_params *pr, gpdb_pose *hands, int32_t n, int32_t *labels, int32_t nthreads) {
+  const Cloud &c = *(Cloud *)cloud;
+  Derived dv = derive(*pr);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nn;
+    PointList pl, plf, plc;
+#pragma omp for schedule(dynamic, 8)
+    for (int i = 0; i < n; i++) {
+      gpdb_pose &h = hands[i];
+      labels[i] = 0;
+      h.half_antipodal = 0;
+      h.full_antipodal = 0;
+      float q[3] = {(float)h.sample[0], (float)h.sample[1], (float)h.sample[2]};
+      radius_search(c, q, dv.nn_radius_hs, nn);
+      if (nn.empty() || h.finger_idx < 0 || h.finger_idx >= pr->num_finger_placements) continue;
+      slice_cloud(c, nn, pl);
+      transform_to_hand_frame(pl, h.sample, h.frame, plf);
+      crop_by_hand_height(plf, pr->hand_height, plc);
+      FingerHand fh(pr->finger_width, pr->hand_outer_diameter, pr->hand_depth, pr->num_finger_placements);
+      fh.evaluate_fingers(plc, h.top, h.finger_idx);
+      std::fill(fh.hand.begin(), fh.hand.end(), 0);  // evaluateHand(idx) (:83-87)
+      fh.hand[h.finger_idx] = fh.fingers[h.finger_idx] && fh.fingers[pr->num_finger_placements + h.finger_idx];
+      if (!fh.any_hand()) continue;
+      std::vector<int> closing = fh.closing_region(plc, -1);
+      if (closing.empty()) continue;
+      int label = antipodal_eval(plc, closing, pr->friction_coeff, pr->min_viable);
+      h.half_antipodal = (label == 1 || label == 2);
+      h.full_antipodal = (label == 2);
+      if (label == 2) labels[i] = 1;
+    }
+  }
+  return n;
+}
+
 // EigenClassifier::classifyImages (eigen_classifier.cpp:59-79); race-free (per-thread scratch).
 int gpdo_classify(const gpdb_params *pr, const float *const *wts /* 8 pointers */, const uint8_t *images, int32_t n,
                   float *scores, float *logits, int32_t nthreads) {

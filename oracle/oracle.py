@@ -49,6 +49,7 @@ def lib():
     L.gpdo_classify.argtypes = [C.POINTER(abi.Params), vp, vp, C.c_int32, vp, vp, C.c_int32]
     L.gpdo_detect.argtypes = [vp, C.POINTER(abi.Params), vp, vp, C.c_int32, C.POINTER(abi.Result), C.c_int32, vp]
     L.gpdo_free_result.argtypes = [C.POINTER(abi.Result)]
+    L.gpdo_reevaluate.argtypes = [vp, C.POINTER(abi.Params), vp, C.c_int32, vp, C.c_int32]
     L.gpdo_dilate_normalize_u8.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.gpdo_conv_forward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp]
     L.gpdo_angle_axis.argtypes = [C.c_double, vp, vp]
@@ -140,6 +141,13 @@ class OracleCloud:
         out = np.zeros((n, S, S, Cc), np.uint8)
         lib().gpdo_images(self.h, C.byref(params), _p(poses), n, _p(out), nthreads or num_threads())
         return out
+
+    def reevaluate(self, params, hands, nthreads=0):
+        """HandSearch::reevaluateHypotheses: labels (1 = full antipodal against THIS cloud) + the re-labelled records."""
+        hands = np.array(hands, dtype=abi.POSE_DTYPE, copy=True)
+        labels = np.zeros(len(hands), np.int32)
+        lib().gpdo_reevaluate(self.h, C.byref(params), _p(hands), len(hands), _p(labels), nthreads or num_threads())
+        return labels, hands
 
     def images_literal_shadow(self, params, poses, lcg_seed, mt_seed):
         """Grasp images with the occlusion channels in the reference's LITERAL semantics (sequential shared LCG stream +

@@ -251,33 +251,60 @@ def test_capacity_error_is_reported_not_crashed():
     ctx.close()
 
 
-def test_dense_cloud_uses_the_large_tile_tier():
-    """1.2 mm lattice (6x the density of a 3 mm voxelised cloud): the hand-search slab exceeds the 4 096-point tile
-    and goes through the 12 800-point pass; results must still equal the oracle."""
-    g = np.arange(-0.09, 0.09, 0.0012)
+def _lattice_cloud(step, half=0.09):
+    g = np.arange(-half, half, step)
     X, Y = np.meshgrid(g, g, indexing="ij")
     Z = 0.6 + 0.01 * np.sin(40 * X) * np.cos(30 * Y)
     xyz = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
     rng = np.random.default_rng(1)
     nrm = np.tile([0.0, 0.0, -1.0], (len(xyz), 1)) + rng.normal(0, 0.05, (len(xyz), 3))
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
-    cloud = {"xyz": xyz, "normals": nrm.astype(np.float32).astype(np.float64), "cam_source": None, "view_points": np.zeros((1, 3))}
-    p, ctx, oc, w = make(cloud, 3)
+    return {"xyz": xyz, "normals": nrm.astype(np.float32).astype(np.float64), "cam_source": None, "view_points": np.zeros((1, 3))}, rng
+
+
+def test_dense_clouds_go_through_the_overflow_tiers():
+    """Lattices 6x / 9x denser than a 3 mm voxelised cloud. The hand-search slab leaves the 2 176-point tile (12 800-point
+    pass) and then shared memory altogether (global-memory tier, 31 k points); the image boxes leave the 1 024- and
+    2 048-point lists (global-list tier of k_images, ~3 400 points). The reference has no capacity limit: frames, hands,
+    images and scores must still equal the oracle."""
+    cloud, rng = _lattice_cloud(0.0012)
+    xyz = cloud["xyz"]
+    p, ctx, oc, w = make(cloud, 15, keep_images=1)
     center = np.argsort(np.linalg.norm(xyz[:, :2], axis=1))[:2000]
-    sidx = center[rng.choice(2000, 16, replace=False)].astype(np.int32)
-    idx, _ = oc.radius_search(xyz[sidx[0]], 0.11)
-    assert len(idx) > 12000  # ~6x a voxelised neighbourhood
-    # (the image stage is not exercised here: such a cloud also exceeds the 2 048-point image-box list)
-    fo, vo = oc.frames(p, sidx)
-    po, flo = oc.hand_search(p, sidx, fo, vo)
-    rg = ctx.hand_search(sidx)
-    assert np.array_equal(rg["frames"], fo) and np.array_equal(rg["pose_flags"], flo)
-    co = po[(flo & 3) == 3]
-    assert len(co) == rg["n_candidates"] > 0
-    for f in ("position", "frame", "top", "bottom", "center", "width"):
-        assert np.allclose(co[f], rg["candidates"][f], atol=1e-9, rtol=0), f
-    assert np.array_equal(co["finger_idx"], rg["candidates"]["finger_idx"])
+    sidx = center[rng.choice(2000, 60, replace=False)].astype(np.int32)
+    assert len(oc.radius_search(xyz[sidx[0]], 0.11)[0]) > 12800
+    ro, rg = oc.detect(p, w, sidx), ctx.detect(sidx)
+    assert rg["n_candidates"] > 0
+    assert_parity(ro, rg, 15)
     ctx.close()
+    # image stage on a 1 mm lattice, for hands found on its 3 mm subset (enough of them, with large boxes)
+    dense, rng = _lattice_cloud(0.001)
+    coarse, _ = _lattice_cloud(0.003)
+    for ch in (15, 12):
+        pc, ctx_c, oc_c, wc = make(coarse, ch)
+        poses = ctx_c.hand_search(np.arange(0, len(coarse["xyz"]), 7, dtype=np.int32))["candidates"][::6]
+        ctx_c.close()
+        assert len(poses) >= 40
+        pd, ctx_d, oc_d, wd = make(dense, ch)
+        assert len(oc_d.radius_search(dense["xyz"][len(dense["xyz"]) // 2 + 90], 0.11)[0]) > 12800
+        box = []  # points inside the image volume of each hand: all three list tiers (<= 1 024, <= 2 048, global) must occur
+        for c in poses:
+            loc = (dense["xyz"].astype(np.float64) - c["sample"]) @ c["frame"].reshape(3, 3).T
+            box.append(np.count_nonzero((loc[:, 0] > c["bottom"]) & (loc[:, 0] < c["bottom"] + 0.06) & (np.abs(loc[:, 1] - c["center"]) < 0.05)
+                                        & (np.abs(loc[:, 2]) < 0.02)))
+        box = np.array(box)
+        assert (box > 2048).sum() >= 10 and ((box > 1024) & (box <= 2048)).sum() >= 5 and (box <= 1024).sum() >= 1, np.percentile(box, [0, 50, 100])
+        io, ig = oc_d.images(pd, poses), ctx_d.images(poses)
+        d = np.abs(io.astype(np.int32).reshape(ig.shape) - ig.astype(np.int32))
+        assert d.max() <= 1 and np.count_nonzero(d) <= 1e-3 * d.size
+        so = oracle.classify(pd, wd, io.reshape(len(poses), -1))[0]
+        sg = ctx_d.classify(ig)[0]
+        assert np.abs(so - sg).max() <= 1e-4 * np.abs(so).max()
+        # re-labelling of the same hands against the dense cloud (one warp per hand, straight from the grid)
+        lo, ho = oc_d.reevaluate(pd, poses)
+        lg, hg = ctx_d.reevaluate(poses)
+        assert np.array_equal(lo, lg) and np.array_equal(ho["half_antipodal"], hg["half_antipodal"])
+        ctx_d.close()
 
 
 def test_config2_krylon_with_replacement():
@@ -430,4 +457,28 @@ def test_image_kernels_agree(ch, two_cams, monkeypatch):
     monkeypatch.delenv("GPD_B200_IMAGES_KERNEL")
     fast = ctx.images(poses)
     assert np.array_equal(general, fast)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_reevaluate_hypotheses_matches_oracle():
+    """gpdb_reevaluate (HandSearch::reevaluateHypotheses / GraspDetector::evalGroundTruth): labels and half / full flags of
+    given hands against the installed cloud — the same cloud, and a thinned "ground-truth" cloud — equal the oracle's."""
+    s = scenes.synthetic_table_scene(7, n_points=60000)
+    p, ctx, oc, w = make(s, 15)
+    c = ctx.hand_search(scenes.sample_indices(3, 60000, 1200))["candidates"]
+    assert len(c) > 300
+    lo, ho = oc.reevaluate(p, c)
+    lg, hg = ctx.reevaluate(c)
+    assert np.array_equal(lo, lg) and np.array_equal(lg, c["full_antipodal"].astype(np.int32))
+    for f in ("half_antipodal", "full_antipodal"):
+        assert np.array_equal(ho[f], hg[f]), f
+    keep = np.arange(60000) % 4 != 1
+    ctx.set_cloud(s["xyz"][keep], s["normals"][keep], s["cam_source"][keep], s["view_points"])
+    thin = oracle.OracleCloud(s["xyz"][keep], s["normals"][keep], s["cam_source"][keep], s["view_points"])
+    lo, ho = thin.reevaluate(p, c)
+    lg, hg = ctx.reevaluate(c)
+    assert np.array_equal(lo, lg) and not np.array_equal(lg, c["full_antipodal"].astype(np.int32))
+    for f in ("half_antipodal", "full_antipodal"):
+        assert np.array_equal(ho[f], hg[f]), f
     ctx.close()

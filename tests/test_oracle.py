@@ -249,3 +249,28 @@ def test_sample_positions_extend_the_sample_indices():
     mix = np.concatenate([sidx[:5], oc.set_samples(off)[:5]]).astype(np.int32)
     d = oc.detect(p, w, mix)
     assert np.array_equal(d["pose_flags"][:5], a["pose_flags"][:5]) and np.array_equal(d["pose_flags"][5:], c["pose_flags"][:5])
+
+
+def test_reevaluate_hypotheses_is_consistent_with_the_hand_search():
+    """HandSearch::reevaluateHypotheses (hand_search.cpp:66-134) restated: re-labelling the hands of a hand search against the
+    SAME cloud goes through another code path (evaluateFingers at the hand's own depth and finger index instead of the sweep
+    + deepenHand) and must return the labels the search gave them; against a thinned cloud (the "other" cloud of
+    GraspDetector::evalGroundTruth) labels may only change where points are missing, and an empty neighbourhood gives 0."""
+    from conftest import load_weights
+    k = scenes.krylon_cloud()
+    p = abi.default_params(15)
+    oc = oracle.OracleCloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
+    w, _ = load_weights(15)
+    c = oc.detect(p, oracle.WeightPack(w), scenes.sample_indices(2, len(k["xyz"]), 150))["candidates"]
+    labels, again = oc.reevaluate(p, c)
+    assert len(c) > 500 and np.array_equal(labels, c["full_antipodal"].astype(np.int32))
+    assert np.array_equal(again["half_antipodal"], c["half_antipodal"]) and np.array_equal(again["full_antipodal"], c["full_antipodal"])
+    keep = np.arange(len(k["xyz"])) % 3 != 0
+    thin = oracle.OracleCloud(k["xyz"][keep], k["normals"][keep], k["cam_source"][keep], k["view_points"])
+    l2, h2 = thin.reevaluate(p, c)
+    assert 0 < l2.sum() < labels.sum() + 200 and not np.array_equal(l2, labels)
+    assert np.all(h2["full_antipodal"] <= h2["half_antipodal"])
+    far = c[:4].copy()
+    far["sample"] += 10.0
+    l3, h3 = oc.reevaluate(p, far)
+    assert not l3.any() and not h3["half_antipodal"].any()
