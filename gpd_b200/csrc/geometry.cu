@@ -2119,7 +2119,7 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
   __shared__ Img2Smem sm;
   constexpr int S = 60, SS = S * S, RW = S / 4, PLB = SS;  // 15 words per row, 3600-byte planes
   constexpr int PIXT = (SS + NT_IMG - 1) / NT_IMG;
-  constexpr int JW = BOX_CAP2 / NT_IMG;  // box points per thread
+  constexpr int JW = (BOX_CAP2 + NT_IMG - 1) / NT_IMG;  // box points per thread
   const int C = P.C;
   unsigned long long *tileA = reinterpret_cast<unsigned long long *>(dyn);
   unsigned long long *tileB = tileA + SS;
