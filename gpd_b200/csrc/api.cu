@@ -683,7 +683,8 @@ static bool arena_reserve(HostArena *a, int which, size_t bytes, size_t keep) {
 
 struct PipeState {
   cudaStream_t copy = nullptr;  // D2H of finished chunks + the per-chunk candidate count, concurrent with compute
-  cudaEvent_t ev_compact[2], ev_count[2], ev_scored[2], ev_copied[2], ev_frames;
+  cudaStream_t hands = nullptr; // hand search + compaction of the chunks ahead, concurrent with images / LeNet of the current one
+  cudaEvent_t ev_compact[2], ev_count[2], ev_scored[2], ev_copied[2], ev_frames, ev_consumed[2], ev_hands_done;
   int *h_count = nullptr;       // pinned [2]
   std::vector<HostArena *> arenas;
   bool ok = false;
@@ -692,9 +693,11 @@ int gpdb_pipe_create(gpdb_ctx *ctx) {
   PipeState *ps = new PipeState();
   ctx->pipe = ps;
   bool ok = cudaStreamCreateWithFlags(&ps->copy, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ps->hands, cudaStreamNonBlocking) == cudaSuccess &&
             cudaHostAlloc((void **)&ps->h_count, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
-  cudaEvent_t *evs[9] = {&ps->ev_compact[0], &ps->ev_compact[1], &ps->ev_count[0], &ps->ev_count[1], &ps->ev_scored[0],
-                         &ps->ev_scored[1], &ps->ev_copied[0], &ps->ev_copied[1], &ps->ev_frames};
+  cudaEvent_t *evs[12] = {&ps->ev_compact[0], &ps->ev_compact[1], &ps->ev_count[0], &ps->ev_count[1], &ps->ev_scored[0],
+                          &ps->ev_scored[1], &ps->ev_copied[0], &ps->ev_copied[1], &ps->ev_frames, &ps->ev_consumed[0],
+                          &ps->ev_consumed[1], &ps->ev_hands_done};
   for (cudaEvent_t *e : evs) {
     *e = nullptr;
     ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
@@ -709,8 +712,13 @@ void gpdb_pipe_destroy(gpdb_ctx *ctx) {
     cudaStreamSynchronize(ps->copy);
     cudaStreamDestroy(ps->copy);
   }
-  cudaEvent_t evs[9] = {ps->ev_compact[0], ps->ev_compact[1], ps->ev_count[0], ps->ev_count[1], ps->ev_scored[0],
-                        ps->ev_scored[1], ps->ev_copied[0], ps->ev_copied[1], ps->ev_frames};
+  if (ps->hands) {
+    cudaStreamSynchronize(ps->hands);
+    cudaStreamDestroy(ps->hands);
+  }
+  cudaEvent_t evs[12] = {ps->ev_compact[0], ps->ev_compact[1], ps->ev_count[0], ps->ev_count[1], ps->ev_scored[0],
+                         ps->ev_scored[1], ps->ev_copied[0], ps->ev_copied[1], ps->ev_frames, ps->ev_consumed[0],
+                         ps->ev_consumed[1], ps->ev_hands_done};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (ps->h_count) cudaFreeHost(ps->h_count);
@@ -832,6 +840,7 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
   // the stage timers and releases the arena on failure, so that a failed call leaves no state behind
   auto finish = [&](int code) -> int {
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ps.hands);
     cudaStreamSynchronize(ps.copy);
     if (code >= 0) {
       int e = check_device_errors(ctx);
@@ -890,8 +899,14 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
   cudaEvent_t t0 = gpdb_st_begin(ctx);
   PIPE_TRY(geo_frames(ctx, d_sidx, n, d_frames, d_valid));
   gpdb_st_end(ctx, 0, t0);
+  // The hand search of the chunks AHEAD runs on its own stream: its CTAs (54 KB, 64 registers) fill what the tensor-core
+  // kernels of the current chunk leave idle (conv1: one 162 KB CTA per SM at 42 % issue utilisation). GPD_B200_OVERLAP=0
+  // puts everything on one stream (A/B aid).
+  static const bool overlap = !(getenv("GPD_B200_OVERLAP") && getenv("GPD_B200_OVERLAP")[0] == '0');
+  cudaStream_t const main_stream = ctx->stream, hs = overlap ? ps.hands : ctx->stream;
+  PIPE_CUDA(cudaEventRecord(ps.ev_frames, main_stream));
+  if (overlap) PIPE_CUDA(cudaStreamWaitEvent(hs, ps.ev_frames, 0));
   if (to_host && n > 0) {
-    PIPE_CUDA(cudaEventRecord(ps.ev_frames, ctx->stream));
     PIPE_CUDA(cudaStreamWaitEvent(ps.copy, ps.ev_frames, 0));
     PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_valid, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ps.copy));
     PIPE_CUDA(cudaMemcpyAsync(h_fixed + off_frames, d_frames, sizeof(double) * 9 * (size_t)n, cudaMemcpyDeviceToHost, ps.copy));
@@ -899,17 +914,21 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
   const int nchunks = (n + chunk - 1) / chunk;
   int total_nc = 0;
   size_t img_host = 0;  // bytes of images already placed in arena buffer 2
-  bool cand_busy[2] = {false, false};  // a D2H copy out of d_cand[b] has been issued (ev_copied[b] marks its end)
+  bool cand_busy[2] = {false, false};      // a D2H copy out of d_cand[b] has been issued (ev_copied[b] marks its end)
+  bool cand_consumed[2] = {false, false};  // ev_consumed[b] marks the end of the main stream's reads of d_cand[b]
   auto launch_hands = [&](int ci) -> int {
     const int c0 = ci * chunk, nn = std::min(chunk, n - c0), b = ci & 1;
-    if (cand_busy[b]) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ps.ev_copied[b], 0));  // chunk ci-2 has left d_cand[b]
+    if (cand_busy[b]) CUDA_TRY(cudaStreamWaitEvent(hs, ps.ev_copied[b], 0));  // chunk ci-2 has left d_cand[b] for the host
+    if (overlap && cand_consumed[b]) CUDA_TRY(cudaStreamWaitEvent(hs, ps.ev_consumed[b], 0));  // ... and images / scatter read it
+    ctx->stream = hs;  // the launchers (and the stage timers) use the context's current stream
     cudaEvent_t t1 = gpdb_st_begin(ctx);
     int r = geo_hands(ctx, d_sidx + c0, nn, c0 + slot_base, d_frames + 9 * (size_t)c0, d_valid + c0, d_poses,
                       d_flags + (size_t)c0 * P);
+    if (r == GPDB_OK) r = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand[b], d_count + b);
+    if (r == GPDB_OK) gpdb_st_end(ctx, 1, t1);
+    ctx->stream = main_stream;
     if (r != GPDB_OK) return r;
-    if ((r = geo_compact(ctx, d_poses, d_flags + (size_t)c0 * P, nn * P, d_cand[b], d_count + b)) != GPDB_OK) return r;
-    gpdb_st_end(ctx, 1, t1);
-    CUDA_TRY(cudaEventRecord(ps.ev_compact[b], ctx->stream));
+    CUDA_TRY(cudaEventRecord(ps.ev_compact[b], hs));
     CUDA_TRY(cudaStreamWaitEvent(ps.copy, ps.ev_compact[b], 0));
     CUDA_TRY(cudaMemcpyAsync(ps.h_count + b, d_count + b, sizeof(int), cudaMemcpyDeviceToHost, ps.copy));
     CUDA_TRY(cudaEventRecord(ps.ev_count[b], ps.copy));
@@ -921,6 +940,7 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
     if (ci + 1 < nchunks) PIPE_TRY(launch_hands(ci + 1));  // queued BEHIND which the host now waits for chunk ci's count
     PIPE_CUDA(cudaEventSynchronize(ps.ev_count[b]));
     const int nc = ps.h_count[b];
+    if (overlap) PIPE_CUDA(cudaStreamWaitEvent(main_stream, ps.ev_compact[b], 0));  // d_cand[b], flags of chunk ci are ready
     total_nc += nc;
     uint8_t *d_img = nullptr;  // keep_images: the chunk's images in the cv::Mat layout
     if (with_images_and_scores && nc > 0) {
@@ -962,6 +982,10 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
         ctx->sel_cap = cap;
       }
       PIPE_CUDA(cudaMemcpyAsync(ctx->d_sel + (total_nc - nc), d_cand[b], sizeof(gpdb_pose) * (size_t)nc, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (overlap) {
+      PIPE_CUDA(cudaEventRecord(ps.ev_consumed[b], main_stream));
+      cand_consumed[b] = true;
     }
     if (to_host) {  // this chunk's results leave for the pinned arena while the next chunk computes
       if (sizeof(gpdb_pose) * (size_t)total_nc > ar->cap[1]) {

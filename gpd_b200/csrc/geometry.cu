@@ -2933,8 +2933,8 @@ int geo_images(gpdb_ctx *ctx, const gpdb_pose *d_cand, int nc, uint8_t *d_p16) {
   const bool fast = S == 60 && (hp.C != 15 || (hp.K <= 2 && bm + 2048 <= (size_t)BOX_CAP2 * 36)) && !(force && force[0] == '1');
   const int *d_work = nullptr, *d_work_n = nullptr;
   if (fast) {
-    int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)nc + 1));
-    if (!ovf) return GPDB_ERR_CUDA;
+    int *ovf = (int *)gpdb_scratch(ctx, 22, sizeof(int) * ((size_t)nc + 1));  // not slot 2: the hand search of the next chunk
+    if (!ovf) return GPDB_ERR_CUDA;                                            // may run concurrently on its own stream
     int *ovf_count = ovf + nc;
     CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
     const size_t smem2 = (size_t)2 * 8 * S * S + (size_t)3 * S * S + (size_t)BOX_CAP2 * 36;
