@@ -310,6 +310,7 @@ int gpdb_create(const gpdb_params *params, gpdb_ctx **ctx_out) {
   }
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   ok = ok && gpdb_pipe_create(ctx) == GPDB_OK;
+  ctx->overlap_hands = !(getenv("GPD_B200_OVERLAP") && getenv("GPD_B200_OVERLAP")[0] == '0');
   if (!ok) {
     gpdb_set_error(nullptr, GPDB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     gpdb_destroy(ctx);
@@ -778,7 +779,7 @@ int check_device_errors(gpdb_ctx *ctx) {
     gpdb_set_error(ctx, GPDB_ERR_CAPACITY,
                    "neighbourhood exceeded an on-chip tile (frame ball: %d samples, hand-search ball: %d samples, "
                    "image box: %d images): the cloud is denser than the supported %d / %d / %d points",
-                   e[0], e[1], e[2], 1024, 131072, 32768);
+                   e[0], e[1], e[2], 16384, 131072, 32768);
     return GPDB_ERR_CAPACITY;
   }
   return GPDB_OK;
@@ -900,9 +901,9 @@ int gpdb_run_pipeline(gpdb_ctx *ctx, const int32_t *sample_idx, int32_t n, gpdb_
   PIPE_TRY(geo_frames(ctx, d_sidx, n, d_frames, d_valid));
   gpdb_st_end(ctx, 0, t0);
   // The hand search of the chunks AHEAD runs on its own stream: its CTAs (54 KB, 64 registers) fill what the tensor-core
-  // kernels of the current chunk leave idle (conv1: one 162 KB CTA per SM at 42 % issue utilisation). GPD_B200_OVERLAP=0
-  // puts everything on one stream (A/B aid).
-  static const bool overlap = !(getenv("GPD_B200_OVERLAP") && getenv("GPD_B200_OVERLAP")[0] == '0');
+  // kernels of the current chunk leave idle (conv1: one 162 KB CTA per SM at 42 % issue utilisation).
+  // gpdb_set_overlap(ctx, 0) / GPD_B200_OVERLAP=0 put everything on one stream (exclusive stage timers, A/B).
+  const bool overlap = ctx->overlap_hands;
   cudaStream_t const main_stream = ctx->stream, hs = overlap ? ps.hands : ctx->stream;
   PIPE_CUDA(cudaEventRecord(ps.ev_frames, main_stream));
   if (overlap) PIPE_CUDA(cudaStreamWaitEvent(hs, ps.ev_frames, 0));
@@ -1085,6 +1086,12 @@ int gpdb_detect_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx, int32_t n, 
     return GPDB_ERR_INVALID;
   }
   return run_pipeline(ctx, d_sample_idx, n, stats, true, true, d_flags_out, d_scores_out);
+}
+
+int gpdb_set_overlap(gpdb_ctx *ctx, int32_t enable) {
+  if (!ctx) return GPDB_ERR_INVALID;
+  ctx->overlap_hands = enable != 0;
+  return GPDB_OK;
 }
 
 int gpdb_set_stream(gpdb_ctx *ctx, void *cuda_stream) {

@@ -114,6 +114,7 @@ struct gpdb_ctx {
   int device;
   cudaStream_t stream;
   bool own_stream;
+  bool overlap_hands;  // hand search of the chunks ahead on its own stream (gpdb_set_overlap)
   StageTimes *st;
   PipeState *pipe;
   CommState *comm;

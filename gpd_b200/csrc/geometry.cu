@@ -36,6 +36,7 @@ constexpr int NT_HANDS = 256;
 #endif
 constexpr int NT_IMG = GPDB_NT_IMG;  // threads of k_images (one CTA per SM: 214 KB of shared memory)
 constexpr int LRF_WARPS = 4;
+constexpr int LRF_CAP_GLOBAL = 16384;  // last tier of k_frames: lists in global memory
 constexpr int LRF_CAP = 1024;  // points of the r = nn_radius ball (dynamic shared memory: 2 x 8 B x LRF_CAP per warp)
 constexpr int BOX_CAP = 2048;  // points inside one image box
 constexpr int MAXPIX = 64 * 64;  // image_size <= 64
@@ -311,15 +312,32 @@ __device__ void eigen3(const double *Min, double *eval, double *Q) {
 // (dist bits << 32 | index), rank-sorted so that N*N^T and sum(n) are accumulated in exactly the
 // (dist, index) order the reference's sorted radiusSearch yields -> bit-identical to the oracle.
 // ------------------------------------------------------------------------------------------------
-// Two tiers: tier 0 runs every sample with a small per-warp list (cap0 keys: 16 CTAs per SM instead of 3), samples
-// whose ball does not fit are appended to `ovf` and re-run by tier 1 with LRF_CAP keys (beyond that: err[0]).
+// Three tiers: tier 0 runs every sample with a small per-warp list (cap0 keys: 16 CTAs per SM instead of 3); samples whose
+// ball does not fit are appended to `ovf` and re-run by tier 1 with LRF_CAP keys in shared memory; what still does not fit
+// goes to `ovf2` and tier 2, whose lists live in a per-warp slice of global memory (`gkeys`, LRF_CAP_GLOBAL keys, a
+// grid-stride loop over the list). Beyond that: err[0]. The reference has no limit (frame_estimator.cpp:6-86); a voxelised
+// cloud never leaves tier 0 (at most ~155 voxels of 3 mm in a 1 cm ball).
+__device__ __forceinline__ bool lrf_sample(const DevParams &P, const DevCloud &cl, const int *sidx, int i, unsigned long long *keys,
+                                           unsigned long long *sorted, int cap, bool last, double *frames, uint8_t *valid, int *err,
+                                           double *s_acc_w);
+
 __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, DevCloud cl, const int *sidx, int n,
                                                             double *frames, uint8_t *valid, int *err, int cap, int *ovf,
-                                                            int *ovf_count, int tier) {
+                                                            int *ovf_count, int *ovf2, int *ovf2_count, unsigned long long *gkeys,
+                                                            int tier) {
   const DevParams &P = *Pp;
   extern __shared__ __align__(16) unsigned char lrf_dyn[];
   __shared__ double s_acc[LRF_WARPS][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (tier == 2) {
+    const int gw = blockIdx.x * LRF_WARPS + warp, nw = gridDim.x * LRF_WARPS, cnt2 = *ovf2_count;
+    unsigned long long *keys = gkeys + (size_t)gw * 2 * cap;
+    for (int j = gw; j < cnt2; j += nw) {
+      lrf_sample(P, cl, sidx, ovf2[j], keys, keys + cap, cap, true, frames, valid, err, s_acc[warp]);
+      __syncwarp();
+    }
+    return;
+  }
   int i = blockIdx.x * LRF_WARPS + warp;
   if (tier == 0) {
     if (i >= n) return;
@@ -327,13 +345,24 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
     if (i >= *ovf_count) return;
     i = ovf[i];
   }
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)warp * cap;
+  unsigned long long *sorted = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)(LRF_WARPS + warp) * cap;
+  if (!lrf_sample(P, cl, sidx, i, keys, sorted, cap, false, frames, valid, err, s_acc[warp]) && lane == 0) {
+    if (tier == 0) ovf[atomicAdd(ovf_count, 1)] = i;  // re-run with the large list
+    else ovf2[atomicAdd(ovf2_count, 1)] = i;          // ... with the global-memory list
+  }
+}
+
+// one sample by one warp; false when the ball holds more than `cap` points and this is not the last tier (nothing written)
+__device__ __forceinline__ bool lrf_sample(const DevParams &P, const DevCloud &cl, const int *sidx, int i, unsigned long long *keys,
+                                           unsigned long long *sorted, int cap, bool last, double *frames, uint8_t *valid, int *err,
+                                           double *s_acc_w) {
+  const int lane = threadIdx.x & 31;
   const int si = sidx[i];
   double sp[3];
   sample_position(cl, si, sp);
   float q[3] = {(float)sp[0], (float)sp[1], (float)sp[2]};
   SegRange sr = seg_range(P, q, P.rf_lrf);
-  unsigned long long *keys = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)warp * cap;
-  unsigned long long *sorted = reinterpret_cast<unsigned long long *>(lrf_dyn) + (size_t)(LRF_WARPS + warp) * cap;
   int cnt = 0;
   for (int row = 0; row < sr.nrows; row++) {
     int st, len;
@@ -355,10 +384,7 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
     }
   }
   if (cnt > cap) {
-    if (tier == 0) {  // re-run with the large list
-      if (lane == 0) ovf[atomicAdd(ovf_count, 1)] = i;
-      return;
-    }
+    if (!last) return false;
     if (lane == 0) atomicAdd(err + 0, 1);
     cnt = cap;
   }
@@ -366,7 +392,7 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
   if (cnt == 0) {
     if (lane == 0) valid[i] = 0;
     if (lane < 9) frames[9 * (size_t)i + lane] = 0.0;
-    return;
+    return true;
   }
   for (int a = lane; a < cnt; a += 32) {
     unsigned long long ka = keys[a];
@@ -385,11 +411,11 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
       const double *nn = cl.nrm + 3 * (size_t)idx;
       if (lane < 6) acc += nn[r] * nn[c]; else acc += nn[r];
     }
-    s_acc[warp][lane] = acc;
+    s_acc_w[lane] = acc;
   }
   __syncwarp();
   if (lane == 0) {
-    const double *a = s_acc[warp];
+    const double *a = s_acc_w;
     double M[9] = {a[0], a[1], a[2], a[1], a[3], a[4], a[2], a[4], a[5]};
     double eval[3], evec[9];
     eigen3(M, eval, evec);
@@ -413,6 +439,7 @@ __global__ void __launch_bounds__(LRF_WARPS * 32) k_frames(const DevParams *Pp, 
     f[6] = curv[0]; f[7] = curv[1]; f[8] = curv[2];
     valid[i] = 1;
   }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2843,17 +2870,25 @@ int geo_frames(gpdb_ctx *ctx, const int *d_sidx, int n, double *d_frames, uint8_
   const size_t smem0 = (size_t)2 * LRF_WARPS * cap0 * sizeof(unsigned long long);
   const size_t smem1 = (size_t)2 * LRF_WARPS * LRF_CAP * sizeof(unsigned long long);
   CUDA_TRY(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * ((size_t)n + 1));
-  if (!ovf) return GPDB_ERR_CUDA;
-  int *ovf_count = ovf + n;
+  int *ovf = (int *)gpdb_scratch(ctx, 2, sizeof(int) * 2 * ((size_t)n + 1));
+  const int g2 = 37;  // tier 2: 148 warps, 2 x 8 B x LRF_CAP_GLOBAL each (38 MB of scratch)
+  unsigned long long *gkeys =
+      (unsigned long long *)gpdb_scratch(ctx, 23, sizeof(unsigned long long) * 2 * LRF_CAP_GLOBAL * (size_t)g2 * LRF_WARPS);
+  if (!ovf || !gkeys) return GPDB_ERR_CUDA;
+  int *ovf_count = ovf + n, *ovf2 = ovf + n + 1, *ovf2_count = ovf2 + n;
   CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
-  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, smem0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
-                                                                               d_valid, ctx->d_err, cap0, ovf, ovf_count, 0);
+  CUDA_TRY(cudaMemsetAsync(ovf2_count, 0, sizeof(int), ctx->stream));
+  const int grid = (n + LRF_WARPS - 1) / LRF_WARPS;
+  k_frames<<<grid, LRF_WARPS * 32, smem0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames, d_valid, ctx->d_err, cap0, ovf,
+                                                       ovf_count, ovf2, ovf2_count, nullptr, 0);
   LAUNCH_CHECK();
-  // overflow tier over the (usually empty) list: the grid is sized for the worst case (every sample overflowed) so no
-  // host round trip is needed; warps beyond the list length exit at once
-  k_frames<<<(n + LRF_WARPS - 1) / LRF_WARPS, LRF_WARPS * 32, smem1, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames,
-                                                                               d_valid, ctx->d_err, LRF_CAP, ovf, ovf_count, 1);
+  // overflow tiers over the (usually empty) lists: the tier-1 grid is sized for the worst case (every sample overflowed) so
+  // no host round trip is needed; warps beyond the list length exit at once
+  k_frames<<<grid, LRF_WARPS * 32, smem1, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames, d_valid, ctx->d_err, LRF_CAP, ovf,
+                                                       ovf_count, ovf2, ovf2_count, nullptr, 1);
+  LAUNCH_CHECK();
+  k_frames<<<g2, LRF_WARPS * 32, 0, ctx->stream>>>(ctx->dp, ctx->cloud, d_sidx, n, d_frames, d_valid, ctx->d_err, LRF_CAP_GLOBAL, ovf,
+                                                 ovf_count, ovf2, ovf2_count, gkeys, 2);
   LAUNCH_CHECK();
   return GPDB_OK;
 }

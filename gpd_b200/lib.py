@@ -23,7 +23,7 @@ EXPORTS = [
     "gpdb_set_stream", "gpdb_debug_phase_cycles", "gpdb_preprocess_params_default", "gpdb_preprocess",
     "gpdb_get_cloud", "gpdb_get_cloud_source_index", "gpdb_preprocess_timings", "gpdb_detect_select", "gpdb_load_weights_file", "gpdb_read_weights_file", "gpdb_set_samples",
     "gpdb_comm_unique_id", "gpdb_comm_init", "gpdb_comm_destroy", "gpdb_shard_bounds", "gpdb_set_cloud_bcast",
-    "gpdb_detect_sharded", "gpdb_detect_sharded_resident", "gpdb_slot_bytes", "gpdb_find_clusters", "gpdb_reevaluate",
+    "gpdb_detect_sharded", "gpdb_detect_sharded_resident", "gpdb_slot_bytes", "gpdb_find_clusters", "gpdb_reevaluate", "gpdb_set_overlap",
 ]
 
 
@@ -83,6 +83,7 @@ def lib():
     L.gpdb_slot_bytes.restype = C.c_int64
     L.gpdb_find_clusters.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     L.gpdb_reevaluate.argtypes = [vp, vp, C.c_int32, vp]
+    L.gpdb_set_overlap.argtypes = [vp, C.c_int32]
     _LIB = L
     return L
 
@@ -322,6 +323,10 @@ class Context:
         """Device-resident path (raw device pointers as ints); returns n_candidates."""
         return self._check(lib().gpdb_detect_resident(self.h, C.c_void_p(d_sidx_ptr), n, C.c_void_p(d_flags_ptr),
                                                       C.c_void_p(d_scores_ptr), C.byref(stats)))
+
+    def set_overlap(self, enable):
+        """Hand search of the chunks ahead on its own stream (default on); off = one stream, exclusive stage timers."""
+        self._check(lib().gpdb_set_overlap(self.h, int(bool(enable))))
 
     def set_stream(self, cuda_stream_ptr):
         self._check(lib().gpdb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

@@ -220,6 +220,13 @@ int gpdb_detect_resident(gpdb_ctx *ctx, const int32_t *d_sample_idx, int32_t n_s
  * host framework's current stream, instead of the context's own stream. */
 int gpdb_set_stream(gpdb_ctx *ctx, void *cuda_stream);
 
+/* The chunk pipeline runs the hand search of the chunks ahead on a second stream, concurrently with the image stage and
+ * the classifier of the current chunk (default: on; environment GPD_B200_OVERLAP=0 turns the default off). With
+ * enable = 0 every kernel of a call runs on the context's stream, one after the other: the stage timers of
+ * gpdb_last_timings are then exclusive per stage (bench.py takes its per-kernel times from such a pass). Results are
+ * identical either way. */
+int gpdb_set_overlap(gpdb_ctx *ctx, int32_t enable);
+
 /* Stage-level entry points (used by the parity tests and by partial drop-ins). */
 
 /* Replaces: FrameEstimator::calculateLocalFrames (frame_estimator.cpp:6-35).

@@ -231,18 +231,41 @@ def test_tensor_core_lenet_matches_simt_and_oracle_on_many_images(ch):
     assert np.abs(out[0] - out[1]).max() <= 1e-4 * np.abs(out[1]).max()
 
 
-def test_capacity_error_is_reported_not_crashed():
-    """A cloud far denser than a voxelised one overflows the on-chip neighbourhood tiles: the call must fail with
-    GPDB_ERR_CAPACITY (-5) and the context must stay usable."""
-    rng = np.random.default_rng(0)
-    xyz = (rng.random((500000, 3)) * 0.1).astype(np.float32)  # 500 k points in a 10 cm cube: ~2 100 points per r=1 cm ball
-    nrm = rng.standard_normal((500000, 3))
+def _random_cube(n, edge, seed=0):
+    rng = np.random.default_rng(seed)
+    xyz = (rng.random((n, 3)) * edge).astype(np.float32)
+    nrm = rng.standard_normal((n, 3))
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    return xyz, nrm.astype(np.float32).astype(np.float64)
+
+
+def test_frames_of_an_unvoxelised_cloud_use_the_global_tier():
+    """500 k points in a 10 cm cube: ~2 100 points per r = 1 cm ball, more than the 1 024-key shared-memory list of
+    k_frames. The global-memory tier (16 384 keys per warp) must give the oracle's frames (same sorted accumulation order)."""
+    xyz, nrm = _random_cube(500000, 0.1)
     p = lib.default_params(channels=3)
     ctx = lib.Context(p)
-    ctx.set_cloud(xyz, nrm.astype(np.float32).astype(np.float64), None, np.zeros((1, 3)))
+    ctx.set_cloud(xyz, nrm, None, np.zeros((1, 3)))
+    oc = oracle.OracleCloud(xyz, nrm, None, np.zeros((1, 3)))
+    sidx = np.arange(0, 500000, 2500, dtype=np.int32)
+    assert max(len(oc.radius_search(xyz[i], 0.01)[0]) for i in sidx[:40]) > 1024
+    fo, vo = oc.frames(p, sidx)
+    fg, vg = ctx.frames(sidx)
+    assert np.array_equal(vo.astype(bool), vg.astype(bool))
+    assert np.array_equal(fo.reshape(fg.shape), fg)
+    ctx.close()
+
+
+def test_capacity_error_is_reported_not_crashed():
+    """A cloud denser than every tier (16 384 points in the r = 1 cm ball) must fail with GPDB_ERR_CAPACITY (-5), and the
+    context must stay usable."""
+    xyz, nrm = _random_cube(400000, 0.03)  # ~62 k points per ball in the interior
+    p = lib.default_params(channels=3)
+    ctx = lib.Context(p)
+    ctx.set_cloud(xyz, nrm, None, np.zeros((1, 3)))
+    mid = np.argsort(np.linalg.norm(xyz - 0.015, axis=1))[:8].astype(np.int32)
     with pytest.raises(lib.GpdbError) as e:
-        ctx.frames(np.arange(2000, dtype=np.int32))
+        ctx.frames(mid)
     assert e.value.code == -5 and "denser" in str(e.value)
     k = scenes.krylon_cloud()
     ctx.set_cloud(k["xyz"], k["normals"], k["cam_source"], k["view_points"])
