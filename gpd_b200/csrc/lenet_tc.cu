@@ -47,8 +47,8 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 // balanced int8 digits; the three digit planes are stacked along N (rows 0..19 | 20..39 | 40..59 of N = 64). The
 // dot products are EXACT integers; the epilogue recombines them in float32 (error ~1e-7 relative, like float32 itself).
 // tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
-// warps [0, 4 NG): NG epilogue groups (tile t -> group t % NG, TMEM buffer t % NG); warp 4 NG: MMA issuer;
-// warp 4 NG + 1: producer — the images arrive from k_images already as 16-byte pixels (P16), so ONE bulk-async copy
+// warps [0, 4 NG): NG epilogue groups (tile t -> group t % NG, TMEM buffer t % NG); warps 4 NG ..: MMA issuers (NMW);
+// last warp: producer — the images arrive from k_images already as 16-byte pixels (P16), so ONE bulk-async copy
 // (cp.async.bulk, mbarrier complete_tx) drops the next image straight into the free operand plane (double-buffered); no
 // thread ever touches the pixels.
 // ---------------------------------------------------------------------------------------------------------
@@ -56,9 +56,20 @@ constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28,
 constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: digit0 0..19 | digit1 20..39 | digit2 40..59 | 4 zero rows
 constexpr int C1_NCH = 25, C1_NMMA = 13;         // chunk c = kh*5 + kw (+1 zero-weight chunk)
 constexpr int C1_NG = 4;                         // epilogue groups = TMEM accumulator buffers
-constexpr int C1_MMA_WARP = 4 * C1_NG, C1_CONV_WARP0 = C1_MMA_WARP + 1, C1_NT = (C1_CONV_WARP0 + 1) * 32;
+// MMA issuer warps per CTA: with two, tiles alternate between them and the descriptor set-up of one tile (~100 dependent
+// uniform-datapath instructions) overlaps the other warp's tile. Measured (B200, 50.6 k images): conv2 (76 instructions per
+// tile) 5.73 -> 5.45 ms with two; conv1 (13 per tile) 4.80 -> 4.91 ms, so it keeps one.
+#ifndef GPDB_C1_MMA_WARPS
+#define GPDB_C1_MMA_WARPS 1
+#endif
+#ifndef GPDB_C2_MMA_WARPS
+#define GPDB_C2_MMA_WARPS 2
+#endif
+constexpr int NMW = GPDB_C1_MMA_WARPS, NMW2 = GPDB_C2_MMA_WARPS;
+constexpr int C1_MMA_WARP = 4 * C1_NG, C1_CONV_WARP0 = C1_MMA_WARP + NMW, C1_NT = (C1_CONV_WARP0 + 1) * 32;
 constexpr int C1_IMG_BYTES = C1_W * C1_W * 16;  // one P16 image
 constexpr int C1_B_BYTES = 2 * C1_NMMA * C1_BCHUNK;
+static_assert(C1_TILES % NMW == 0 && C1_NG % NMW == 0 && (NMW == 1 || NMW == 2) && (NMW2 == 1 || NMW2 == 2), "tiles alternate between the MMA warps");
 
 // chunk c -> byte offset of row 0 inside the plane (monotonic in c)
 __host__ __device__ constexpr uint32_t c1_off(int c) {
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
     }
     for (int b = 0; b < 2; b++) {
       umma::mbar_init(&pl_full[b], 1);   // the producer's expect_tx arrival + the bulk copy's bytes
-      umma::mbar_init(&pl_empty[b], 1);  // tcgen05.commit after the image's last tile
+      umma::mbar_init(&pl_empty[b], NMW);  // tcgen05.commit of every MMA warp after its last tile of the image
     }
     umma::fence_mbar_init();
   }
@@ -116,8 +127,8 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
       }
     }
     __syncwarp();
-  } else if (warp == C1_MMA_WARP) {
-    // ===== MMA issuer warp: tile t accumulates into TMEM columns [64 (gt % NG), +64) as soon as that buffer has been
+  } else if (warp >= C1_MMA_WARP) {
+    // ===== MMA issuer warps (tile t belongs to warp t % NMW; C1_TILES and C1_NG are multiples of NMW): tile t accumulates into TMEM columns [64 (gt % NG), +64) as soon as that buffer has been
     // drained. The whole warp runs the (fully unrolled) loop so that every descriptor is a uniform-register
     // expression base + compile-time constant; one elected lane issues the instructions.
     const uint32_t sB_u = umma::smem_u32(sB);
@@ -129,6 +140,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
       umma::fence_after_sync();
       const uint32_t sPl_u = umma::smem_u32(sPl) + (uint32_t)buf * C1_PLANE;
       for (int t = 0; t < C1_TILES; t++, gt++) {
+        if (t % NMW != warp - C1_MMA_WARP) continue;
         const int b = gt % C1_NG;
         umma::mbar_wait(&empty[b], ((gt / C1_NG) & 1) ^ 1);
         umma::fence_after_sync();
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
                          idesc, i > 0);
           }
           umma::commit(&full[b]);
-          if (t == C1_TILES - 1) umma::commit(&pl_empty[buf]);  // every MMA that reads this plane has completed
+          if (t >= C1_TILES - NMW) umma::commit(&pl_empty[buf]);  // every MMA of this warp that reads the plane has completed
         }
         __syncwarp();
       }
@@ -202,23 +214,28 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
 // ---------------------------------------------------------------------------------------------------------
 // conv2: P1 [784 px][20] f32 -> P2 [j = 12x12][50] f32 (k = c + 50 j, the ip1 input order), max-pooled.
 // Tile T (6 per image) = output rows 4T .. 4T+3 = GEMM rows m = y*28 + x (112 of 128) over the EIGHT input rows
-// 4T .. 4T+7, held as six fp16 channel planes (hi p0..2, lo p0..2) of 232 pixels. The planes are DOUBLE-BUFFERED and
+// 4T .. 4T+7, held as six fp16 channel planes (hi p0..2, lo p0..2; plane 2 pairs two pixels, see c2_off) of 232 pixels. The planes are DOUBLE-BUFFERED and
 // written by four dedicated converter warps (float32 -> scaled fp16 hi/lo), so that the conversion of tile T+1 — and
 // the global loads of tile T+2, prefetched into registers — overlap the MMAs of tile T; no CTA-wide barrier exists in
 // the steady state (round 1 converted half an image with the whole CTA between two __syncthreads: 7.6 ms against an
 // MMA floor of 4.2 ms per 50 k images). The 4 halo rows of a tile are converted twice (converters have the slack).
-//   warps 0-7: two epilogue groups (TMEM buffer = tile parity); warp 8: MMA issuer; warps 9-12: converters
+//   warps 0-7: two epilogue groups (TMEM buffer = tile parity); warps 8..: MMA issuers (tiles alternate); then 4 converter warps
 //   barriers: pl_full[2] (4 converter-warp arrivals) / pl_empty[2] (tcgen05.commit); full[2] / empty[2] for TMEM
 // ---------------------------------------------------------------------------------------------------------
-constexpr int C2_W = 28, C2_NPIX = 232, C2_PLANE = C2_NPIX * 16, C2_NCH = 75, C2_NMMA = 38;
+constexpr int C2_W = 28, C2_NPIX = 232, C2_PLANE = C2_NPIX * 16, C2_NCH = 65, C2_NMMA = 33;
 constexpr int C2_BCHUNK = 128 * 16;
 constexpr int C2_TILES = 6, C2_TILE_PIX = 8 * C2_W;  // 224 input pixels per tile
 
-constexpr int C2_MMA_WARP = 8, C2_CONV_WARP0 = 9, C2_NCONV = 4 * 32, C2_NT = (C2_CONV_WARP0 + 4) * 32;
+constexpr int C2_MMA_WARP = 8, C2_CONV_WARP0 = C2_MMA_WARP + NMW2, C2_NCONV = 4 * 32, C2_NT = (C2_CONV_WARP0 + 4) * 32;
 constexpr int IP_K = 7200, IP_KCH = IP_K / 8;  // ip1 reduction length, in 8-element chunks
+// K-chunks (8 fp16 = 16 B per GEMM row): c < 50: plane p = c / 25 (channels 8p .. 8p+7), tap (kh, kw) = c % 25.
+// c >= 50: plane 2 holds, per pixel, channels 16..19 of that pixel AND of its right neighbour, so one chunk covers the two
+// taps (kh, 2j) and (kh, 2j+1) of the last four channels, j = (c - 50) % 3, kh = (c - 50) / 3 (the tap kw = 5 of j = 2 has
+// zero weights): 65 chunks instead of 75 with a zero-padded third plane (-13 % tensor-core work).
 __host__ __device__ constexpr uint32_t c2_off(int c) {
-  return (uint32_t)(((c >= C2_NCH ? C2_NCH - 1 : c) / 25) * C2_PLANE +
-                    ((((c >= C2_NCH ? C2_NCH - 1 : c) / 5) % 5) * C2_W + (c >= C2_NCH ? C2_NCH - 1 : c) % 5) * 16);
+  const int cc = c >= C2_NCH ? C2_NCH - 1 : c;
+  return cc < 50 ? (uint32_t)((cc / 25) * C2_PLANE + (((cc / 5) % 5) * C2_W + cc % 5) * 16)
+                 : (uint32_t)(2 * C2_PLANE + (((cc - 50) / 3) * C2_W + 2 * ((cc - 50) % 3)) * 16);
 }
 
 __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__ p1, int n, const uint8_t *__restrict__ wblob,
@@ -269,6 +286,7 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
           const float *src = p1 + (size_t)im2 * 784 * NF1 + (size_t)(4 * T2 * C2_W + lp) * NF1 + p * 8;
           pre[j][0] = __ldg(reinterpret_cast<const float4 *>(src));
           if (p < 2) pre[j][1] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+          else if (lp + 1 < C2_TILE_PIX) pre[j][1] = __ldg(reinterpret_cast<const float4 *>(src + NF1));  // right neighbour, channels 16..19
         }
       }
     };
@@ -303,11 +321,12 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
         if ((tid & 31) == 0) umma::mbar_arrive(&pl_full[buf]);
       }
     }
-  } else if (warp == C2_MMA_WARP) {
+  } else if (warp >= C2_MMA_WARP) {  // tile gt belongs to MMA warp gt % NMW2 (= its plane / TMEM buffer when NMW2 = 2)
     const uint32_t sPl_u = umma::smem_u32(sPl), sB_u = umma::smem_u32(sB);
     int gt = 0;
     for (int im = blockIdx.x; im < n; im += gridDim.x) {
       for (int T = 0; T < C2_TILES; T++, gt++) {
+        if (gt % NMW2 != warp - C2_MMA_WARP) continue;
         const int b = gt & 1;
         umma::mbar_wait(&pl_full[b], (gt >> 1) & 1);
         umma::mbar_wait(&empty[b], ((gt >> 1) & 1) ^ 1);
@@ -570,11 +589,15 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
   t.a2_scale = safe_scale(a1_bound, 1.0f / 16.0f);
   std::vector<__half> b2((size_t)(2 * C2_NMMA) * 128 * 8, __float2half(0.0f));
   for (int c = 0; c < C2_NCH; c++) {
-    int p = c / 25, kh = (c / 5) % 5, kw = c % 5;
     for (int o = 0; o < NF2; o++)
       for (int e = 0; e < 8; e++) {
-        int ch = p * 8 + e;
-        if (ch >= NF1) continue;
+        int ch, kh, kw;
+        if (c < 50) {
+          ch = (c / 25) * 8 + e, kh = (c / 5) % 5, kw = c % 5;
+        } else {  // channels 16..19 of two neighbouring taps (c2_off)
+          ch = 16 + (e & 3), kh = (c - 50) / 3, kw = 2 * ((c - 50) % 3) + (e >> 2);
+          if (kw >= 5) continue;
+        }
         float wv = w[2][(((size_t)o * NF1 + ch) * 5 + kh) * 5 + kw] * t.w2_scale;
         __half hi = __float2half_rn(wv);
         __half lo = __float2half_rn(wv - __half2float(hi));
