@@ -96,8 +96,12 @@ struct LenetWeights {  // device pointers, layouts documented in lenet_simt.cu
   bool set;
 };
 
+struct C1Affine {  // conv1 epilogue: per-filter weight scale and bias (kernel parameter = constant bank)
+  float scale[20], bias[20];
+};
 struct LenetTc {  // tensor-core (tcgen05) weight blobs, lenet_tc.cu
   void *b1, *b2, *b3;
+  C1Affine c1_aff;
   int npl, nch1;
   float w2_scale, a2_scale, w3_scale, x3_scale;
   bool ready;

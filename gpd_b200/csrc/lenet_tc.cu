@@ -46,7 +46,16 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 // Weights: w = s_o * W, W a 24-bit signed integer (s_o = max|w_o| / 8.3e6 per filter), W = 65536 d0 + 256 d1 + d2 with
 // balanced int8 digits; the three digit planes are stacked along N (rows 0..19 | 20..39 | 40..59 of N = 64). The
 // dot products are EXACT integers; the epilogue recombines them in float32 (error ~1e-7 relative, like float32 itself).
-// tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128)
+// tiles: 28 per image, tile t = output rows 2t, 2t+1 = GEMM rows m0 = 120 t .. +119 (of 128): 120 CONSECUTIVE pixels, so the
+// sixteen 8-row core matrices of an A chunk are one contiguous 2 KB range (SBO = 128 B) and an unaligned start costs one extra
+// 128-byte wavefront per chunk. tcgen05.mma streams its operands from shared memory at the 128 B / clock the LSU also uses
+// (tools/umma_rate.cu on B200: kind::i8 128x64x32 = 48 clocks = 6 KB / 128 B with fixed descriptors, 716 clocks per 13-MMA
+// tile with this kernel's descriptors and nothing else running; a 16 x 8-pixel tile whose core matrices lie one image row apart,
+// SBO = 960 B, pools with two shuffles and needs no stage, but its scattered core matrices cost 804 clocks per tile — tried,
+// no gain). Every shared-memory access of the epilogue therefore takes a cycle from the operand stream: the 2x2 max-pool
+// stages only the UPPER output row of a tile (x-pair max by shuffle first), 28 pixels x 20 floats moved as float4 (conflict
+// free), and the lower row's threads finish the pixel (max, scale and bias from the constant bank, store): ~90 wavefronts
+// per tile instead of ~290 (both rows staged with scalar stores + a pooled pass reading stage, scale and bias from shared memory).
 // warps [0, 4 NG): NG epilogue groups (tile t -> group t % NG, TMEM buffer t % NG); warps 4 NG ..: MMA issuers (NMW);
 // last warp: producer — the images arrive from k_images already as 16-byte pixels (P16), so ONE bulk-async copy
 // (cp.async.bulk, mbarrier complete_tx) drops the next image straight into the free operand plane (double-buffered); no
@@ -55,7 +64,12 @@ struct MmaTab {  // per-instruction operand offsets (bytes) relative to tile row
 constexpr int C1_W = 60, C1_NPIX = 3616, C1_PLANE = C1_NPIX * 16, C1_TILES = 28, C1_TILE_ROWS = 120;
 constexpr int C1_N = 64, C1_BCHUNK = C1_N * 16;  // B rows: digit0 0..19 | digit1 20..39 | digit2 40..59 | 4 zero rows
 constexpr int C1_NCH = 25, C1_NMMA = 13;         // chunk c = kh*5 + kw (+1 zero-weight chunk)
-constexpr int C1_NG = 4;                         // epilogue groups = TMEM accumulator buffers
+// measured on B200 (50.6 k images): 4 groups 4.90 ms, 5 groups 4.73 ms, 6 groups 4.97 ms, 7 groups 4.95 ms
+#ifndef GPDB_C1_NG
+#define GPDB_C1_NG 5
+#endif
+constexpr int C1_NG = GPDB_C1_NG;                 // epilogue groups = TMEM accumulator buffers
+constexpr int C1_TMEM_COLS = 64 * C1_NG <= 256 ? 256 : 512;  // allocation: a power of two
 // MMA issuer warps per CTA: with two, tiles alternate between them and the descriptor set-up of one tile (~100 dependent
 // uniform-datapath instructions) overlaps the other warp's tile. Measured (B200, 50.6 k images): conv2 (76 instructions per
 // tile) 5.73 -> 5.45 ms with two; conv1 (13 per tile) 4.80 -> 4.91 ms, so it keeps one.
@@ -80,23 +94,18 @@ __host__ __device__ constexpr uint32_t instr_desc_i8(int M, int N) {  // D = s32
 }
 
 __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict__ images /* P16 */, int n,
-                                                       const uint8_t *__restrict__ wblob, const float *__restrict__ bias,
+                                                       const uint8_t *__restrict__ wblob, const C1Affine aff /* constant bank */,
                                                        int relu, float *__restrict__ p1) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[C1_NG], empty[C1_NG], pl_full[2], pl_empty[2];
   __shared__ uint32_t tmem_base;
-  __shared__ float sbias[NF1], sscale[NF1];
   uint8_t *sB = smem;                                   // 26 chunks x 64 rows x 16 B (int8)
   uint8_t *sPl = sB + C1_B_BYTES;                       // 2 planes of 3616 px x 16 B (uint8)
-  float *stage = reinterpret_cast<float *>(sPl + 2 * C1_PLANE);        // NG x [60][20]
+  float *stage = reinterpret_cast<float *>(sPl + 2 * C1_PLANE);        // NG x [28][20]: x-pooled upper row of a tile
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
 
   for (int i = tid; i < C1_B_BYTES / 16; i += C1_NT) reinterpret_cast<uint4 *>(sB)[i] = reinterpret_cast<const uint4 *>(wblob)[i];
   for (int i = tid; i < 2 * C1_PLANE / 16; i += C1_NT) reinterpret_cast<uint4 *>(sPl)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < NF1) {
-    sbias[tid] = bias[tid];
-    sscale[tid] = reinterpret_cast<const float *>(wblob + C1_B_BYTES)[tid];
-  }
   if (tid == 0) {
     for (int b = 0; b < C1_NG; b++) {
       umma::mbar_init(&full[b], 1);   // tcgen05.commit of the MMA warp
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
     }
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base, 64 * C1_NG);
+  if (warp == 0) umma::tmem_alloc(&tmem_base, C1_TMEM_COLS);
   umma::fence_async_smem();  // the zero fill of the planes (generic proxy) before the bulk copies / MMAs (async proxy)
   umma::fence_before_sync();
   __syncthreads();
@@ -161,10 +170,13 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
       }
     }
   } else {
-    // ===== epilogue groups drain the tiles round-robin: TMEM -> registers (recombine the three digit planes) ->
-    // x-pair max -> stage -> y-pair max -> scale, bias -> global. Group g owns TMEM buffer g, stage g, named barrier 1+g.
-    const int grp = warp >> 2, r = tid & 127;
-    float *stg = stage + grp * (60 * NF1);
+    // ===== epilogue groups drain the tiles round-robin: TMEM -> registers (recombine the three digit planes) -> x-pair max
+    // by shuffle -> the upper row's even threads stage their 20 values -> the lower row's even threads take the max with
+    // them, scale, add the bias and store the pooled pixel. Group g owns TMEM buffer g, stage g, named barrier 1 + g.
+    const int grp = warp >> 2, r = tid & 127;  // r = GEMM row = pixel (dy, x): dy = r / 60, x = r % 60
+    const int dy = r >= C1_W ? 1 : 0, x = r - dy * C1_W;
+    const bool pooled = (x & 1) == 0 && x < 56 && r < C1_TILE_ROWS;  // left pixel of a valid x-pair
+    float4 *stg = reinterpret_cast<float4 *>(stage + grp * (28 * NF1)) + (x >> 1) * (NF1 / 4);
     int gt = 0;
     for (int im = blockIdx.x; im < n; im += gridDim.x) {
       float *out = p1 + (size_t)im * 784 * NF1;
@@ -188,27 +200,32 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
           v[j] = fmaf(f0, 65536.0f, fmaf(f1, 256.0f, f2));
           v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
         }
-        umma::named_bar_sync(1 + grp, 128);  // the previous tile's pooled reads of this stage are done
-        if ((r & 1) == 0 && r < C1_TILE_ROWS) {
-          int rr = r >> 1;  // 0..59: [dy][x/2]
-          if ((rr % 30) < 28) {
+        umma::named_bar_sync(1 + grp, 128);  // the previous tile's reads of this stage are done
+        if (pooled && dy == 0) {
 #pragma unroll
-            for (int j = 0; j < NF1; j++) stg[rr * NF1 + j] = v[j];
-          }
+          for (int j4 = 0; j4 < NF1 / 4; j4++) stg[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         }
         umma::named_bar_sync(1 + grp, 128);
-        for (int i = r; i < 28 * NF1; i += 128) {
-          int px = i / NF1, ch = i - px * NF1;
-          float m = fmaf(fmaxf(stg[px * NF1 + ch], stg[(30 + px) * NF1 + ch]), sscale[ch], sbias[ch]);
-          if (relu) m = fmaxf(m, 0.0f);
-          out[(size_t)(t * 28 + px) * NF1 + ch] = m;
+        if (pooled && dy == 1) {
+          float4 *o = reinterpret_cast<float4 *>(out + (size_t)(t * 28 + (x >> 1)) * NF1);
+#pragma unroll
+          for (int j4 = 0; j4 < NF1 / 4; j4++) {
+            const float4 u = stg[j4];
+            float m[4] = {fmaxf(v[4 * j4], u.x), fmaxf(v[4 * j4 + 1], u.y), fmaxf(v[4 * j4 + 2], u.z), fmaxf(v[4 * j4 + 3], u.w)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              m[k] = fmaf(m[k], aff.scale[4 * j4 + k], aff.bias[4 * j4 + k]);
+              if (relu) m[k] = fmaxf(m[k], 0.0f);
+            }
+            o[j4] = make_float4(m[0], m[1], m[2], m[3]);
+          }
         }
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, 64 * C1_NG);
+  if (warp == 0) umma::tmem_dealloc(tb, C1_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -544,6 +561,8 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
       for (size_t i = 0; i < (size_t)C * 25; i++) mxo = std::fmax(mxo, std::fabs(w[0][(size_t)o * C * 25 + i]));
       const double so = mxo > 0.0f ? (double)mxo / 8300000.0 : 1.0;
       scales[o] = (float)so;
+      t.c1_aff.scale[o] = (float)so;
+      t.c1_aff.bias[o] = w[1][o];
       for (int ch = 0; ch < C && ch < 16; ch++)
         for (int kh = 0; kh < 5; kh++)
           for (int kw = 0; kw < 5; kw++) {
@@ -648,14 +667,14 @@ int lenet_tc_upload(gpdb_ctx *ctx, const float *const w[8]) {
 int lenet_tc_forward(gpdb_ctx *ctx, const uint8_t *d_images, int n, float *p1, __half *xc, float *h3) {
   const LenetTc &t = ctx->tc;
   const int relu = ctx->prm.relu_after_conv;
-  size_t sm1 = (size_t)C1_B_BYTES + 2 * (size_t)C1_PLANE + C1_NG * 60 * NF1 * sizeof(float) + 32;
+  size_t sm1 = (size_t)C1_B_BYTES + 2 * (size_t)C1_PLANE + C1_NG * 28 * NF1 * sizeof(float) + 32;
   size_t sm2 = (size_t)(2 * C2_NMMA) * C2_BCHUNK + 2 * 6 * C2_PLANE + 2 * 56 * NF2 * sizeof(float);
   size_t sm3 = (size_t)IP_STAGES * IP_STAGE_BYTES;
   CUDA_TRY(cudaFuncSetAttribute(k_conv1_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   CUDA_TRY(cudaFuncSetAttribute(k_conv2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   CUDA_TRY(cudaFuncSetAttribute(k_ip1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   cudaEvent_t e1 = gpdb_st_begin(ctx);
-  k_conv1_i8<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, (const uint8_t *)t.b1, ctx->w.c1b, relu, p1);
+  k_conv1_i8<<<std::min(n, ctx->sm_count), C1_NT, sm1, ctx->stream>>>(d_images, n, (const uint8_t *)t.b1, t.c1_aff, relu, p1);
   LAUNCH_CHECK();
   gpdb_st_end(ctx, 5, e1);
   cudaEvent_t e2 = gpdb_st_begin(ctx);
