@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(C1_NT, 1) k_conv1_i8(const uint8_t *__restrict
       for (int t = 0; t < C1_TILES; t++, gt++) {
         const int b = gt % C1_NG;
         if (b != grp) continue;
-        umma::mbar_wait(&full[b], (gt / C1_NG) & 1);
+        umma::mbar_wait_relaxed(&full[b], (gt / C1_NG) & 1);
         umma::fence_after_sync();
         const uint32_t trow = tb + (uint32_t)b * 64 + ((uint32_t)((warp & 3) * 32) << 16);
         float d[64];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(C2_NT, 1) k_conv2_tc(const float *__restrict__
       for (int T = 0; T < C2_TILES; T++, gt++) {
         const int b = gt & 1;
         if (b != grp) continue;
-        umma::mbar_wait(&full[b], (gt >> 1) & 1);
+        umma::mbar_wait_relaxed(&full[b], (gt >> 1) & 1);
         umma::fence_after_sync();
         const uint32_t trow = tb + (uint32_t)b * 128 + ((uint32_t)((warp & 3) * 32) << 16);
         const int rr = r >> 1;  // [dy 0..3][x/2 0..13]

@@ -94,6 +94,48 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
       : "memory");
 }
 
+// consumer-side wait of the epilogue warps for a tile. GPDB_WAIT_MODE: 0 = tight try_wait loop (mbar_wait, the default),
+// 1 = __nanosleep(100) back-off, 2 = try_wait with a 100 us suspend-time hint. Measured on B200 (conv1 / conv2 per 50.6 k
+// images): 4.73 / 5.11 ms, 4.80 / 5.19 ms, 4.99 / 5.20 ms — the polling does not disturb the operand stream, the wake-up
+// latency is on the critical path, so the tight loop stays.
+#ifndef GPDB_WAIT_MODE
+#define GPDB_WAIT_MODE 0
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *mbar, uint32_t parity) {
+#if GPDB_WAIT_MODE == 1
+  uint32_t ok = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(100);
+  }
+#elif GPDB_WAIT_MODE == 2
+  uint32_t ok = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity), "r"(100000u)
+        : "memory");
+    if (ok) break;
+  }
+#else
+  mbar_wait(mbar, parity);
+#endif
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
