@@ -1213,9 +1213,17 @@ __device__ __forceinline__ void unit_axis(double v, double lo, double extent, do
   cell = min((int)fq, S - 1);
 }
 __device__ __forceinline__ unsigned unit_q32(double u) {
-  double t = u * 4294967296.0;
-  t = fmin(fmax(t, 0.0), 4294967295.0);
-  return (unsigned)t;
+  return __double2uint_rz(u * 4294967296.0);  // cvt.rzi.u32.f64 saturates: the same result as clamping to [0, 2^32 - 1] first
+}
+
+// mean of a cell from its packed accumulator (count << 48 | fixed-point sum, 32 fractional bits): sum / (count 2^32). The
+// per-count reciprocals 1 / (c 2^32), c < RCP_N, are tabulated once per image in the (then idle) reduction scratch of the
+// ball scan: one multiplication instead of a float64 division per occupied cell (count 1: an exact scaling either way).
+constexpr int RCP_N = (NT_IMG / 32) * 4;
+__device__ __forceinline__ double cell_mean(unsigned long long acc, const double *rcp) {
+  const unsigned c = (unsigned)(acc >> 48);
+  const double sum = (double)(acc & 0xffffffffffffull);
+  return c < (unsigned)RCP_N ? sum * rcp[c] : sum / ((double)c * 4294967296.0);
 }
 
 __device__ __forceinline__ bool fully_covered(const unsigned *occf, int S);
@@ -1485,6 +1493,8 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
     PHASE(2);  // scan 1 + reductions done
     if (sm.box_n > BC) continue;  // handed to the next tier (uniform; without a next tier box_n was clamped)
     const int bn = sm.box_n;
+    double *rcp = &sm.red[0][0];  // the scan's reduction scratch is idle from here to the next image: reciprocal table (cell_mean)
+    if (tid < RCP_N) rcp[tid] = 1.0 / ((double)tid * 4294967296.0);  // visible after the barrier that ends the box-point pass
     // dense pass over the box points: hand-frame coordinates -> unit cube, cell indices, |R^T n| (all lanes busy)
     for (int k = tid; k < bn; k += NT_IMG) {
       const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BC + k]),
@@ -1534,11 +1544,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
         n0 = bnrm[k];
         n1 = bnrm[BC + k];
         n2 = bnrm[2 * BC + k];
-        const unsigned long long acc = tileB[pix];
-        const unsigned cntc = (unsigned)(acc >> 48);
-        const double sum = (double)(acc & 0xffffffffffffull);
-        const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);  // exact scaling
-        const float avg = (float)mean;
+        const float avg = (float)cell_mean(tileB[pix], rcp);
         dv = (float)(1.0 - (double)avg);
         return true;
       };
@@ -2014,10 +2020,7 @@ __global__ void __launch_bounds__(NT_IMG, 1) k_images(const DevParams *Pp, DevCl
             const unsigned long long acc = tile[pix];
             const unsigned cntc = (unsigned)(acc >> 48);
             if (cntc) {
-              const double sum = (double)(acc & 0xffffffffffffull);
-              // one voxel in the cell: sum / 2^32 is an exact scaling, the same bits as the division
-              const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
-              avgr[t] = (float)mean;
+              avgr[t] = (float)cell_mean(acc, rcp);
               occm |= 1u << t;
               oc = true;
               mm[0] = fmaxf(mm[0], avgr[t]);
@@ -2263,6 +2266,8 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
     PHASE(2);
     if (sm.box_n > BOX_CAP2) continue;  // uniform
     const int bn = sm.box_n;
+    double *rcp = &sm.red[0][0];  // the scan's reduction scratch is idle from here to the next image: reciprocal table (cell_mean)
+    if (tid < RCP_N) rcp[tid] = 1.0 / ((double)tid * 4294967296.0);  // visible after the barrier that ends the box-point pass
     for (int k = tid; k < bn; k += NT_IMG) {
       const double px = (double)__uint_as_float(bq[k]), py = (double)__uint_as_float(bq[BOX_CAP2 + k]),
                    pz = (double)__uint_as_float(bq[2 * BOX_CAP2 + k]);
@@ -2310,11 +2315,7 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
             wv[j][0] = (float)fabs(n0);
             wv[j][1] = (float)fabs(n1);
             wv[j][2] = (float)fabs(n2);
-            const unsigned long long acc = tileB[pix];
-            const unsigned cntc = (unsigned)(acc >> 48);
-            const double sum = (double)(acc & 0xffffffffffffull);
-            const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
-            const float avg = (float)mean;
+            const float avg = (float)cell_mean(tileB[pix], rcp);
             wv[j][3] = (float)(1.0 - (double)avg);
             mxv[0] = fmaxf(mxv[0], fmaxf(fmaxf(wv[j][0], wv[j][1]), wv[j][2]));
             mxv[1] = fmaxf(mxv[1], wv[j][3]);
@@ -2669,9 +2670,7 @@ __global__ void __launch_bounds__(NT_IMG, 2) k_images2(const DevParams *Pp, DevC
             const unsigned long long acc = tile[pix];
             const unsigned cntc = (unsigned)(acc >> 48);
             if (cntc) {
-              const double sum = (double)(acc & 0xffffffffffffull);
-              const double mean = cntc == 1 ? sum * (1.0 / 4294967296.0) : sum / ((double)cntc * 4294967296.0);
-              avgr[t] = (float)mean;
+              avgr[t] = (float)cell_mean(acc, rcp);
               occm |= 1u << t;
               oc = true;
               mm[0] = fmaxf(mm[0], avgr[t]);
