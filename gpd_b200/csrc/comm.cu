@@ -33,8 +33,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
-const char *load_nccl() {  // returns nullptr on success, else the reason
-  if (g_nccl.handle) return nullptr;
+const char *load_nccl_once() {
   void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the process's own copy first (PyTorch's)
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -56,6 +55,12 @@ const char *load_nccl() {  // returns nullptr on success, else the reason
 #undef SYM
   g_nccl = a;
   return nullptr;
+}
+// returns nullptr on success, else the reason. Thread-safe (one context per host thread in the multi-GPU shim): the
+// function-local static is initialised exactly once, and g_nccl is complete before any caller sees the result.
+const char *load_nccl() {
+  static const char *const why = load_nccl_once();
+  return why;
 }
 
 }  // namespace
@@ -141,6 +146,12 @@ int gpdb_comm_destroy(gpdb_ctx *ctx) {
 }
 
 void gpdb_shard_bounds(int32_t n, int32_t rank, int32_t nranks, int32_t *lo, int32_t *hi, int32_t *slot_samples) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || n < 0) {  // malformed request: an empty slice
+    if (lo) *lo = 0;
+    if (hi) *hi = 0;
+    if (slot_samples) *slot_samples = 0;
+    return;
+  }
   const int64_t a = ((int64_t)rank * n) / nranks, b = ((int64_t)(rank + 1) * n) / nranks;
   if (lo) *lo = (int32_t)a;
   if (hi) *hi = (int32_t)b;
