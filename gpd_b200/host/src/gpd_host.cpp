@@ -953,19 +953,33 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGraspsMultiGp
   }
   std::vector<std::vector<gpdb_pose>> per_rank(num_gpus);
   std::vector<int> rc(num_gpus, 0), total(num_gpus, 0);
+  // phase 1, before any collective: one context per device + the weights. A rank that failed here would leave the others
+  // blocked in ncclCommInitRank, so nothing collective starts unless every context exists.
+  std::vector<gpdb_ctx *> ctxs(num_gpus, nullptr);
+  bool all_ok = true;
+  for (int r = 0; r < num_gpus && all_ok; r++) {
+    gpdb_params p = params_;
+    p.device = r;
+    if (gpdb_create(&p, &ctxs[r]) != GPDB_OK ||
+        gpdb_load_weights_file(ctxs[r], model_file_.empty() ? nullptr : model_file_.c_str(), weights_file_.c_str()) != GPDB_OK) {
+      printf("ERROR (GPU %d): %s\n", r, gpdb_last_error(ctxs[r]));
+      all_ok = false;
+    }
+  }
+  if (!all_ok) {
+    for (gpdb_ctx *c : ctxs)
+      if (c) gpdb_destroy(c);
+    return hands;
+  }
+  // phase 2: one host thread per rank (the collectives block until every rank has joined)
   std::vector<std::thread> th;
   for (int r = 0; r < num_gpus; r++)
     th.emplace_back([&, r]() {
-      gpdb_params p = params_;
-      p.device = r;
-      gpdb_ctx *c = nullptr;
-      // every rank joins every collective even after a local failure would deadlock the others: fail before the first one
-      if (gpdb_create(&p, &c) != GPDB_OK ||
-          gpdb_load_weights_file(c, model_file_.empty() ? nullptr : model_file_.c_str(), weights_file_.c_str()) != GPDB_OK) {
+      gpdb_ctx *c = ctxs[r];
+      if (gpdb_comm_init(c, uid, r, num_gpus) != GPDB_OK) {
         printf("ERROR (GPU %d): %s\n", r, gpdb_last_error(c));
         rc[r] = -1;
       }
-      if (gpdb_comm_init(c, uid, r, num_gpus) != GPDB_OK) rc[r] = -1;
       if (rc[r] == 0) {
         int n = r == 0 ? gpdb_set_cloud_bcast(c, 0, cloud.getPoints().data(), cloud.getNormals().data(),
                                               cloud.getCameraSource().empty() ? nullptr : cloud.getCameraSource().data(),
@@ -985,7 +999,7 @@ std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::detectGraspsMultiGp
           gpdb_free_result(&res);
         }
       }
-      if (c) gpdb_destroy(c);
+      gpdb_destroy(c);
     });
   for (auto &t : th) t.join();
   for (int r = 0; r < num_gpus; r++)
