@@ -120,3 +120,6 @@ def test_c_abi_shard_bounds_match_the_python_plumbing():
                     assert st == sharding.slot_stride(n, world)
             assert covered == n
     assert lib.slot_bytes(12501, 8) == 12501 * 8 * 4 + (12501 * 8 + 15) // 16 * 16 + 16
+    # malformed requests give an empty slice instead of dividing by zero
+    for bad in ((10, 0, 0), (10, -1, 4), (10, 4, 4), (-5, 0, 2)):
+        assert lib.shard_bounds(*bad) == (0, 0, 0)
