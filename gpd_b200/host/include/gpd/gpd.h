@@ -259,6 +259,14 @@ class GraspDetector {
   // + classifier on the device, hands with score > min_score, in (sample, pose) order
   std::vector<std::unique_ptr<candidate::Hand>> classifyAtPositions(const util::Cloud &cloud, const std::vector<double> &positions,
                                                                     double min_score);
+  // GraspDetector::createGraspImages (grasp_detector.cpp:458-521): candidates -> workspace / direction filters -> grasp images,
+  // no classification. images_out[i] = the cv::Mat bytes (image_size x image_size x channels, HWC) of hands_out[i]
+  bool createGraspImages(util::Cloud &cloud, std::vector<std::unique_ptr<candidate::Hand>> &hands_out,
+                         std::vector<std::vector<uint8_t>> &images_out);
+  // GraspDetector::generateGraspCandidates (grasp_detector.cpp:330-332) flattened to its valid hands, as
+  // detect_grasps_python.cpp:310-329 does. The device path returns the hands that ALSO pass filterGraspsWorkspace /
+  // filterGraspsDirection (the only pose records that leave the GPU); with the shipped cfgs the filters are wide open
+  std::vector<std::unique_ptr<candidate::Hand>> generateGraspCandidates(const util::Cloud &cloud);
   // GraspDetector::evalGroundTruth (grasp_detector.cpp:523-527) -> HandSearch::reevaluateHypotheses: re-labels the hands
   // against `cloud_gt` (e.g. a ground-truth mesh cloud) on the device; returns 1 per full-antipodal hand, updates the flags
   std::vector<int> evalGroundTruth(const util::Cloud &cloud_gt, std::vector<std::unique_ptr<candidate::Hand>> &hands);
@@ -326,7 +334,8 @@ bool preprocessParamsFromConfig(const std::string &config_filename, gpdb_preproc
 
 }  // namespace gpd
 
-// ---- the reference's own C interface for Python callers (src/detect_grasps_python.cpp:49-65,431-475,598-601),
+// ---- the reference's own C interface for Python callers (src/detect_grasps_python.cpp:49-65,431-549,598-607; the two
+// calcGraspDescriptors* entry points write HDF5 through cv::hdf and are not provided),
 // same names, argument order and struct layout, over the B200 path (exported by libgpd_host.so) -----------------
 extern "C" {
 struct Grasp {       // detect_grasps_python.cpp:49-56
@@ -345,6 +354,18 @@ int detectGraspsInCloud(char *config_filename, float *points, int *camera_index,
 int detectGraspsInCloudNormals(char *config_filename, float *points, float *normals, int *camera_index,
                                float *view_points, int size, int num_view_points, struct Grasp **grasps_out);
 int freeMemoryGrasps(struct Grasp *in);  // unlike the reference (`delete[] in` only) this also frees the members
+// detect_grasps_python.cpp:468-488: cloud from a .pcd / .ply file (+ optional normals file, "" = none); returns 0 when the
+// file is missing or empty
+int detectGraspsInFile(char *config_filename, char *pcd_filename, char *normals_filename, float *view_points, int num_view_points,
+                       struct Grasp **grasps_out);
+// :530-549: preprocessing + hand search + filters, no classification (score 0)
+int generateGraspCandidatesInFile(char *config_filename, char *pcd_filename, char *normals_filename, float *view_points,
+                                  int num_view_points, struct Grasp **grasps_out);
+// :490-528: candidates + images in the camera cloud, `label` from HandSearch::reevaluateHypotheses against the ground-truth mesh
+// cloud (points_gt / normals_gt: 3 x size_gt, packed per point); Grasp.image = the hand's image as image_size^2 x channels ints
+int detectAndEvalGrasps(char *config_filename, float *points, int *camera_index, float *view_points, int size, int num_view_points,
+                        float *points_gt, float *normals_gt, int size_gt, struct Grasp **grasps_out);
+int CopyAndFree(float *in, float *out, int n);  // :603-607 (`in` must come from new float[])
 // Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other,3,3>):
 // m column-major 3x3 -> q = x, y, z, w
 void gpdQuaternionFromMatrix(const double *m, double *q);

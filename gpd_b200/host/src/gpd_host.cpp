@@ -858,6 +858,47 @@ static bool sample_indices_of(gpdb_ctx *ctx, const util::Cloud &cloud, std::vect
   return true;
 }
 
+std::vector<std::unique_ptr<candidate::Hand>> GraspDetector::generateGraspCandidates(const util::Cloud &cloud) {
+  std::vector<std::unique_ptr<candidate::Hand>> hands;
+  if (!ctx_ || !ensureCloud(cloud)) return hands;
+  std::vector<int> idx;
+  if (!sample_indices_of(ctx_, cloud, idx) || idx.empty()) return hands;
+  gpdb_result r;
+  if (gpdb_hand_search(ctx_, idx.data(), (int)idx.size(), &r) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    return hands;
+  }
+  for (int i = 0; i < r.n_candidates; i++) hands.push_back(std::make_unique<candidate::Hand>(r.candidates[i]));
+  gpdb_free_result(&r);
+  return hands;
+}
+
+bool GraspDetector::createGraspImages(util::Cloud &cloud, std::vector<std::unique_ptr<candidate::Hand>> &hands_out,
+                                      std::vector<std::vector<uint8_t>> &images_out) {
+  hands_out.clear();
+  images_out.clear();
+  if (cloud.size() == 0) {
+    printf("ERROR: Point cloud is empty!");
+    return false;
+  }
+  hands_out = generateGraspCandidates(cloud);  // 1. candidates, 2. filters (fused in the hand-search kernel)
+  printf("Generated %zu filtered grasp candidates.\n", hands_out.size());
+  if (hands_out.empty()) return false;
+  // 3. grasp descriptors (ImageGenerator::createImages) for exactly these hands
+  const size_t isz = (size_t)params_.image_size * params_.image_size * params_.image_num_channels;
+  std::vector<gpdb_pose> rec(hands_out.size());
+  for (size_t i = 0; i < rec.size(); i++) rec[i] = hands_out[i]->raw();
+  std::vector<uint8_t> all(isz * rec.size());
+  if (gpdb_images(ctx_, rec.data(), (int)rec.size(), all.data()) < 0) {
+    printf("ERROR: %s\n", gpdb_last_error(ctx_));
+    hands_out.clear();
+    return false;
+  }
+  images_out.resize(rec.size());
+  for (size_t i = 0; i < rec.size(); i++) images_out[i].assign(all.begin() + isz * i, all.begin() + isz * (i + 1));
+  return true;
+}
+
 std::vector<int> GraspDetector::evalGroundTruth(const util::Cloud &cloud_gt, std::vector<std::unique_ptr<candidate::Hand>> &hands) {
   std::vector<int> labels(hands.size(), 0);
   if (!ctx_ || hands.empty() || !ensureCloud(cloud_gt)) return labels;
@@ -1172,15 +1213,12 @@ gpd::util::Cloud make_cloud(float *points, float *normals, int *camera_index, fl
   return gpd::util::Cloud(xyz, nrm, cam, vp);
 }
 
-int detect_to_structs(char *config_filename, gpd::util::Cloud &cloud, Grasp **grasps_out) {
-  if (!config_filename || !grasps_out) return -1;
-  *grasps_out = nullptr;
-  gpd::GraspDetector detector(config_filename);  // detect_grasps_python.cpp:298-308
-  detector.preprocessPointCloud(cloud);
-  std::vector<std::unique_ptr<gpd::candidate::Hand>> hands = detector.detectGrasps(cloud);
+// handsToGraspsStruct (detect_grasps_python.cpp:251-295); images (optional) -> Grasp.image as ints, else {-1}
+int hands_to_structs(const std::vector<std::unique_ptr<gpd::candidate::Hand>> &hands, const std::vector<std::vector<uint8_t>> *images,
+                     int, Grasp **grasps_out) {
   const int n = (int)hands.size();
   Grasp *g = new Grasp[n > 0 ? n : 1];
-  for (int i = 0; i < n; i++) {  // handsToGraspsStruct (detect_grasps_python.cpp:251-268)
+  for (int i = 0; i < n; i++) {
     const gpdb_pose &p = hands[i]->raw();
     g[i].pos = new double[3]{p.position[0], p.position[1], p.position[2]};
     g[i].orient = new double[4];
@@ -1188,12 +1226,42 @@ int detect_to_structs(char *config_filename, gpd::util::Cloud &cloud, Grasp **gr
     g[i].sample = new double[3]{p.sample[0], p.sample[1], p.sample[2]};
     g[i].score = hands[i]->getScore();
     g[i].label = hands[i]->isFullAntipodal();
-    g[i].image = new int[1]{-1};
+    if (images && (size_t)i < images->size()) {
+      const std::vector<uint8_t> &im = (*images)[i];
+      g[i].image = new int[im.size() > 0 ? im.size() : 1];
+      for (size_t k = 0; k < im.size(); k++) g[i].image[k] = (int)im[k];
+    } else {
+      g[i].image = new int[1]{-1};
+    }
   }
   g_grasp_arrays.push_back(g);
   g_grasp_counts.push_back(n);
   *grasps_out = g;
   return n;
+}
+
+int detect_to_structs(char *config_filename, gpd::util::Cloud &cloud, Grasp **grasps_out) {
+  if (!config_filename || !grasps_out) return -1;
+  *grasps_out = nullptr;
+  gpd::GraspDetector detector(config_filename);  // detect_grasps_python.cpp:298-308
+  detector.preprocessPointCloud(cloud);
+  std::vector<std::unique_ptr<gpd::candidate::Hand>> hands = detector.detectGrasps(cloud);
+  return hands_to_structs(hands, nullptr, 0, grasps_out);
+}
+
+// initCloud (detect_grasps_python.cpp:212-237)
+gpd::util::Cloud init_cloud(char *pcd_filename, char *normals_filename, float *view_points, int num_view_points) {
+  std::vector<double> vp(view_points, view_points + 3 * (size_t)num_view_points);
+  gpd::util::Cloud cloud(std::string(pcd_filename), vp);
+  if (cloud.size() == 0) {
+    printf("Error: Input point cloud is empty or does not exist!\n");
+    return cloud;
+  }
+  if (normals_filename && std::string(normals_filename).size() > 0) {
+    cloud.setNormalsFromFile(normals_filename);
+    printf("Loaded surface normals from file: %s\n", normals_filename);
+  }
+  return cloud;
 }
 }  // namespace
 
@@ -1281,6 +1349,62 @@ int detectGraspsInCloudNormals(char *config_filename, float *points, float *norm
   if (!points || !normals || !camera_index || !view_points || size <= 0 || num_view_points <= 0) return -1;
   gpd::util::Cloud cloud = make_cloud(points, normals, camera_index, view_points, size, num_view_points);
   return detect_to_structs(config_filename, cloud, grasps_out);
+}
+
+// detectGraspsInFile (detect_grasps_python.cpp:468-488): cloud from a .pcd / .ply file, optional normals file ("" = none)
+int detectGraspsInFile(char *config_filename, char *pcd_filename, char *normals_filename, float *view_points, int num_view_points,
+                       struct Grasp **grasps_out) {
+  if (!config_filename || !pcd_filename || !view_points || num_view_points <= 0 || !grasps_out) return 0;
+  *grasps_out = nullptr;
+  gpd::util::Cloud cloud = init_cloud(pcd_filename, normals_filename, view_points, num_view_points);
+  if (cloud.size() == 0) return 0;
+  return detect_to_structs(config_filename, cloud, grasps_out);
+}
+
+// generateGraspCandidatesInFile (detect_grasps_python.cpp:530-549): preprocessing + hand search, no classification
+int generateGraspCandidatesInFile(char *config_filename, char *pcd_filename, char *normals_filename, float *view_points,
+                                  int num_view_points, struct Grasp **grasps_out) {
+  if (!config_filename || !pcd_filename || !view_points || num_view_points <= 0 || !grasps_out) return 0;
+  *grasps_out = nullptr;
+  gpd::util::Cloud cloud = init_cloud(pcd_filename, normals_filename, view_points, num_view_points);
+  if (cloud.size() == 0) return 0;
+  gpd::GraspDetector detector(config_filename);
+  detector.preprocessPointCloud(cloud);
+  std::vector<std::unique_ptr<gpd::candidate::Hand>> hands = detector.generateGraspCandidates(cloud);
+  return hands_to_structs(hands, nullptr, 0, grasps_out);
+}
+
+// detectAndEvalGrasps (detect_grasps_python.cpp:490-528): candidates + images in the camera cloud, labels against the
+// ground-truth mesh cloud (points_gt / normals_gt, 3 x size_gt). Grasp.image = the hand's own image as ints (HWC); the
+// reference's cvMatToArray never fills its array and passes images[0] for every hand.
+int detectAndEvalGrasps(char *config_filename, float *points, int *camera_index, float *view_points, int size, int num_view_points,
+                        float *points_gt, float *normals_gt, int size_gt, struct Grasp **grasps_out) {
+  if (!config_filename || !points || !camera_index || !view_points || size <= 0 || num_view_points <= 0 || !points_gt ||
+      !normals_gt || size_gt <= 0 || !grasps_out)
+    return 0;
+  *grasps_out = nullptr;
+  gpd::util::Cloud cloud = make_cloud(points, nullptr, camera_index, view_points, size, num_view_points);
+  std::vector<int> ones((size_t)size_gt, 1);  // createGroundTruthCloud (:178-190): one camera at the origin seeing everything
+  float origin[3] = {0.f, 0.f, 0.f};
+  gpd::util::Cloud mesh_cloud = make_cloud(points_gt, normals_gt, ones.data(), origin, size_gt, 1);
+  gpd::GraspDetector detector(config_filename);
+  detector.preprocessPointCloud(cloud);
+  std::vector<std::unique_ptr<gpd::candidate::Hand>> hands;
+  std::vector<std::vector<uint8_t>> images;
+  if (!detector.createGraspImages(cloud, hands, images)) {
+    printf("No grasps found!\n");
+    return 0;
+  }
+  printf("Created %d grasps and %d images.\n", (int)hands.size(), (int)images.size());
+  detector.evalGroundTruth(mesh_cloud, hands);
+  return hands_to_structs(hands, &images, 0, grasps_out);
+}
+
+int CopyAndFree(float *in, float *out, int n) {  // detect_grasps_python.cpp:603-607
+  if (!in || !out || n < 0) return -1;
+  memcpy(out, in, sizeof(float) * (size_t)n);
+  delete[] in;
+  return 0;
 }
 
 int freeMemoryGrasps(struct Grasp *in) {

@@ -165,6 +165,26 @@ def test_python_c_interface_symbols_and_quaternion(cli):
     assert L.detectGraspsInCloud(None, None, None, None, 0, 0, None) == -1
 
 
+def test_python_c_interface_file_entry_points_reject_bad_input(cli, tmp_path):
+    """detectGraspsInFile / generateGraspCandidatesInFile / detectAndEvalGrasps / CopyAndFree (detect_grasps_python.cpp:468-549,
+    603-607) are exported; missing arguments and a missing cloud file give 0 grasps before any device is touched (the reference
+    returns 0 when the cloud is empty, :474-476)."""
+    import ctypes as C
+    L = _host_lib(cli)
+    out = C.POINTER(GraspStruct)()
+    vp = np.zeros(3, np.float32)
+    for f in (L.detectGraspsInFile, L.generateGraspCandidatesInFile):
+        f.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.POINTER(GraspStruct))]
+        assert f(None, None, None, None, 0, None) == 0
+        assert f(b"none.cfg", str(tmp_path / "missing.pcd").encode(), b"", vp.ctypes.data, 1, C.byref(out)) == 0
+        assert not out
+    L.detectAndEvalGrasps.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.POINTER(C.POINTER(GraspStruct))]
+    assert L.detectAndEvalGrasps(None, None, None, None, 0, 0, None, None, 0, None) == 0
+    L.CopyAndFree.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    assert L.CopyAndFree(None, None, 0) == -1
+
+
 @pytest.mark.gpu
 def test_python_c_interface_detects_like_the_library(cli, tmp_path, golden_dir):
     import ctypes as C
