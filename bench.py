@@ -523,8 +523,11 @@ def main():
             else:
                 a = v["flops"] / max(v["ms"], 1e-9) / 1e9
                 per_kernel[k] = {"ms_per_step": round(v["ms"], 3), "TFLOP/s": round(a, 2), "frac_tensor": round(a / tf_peak, 4)}
-        if dom == "lenet_conv1":
-            per_kernel[dom]["note"] = "conv1 issues tcgen05 kind::i8 (3 int8 digit planes): the bf16 peak is only a reference scale"
+        # conv1 issues tcgen05 kind::i8 (3 int8 digit planes stacked along N): its instruction peak, measured on B200 with
+        # tools/umma_rate.cu, is 8192 MAC / clock / SM = twice the f16 / bf16 rate (profiles/r02_umma_rate.txt)
+        per_kernel["lenet_conv1"]["frac_tensor_int8"] = round(per_kernel["lenet_conv1"]["frac_tensor"] / 2.0, 4)
+        per_kernel["lenet_conv1"]["note"] = ("kind::i8: frac_tensor is against the bf16 peak (reference scale), frac_tensor_int8 against "
+                                             "2 x that, the measured int8 instruction rate")
         line = {
             "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
