@@ -558,7 +558,7 @@ def main():
         }
         if parity is not None:
             line["parity_check"] = parity
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm beside our line: at N = 1 only (the other ranks would idle in a barrier)
             cb, _ = cpu_baseline(cloud, sidx_all, weights, args.config)
             line["cpu_baseline"] = cb
         if world == 1 and not args.no_preprocess and args.config == 3:
