@@ -227,6 +227,52 @@ def test_python_c_interface_detects_like_the_library(cli, tmp_path, golden_dir):
     ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("GPD_B200_UNVERIFIED_TESTS"),
+                    reason="written after the round's GPU budget was spent: never run on a GPU yet (set GPD_B200_UNVERIFIED_TESTS=1)")
+def test_python_c_interface_candidates_and_eval_entry_points(cli, tmp_path, golden_dir):
+    """detectAndEvalGrasps (candidates + images + labels against a ground-truth cloud) and the library calls it composes:
+    the hands equal gpdb_hand_search's candidates on the preprocessed cloud, the images gpdb_images', the labels
+    gpdb_reevaluate's against the ground-truth cloud."""
+    import ctypes as C
+    from conftest import load_weights
+    from gpd_b200 import lib
+    L = _host_lib(cli)
+    raw = np.ascontiguousarray(np.load(os.path.join(golden_dir, "krylon_preprocess.npz"))["raw"], np.float32)
+    w, _ = load_weights(15)
+    os.makedirs(tmp_path / "params")
+    names = ["conv1_weights", "conv1_biases", "conv2_weights", "conv2_biases", "ip1_weights", "ip1_biases", "ip2_weights", "ip2_biases"]
+    for n, a in zip(names, w):
+        a.astype(np.float32).tofile(tmp_path / "params" / (n + ".bin"))
+    (tmp_path / "main.cfg").write_text(f"hand_geometry_filename = 0\nimage_geometry_filename = 0\nweights_file = {tmp_path}/params/\n"
+                                       "num_samples = 5000\nmin_inliers = 0\nnum_selected = 25\nimage_num_channels = 15\n")
+    cam = np.ones((len(raw), 1), np.int32)
+    vp = np.zeros(3, np.float32)
+    ctx = lib.Context(lib.default_params(channels=15))
+    ctx.set_weights(w)
+    c = ctx.preprocess(raw, cam, np.zeros((1, 3)), lib.preprocess_params())
+    sidx = np.arange(len(c["xyz"]), dtype=np.int32)
+    cand = ctx.hand_search(sidx)["candidates"]
+    imgs = ctx.images(cand)
+    gt_xyz = np.ascontiguousarray(c["xyz"][::2], np.float32)  # a thinned copy of the processed cloud as "ground truth"
+    gt_nrm = np.ascontiguousarray(c["normals"][::2], np.float32)
+    L.detectAndEvalGrasps.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.POINTER(C.POINTER(GraspStruct))]
+    out = C.POINTER(GraspStruct)()
+    n = L.detectAndEvalGrasps(str(tmp_path / "main.cfg").encode(), raw.ctypes.data, cam.ctypes.data, vp.ctypes.data, len(raw), 1,
+                              gt_xyz.ctypes.data, gt_nrm.ctypes.data, len(gt_xyz), C.byref(out))
+    assert n == len(cand) > 0
+    ctx.set_cloud(gt_xyz, gt_nrm.astype(np.float64), None, np.zeros((1, 3)))
+    labels, _ = ctx.reevaluate(cand)
+    isz = imgs[0].size
+    for i in (0, n // 2, n - 1):
+        assert np.allclose([out[i].pos[k] for k in range(3)], cand["position"][i])
+        assert bool(out[i].label) == bool(labels[i])
+        assert np.array_equal(np.ctypeslib.as_array(out[i].image, (isz,)), imgs[i].ravel().astype(np.int32))
+    assert L.freeMemoryGrasps(out) == 0
+    ctx.close()
+
+
 def test_clustering_matches_a_python_restatement(cli):
     """Clustering::findClusters (clustering.cpp:5-105) in the host shim against a line-by-line numpy restatement."""
     import ctypes as C
